@@ -1,0 +1,214 @@
+/*
+ * mspi_b200 — C ABI of the B200 (sm_100a) kernels behind MSPI's batched clip forward.
+ *
+ * The reference (oraclefina/MSPI) is pure Python/PyTorch and has no FFI of its own;
+ * every entry point below replaces the PyTorch library call(s) that the reference
+ * makes at the cited file:line (paths relative to the reference root).  All pointers
+ * are DEVICE pointers unless stated otherwise, sizes are element counts, `stream` is a
+ * cudaStream_t passed as void*.  Every function returns 0 on success and a negative
+ * code on failure; mspi_last_error() returns the message for the calling thread.
+ *
+ * Activation layout is channels-last ("NDHWC": [N][T][H][W][C], C contiguous), bf16
+ * unless a dtype field says otherwise.  There is no CPU fallback: with no usable GPU
+ * every compute entry point fails with MSPI_ERR_CUDA.
+ */
+#ifndef MSPI_B200_H
+#define MSPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSPI_OK 0
+#define MSPI_ERR_ARG (-1)
+#define MSPI_ERR_CUDA (-2)
+#define MSPI_ERR_UNSUPPORTED (-3)
+
+/* dtype codes */
+#define MSPI_BF16 0
+#define MSPI_F32 1
+/* activation codes (epilogues) */
+#define MSPI_ACT_NONE 0
+#define MSPI_ACT_RELU 1
+#define MSPI_ACT_GELU 2    /* exact erf GELU, nn.GELU() default (model_utils.py:325) */
+#define MSPI_ACT_SIGMOID 3 /* nn.Sigmoid (model_utils.py:164) */
+
+#define MSPI_MAX_TAPS 32
+
+const char* mspi_last_error(void);
+/* Library/ABI version and the SM architecture the kernels were compiled for ("sm_100a"). */
+int mspi_version(void);
+const char* mspi_arch(void);
+/* Number of kernels launched by this library since load (process-wide counter). */
+int64_t mspi_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces: nn.Conv3d / nn.Conv2d / nn.Linear + BatchNorm(eval) + ReLU/GELU/Sigmoid + residual
+ *   backbones/s3d.py:41-52,95-116 (BasicConv3d, SepConv3d), backbones/resnet.py:17-54,
+ *   model/model_utils.py:43-46,92-94,155-170,324-327,367-377,404-435,437-504.
+ *
+ * The activation tensor is described as a 5-D view (inner -> outer) C, d1, d2, d3, d4 with
+ * arbitrary element strides (stride of C must be 1).  One M-tile is a box of up to 128 output
+ * positions (box[1]*box[2]*box[3]*box[4] <= 128); for every filter tap the same box shifted by
+ * tap_off[tap][*] is fetched by one TMA bulk-tensor load, out-of-bounds elements read as zero
+ * (this is the convolution's zero padding).  K is ordered (tap, cin); the weight matrix is
+ * [cout_padded][ntaps*cin_pad], K contiguous, zero padded.
+ *   y[pos][n] = act( scale[n] * sum_k A[pos][k] W[n][k] + shift[n] (+ residual[pos][n]) )
+ * A plain GEMM is the special case ntaps=1, a_dims={K,M,1,1,1}, box={*,128,1,1,1}.
+ */
+typedef struct {
+  int32_t a_dtype;      /* MSPI_BF16 (kind::f16) or MSPI_F32 (kind::tf32); weights use the same */
+  int32_t a_dims[5];    /* extents of the activation view; a_dims[0] = input channels visible */
+  int64_t a_strides[5]; /* element strides; a_strides[0] == 1; byte strides must be 16B multiples */
+  int32_t box[5];       /* box[0] ignored (K chunk is 128 bytes); box[1..4] output-position box */
+  int32_t ntaps;
+  int32_t tap_off[MSPI_MAX_TAPS][4]; /* coordinate offset of each tap along d1..d4 */
+  int32_t cin_pad;      /* K extent of one tap inside the weight matrix (multiple of the K chunk) */
+  int32_t cout;         /* valid output channels */
+  int32_t w_rows;       /* rows of the weight matrix (>= cout) */
+  int32_t bn;           /* N tile: multiple of 16, 16..256 */
+  int32_t o_dims[4];    /* output extents along d1..d4 */
+  int64_t o_strides[4]; /* element strides of the output rows (channel stride 1) */
+  int64_t r_strides[4]; /* same for the residual tensor */
+  int32_t o_dtype;      /* MSPI_BF16 or MSPI_F32 */
+  int32_t r_dtype;      /* dtype of the residual */
+  int32_t act;          /* MSPI_ACT_* */
+  int32_t has_residual;
+  int32_t res_after_act; /* 0: act(v + res)   1: act(v) + res */
+} MspiConvDesc;
+
+int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
+                   const float* shift, const void* residual, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch gather (explicit im2col) for the layers whose input has too few channels for a TMA
+ * K-chunk (Cin = 3 or 1) or an odd-size strided grid: S3D stem conv_s (backbones/s3d.py:383),
+ * ConvNeXt stem 4x4/s4 (timm convnext_tiny, model_utils.py:361), ResNet conv1 and its stride-2
+ * convs (backbones/resnet.py:79, 8-14).  Writes bf16 rows [M][k_pad], K ordered (kt,kh,kw,c),
+ * zero padded to k_pad.  src layout: 0 = fp32 NCDHW (the model's input contract), 1 = bf16 NDHWC.
+ */
+typedef struct {
+  int32_t src_layout;
+  int32_t n, c, t, h, w;      /* input extents */
+  int64_t src_cstride;        /* NDHWC only: elements between consecutive pixels (>= c) */
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+  int32_t ot, oh, ow;         /* output extents */
+  int32_t k_pad;              /* row length of dst (>= kt*kh*kw*c, multiple of 8) */
+} MspiPatchDesc;
+int mspi_patch_gather(const MspiPatchDesc* d, const void* src, void* dst, void* stream);
+
+/* fp32 NCDHW -> bf16 NDHWC (clips, model_utils.py:557 rearrange; audio [B,1,F,T]) */
+int mspi_ncdhw_to_ndhwc(const float* src, void* dst, int n, int c, int thw, int64_t dst_cstride,
+                        void* stream);
+/* bf16/fp32 NDHWC (channel slice) -> fp32 NCDHW, used to hand taps back to PyTorch callers */
+int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n,
+                        int c, int thw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MaxPool3d, channels-last bf16, -inf padding.  Replaces nn.MaxPool3d / nn.MaxPool2d at
+ * backbones/s3d.py:134,384-401, backbones/resnet.py:83, model_utils.py:189,206.
+ */
+typedef struct {
+  int32_t n, t, h, w, c;
+  int64_t in_cstride, out_cstride; /* elements between pixels (channel-slice views) */
+  int32_t kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int32_t ot, oh, ow;
+} MspiPoolDesc;
+int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear (1,k,k) upsample, align_corners=False, channels-last.  Replaces
+ * nn.Upsample(mode='trilinear', scale_factor=(1,k,k)) at model_utils.py:158,208,486-488,498.
+ *   y = up(x) (+ y if accumulate)        in/out dtype bf16 or fp32
+ */
+typedef struct {
+  int32_t nt;        /* N*T planes */
+  int32_t h, w, c;   /* input plane */
+  int32_t k;         /* integer scale */
+  int64_t in_cstride, out_cstride;
+  int32_t in_dtype, out_dtype;
+  int32_t accumulate;
+} MspiUpDesc;
+int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Depthwise convolution (+ optional LayerNorm over C), channels-last.
+ * Replaces ConvNextBlock.dwconv_t/dwconv_s + LayerNorm3d (model_utils.py:321-323,293-303)
+ * and timm ConvNeXt conv_dw + norm (model_utils.py:361).
+ *   y = LN_C( dwconv(x) + bias ) * ln_w + ln_b        (LN skipped when ln_w == NULL)
+ * weights: fp32 [kt*kh*kw][C] (tap-major), bias fp32 [C].
+ */
+typedef struct {
+  int32_t n, t, h, w, c;
+  int32_t kt, kh, kw; /* odd, "same" padding */
+  float ln_eps;
+  int32_t out_dtype;
+} MspiDwDesc;
+int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias,
+                   const float* ln_w, const float* ln_b, void* y, void* stream);
+
+/* LayerNorm over the last dim of [rows][c]; in/out dtype selectable; optional ReLU and an
+ * optional additive table pos[(row % pos_rows)][c] (sinusoid position table, model_utils.py:18-29,
+ * 270-274).  Replaces nn.LayerNorm at model_utils.py:231-233,138-144,406-434 and LayerNorm2d. */
+typedef struct {
+  int64_t rows;
+  int32_t c;
+  int64_t in_rstride, out_rstride;
+  int32_t in_dtype, out_dtype;
+  float eps;
+  int32_t relu;
+  int32_t pos_rows; /* 0 = no table */
+  int64_t rows_per_group, out_gstride; /* output row r -> (r / rows_per_group)*out_gstride + (r % rows_per_group)*out_rstride */
+} MspiLnDesc;
+int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w, const float* b,
+                   const float* pos, void* y, void* stream);
+
+/* Multi-head self attention over short sequences (model_utils.py:97-109): qkv bf16
+ * [B][N][3][heads][hd] -> out bf16 [B][N][heads*hd]; softmax(q k^T * scale) v in fp32. */
+int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, float scale,
+                   void* stream);
+
+/* SA gating + top-down sums (model_utils.py:167-170,566-568):
+ *   y = x * sigmoid_mask + x ; the mask logits are fp32 [N*T*H*W] (one channel). */
+int mspi_sa_gate(const void* x, const float* mask_logits, void* y, int64_t pixels, int c,
+                 void* stream);
+
+/* Elementwise y = a + b over bf16 (used for ViT residuals when not fused) */
+int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+
+/* Mean over tokens: x bf16 [B][rows][C] (row range [r0, r1)) -> fp32 [B][C]
+ * (AdaptiveAvgPool3d/2d to 1, model_utils.py:401-402,545-546). */
+int mspi_token_mean(const void* x, float* y, int b, int rows, int r0, int r1, int c, void* stream);
+
+/* SimSiam negative cosine loss (model_utils.py:285-290,551):
+ *   out[0] = 0.5*( -mean_b cos(p_v, z_a) - mean_b cos(p_a, z_v) ), all fp32 [B][C]. */
+int mspi_simsiam_loss(const float* p_v, const float* z_a, const float* p_a, const float* z_v,
+                      float* out, int b, int c, void* stream);
+
+/* out[b] = x[b] - logsumexp(x[b]) over H*W pixels, fp32 (model_utils.py:571-572). */
+int mspi_logsoftmax2d(const float* x, float* y, int b, int64_t pixels, void* stream);
+
+/* Saliency metrics (utils/compute_saliency_metrics.py:9-108, utils/loss.py:26-49).
+ * pred: fp32 [B][P]; if pred_is_log != 0 the kernel uses exp(pred) (SalLoss passes the log map).
+ * gt: fp32 [B][P]; fix: fp32 [B][P] or NULL.  out fp32[5] = {kld, cc, sim, nss, loss}, batch
+ * means; loss = kld - cc (- 0.1*nss when fix != NULL); nss = 0 when fix == NULL.
+ * work: fp32 scratch of at least 16*B floats. */
+int mspi_saliency_metrics(const float* pred, int pred_is_log, const float* gt, const float* fix,
+                          float* out, float* work, int b, int64_t pixels, void* stream);
+
+/* Log power spectrogram front end (inference.py:24-63, avsp_dataloader.py:51-80):
+ * wave fp32 [B][n] -> out fp32 [B][257][frames_out]; STFT n_fft=512, hop=160, periodic Hann,
+ * center=True reflect pad, |.|^2, log(x+1e-6), per-frame standardise over the 257 bins
+ * (unbiased std, +1e-6), columns beyond the signal's frames filled with 0.02, cropped to
+ * frames_out. */
+int mspi_logspec(const float* wave, float* out, int b, int n, int frames_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSPI_B200_H */

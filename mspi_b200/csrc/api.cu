@@ -1,0 +1,35 @@
+// Error reporting, version and launch accounting for the mspi_b200 C ABI.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mspi {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    sms = n;
+  }
+  return sms;
+}
+
+}  // namespace mspi
+
+extern "C" const char* mspi_last_error(void) { return mspi::g_err; }
+extern "C" int mspi_version(void) { return 1; }
+extern "C" const char* mspi_arch(void) { return "sm_100a"; }
+extern "C" int64_t mspi_launch_count(void) { return mspi::g_launches.load(); }

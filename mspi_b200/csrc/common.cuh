@@ -1,0 +1,98 @@
+// Shared helpers for the mspi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/mspi_b200.h"
+
+namespace mspi {
+
+// ---- host side -----------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define MSPI_CHECK_ARG(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) return mspi::set_error(MSPI_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define MSPI_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return mspi::set_error(MSPI_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+  } while (0)
+
+#define MSPI_LAUNCH_CHECK()                  \
+  do {                                       \
+    mspi::count_launch();                    \
+    MSPI_CUDA(cudaGetLastError());           \
+  } while (0)
+
+int num_sms();
+
+// ---- device side ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  lo = __bfloat162float(v.x);
+  hi = __bfloat162float(v.y);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` is >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MSPI_ACT_RELU: return fmaxf(v, 0.f);
+    case MSPI_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case MSPI_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace mspi

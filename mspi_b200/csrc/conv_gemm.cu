@@ -1,0 +1,506 @@
+// Implicit-GEMM convolution / linear kernel for sm_100a.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (UMMA 128 x BN x 16,
+//   cta_group::1, accumulators in TMEM, double buffered) -> tcgen05.ld epilogue (scale/shift = folded
+//   BatchNorm or bias, activation, residual) -> global stores into a channel slice of the output.
+//
+// One CTA per SM, persistent over output tiles, warp specialised:
+//   warp 0     : TMA producer (one elected lane)
+//   warp 1     : TMEM allocation + MMA issue (one elected lane)
+//   warps 2..5 : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31
+//
+// The convolution is never materialised as an im2col matrix: an M-tile is a box of output positions in
+// the (d1,d2,d3,d4) view of the NDHWC activation, and for filter tap `tap` the A operand is the same box
+// shifted by tap_off[tap]; TMA zero-fills whatever falls outside the tensor, which is exactly the
+// convolution's zero padding.  See include/mspi_b200.h (MspiConvDesc) for the contract.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mspi {
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kRowBytes = 128;               // one K chunk of one row: 64 bf16 or 32 tf32
+constexpr int kABytes = kTileM * kRowBytes;  // 16 KB
+constexpr int kBarrierBytes = 1024;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 220 * 1024;
+
+struct GemmParams {
+  int box[4];
+  int tiles_d[4];
+  int n_tiles, m_tiles;
+  int ntaps, kchunks, cin_pad, bk_elems;
+  int tap_off[MSPI_MAX_TAPS][4];
+  int cout, bn;
+  int o_dims[4];
+  long long o_strides[4];
+  long long r_strides[4];
+  int o_dtype, r_dtype, act, has_res, res_after_act;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  void* y;
+  uint32_t idesc;
+  int num_stages, b_bytes, a_tx_bytes, tmem_cols;
+};
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > (1ll << 32)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (KIND == MSPI_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+  d |= static_cast<uint64_t>(1) << 46;                  // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------ kernel
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // barrier block: full[8] empty[8] tmem_full[2] tmem_empty[2] tmem_ptr
+  const uint32_t bar_full = smem_base;
+  const uint32_t bar_empty = smem_base + 8 * kMaxStages;
+  const uint32_t bar_tfull = smem_base + 16 * kMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t tiles_base = smem_base + kBarrierBytes;
+  const uint32_t stage_bytes = kABytes + p.b_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        int org[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          org[j] = (mt % p.tiles_d[j]) * p.box[j];
+          mt /= p.tiles_d[j];
+        }
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int c1 = org[0] + p.tap_off[tap][0], c2 = org[1] + p.tap_off[tap][1];
+          const int c3 = org[2] + p.tap_off[tap][2], c4 = org[3] + p.tap_off[tap][3];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
+            const uint32_t sa = tiles_base + stage * stage_bytes;
+            tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
+            tma_load_2d(sa + kABytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.bn);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = tiles_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K * elsize = 32 B) per 128 B swizzle row
+            tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(bar_tfull + 8 * as);  // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const bool out_bf16 = p.o_dtype == MSPI_BF16;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      int r = row;
+      bool valid = true;
+      long long yoff = 0, roff = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int org = (mt % p.tiles_d[j]) * p.box[j];
+        mt /= p.tiles_d[j];
+        const int c = org + (r % p.box[j]);
+        r /= p.box[j];
+        valid = valid && (c < p.o_dims[j]);
+        yoff += static_cast<long long>(c) * p.o_strides[j];
+        roff += static_cast<long long>(c) * p.r_strides[j];
+      }
+      valid = valid && (r == 0);
+
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(as * p.bn);
+      const int n_base = nt * p.bn;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t acc[16];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
+        tmem_ld16(taddr + c0, acc);
+        tmem_ld_wait();
+        const int n0 = n_base + c0;
+        if (!valid || n0 >= p.cout) continue;
+        float v[16];
+        const bool full16 = (n0 + 16 <= p.cout);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = full16 ? (n0 + j) : min(n0 + j, p.cout - 1);
+          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
+          const float sh = p.shift ? __ldg(p.shift + n) : 0.f;
+          v[j] = fmaf(__uint_as_float(acc[j]), sc, sh);
+        }
+        float res[16];
+        if (p.has_res) {
+          if (full16 && p.r_dtype == MSPI_BF16) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + n0);
+            const uint4 a = __ldg(rp), b = __ldg(rp + 1);
+            unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
+            unpack_bf16x2(a.z, res[4], res[5]); unpack_bf16x2(a.w, res[6], res[7]);
+            unpack_bf16x2(b.x, res[8], res[9]); unpack_bf16x2(b.y, res[10], res[11]);
+            unpack_bf16x2(b.z, res[12], res[13]); unpack_bf16x2(b.w, res[14], res[15]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = min(n0 + j, p.cout - 1);
+              res[j] = p.r_dtype == MSPI_BF16
+                           ? bf2f(static_cast<const __nv_bfloat16*>(p.residual)[roff + n])
+                           : static_cast<const float*>(p.residual)[roff + n];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[j];
+          if (p.has_res && !p.res_after_act) x += res[j];
+          x = apply_act(x, p.act);
+          if (p.has_res && p.res_after_act) x += res[j];
+          v[j] = x;
+        }
+        if (out_bf16) {
+          __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) + yoff + n0;
+          if (full16) {
+            uint4 a, b;
+            a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
+            a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+            b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]);
+            b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+            reinterpret_cast<uint4*>(yp)[0] = a;
+            reinterpret_cast<uint4*>(yp)[1] = b;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* yp = static_cast<float*>(p.y) + yoff + n0;
+          if (full16 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<float4*>(yp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < p.cout) yp[j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+// -------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+}  // namespace
+}  // namespace mspi
+
+using namespace mspi;
+
+extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
+                              const float* shift, const void* residual, void* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && w && y, "mspi_conv_gemm: null argument");
+  MSPI_CHECK_ARG(d->a_dtype == MSPI_BF16 || d->a_dtype == MSPI_F32, "a_dtype %d", d->a_dtype);
+  const int elsize = d->a_dtype == MSPI_BF16 ? 2 : 4;
+  const int bk = kRowBytes / elsize;
+  MSPI_CHECK_ARG(d->a_strides[0] == 1, "channel stride must be 1");
+  MSPI_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= MSPI_MAX_TAPS, "ntaps %d", d->ntaps);
+  MSPI_CHECK_ARG(d->bn >= 16 && d->bn <= 256 && d->bn % 16 == 0, "bn %d", d->bn);
+  MSPI_CHECK_ARG(d->cin_pad > 0 && d->cin_pad % bk == 0, "cin_pad %d not a multiple of %d", d->cin_pad, bk);
+  MSPI_CHECK_ARG(d->cout >= 1 && d->w_rows >= d->cout, "cout %d w_rows %d", d->cout, d->w_rows);
+  MSPI_CHECK_ARG(!d->has_residual || residual, "residual requested but null");
+  MSPI_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 "operands must be 16-byte aligned");
+  long long rows = 1;
+  for (int j = 1; j < 5; ++j) {
+    MSPI_CHECK_ARG(d->box[j] >= 1 && d->box[j] <= 256, "box[%d]=%d", j, d->box[j]);
+    MSPI_CHECK_ARG(d->a_dims[j] >= 1 && d->o_dims[j - 1] >= 1, "dims[%d]", j);
+    MSPI_CHECK_ARG((d->a_strides[j] * elsize) % 16 == 0, "a_strides[%d] not 16B aligned", j);
+    rows *= d->box[j];
+  }
+  MSPI_CHECK_ARG(rows <= kTileM, "box has %lld rows (> %d)", rows, kTileM);
+  if (d->o_dtype == MSPI_BF16 && d->cout >= 8)
+    for (int j = 0; j < 4; ++j)
+      MSPI_CHECK_ARG(d->o_strides[j] % 8 == 0 || d->o_dims[j] == 1, "o_strides[%d] must be a multiple of 8", j);
+  MSPI_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "output must be 16-byte aligned");
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int j = 0; j < 5; ++j) gdim[j] = static_cast<cuuint64_t>(d->a_dims[j]);
+    for (int j = 1; j < 5; ++j) gstr[j - 1] = static_cast<cuuint64_t>(d->a_strides[j]) * elsize;
+    bdim[0] = bk;
+    for (int j = 1; j < 5; ++j) bdim[j] = d->box[j];
+    CUresult r = encode(&map_a, d->a_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                        5, const_cast<void*>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d dims=[%d,%d,%d,%d,%d] box=[%d,%d,%d,%d,%d]",
+                       (int)r, d->a_dims[0], d->a_dims[1], d->a_dims[2], d->a_dims[3], d->a_dims[4], bk,
+                       d->box[1], d->box[2], d->box[3], d->box[4]);
+  }
+  {
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d->ntaps) * d->cin_pad, static_cast<cuuint64_t>(d->w_rows)};
+    cuuint64_t gstr[1] = {gdim[0] * elsize};
+    cuuint32_t bdim[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_b, d->a_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                        2, const_cast<void*>(w), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d K=%llu rows=%d bn=%d", (int)r,
+                       (unsigned long long)gdim[0], d->w_rows, d->bn);
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = 1;
+  for (int j = 0; j < 4; ++j) {
+    p.box[j] = d->box[j + 1];
+    p.tiles_d[j] = (d->o_dims[j] + p.box[j] - 1) / p.box[j];
+    p.m_tiles *= p.tiles_d[j];
+    p.o_dims[j] = d->o_dims[j];
+    p.o_strides[j] = d->o_strides[j];
+    p.r_strides[j] = d->r_strides[j];
+  }
+  p.n_tiles = (d->cout + d->bn - 1) / d->bn;
+  p.ntaps = d->ntaps;
+  p.bk_elems = bk;
+  p.kchunks = (d->a_dims[0] + bk - 1) / bk;
+  MSPI_CHECK_ARG(p.kchunks * bk <= d->cin_pad, "cin_pad %d smaller than padded channels %d", d->cin_pad, p.kchunks * bk);
+  p.cin_pad = d->cin_pad;
+  memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
+  p.cout = d->cout;
+  p.bn = d->bn;
+  p.o_dtype = d->o_dtype;
+  p.r_dtype = d->r_dtype;
+  p.act = d->act;
+  p.has_res = d->has_residual;
+  p.res_after_act = d->res_after_act;
+  p.scale = scale;
+  p.shift = shift;
+  p.residual = residual;
+  p.y = y;
+  const uint32_t fmt = d->a_dtype == MSPI_BF16 ? 1u : 2u;  // UMMA F16F32Format: BF16 = 1, TF32 = 2
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(d->bn >> 3) << 17) |
+            (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.b_bytes = d->bn * kRowBytes;
+  p.a_tx_bytes = static_cast<int>(rows) * kRowBytes;
+  const int stage_bytes = kABytes + p.b_bytes;
+  p.num_stages = (kSmemBudget - kBarrierBytes - 1024) / stage_bytes;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  int cols = 32;
+  while (cols < 2 * d->bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = 1024 + kBarrierBytes + static_cast<size_t>(p.num_stages) * stage_bytes;
+
+  auto kern = d->a_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16> : conv_gemm_kernel<MSPI_F32>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[d->a_dtype]) {
+    MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[d->a_dtype] = true;
+  }
+  const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  MSPI_CHECK_ARG(total < (1ll << 31), "too many tiles");
+  int grid = num_sms();
+  if (grid <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  if (total < grid) grid = static_cast<int>(total);
+  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}

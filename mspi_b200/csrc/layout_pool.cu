@@ -1,0 +1,347 @@
+// Layout changes, patch gather, max-pool, bilinear upsample and SA gating — HBM-bound kernels,
+// 16-byte vectorised along the contiguous channel dimension of the NDHWC layout.
+#include "common.cuh"
+
+namespace mspi {
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ------------------------------------------------------------------------- patch gather
+// bf16 NDHWC source, C % 8 == 0: one thread moves 8 channels of one tap (16 B).
+__global__ void patch_gather_nhwc_kernel(MspiPatchDesc d, const __nv_bfloat16* __restrict__ src,
+                                         __nv_bfloat16* __restrict__ dst, long long total_chunks, int chunks_per_row,
+                                         int c8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / chunks_per_row;
+    const int ch = static_cast<int>(i - m * chunks_per_row);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int tap = ch / c8, cc = ch - tap * c8;
+    if (tap < d.kt * d.kh * d.kw) {
+      long long r = m;
+      const int ow = static_cast<int>(r % d.ow); r /= d.ow;
+      const int oh = static_cast<int>(r % d.oh); r /= d.oh;
+      const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+      const int n = static_cast<int>(r);
+      const int kw = tap % d.kw, kh = (tap / d.kw) % d.kh, kt = tap / (d.kw * d.kh);
+      const int it = ot * d.st - d.pt + kt, ih = oh * d.sh - d.ph + kh, iw = ow * d.sw - d.pw + kw;
+      if (it >= 0 && it < d.t && ih >= 0 && ih < d.h && iw >= 0 && iw < d.w) {
+        const long long pix = ((static_cast<long long>(n) * d.t + it) * d.h + ih) * d.w + iw;
+        v = ldg16(src + pix * d.src_cstride + cc * 8);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + m * d.k_pad + static_cast<long long>(ch) * 8) = v;
+  }
+}
+
+// Generic element-wise gather: fp32 NCDHW (src_layout 0) or bf16 NDHWC with any C.  One thread
+// produces 8 consecutive K elements of one row (one 16 B store).
+__global__ void patch_gather_generic_kernel(MspiPatchDesc d, const void* __restrict__ src,
+                                            __nv_bfloat16* __restrict__ dst, long long total_chunks, int chunks_per_row) {
+  const int ktot = d.kt * d.kh * d.kw * d.c;
+  const long long thw = static_cast<long long>(d.t) * d.h * d.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / chunks_per_row;
+    const int ch = static_cast<int>(i - m * chunks_per_row);
+    long long r = m;
+    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
+    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
+    const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+    const int n = static_cast<int>(r);
+    float vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = ch * 8 + e;
+      float v = 0.f;
+      if (k < ktot) {
+        const int c = k % d.c;
+        int tap = k / d.c;
+        const int kw = tap % d.kw; tap /= d.kw;
+        const int kh = tap % d.kh;
+        const int kt = tap / d.kh;
+        const int it = ot * d.st - d.pt + kt, ih = oh * d.sh - d.ph + kh, iw = ow * d.sw - d.pw + kw;
+        if (it >= 0 && it < d.t && ih >= 0 && ih < d.h && iw >= 0 && iw < d.w) {
+          const long long sp = (static_cast<long long>(it) * d.h + ih) * d.w + iw;
+          if (d.src_layout == 0)
+            v = __ldg(static_cast<const float*>(src) + (static_cast<long long>(n) * d.c + c) * thw + sp);
+          else
+            v = bf2f(static_cast<const __nv_bfloat16*>(src)[(static_cast<long long>(n) * thw + sp) * d.src_cstride + c]);
+        }
+      }
+      vals[e] = v;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(vals[0], vals[1]); o.y = pack_bf16x2(vals[2], vals[3]);
+    o.z = pack_bf16x2(vals[4], vals[5]); o.w = pack_bf16x2(vals[6], vals[7]);
+    *reinterpret_cast<uint4*>(dst + m * d.k_pad + static_cast<long long>(ch) * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------- layout changes
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int c,
+                                      long long thw, long long cstride) {
+  const long long total = static_cast<long long>(n) * thw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / thw, sp = i - b * thw;
+    for (int ch = 0; ch < c; ++ch)
+      dst[i * cstride + ch] = __float2bfloat16_rn(__ldg(src + (b * c + ch) * thw + sp));
+  }
+}
+
+// [N][THW][C] -> [N][C][THW] through a 32x33 shared tile.
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, long long cstride, float* __restrict__ dst, int c,
+                                      long long thw) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long sp0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long sp = sp0 + r;
+    const int ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (sp < thw && ch < c) v = static_cast<float>(src[(static_cast<long long>(n) * thw + sp) * cstride + ch]);
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ch = c0 + r;
+    const long long sp = sp0 + threadIdx.x;
+    if (sp < thw && ch < c) dst[(static_cast<long long>(n) * c + ch) * thw + sp] = tile[threadIdx.x][r];
+  }
+}
+
+// ------------------------------------------------------------------------- max pool
+__global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                 long long total, int c8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    long long r = i / c8;
+    const long long opix = r;
+    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
+    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
+    const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+    const int n = static_cast<int>(r);
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    __nv_bfloat162 m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
+    const int t0 = ot * d.st - d.pt, h0 = oh * d.sh - d.ph, w0 = ow * d.sw - d.pw;
+    for (int kt = 0; kt < d.kt; ++kt) {
+      const int it = t0 + kt;
+      if (it < 0 || it >= d.t) continue;
+      for (int kh = 0; kh < d.kh; ++kh) {
+        const int ih = h0 + kh;
+        if (ih < 0 || ih >= d.h) continue;
+        for (int kw = 0; kw < d.kw; ++kw) {
+          const int iw = w0 + kw;
+          if (iw < 0 || iw >= d.w) continue;
+          const long long pix = ((static_cast<long long>(n) * d.t + it) * d.h + ih) * d.w + iw;
+          const uint4 v = ldg16(x + pix * d.in_cstride + cc * 8);
+          m0 = __hmax2(m0, *reinterpret_cast<const __nv_bfloat162*>(&v.x));
+          m1 = __hmax2(m1, *reinterpret_cast<const __nv_bfloat162*>(&v.y));
+          m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&v.z));
+          m3 = __hmax2(m3, *reinterpret_cast<const __nv_bfloat162*>(&v.w));
+        }
+      }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+    o.z = *reinterpret_cast<uint32_t*>(&m2); o.w = *reinterpret_cast<uint32_t*>(&m3);
+    *reinterpret_cast<uint4*>(y + opix * d.out_cstride + cc * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------- bilinear upsample
+// align_corners=False, integer scale k: src = (dst + 0.5)/k - 0.5 clamped at 0 (PyTorch's
+// area_pixel_compute_source_index), second index clamped at size-1.
+template <typename TI, typename TO, int VEC>
+__global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __restrict__ y, long long total, int cv) {
+  const int oh_ = d.h * d.k, ow_ = d.w * d.k;
+  const float inv = 1.f / static_cast<float>(d.k);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = static_cast<int>(i % cv);
+    long long r = i / cv;
+    const long long opix = r;
+    const int ox = static_cast<int>(r % ow_); r /= ow_;
+    const int oy = static_cast<int>(r % oh_); r /= oh_;
+    const long long plane = r;
+    float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, d.h - 1), x1 = min(x0 + 1, d.w - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const long long base = plane * d.h * d.w;
+    const TI* p00 = x + (base + static_cast<long long>(y0) * d.w + x0) * d.in_cstride + cc * VEC;
+    const TI* p01 = x + (base + static_cast<long long>(y0) * d.w + x1) * d.in_cstride + cc * VEC;
+    const TI* p10 = x + (base + static_cast<long long>(y1) * d.w + x0) * d.in_cstride + cc * VEC;
+    const TI* p11 = x + (base + static_cast<long long>(y1) * d.w + x1) * d.in_cstride + cc * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      v[e] = w00 * static_cast<float>(p00[e]) + w01 * static_cast<float>(p01[e]) +
+             w10 * static_cast<float>(p10[e]) + w11 * static_cast<float>(p11[e]);
+    TO* yp = y + opix * d.out_cstride + cc * VEC;
+    if (d.accumulate) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] += static_cast<float>(yp[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) yp[e] = static_cast<TO>(v[e]);
+  }
+}
+
+// ------------------------------------------------------------------------- SA gate, add
+__global__ void sa_gate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ m,
+                               __nv_bfloat16* __restrict__ y, long long total, int c8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const float g = 1.f + 1.f / (1.f + __expf(-__ldg(m + pix)));  // x*mask + x
+    const uint4 v = ldg16(x + i * 8);
+    float f[8];
+    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+    unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+    uint4 o;
+    o.x = pack_bf16x2(f[0] * g, f[1] * g); o.y = pack_bf16x2(f[2] * g, f[3] * g);
+    o.z = pack_bf16x2(f[4] * g, f[5] * g); o.w = pack_bf16x2(f[6] * g, f[7] * g);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = ldg16(a + i * 8), v = ldg16(b + i * 8);
+    float f[8], g[8];
+    unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+    unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+    unpack_bf16x2(v.x, g[0], g[1]); unpack_bf16x2(v.y, g[2], g[3]);
+    unpack_bf16x2(v.z, g[4], g[5]); unpack_bf16x2(v.w, g[6], g[7]);
+    uint4 o;
+    o.x = pack_bf16x2(f[0] + g[0], f[1] + g[1]); o.y = pack_bf16x2(f[2] + g[2], f[3] + g[3]);
+    o.z = pack_bf16x2(f[4] + g[4], f[5] + g[5]); o.w = pack_bf16x2(f[6] + g[6], f[7] + g[7]);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+inline int grid_for(long long work) {
+  const long long blocks = (work + kBlock - 1) / kBlock;
+  const long long cap = static_cast<long long>(num_sms()) * 16;  // a few waves of resident CTAs
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+}  // namespace mspi
+
+using namespace mspi;
+
+extern "C" int mspi_patch_gather(const MspiPatchDesc* d, const void* src, void* dst, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && src && dst, "mspi_patch_gather: null argument");
+  MSPI_CHECK_ARG(d->k_pad % 8 == 0 && d->k_pad >= d->kt * d->kh * d->kw * d->c, "k_pad %d", d->k_pad);
+  MSPI_CHECK_ARG(d->src_layout == 0 || d->src_layout == 1, "src_layout");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const long long m = static_cast<long long>(d->n) * d->ot * d->oh * d->ow;
+  const int cpr = d->k_pad / 8;
+  const long long total = m * cpr;
+  if (d->src_layout == 1 && d->c % 8 == 0 && d->src_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    patch_gather_nhwc_kernel<<<grid_for(total), kBlock, 0, stream>>>(
+        *d, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), total, cpr, d->c / 8);
+  } else {
+    patch_gather_generic_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, src, static_cast<__nv_bfloat16*>(dst),
+                                                                        total, cpr);
+  }
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_ncdhw_to_ndhwc(const float* src, void* dst, int n, int c, int thw, int64_t dst_cstride,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(src && dst && n > 0 && c > 0 && thw > 0 && dst_cstride >= c, "mspi_ncdhw_to_ndhwc: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  ncdhw_to_ndhwc_kernel<<<grid_for(static_cast<long long>(n) * thw), kBlock, 0, stream>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n, c, thw, dst_cstride);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n, int c,
+                                   int thw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(src && dst && n > 0 && c > 0 && thw > 0, "mspi_ndhwc_to_ncdhw: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  dim3 grid((thw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  if (src_dtype == MSPI_BF16)
+    ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(src),
+                                                                     src_cstride, dst, c, thw);
+  else
+    ndhwc_to_ncdhw_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), src_cstride, dst, c, thw);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && y, "mspi_maxpool3d: null argument");
+  MSPI_CHECK_ARG(d->c % 8 == 0 && d->in_cstride % 8 == 0 && d->out_cstride % 8 == 0, "channels must be multiples of 8");
+  MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "16-byte alignment");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int c8 = d->c / 8;
+  const long long total = static_cast<long long>(d->n) * d->ot * d->oh * d->ow * c8;
+  maxpool3d_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
+                                                           static_cast<__nv_bfloat16*>(y), total, c8);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && y && d->k >= 1, "mspi_upsample_bilinear: bad argument");
+  MSPI_CHECK_ARG(d->c % 8 == 0, "channels must be a multiple of 8");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  constexpr int VEC = 8;
+  const int cv = d->c / VEC;
+  const long long total = static_cast<long long>(d->nt) * d->h * d->k * d->w * d->k * cv;
+  const int g = grid_for(total);
+  using bf = __nv_bfloat16;
+  if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16)
+    upsample_kernel<bf, bf, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const bf*>(x), static_cast<bf*>(y), total, cv);
+  else if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_F32)
+    upsample_kernel<bf, float, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const bf*>(x), static_cast<float*>(y), total, cv);
+  else if (d->in_dtype == MSPI_F32 && d->out_dtype == MSPI_F32)
+    upsample_kernel<float, float, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const float*>(x), static_cast<float*>(y), total, cv);
+  else
+    upsample_kernel<float, bf, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const float*>(x), static_cast<bf*>(y), total, cv);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_sa_gate(const void* x, const float* mask_logits, void* y, int64_t pixels, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0, "mspi_sa_gate: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const long long total = pixels * (c / 8);
+  sa_gate_kernel<<<grid_for(total), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), mask_logits,
+                                                         static_cast<__nv_bfloat16*>(y), total, c / 8);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(a && b && y && n % 8 == 0, "mspi_add_bf16: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  add_bf16_kernel<<<grid_for(n / 8), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
+                                                          static_cast<const __nv_bfloat16*>(b),
+                                                          static_cast<__nv_bfloat16*>(y), n / 8);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}

@@ -1,0 +1,348 @@
+// Depthwise conv + LayerNorm, LayerNorm, small-sequence attention, token mean, SimSiam loss.
+// One warp per pixel/row with the channel dimension spread over lanes (coalesced bf16x2 accesses),
+// fp32 arithmetic, warp-shuffle reductions.
+#include "common.cuh"
+
+namespace mspi {
+namespace {
+
+// ------------------------------------------------------------------------- depthwise conv (+LN)
+// MAXP = channel pairs per lane (C <= 64*MAXP).
+template <int MAXP>
+__global__ void dwconv_ln_kernel(MspiDwDesc d, const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                                 const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                 const float* __restrict__ ln_b, void* __restrict__ y, long long pixels) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int c = d.c, pairs = c >> 1;
+  const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
+  for (long long pix = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); pix < pixels;
+       pix += static_cast<long long>(gridDim.x) * warps) {
+    long long r = pix;
+    const int ow = static_cast<int>(r % d.w); r /= d.w;
+    const int oh = static_cast<int>(r % d.h); r /= d.h;
+    const int ot = static_cast<int>(r % d.t); r /= d.t;
+    const long long n = r;
+    float acc[2 * MAXP];
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = lane + 32 * i;
+      const float2 b = p < pairs ? __ldg(reinterpret_cast<const float2*>(bias) + p) : make_float2(0.f, 0.f);
+      acc[2 * i] = b.x;
+      acc[2 * i + 1] = b.y;
+    }
+    for (int kt = 0; kt < d.kt; ++kt) {
+      const int it = ot + kt - pt;
+      if (it < 0 || it >= d.t) continue;
+      for (int kh = 0; kh < d.kh; ++kh) {
+        const int ih = oh + kh - ph;
+        if (ih < 0 || ih >= d.h) continue;
+        for (int kw = 0; kw < d.kw; ++kw) {
+          const int iw = ow + kw - pw;
+          if (iw < 0 || iw >= d.w) continue;
+          const int tap = (kt * d.kh + kh) * d.kw + kw;
+          const __nv_bfloat162* xp =
+              reinterpret_cast<const __nv_bfloat162*>(x + (((n * d.t + it) * d.h + ih) * d.w + iw) * c);
+          const float2* wp = reinterpret_cast<const float2*>(wgt + static_cast<long long>(tap) * c);
+#pragma unroll
+          for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            if (p < pairs) {
+              const float2 xv = __bfloat1622float2(xp[p]);
+              const float2 wv = __ldg(wp + p);
+              acc[2 * i] = fmaf(xv.x, wv.x, acc[2 * i]);
+              acc[2 * i + 1] = fmaf(xv.y, wv.y, acc[2 * i + 1]);
+            }
+          }
+        }
+      }
+    }
+    if (ln_w != nullptr) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i)
+        if (lane + 32 * i < pairs) s += acc[2 * i] + acc[2 * i + 1];
+      const float mean = warp_sum(s) / c;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i)
+        if (lane + 32 * i < pairs) {
+          const float a = acc[2 * i] - mean, b = acc[2 * i + 1] - mean;
+          q += a * a + b * b;
+        }
+      const float rstd = rsqrtf(warp_sum(q) / c + d.ln_eps);
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i) {
+        const int p = lane + 32 * i;
+        if (p < pairs) {
+          const float2 g = __ldg(reinterpret_cast<const float2*>(ln_w) + p);
+          const float2 b = __ldg(reinterpret_cast<const float2*>(ln_b) + p);
+          acc[2 * i] = (acc[2 * i] - mean) * rstd * g.x + b.x;
+          acc[2 * i + 1] = (acc[2 * i + 1] - mean) * rstd * g.y + b.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pairs) {
+        if (d.out_dtype == MSPI_BF16)
+          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + pix * c)[p] =
+              __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+        else
+          reinterpret_cast<float2*>(static_cast<float*>(y) + pix * c)[p] = make_float2(acc[2 * i], acc[2 * i + 1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- LayerNorm rows
+template <typename TI>
+__device__ __forceinline__ float ld_elem(const TI* p, long long i) { return static_cast<float>(p[i]); }
+
+template <typename TI, typename TO>
+__global__ void layernorm_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ b, const float* __restrict__ pos, TO* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < d.rows;
+       row += static_cast<long long>(gridDim.x) * warps) {
+    const TI* xr = x + row * d.in_rstride;
+    float s = 0.f;
+    for (int i = lane; i < d.c; i += 32) s += ld_elem(xr, i);
+    const float mean = warp_sum(s) / d.c;
+    float q = 0.f;
+    for (int i = lane; i < d.c; i += 32) {
+      const float a = ld_elem(xr, i) - mean;
+      q += a * a;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d.c + d.eps);
+    const long long g = row / d.rows_per_group, within = row - g * d.rows_per_group;
+    TO* yr = y + g * d.out_gstride + within * d.out_rstride;
+    const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c : nullptr;
+    for (int i = lane; i < d.c; i += 32) {
+      float v = (ld_elem(xr, i) - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+      if (d.relu) v = fmaxf(v, 0.f);
+      if (pr) v += __ldg(pr + i);
+      yr[i] = static_cast<TO>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- attention
+// qkv: [B][N][3][H][HD] bf16.  Block = (b*H + h, query tile of QT rows).  Scores for the whole
+// key range live in shared memory (N <= 1024), softmax in fp32, then P·V.
+constexpr int kQT = 16;
+constexpr int kAttnThreads = 128;
+
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n, int heads, int hd,
+                 float scale, int n_pad) {
+  extern __shared__ float sm[];
+  float* q_s = sm;                 // [kQT][hd]
+  float* s_s = sm + kQT * hd;      // [kQT][n_pad]
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int q0 = blockIdx.y * kQT;
+  const int tid = threadIdx.x;
+  const long long row_stride = 3ll * heads * hd;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * n * row_stride + h * hd;
+  for (int i = tid; i < kQT * hd; i += kAttnThreads) {
+    const int qi = i / hd, dd = i % hd;
+    const int qr = q0 + qi;
+    q_s[i] = qr < n ? bf2f(base[static_cast<long long>(qr) * row_stride + dd]) * scale : 0.f;
+  }
+  __syncthreads();
+  // phase 1: scores
+  for (int k = tid; k < n; k += kAttnThreads) {
+    const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<long long>(k) * row_stride + heads * hd);
+    float acc[kQT];
+#pragma unroll
+    for (int qi = 0; qi < kQT; ++qi) acc[qi] = 0.f;
+    for (int d8 = 0; d8 < hd / 8; ++d8) {
+      const uint4 kv = __ldg(kp + d8);
+      float kf[8];
+      unpack_bf16x2(kv.x, kf[0], kf[1]); unpack_bf16x2(kv.y, kf[2], kf[3]);
+      unpack_bf16x2(kv.z, kf[4], kf[5]); unpack_bf16x2(kv.w, kf[6], kf[7]);
+#pragma unroll
+      for (int qi = 0; qi < kQT; ++qi) {
+        const float* qq = q_s + qi * hd + d8 * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[qi] = fmaf(qq[e], kf[e], acc[qi]);
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < kQT; ++qi) s_s[qi * n_pad + k] = acc[qi];
+  }
+  __syncthreads();
+  // phase 2: softmax per query row (one warp per row, 4 warps -> 4 rows at a time)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int qi = warp; qi < kQT; qi += kAttnThreads / 32) {
+    float* sr = s_s + qi * n_pad;
+    float m = -INFINITY;
+    for (int k = lane; k < n; k += 32) m = fmaxf(m, sr[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < n; k += 32) {
+      const float e = __expf(sr[k] - m);
+      sr[k] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    for (int k = lane; k < n; k += 32) sr[k] *= inv;
+  }
+  __syncthreads();
+  // phase 3: O = P V ; thread owns output dim(s) dd, all kQT queries
+  for (int dd = tid; dd < hd; dd += kAttnThreads) {
+    float acc[kQT];
+#pragma unroll
+    for (int qi = 0; qi < kQT; ++qi) acc[qi] = 0.f;
+    const __nv_bfloat16* vp = base + 2ll * heads * hd + dd;
+    for (int k = 0; k < n; ++k) {
+      const float v = bf2f(vp[static_cast<long long>(k) * row_stride]);
+#pragma unroll
+      for (int qi = 0; qi < kQT; ++qi) acc[qi] = fmaf(s_s[qi * n_pad + k], v, acc[qi]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < kQT; ++qi) {
+      const int qr = q0 + qi;
+      if (qr < n)
+        out[(static_cast<long long>(b) * n + qr) * (heads * hd) + h * hd + dd] = __float2bfloat16_rn(acc[qi]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- token mean
+__global__ void token_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int rows, int r0, int r1,
+                                  int c) {
+  const int b = blockIdx.y;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const __nv_bfloat16* p = x + (static_cast<long long>(b) * rows + r0) * c + ch;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r, p += c) s += bf2f(*p);
+  y[static_cast<long long>(b) * c + ch] = s / static_cast<float>(r1 - r0);
+}
+
+// ------------------------------------------------------------------------- SimSiam loss
+__global__ void simsiam_kernel(const float* __restrict__ pv, const float* __restrict__ za, const float* __restrict__ pa,
+                               const float* __restrict__ zv, float* __restrict__ out, int bsz, int c) {
+  __shared__ float red[32];
+  float total = 0.f;
+  for (int b = 0; b < bsz; ++b) {
+    for (int pair = 0; pair < 2; ++pair) {
+      const float* p = (pair == 0 ? pv : pa) + static_cast<long long>(b) * c;
+      const float* z = (pair == 0 ? za : zv) + static_cast<long long>(b) * c;
+      float dot = 0.f, pp = 0.f, zz = 0.f;
+      for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const float a = p[i], q = z[i];
+        dot = fmaf(a, q, dot);
+        pp = fmaf(a, a, pp);
+        zz = fmaf(q, q, zz);
+      }
+      dot = block_sum(dot, red);
+      pp = block_sum(pp, red);
+      zz = block_sum(zz, red);
+      // F.cosine_similarity: x.y / sqrt(max(|x|^2 |y|^2, eps^2)), eps = 1e-8
+      total += dot * rsqrtf(fmaxf(pp * zz, 1e-16f));
+    }
+  }
+  if (threadIdx.x == 0) out[0] = -0.5f * total / static_cast<float>(bsz);
+}
+
+}  // namespace
+}  // namespace mspi
+
+using namespace mspi;
+
+extern "C" int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias,
+                              const float* ln_w, const float* ln_b, void* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && wgt && bias && y, "mspi_dwconv_ln: null argument");
+  MSPI_CHECK_ARG(d->c % 2 == 0 && d->c <= 1024, "channels %d unsupported", d->c);
+  MSPI_CHECK_ARG((d->kt & 1) && (d->kh & 1) && (d->kw & 1), "kernel extents must be odd");
+  MSPI_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "ln_w / ln_b must both be given or both null");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const long long pixels = static_cast<long long>(d->n) * d->t * d->h * d->w;
+  const int threads = 256, warps = threads / 32;
+  long long blocks = (pixels + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const int pairs = d->c / 2;
+  if (pairs <= 96)
+    dwconv_ln_kernel<3><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
+  else if (pairs <= 192)
+    dwconv_ln_kernel<6><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
+  else if (pairs <= 384)
+    dwconv_ln_kernel<12><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
+  else
+    dwconv_ln_kernel<16><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w, const float* b, const float* pos,
+                              void* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && w && b && y, "mspi_layernorm: null argument");
+  MSPI_CHECK_ARG(d->pos_rows == 0 || pos, "pos table missing");
+  MSPI_CHECK_ARG(d->rows_per_group > 0, "rows_per_group");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int threads = 256, warps = threads / 32;
+  long long blocks = (d->rows + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  using bf = __nv_bfloat16;
+  const int g = static_cast<int>(blocks);
+  if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16)
+    layernorm_kernel<bf, bf><<<g, threads, 0, stream>>>(*d, static_cast<const bf*>(x), w, b, pos, static_cast<bf*>(y));
+  else if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_F32)
+    layernorm_kernel<bf, float><<<g, threads, 0, stream>>>(*d, static_cast<const bf*>(x), w, b, pos, static_cast<float*>(y));
+  else if (d->in_dtype == MSPI_F32 && d->out_dtype == MSPI_BF16)
+    layernorm_kernel<float, bf><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), w, b, pos, static_cast<bf*>(y));
+  else
+    layernorm_kernel<float, float><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), w, b, pos, static_cast<float*>(y));
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(qkv && out && b > 0 && n > 0 && heads > 0, "mspi_attention: bad argument");
+  MSPI_CHECK_ARG(hd % 8 == 0 && n <= 1024, "hd %d / n %d unsupported", hd, n);
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int n_pad = n + 1;  // odd-ish stride: rows of the score tile land in different banks
+  const size_t smem = static_cast<size_t>(kQT) * (hd + n_pad) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    MSPI_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  MSPI_CHECK_ARG(smem <= 100 * 1024, "attention tile needs %zu bytes of shared memory", smem);
+  dim3 grid(b * heads, (n + kQT - 1) / kQT);
+  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                         static_cast<__nv_bfloat16*>(out), n, heads, hd, scale, n_pad);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_token_mean(const void* x, float* y, int b, int rows, int r0, int r1, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && y && b > 0 && 0 <= r0 && r0 < r1 && r1 <= rows && c > 0, "mspi_token_mean: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  dim3 grid((c + 127) / 128, b);
+  token_mean_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, rows, r0, r1, c);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_simsiam_loss(const float* p_v, const float* z_a, const float* p_a, const float* z_v, float* out,
+                                 int b, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(p_v && z_a && p_a && z_v && out && b > 0 && c > 0, "mspi_simsiam_loss: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  simsiam_kernel<<<1, 256, 0, stream>>>(p_v, z_a, p_a, z_v, out, b, c);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}

@@ -1,0 +1,448 @@
+"""Host-side operator layer: turns PyTorch tensors + layer geometry into C-ABI calls.
+
+PyTorch is used for device memory and streams only; every arithmetic op below is a call into
+``libmspi_b200.so`` (hand-written sm_100a kernels).  Activations are channels-last
+([N, T, H, W, C], C contiguous) views described by :class:`Act`; a view may be a channel slice
+of a wider buffer, which is how concatenations (torch.cat in the reference, e.g.
+backbones/s3d.py:143, model/model_utils.py:198,559,570) are produced without a copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MSPI_BF16, MSPI_F32, ConvDesc, DwDesc,
+                   LnDesc, PatchDesc, PoolDesc, UpDesc)
+
+_DT = {torch.bfloat16: MSPI_BF16, torch.float32: MSPI_F32}
+_ES = {torch.bfloat16: 2, torch.float32: 4}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor], byte_off: int = 0) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr() + byte_off)
+
+
+class Act:
+    """Channels-last activation view: channels [c0, c0+c) of a [N,T,H,W,Cs] buffer."""
+
+    __slots__ = ("buf", "n", "t", "h", "w", "cs", "c0", "c")
+
+    def __init__(self, buf: torch.Tensor, c0: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 5 and buf.is_contiguous(), "Act needs a contiguous [N,T,H,W,C] buffer"
+        self.buf = buf
+        self.n, self.t, self.h, self.w, self.cs = buf.shape
+        self.c0 = c0
+        self.c = self.cs - c0 if c is None else c
+        assert 0 <= c0 and c0 + self.c <= self.cs
+
+    @staticmethod
+    def empty(n, t, h, w, c, dtype=torch.bfloat16, device="cuda") -> "Act":
+        return Act(torch.empty((n, t, h, w, c), dtype=dtype, device=device))
+
+    @staticmethod
+    def zeros(n, t, h, w, c, dtype=torch.bfloat16, device="cuda") -> "Act":
+        return Act(torch.zeros((n, t, h, w, c), dtype=dtype, device=device))
+
+    def slice(self, c0: int, c: int) -> "Act":
+        return Act(self.buf, self.c0 + c0, c)
+
+    @property
+    def dtype(self):
+        return self.buf.dtype
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return _ptr(self.buf, self.c0 * _ES[self.buf.dtype])
+
+    @property
+    def pixels(self) -> int:
+        return self.n * self.t * self.h * self.w
+
+    def rows(self) -> torch.Tensor:
+        """[pixels, c] strided torch view (for tests / hand-off)."""
+        return self.buf.view(-1, self.cs)[:, self.c0:self.c0 + self.c]
+
+    def to_ncdhw(self) -> torch.Tensor:
+        """fp32 NCDHW copy (the reference's layout) made by the CUDA transpose kernel."""
+        out = torch.empty((self.n, self.c, self.t, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        lib = _lib.load()
+        _lib.check(lib.mspi_ndhwc_to_ncdhw(self.ptr, _DT[self.dtype], self.cs, _ptr(out), self.n, self.c,
+                                           self.t * self.h * self.w, _stream()), "ndhwc_to_ncdhw")
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def choose_box(dims: Tuple[int, int, int, int], max_rows: int = 128) -> Tuple[int, int, int, int]:
+    """Pick the output-position box (b1..b4), b1*b2*b3*b4 <= 128, that wastes the fewest MMA rows.
+
+    Cost = number of tiles (each tile costs one 128-row MMA pass whatever its fill); ties prefer
+    a long innermost run (contiguous TMA rows)."""
+    best, best_key = None, None
+
+    def cands(d):
+        out = {d} if d <= max_rows else set()
+        for b in range(1, min(d, max_rows) + 1):
+            # only sizes that tile d evenly, or powers of two / the remainder-minimal splits
+            if d % b == 0 or (b & (b - 1)) == 0:
+                out.add(b)
+        k = 1
+        while k <= d:  # ceil splits: d/2, d/3, ...
+            b = -(-d // k)
+            if b <= max_rows:
+                out.add(b)
+            k += 1
+            if k > 64:
+                break
+        return sorted(out)
+
+    c = [cands(d) for d in dims]
+    for b1 in c[0]:
+        for b2 in c[1]:
+            if b1 * b2 > max_rows:
+                break
+            for b3 in c[2]:
+                if b1 * b2 * b3 > max_rows:
+                    break
+                for b4 in c[3]:
+                    if b1 * b2 * b3 * b4 > max_rows:
+                        break
+                    tiles = 1
+                    for d, b in zip(dims, (b1, b2, b3, b4)):
+                        tiles *= -(-d // b)
+                    key = (tiles, -b1, -b2, -b3)
+                    if best_key is None or key < best_key:
+                        best, best_key = (b1, b2, b3, b4), key
+    return best
+
+
+def choose_bn(cout: int) -> int:
+    n_tiles = -(-cout // 256)
+    bn = -(-cout // n_tiles)
+    return max(16, -(-bn // 16) * 16)
+
+
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype) -> Tuple[torch.Tensor, int, int]:
+    """[Cout, Cin, kt, kh, kw] fp32 -> K-major GEMM matrix [rows16, taps*cin_pad] (tap-major K,
+    zero padded so that one tap's K extent is a whole number of 128-byte chunks)."""
+    cout, cin, kt, kh, kw = w.shape
+    bk = 128 // _ES[dtype]
+    cin_pad = -(-cin // bk) * bk
+    rows = -(-cout // 16) * 16
+    taps = kt * kh * kw
+    m = torch.zeros((rows, taps, cin_pad), dtype=torch.float32, device=w.device)
+    m[:cout, :, :cin] = w.permute(0, 2, 3, 4, 1).reshape(cout, taps, cin)
+    return m.reshape(rows, taps * cin_pad).to(dtype).contiguous(), taps, cin_pad
+
+
+def fold_bn(bn_w, bn_b, bn_mean, bn_var, eps: float, conv_bias=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm (+ optional conv bias) as per-channel scale/shift applied to the fp32 accumulator."""
+    scale = bn_w.float() / torch.sqrt(bn_var.float() + eps)
+    shift = bn_b.float() - bn_mean.float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class Conv:
+    """A convolution / linear layer with its epilogue, prepared once and planned per input view.
+
+    weight: [Cout, Cin, kt, kh, kw] (Conv3d), [Cout, Cin, kh, kw] (Conv2d) or [Cout, Cin] (Linear), fp32.
+    y = act(scale * conv(x) + shift (+res))  or  act(scale*conv(x)+shift) + res  (res_after_act).
+    """
+
+    def __init__(self, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+                 shift: Optional[torch.Tensor] = None, stride=(1, 1, 1), pad=(0, 0, 0), act: int = ACT_NONE,
+                 dtype: torch.dtype = torch.bfloat16, res_after_act: bool = False, device="cuda", name: str = ""):
+        w = weight.detach().float()
+        if w.dim() == 2:
+            w = w[:, :, None, None, None]
+        elif w.dim() == 4:
+            w = w[:, :, None]
+        self.name = name
+        self.cout, self.cin, self.kt, self.kh, self.kw = w.shape
+        self.stride = tuple(stride) if len(stride) == 3 else (1,) + tuple(stride)
+        self.pad = tuple(pad) if len(pad) == 3 else (0,) + tuple(pad)
+        self.act = act
+        self.dtype = dtype
+        self.res_after_act = res_after_act
+        self.device = device
+        self.w_raw = w
+        self.packed = None  # built lazily, the packing depends on the execution mode
+        self.scale = None if scale is None else scale.detach().float().contiguous().to(device)
+        self.shift = None if shift is None else shift.detach().float().contiguous().to(device)
+        self.bn = choose_bn(self.cout)
+
+    # -- geometry ---------------------------------------------------------------------------
+    def out_shape(self, t, h, w):
+        (st, sh, sw), (pt, ph, pw) = self.stride, self.pad
+        return ((t + 2 * pt - self.kt) // st + 1, (h + 2 * ph - self.kh) // sh + 1, (w + 2 * pw - self.kw) // sw + 1)
+
+    def _mode(self, x: Act) -> str:
+        st, sh, sw = self.stride
+        if x.c % 8 != 0 or x.cs % 8 != 0 or x.c0 % 8 != 0 or x.dtype != self.dtype:
+            return "gather"
+        if (st, sh, sw) == (1, 1, 1):
+            return "shift"
+        if sh == 1 and sw == 1 and self.kh == 1 and self.kw == 1 and x.t % st == 0:
+            return "tstride"
+        return "gather"
+
+    def _pack(self, w5: torch.Tensor):
+        packed, taps, cin_pad = pack_conv_weight(w5.to(self.device), self.dtype)
+        return packed, taps, cin_pad
+
+    def plan(self, x: Act, y: Act, residual: Optional[Act] = None) -> Callable[[], None]:
+        """Build the descriptor(s) for this input/output pair; returns a closure that enqueues the kernels."""
+        lib = _lib.load()
+        ot, oh, ow = self.out_shape(x.t, x.h, x.w)
+        assert (y.n, y.t, y.h, y.w) == (x.n, ot, oh, ow), f"{self.name}: out {(y.n, y.t, y.h, y.w)} vs {(x.n, ot, oh, ow)}"
+        assert y.c == self.cout and x.c == self.cin, f"{self.name}: channels x={x.c}/{self.cin} y={y.c}/{self.cout}"
+        mode = self._mode(x)
+        d = ConvDesc()
+        d.a_dtype = _DT[self.dtype]
+        d.cout, d.bn = self.cout, self.bn
+        d.o_dtype = _DT[y.dtype]
+        d.act = self.act
+        d.has_residual = 0 if residual is None else 1
+        d.res_after_act = 1 if self.res_after_act else 0
+        d.r_dtype = _DT[residual.dtype] if residual is not None else 0
+        es = _ES[self.dtype]
+        pre = None
+        (st, sh, sw), (pt, ph, pw) = self.stride, self.pad
+        if mode == "shift":
+            packed, taps, cin_pad = self._pack(self.w_raw)
+            a_dims = (x.c, x.w, x.h, x.t, x.n)
+            a_str = (1, x.cs, x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
+            o_dims = (ow, oh, ot, x.n)
+            offs = [(kw - pw, kh - ph, kt - pt, 0) for kt in range(self.kt) for kh in range(self.kh) for kw in range(self.kw)]
+            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+            x_ptr = x.ptr
+        elif mode == "tstride":
+            packed, taps, cin_pad = self._pack(self.w_raw)
+            hw = x.h * x.w
+            a_dims = (x.c, hw, st, x.t // st, x.n)
+            a_str = (1, x.cs, hw * x.cs, st * hw * x.cs, x.t * hw * x.cs)
+            o_dims = (hw, 1, ot, x.n)
+            offs = []
+            for kt in range(self.kt):
+                dlt = kt - pt
+                q = dlt // st  # floor
+                offs.append((0, dlt - q * st, q, 0))
+            ostr = lambda a: (a.cs, 0, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+            x_ptr = x.ptr
+        else:  # explicit patch gather + flat GEMM
+            k = self.kt * self.kh * self.kw * self.cin
+            bk = 128 // es
+            k_pad = -(-k // bk) * bk
+            w_flat = self.w_raw.permute(0, 2, 3, 4, 1).reshape(self.cout, k)
+            packed, taps, cin_pad = self._pack(w_flat[:, :, None, None, None])
+            m = x.n * ot * oh * ow
+            patches = torch.empty((m, k_pad), dtype=self.dtype, device=self.device)
+            assert self.dtype == torch.bfloat16, "patch gather writes bf16"
+            pd = PatchDesc()
+            pd.src_layout = 1
+            pd.n, pd.c, pd.t, pd.h, pd.w = x.n, x.c, x.t, x.h, x.w
+            pd.src_cstride = x.cs
+            pd.kt, pd.kh, pd.kw = self.kt, self.kh, self.kw
+            pd.st, pd.sh, pd.sw = st, sh, sw
+            pd.pt, pd.ph, pd.pw = pt, ph, pw
+            pd.ot, pd.oh, pd.ow = ot, oh, ow
+            pd.k_pad = k_pad
+            assert x.dtype == torch.bfloat16
+            xp = x.ptr
+
+            def pre():
+                _lib.check(lib.mspi_patch_gather(C.byref(pd), xp, _ptr(patches), _stream()), f"{self.name}: patch_gather")
+
+            a_dims = (k_pad, m, 1, 1, 1)
+            a_str = (1, k_pad, m * k_pad, m * k_pad, m * k_pad)
+            o_dims = (m, 1, 1, 1)
+            offs = [(0, 0, 0, 0)]
+            ostr = lambda a: (a.cs, 0, 0, 0)
+            x_ptr = _ptr(patches)
+            self._patches = patches
+        box = choose_box(tuple(o_dims))
+        for j in range(5):
+            d.a_dims[j] = a_dims[j]
+            d.a_strides[j] = a_str[j]
+        d.box[0] = 0
+        for j in range(4):
+            d.box[j + 1] = box[j]
+            d.o_dims[j] = o_dims[j]
+            d.o_strides[j] = ostr(y)[j]
+            d.r_strides[j] = ostr(residual)[j] if residual is not None else 0
+        assert len(offs) == taps and taps <= _lib.MAX_TAPS, f"{self.name}: {len(offs)} taps"
+        d.ntaps = taps
+        for i, o in enumerate(offs):
+            for j in range(4):
+                d.tap_off[i][j] = o[j]
+        d.cin_pad = cin_pad
+        d.w_rows = packed.shape[0]
+        self.packed = packed  # keep alive
+        w_ptr, sc_ptr, sh_ptr = _ptr(packed), _ptr(self.scale), _ptr(self.shift)
+        y_ptr = y.ptr
+        r_ptr = residual.ptr if residual is not None else C.c_void_p(0)
+        keep = (packed, x.buf, y.buf, None if residual is None else residual.buf, d)
+        name = self.name
+
+        def run(_keep=keep):
+            if pre is not None:
+                pre()
+            _lib.check(lib.mspi_conv_gemm(C.byref(d), x_ptr, w_ptr, sc_ptr, sh_ptr, r_ptr, y_ptr, _stream()),
+                       f"conv_gemm[{name}]")
+
+        run.mode = mode
+        run.desc = d
+        return run
+
+    def flops(self, x: Act) -> float:
+        ot, oh, ow = self.out_shape(x.t, x.h, x.w)
+        return 2.0 * x.n * ot * oh * ow * self.cout * self.cin * self.kt * self.kh * self.kw
+
+
+# ------------------------------------------------------------------------------------------ other ops
+def patch_gather_ncdhw(src: torch.Tensor, kernel, stride, pad, k_pad: int, out: torch.Tensor) -> Callable[[], None]:
+    """fp32 NCDHW input (the model's input contract) -> bf16 patch rows [M, k_pad]."""
+    lib = _lib.load()
+    n, c, t, h, w = src.shape
+    pd = PatchDesc()
+    pd.src_layout = 0
+    pd.n, pd.c, pd.t, pd.h, pd.w = n, c, t, h, w
+    pd.src_cstride = 0
+    pd.kt, pd.kh, pd.kw = kernel
+    pd.st, pd.sh, pd.sw = stride
+    pd.pt, pd.ph, pd.pw = pad
+    pd.ot = (t + 2 * pad[0] - kernel[0]) // stride[0] + 1
+    pd.oh = (h + 2 * pad[1] - kernel[1]) // stride[1] + 1
+    pd.ow = (w + 2 * pad[2] - kernel[2]) // stride[2] + 1
+    pd.k_pad = k_pad
+    assert out.shape == (n * pd.ot * pd.oh * pd.ow, k_pad) and out.dtype == torch.bfloat16
+    sp, op = _ptr(src), _ptr(out)
+
+    def run(_keep=(src, out, pd)):
+        _lib.check(lib.mspi_patch_gather(C.byref(pd), sp, op, _stream()), "patch_gather")
+
+    return run
+
+
+def maxpool3d(x: Act, y: Act, kernel, stride, pad) -> Callable[[], None]:
+    lib = _lib.load()
+    d = PoolDesc()
+    d.n, d.t, d.h, d.w, d.c = x.n, x.t, x.h, x.w, x.c
+    d.in_cstride, d.out_cstride = x.cs, y.cs
+    d.kt, d.kh, d.kw = kernel
+    d.st, d.sh, d.sw = stride
+    d.pt, d.ph, d.pw = pad
+    d.ot, d.oh, d.ow = y.t, y.h, y.w
+    assert y.c == x.c and y.n == x.n
+    assert d.ot == (x.t + 2 * pad[0] - kernel[0]) // stride[0] + 1
+    assert d.oh == (x.h + 2 * pad[1] - kernel[1]) // stride[1] + 1
+    assert d.ow == (x.w + 2 * pad[2] - kernel[2]) // stride[2] + 1
+    xp, yp = x.ptr, y.ptr
+
+    def run(_keep=(x.buf, y.buf, d)):
+        _lib.check(lib.mspi_maxpool3d(C.byref(d), xp, yp, _stream()), "maxpool3d")
+
+    return run
+
+
+def upsample(x: Act, y: Act, k: int, accumulate: bool = False) -> Callable[[], None]:
+    lib = _lib.load()
+    d = UpDesc()
+    d.nt, d.h, d.w, d.c, d.k = x.n * x.t, x.h, x.w, x.c, k
+    d.in_cstride, d.out_cstride = x.cs, y.cs
+    d.in_dtype, d.out_dtype = _DT[x.dtype], _DT[y.dtype]
+    d.accumulate = 1 if accumulate else 0
+    assert (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h * k, x.w * k, x.c)
+    xp, yp = x.ptr, y.ptr
+
+    def run(_keep=(x.buf, y.buf, d)):
+        _lib.check(lib.mspi_upsample_bilinear(C.byref(d), xp, yp, _stream()), "upsample")
+
+    return run
+
+
+def dwconv_ln(x: Act, y: Act, weight: torch.Tensor, bias: torch.Tensor, ln_w=None, ln_b=None,
+              eps: float = 1e-5) -> Callable[[], None]:
+    """weight: [C, 1, kt, kh, kw] or [C, 1, kh, kw] depthwise conv weight (fp32)."""
+    lib = _lib.load()
+    w = weight.detach().float()
+    if w.dim() == 4:
+        w = w[:, :, None]
+    c, _, kt, kh, kw = w.shape
+    assert x.c == c and x.c0 == 0 and x.cs == c and y.c0 == 0 and y.cs == c, "dwconv works on whole buffers"
+    wt = w.reshape(c, kt * kh * kw).t().contiguous().to(x.buf.device)
+    b = bias.detach().float().contiguous().to(x.buf.device)
+    lw = None if ln_w is None else ln_w.detach().float().contiguous().to(x.buf.device)
+    lb = None if ln_b is None else ln_b.detach().float().contiguous().to(x.buf.device)
+    d = DwDesc()
+    d.n, d.t, d.h, d.w, d.c = x.n, x.t, x.h, x.w, c
+    d.kt, d.kh, d.kw = kt, kh, kw
+    d.ln_eps = eps
+    d.out_dtype = _DT[y.dtype]
+    xp, yp = x.ptr, y.ptr
+
+    def run(_keep=(x.buf, y.buf, wt, b, lw, lb, d)):
+        _lib.check(lib.mspi_dwconv_ln(C.byref(d), xp, _ptr(wt), _ptr(b), _ptr(lw), _ptr(lb), yp, _stream()), "dwconv_ln")
+
+    return run
+
+
+def layernorm(x: torch.Tensor, y: torch.Tensor, rows: int, c: int, w: torch.Tensor, b: torch.Tensor, eps: float,
+              in_rstride: Optional[int] = None, out_rstride: Optional[int] = None, relu: bool = False,
+              pos: Optional[torch.Tensor] = None, rows_per_group: int = 0, out_gstride: int = 0,
+              x_off: int = 0, y_off: int = 0) -> Callable[[], None]:
+    """LayerNorm over the last dim of `rows` rows; x_off / y_off are element offsets into x / y."""
+    lib = _lib.load()
+    d = LnDesc()
+    d.rows, d.c = rows, c
+    d.in_rstride = c if in_rstride is None else in_rstride
+    d.out_rstride = c if out_rstride is None else out_rstride
+    d.in_dtype, d.out_dtype = _DT[x.dtype], _DT[y.dtype]
+    d.eps = eps
+    d.relu = 1 if relu else 0
+    d.pos_rows = 0 if pos is None else pos.shape[0]
+    d.rows_per_group = rows_per_group if rows_per_group else rows
+    d.out_gstride = out_gstride
+    wf = w.detach().float().contiguous().to(x.device)
+    bf = b.detach().float().contiguous().to(x.device)
+    xp, yp = _ptr(x, x_off * _ES[x.dtype]), _ptr(y, y_off * _ES[y.dtype])
+
+    def run(_keep=(x, y, wf, bf, pos, d)):
+        _lib.check(lib.mspi_layernorm(C.byref(d), xp, _ptr(wf), _ptr(bf), _ptr(pos), yp, _stream()), "layernorm")
+
+    return run
+
+
+def attention(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, hd: int) -> Callable[[], None]:
+    lib = _lib.load()
+    scale = float(hd) ** -0.5
+
+    def run(_keep=(qkv, out)):
+        _lib.check(lib.mspi_attention(_ptr(qkv), _ptr(out), b, n, heads, hd, scale, _stream()), "attention")
+
+    return run
+
+
+def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
+    lib = _lib.load()
+    assert x.c0 == 0 and x.cs == x.c and y.c0 == 0 and y.cs == y.c and mask_logits.dtype == torch.float32
+    pixels, c = x.pixels, x.c
+    assert mask_logits.numel() == pixels
+
+    def run(_keep=(x.buf, y.buf, mask_logits)):
+        _lib.check(lib.mspi_sa_gate(x.ptr, _ptr(mask_logits), y.ptr, pixels, c, _stream()), "sa_gate")
+
+    return run

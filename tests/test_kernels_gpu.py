@@ -1,0 +1,284 @@
+"""GPU parity tests of the individual C-ABI kernels against plain PyTorch fp32 (CPU) references.
+
+Tolerances: bf16 tensor-core paths are compared on bf16-rounded operands with fp32 accumulation,
+so the only differences are accumulation order and the final bf16 rounding of the output (2^-8
+relative); fp32 paths are compared at 1e-5-class tolerances.  Each tolerance is stated at its use.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def _act_from_ncdhw(x, cs=None, c0=0, dtype=torch.bfloat16):
+    """NCDHW fp32 CPU tensor -> Act on the GPU (optionally as a slice of a wider buffer)."""
+    from mspi_b200.ops import Act
+    n, c, t, h, w = x.shape
+    cs = cs or c
+    buf = torch.randn(n, t, h, w, cs).to(dtype).cuda()  # garbage around the slice
+    buf[..., c0:c0 + c] = x.permute(0, 2, 3, 4, 1).to(dtype).cuda()
+    return Act(buf.contiguous(), c0, c)
+
+
+def _run_conv(cin, cout, k, stride, pad, shape, act=0, residual=False, out_dtype=torch.bfloat16, dtype=torch.bfloat16,
+              in_slice=None, out_slice=None, res_after_act=False, seed=0):
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(seed)
+    n, t, h, w = shape
+    x = torch.randn(n, cin, t, h, w, generator=g)
+    wgt = torch.randn(cout, cin, *k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    rnd = _bf if dtype == torch.bfloat16 else (lambda v: v)
+    conv = ops.Conv(wgt, scale, shift, stride=stride, pad=pad, act=act, dtype=dtype, res_after_act=res_after_act, name="t")
+    xa = _act_from_ncdhw(x, *(in_slice or (None, 0)), dtype=dtype)
+    ot, oh, ow = conv.out_shape(t, h, w)
+    ocs, oc0 = out_slice or (cout, 0)
+    ybuf = torch.full((n, ot, oh, ow, ocs), 7.0, dtype=out_dtype, device="cuda")
+    ya = Act(ybuf, oc0, cout)
+    ra = None
+    ref = F.conv3d(rnd(x), rnd(wgt), None, stride, pad) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    if residual:
+        r = torch.randn(n, cout, ot, oh, ow, generator=g)
+        ra = _act_from_ncdhw(r)
+        if not res_after_act:
+            ref = ref + _bf(r)
+    if act == 1:
+        ref = ref.relu()
+    elif act == 2:
+        ref = F.gelu(ref)
+    elif act == 3:
+        ref = ref.sigmoid()
+    if residual and res_after_act:
+        ref = ref + _bf(r)
+    run = conv.plan(xa, ya, ra)
+    run()
+    torch.cuda.synchronize()
+    got = ya.to_ncdhw().cpu()
+    # untouched channels of a wider output buffer must keep their fill value
+    if out_slice:
+        rest = torch.cat([ybuf[..., :oc0], ybuf[..., oc0 + cout:]], -1)
+        assert (rest.float() == 7.0).all(), "conv wrote outside its channel slice"
+    return got, ref, run.mode
+
+
+# bf16 out: 2^-8 relative rounding of the output + accumulation-order noise -> 1.5e-2 of max is ample
+BF16_TOL = 1.5e-2
+
+
+def test_gemm_plain_linear():
+    got, ref, mode = _run_conv(192, 96, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1, 300))
+    assert mode == "shift"
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_gemm_multi_ntile_gelu_fp32out():
+    got, ref, _ = _run_conv(96, 384, (1, 1, 1), (1, 1, 1), (0, 0, 0), (2, 1, 5, 77), act=2, out_dtype=torch.float32)
+    assert _rel(got, ref) < 2e-3  # fp32 output: only accumulation order differs
+
+
+@pytest.mark.parametrize("k,pad", [((1, 3, 3), (0, 1, 1)), ((3, 1, 1), (1, 0, 0)), ((3, 3, 3), (1, 1, 1)),
+                                   ((7, 1, 1), (3, 0, 0))])
+def test_conv_shift_mode(k, pad):
+    got, ref, mode = _run_conv(64, 192, k, (1, 1, 1), pad, (2, 4, 14, 24), act=1)
+    assert mode == "shift"
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_small_channels_and_slices():
+    # Cin=16 (quarter of a K chunk), input is a slice of a wider buffer, output goes into a concat slice
+    got, ref, _ = _run_conv(16, 48, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 4, 7, 12), act=1, in_slice=(112, 96),
+                            out_slice=(512, 400))
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_cin_not_multiple_of_chunk():
+    got, ref, _ = _run_conv(96, 208, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 4, 14, 24), act=1)
+    assert _rel(got, ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("k,stride,pad,t", [((7, 1, 1), (2, 1, 1), (3, 0, 0), 16), ((2, 1, 1), (2, 1, 1), (0, 0, 0), 8),
+                                            ((4, 1, 1), (4, 1, 1), (0, 0, 0), 4)])
+def test_conv_temporal_stride(k, stride, pad, t):
+    got, ref, mode = _run_conv(64, 64, k, stride, pad, (2, t, 12, 20), act=1)
+    assert mode == "tstride"
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_gather_mode_strided_odd():
+    got, ref, mode = _run_conv(64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), (2, 1, 65, 28), act=1)
+    assert mode == "gather"
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_residual_relu():
+    got, ref, _ = _run_conv(64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), (2, 1, 33, 14), act=1, residual=True)
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_residual_after_act_layer_scale():
+    got, ref, _ = _run_conv(384, 96, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 20, 31), act=0, residual=True, res_after_act=True)
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_conv_single_output_channel_fp32():
+    got, ref, _ = _run_conv(32, 1, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 32, 64), out_dtype=torch.float32)
+    assert _rel(got, ref) < 2e-3
+
+
+def test_conv_tf32_path():
+    # kind::tf32: 10-bit mantissa operands (2^-11 relative), fp32 accumulate and fp32 output
+    got, ref, _ = _run_conv(32, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 24, 40), act=1, dtype=torch.float32,
+                            out_dtype=torch.float32)
+    assert _rel(got, ref) < 3e-3
+
+
+def test_conv_large_k_many_tiles():
+    got, ref, _ = _run_conv(192, 192, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 4, 28, 48), act=1)
+    assert _rel(got, ref) < BF16_TOL
+
+
+def test_patch_gather_from_ncdhw_stem():
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 4, 20, 36, generator=g)
+    k, s, p = (1, 7, 7), (1, 2, 2), (0, 3, 3)
+    kk = 3 * 49
+    k_pad = 192
+    ot, oh, ow = 4, 10, 18
+    out = torch.empty(2 * ot * oh * ow, k_pad, dtype=torch.bfloat16, device="cuda")
+    ops.patch_gather_ncdhw(x.cuda(), k, s, p, k_pad, out)()
+    torch.cuda.synchronize()
+    cols = F.unfold(x.permute(0, 2, 1, 3, 4).reshape(8, 3, 20, 36), (7, 7), padding=3, stride=2)  # [NT, C*49, L]
+    cols = cols.view(8, 3, 49, oh * ow).permute(0, 3, 2, 1).reshape(8 * oh * ow, kk)  # K order (kh,kw,c)
+    got = out.float().cpu()
+    assert torch.equal(got[:, :kk], _bf(cols)), "patch rows differ"  # pure data movement: bit-exact
+    assert (got[:, kk:] == 0).all()
+
+
+def test_maxpool_variants():
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(2)
+    for (k, s, p) in [((1, 3, 3), (1, 2, 2), (0, 1, 1)), ((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                      ((1, 2, 2), (1, 2, 2), (0, 0, 0)), ((4, 1, 1), (4, 1, 1), (0, 0, 0))]:
+        x = torch.randn(2, 24, 8, 14, 12, generator=g)
+        xa = _act_from_ncdhw(x, 40, 8)
+        ref = F.max_pool3d(_bf(x), k, s, p)
+        ya = Act.empty(2, *ref.shape[2:], 24)
+        ops.maxpool3d(xa, ya, k, s, p)()
+        torch.cuda.synchronize()
+        assert torch.equal(ya.to_ncdhw().cpu(), ref), f"maxpool {k} {s} {p}"  # selection only: bit-exact
+
+
+@pytest.mark.parametrize("k", [2, 4, 8])
+def test_upsample_bilinear(k):
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 3, 7, 12, generator=g)
+    xa = _act_from_ncdhw(x)
+    ref = F.interpolate(_bf(x), scale_factor=(1, k, k), mode="trilinear", align_corners=False)
+    ya = Act.zeros(2, 3, 7 * k, 12 * k, 16, dtype=torch.float32)
+    ops.upsample(xa, ya, k)()
+    torch.cuda.synchronize()
+    assert (ya.to_ncdhw().cpu() - ref).abs().max() < 1e-5  # fp32 interpolation weights, exact powers of two
+    # accumulate into a bf16 buffer
+    base = torch.randn(2, 16, 3, 7 * k, 12 * k, generator=g)
+    yb = _act_from_ncdhw(base)
+    ops.upsample(xa, yb, k, accumulate=True)()
+    torch.cuda.synchronize()
+    assert (yb.to_ncdhw().cpu() - (ref + _bf(base))).abs().max() < 4e-2  # one bf16 rounding of values up to ~6
+
+
+@pytest.mark.parametrize("c,kern", [(192, (7, 1, 1)), (192, (1, 7, 7)), (96, (1, 7, 7)), (768, (1, 7, 7))])
+def test_dwconv_ln(c, kern):
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, c, 4, 9, 11, generator=g)
+    w = torch.randn(c, 1, *kern, generator=g) * 0.2
+    b = torch.randn(c, generator=g) * 0.1
+    lw, lb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    xa = _act_from_ncdhw(x)
+    pad = tuple(k // 2 for k in kern)
+    conv = F.conv3d(_bf(x), w, b, padding=pad, groups=c)
+    ya = Act.empty(1, 4, 9, 11, c, dtype=torch.float32)
+    ops.dwconv_ln(xa, ya, w, b)()
+    torch.cuda.synchronize()
+    assert (ya.to_ncdhw().cpu() - conv).abs().max() < 1e-4  # fp32 math, order only
+    ref = F.layer_norm(conv.permute(0, 2, 3, 4, 1), (c,), lw, lb, 1e-6).permute(0, 4, 1, 2, 3)
+    ops.dwconv_ln(xa, ya, w, b, lw, lb, eps=1e-6)()
+    torch.cuda.synchronize()
+    assert (ya.to_ncdhw().cpu() - ref).abs().max() < 2e-4
+
+
+def test_layernorm_pos_groups():
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    b, nv, na, c = 2, 10, 4, 512
+    xv = torch.randn(b * nv, c, generator=g)
+    w, bb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    pos = torch.randn(nv, c, generator=g)
+    out = torch.zeros(b, nv + na, c, dtype=torch.bfloat16, device="cuda")
+    ops.layernorm(xv.cuda(), out, b * nv, c, w, bb, 1e-5, pos=pos.cuda(), rows_per_group=nv, out_gstride=(nv + na) * c)()
+    torch.cuda.synchronize()
+    ref = F.layer_norm(xv, (c,), w, bb, 1e-5).view(b, nv, c) + pos
+    assert (out[:, :nv].float().cpu() - ref).abs().max() < 3e-2  # bf16 output of values up to ~5
+    assert (out[:, nv:] == 0).all()
+
+
+def test_attention_small():
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    b, n, heads, hd = 2, 52, 4, 128
+    qkv = torch.randn(b, n, 3, heads, hd, generator=g)
+    out = torch.empty(b, n, heads * hd, dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv.to(torch.bfloat16).cuda(), out, b, n, heads, hd)()
+    torch.cuda.synchronize()
+    q, k, v = _bf(qkv).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v
+    ref = ref.transpose(1, 2).reshape(b, n, heads * hd)
+    assert (out.float().cpu() - ref).abs().max() < 2e-2  # bf16 output rounding
+
+
+def test_sa_gate_token_mean_simsiam():
+    from mspi_b200 import _lib, ops
+    from mspi_b200.ops import Act
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 192, 2, 5, 6, generator=g)
+    m = torch.randn(1 * 2 * 5 * 6, generator=g)
+    xa = _act_from_ncdhw(x)
+    ya = Act.empty(1, 2, 5, 6, 192)
+    ops.sa_gate(xa, m.cuda(), ya)()
+    torch.cuda.synchronize()
+    ref = _bf(x) * (1 + torch.sigmoid(m).view(1, 1, 2, 5, 6))
+    assert (ya.to_ncdhw().cpu() - ref).abs().max() < 4e-2
+    # token mean
+    t = torch.randn(3, 20, 512, generator=g).to(torch.bfloat16)
+    y = torch.empty(3, 512, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.mspi_token_mean(C.c_void_p(t.cuda().data_ptr()), C.c_void_p(y.data_ptr()), 3, 20, 4, 17, 512, st))
+    torch.cuda.synchronize()
+    assert (y.cpu() - t.float()[:, 4:17].mean(1)).abs().max() < 1e-5
+    # simsiam
+    pv, za, pa, zv = (torch.randn(3, 2048, generator=g) for _ in range(4))
+    o = torch.empty(1, device="cuda")
+    dev = [v.cuda() for v in (pv, za, pa, zv)]
+    _lib.check(lib.mspi_simsiam_loss(*(C.c_void_p(v.data_ptr()) for v in dev), C.c_void_p(o.data_ptr()), 3, 2048, st))
+    torch.cuda.synchronize()
+    ref = -0.5 * (F.cosine_similarity(pv, za, dim=-1).mean() + F.cosine_similarity(pa, zv, dim=-1).mean())
+    assert abs(o.item() - ref.item()) < 1e-5
