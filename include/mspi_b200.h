@@ -175,15 +175,22 @@ int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, 
 
 /* SA gating + top-down sums (model_utils.py:167-170,566-568):
  *   y = x * sigmoid_mask + x ; the mask logits are fp32 [N*T*H*W] (one channel). */
-int mspi_sa_gate(const void* x, const float* mask_logits, void* y, int64_t pixels, int c,
-                 void* stream);
+int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, void* y, int64_t y_cstride,
+                 int64_t pixels, int c, void* stream);
 
 /* Elementwise y = a + b over bf16 (used for ViT residuals when not fused) */
 int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
 
-/* Mean over tokens: x bf16 [B][rows][C] (row range [r0, r1)) -> fp32 [B][C]
+/* Mean over tokens: x (bf16 or fp32) [B][rows][C] (row range [r0, r1)) -> fp32 [B][C]
  * (AdaptiveAvgPool3d/2d to 1, model_utils.py:401-402,545-546). */
-int mspi_token_mean(const void* x, float* y, int b, int rows, int r0, int r1, int c, void* stream);
+int mspi_token_mean(const void* x, int x_dtype, float* y, int b, int rows, int r0, int r1, int c, void* stream);
+
+/* Strided row copy with dtype conversion: dst[g][r][0..c) = src[g][r][0..c) for g < groups,
+ * r < rows; strides in elements.  Moves the fused visual tokens into the channel slice that
+ * torch.cat([v4, vis_sync]) occupies (model_utils.py:541-543,559). */
+int mspi_cast_rows(const void* src, int src_dtype, int64_t src_rstride, int64_t src_gstride, void* dst,
+                   int dst_dtype, int64_t dst_rstride, int64_t dst_gstride, int groups, int rows, int c,
+                   void* stream);
 
 /* SimSiam negative cosine loss (model_utils.py:285-290,551):
  *   out[0] = 0.5*( -mean_b cos(p_v, z_a) - mean_b cos(p_a, z_v) ), all fp32 [B][C]. */

@@ -109,9 +109,10 @@ _SIGNATURES = {
     "mspi_dwconv_ln": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_layernorm": (C.c_int, [C.POINTER(LnDesc), _P, _P, _P, _P, _P, _P]),
     "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
-    "mspi_sa_gate": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "mspi_add_bf16": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
-    "mspi_token_mean": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mspi_token_mean": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mspi_cast_rows": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_simsiam_loss": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "mspi_logsoftmax2d": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "mspi_saliency_metrics": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int64, _P]),

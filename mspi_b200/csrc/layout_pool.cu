@@ -197,20 +197,21 @@ __global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __re
 }
 
 // ------------------------------------------------------------------------- SA gate, add
-__global__ void sa_gate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ m,
-                               __nv_bfloat16* __restrict__ y, long long total, int c8) {
+__global__ void sa_gate_kernel(const __nv_bfloat16* __restrict__ x, long long xcs, const float* __restrict__ m,
+                               __nv_bfloat16* __restrict__ y, long long ycs, long long total, int c8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / c8;
+    const int cc = static_cast<int>(i - pix * c8);
     const float g = 1.f + 1.f / (1.f + __expf(-__ldg(m + pix)));  // x*mask + x
-    const uint4 v = ldg16(x + i * 8);
+    const uint4 v = ldg16(x + pix * xcs + cc * 8);
     float f[8];
     unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
     unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
     uint4 o;
     o.x = pack_bf16x2(f[0] * g, f[1] * g); o.y = pack_bf16x2(f[2] * g, f[3] * g);
     o.z = pack_bf16x2(f[4] * g, f[5] * g); o.w = pack_bf16x2(f[6] * g, f[7] * g);
-    *reinterpret_cast<uint4*>(y + i * 8) = o;
+    *reinterpret_cast<uint4*>(y + pix * ycs + cc * 8) = o;
   }
 }
 
@@ -228,6 +229,19 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
     o.x = pack_bf16x2(f[0] + g[0], f[1] + g[1]); o.y = pack_bf16x2(f[2] + g[2], f[3] + g[3]);
     o.z = pack_bf16x2(f[4] + g[4], f[5] + g[5]); o.w = pack_bf16x2(f[6] + g[6], f[7] + g[7]);
     *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_rows_kernel(const TI* __restrict__ src, long long srs, long long sgs, TO* __restrict__ dst,
+                                 long long drs, long long dgs, int rows, int c, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const long long rr = i / c;
+    const int r = static_cast<int>(rr % rows);
+    const long long g = rr / rows;
+    dst[g * dgs + r * drs + ch] = static_cast<TO>(static_cast<float>(src[g * sgs + r * srs + ch]));
   }
 }
 
@@ -324,13 +338,15 @@ extern "C" int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* 
   return MSPI_OK;
 }
 
-extern "C" int mspi_sa_gate(const void* x, const float* mask_logits, void* y, int64_t pixels, int c, void* stream_) {
+extern "C" int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, void* y, int64_t y_cstride,
+                            int64_t pixels, int c, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0, "mspi_sa_gate: bad argument");
+  MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0,
+                 "mspi_sa_gate: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const long long total = pixels * (c / 8);
-  sa_gate_kernel<<<grid_for(total), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), mask_logits,
-                                                         static_cast<__nv_bfloat16*>(y), total, c / 8);
+  sa_gate_kernel<<<grid_for(total), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_cstride, mask_logits,
+                                                         static_cast<__nv_bfloat16*>(y), y_cstride, total, c / 8);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -342,6 +358,31 @@ extern "C" int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, v
   add_bf16_kernel<<<grid_for(n / 8), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
                                                           static_cast<const __nv_bfloat16*>(b),
                                                           static_cast<__nv_bfloat16*>(y), n / 8);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_cast_rows(const void* src, int src_dtype, int64_t src_rstride, int64_t src_gstride, void* dst,
+                              int dst_dtype, int64_t dst_rstride, int64_t dst_gstride, int groups, int rows, int c,
+                              void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(src && dst && groups > 0 && rows > 0 && c > 0, "mspi_cast_rows: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const long long total = static_cast<long long>(groups) * rows * c;
+  const int g = grid_for(total);
+  using bf = __nv_bfloat16;
+  if (src_dtype == MSPI_F32 && dst_dtype == MSPI_BF16)
+    cast_rows_kernel<float, bf><<<g, kBlock, 0, stream>>>(static_cast<const float*>(src), src_rstride, src_gstride,
+                                                          static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total);
+  else if (src_dtype == MSPI_BF16 && dst_dtype == MSPI_F32)
+    cast_rows_kernel<bf, float><<<g, kBlock, 0, stream>>>(static_cast<const bf*>(src), src_rstride, src_gstride,
+                                                          static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total);
+  else if (src_dtype == MSPI_BF16)
+    cast_rows_kernel<bf, bf><<<g, kBlock, 0, stream>>>(static_cast<const bf*>(src), src_rstride, src_gstride,
+                                                       static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total);
+  else
+    cast_rows_kernel<float, float><<<g, kBlock, 0, stream>>>(static_cast<const float*>(src), src_rstride, src_gstride,
+                                                             static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -212,14 +212,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 }
 
 // ------------------------------------------------------------------------- token mean
-__global__ void token_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int rows, int r0, int r1,
-                                  int c) {
+template <typename T>
+__global__ void token_mean_kernel(const T* __restrict__ x, float* __restrict__ y, int rows, int r0, int r1, int c) {
   const int b = blockIdx.y;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const __nv_bfloat16* p = x + (static_cast<long long>(b) * rows + r0) * c + ch;
+  const T* p = x + (static_cast<long long>(b) * rows + r0) * c + ch;
   float s = 0.f;
-  for (int r = r0; r < r1; ++r, p += c) s += bf2f(*p);
+  for (int r = r0; r < r1; ++r, p += c) s += static_cast<float>(*p);
   y[static_cast<long long>(b) * c + ch] = s / static_cast<float>(r1 - r0);
 }
 
@@ -327,12 +327,16 @@ extern "C" int mspi_attention(const void* qkv, void* out, int b, int n, int head
   return MSPI_OK;
 }
 
-extern "C" int mspi_token_mean(const void* x, float* y, int b, int rows, int r0, int r1, int c, void* stream_) {
+extern "C" int mspi_token_mean(const void* x, int x_dtype, float* y, int b, int rows, int r0, int r1, int c,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(x && y && b > 0 && 0 <= r0 && r0 < r1 && r1 <= rows && c > 0, "mspi_token_mean: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   dim3 grid((c + 127) / 128, b);
-  token_mean_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, rows, r0, r1, c);
+  if (x_dtype == MSPI_BF16)
+    token_mean_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, rows, r0, r1, c);
+  else
+    token_mean_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), y, rows, r0, r1, c);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

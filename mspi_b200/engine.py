@@ -1,0 +1,528 @@
+"""Forward plan of the MSPI clip forward pass on B200.
+
+A :class:`ForwardPlan` is built once per (batch, frames, height, width): it allocates every
+activation buffer (channels-last bf16, fp32 where the result feeds a normalisation or the final
+log-softmax), packs the weights for the tcgen05 implicit-GEMM kernel (BatchNorm folded into the
+epilogue's scale/shift), and records the forward as a flat list of C-ABI kernel launches.
+``run()`` replays the list on the current CUDA stream — eagerly or, with ``use_graph=True``,
+as one captured CUDA graph.
+
+The op order follows the reference forward (model/model_utils.py:556-574) and each builder
+cites the reference lines it re-implements.  Nothing here calls a PyTorch operator on the data
+path; PyTorch only owns the memory.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Act, Conv, fold_bn
+
+
+class ForwardPlan:
+    def __init__(self, sd: Dict[str, torch.Tensor], batch: int, frames: int, height: int, width: int,
+                 audio: bool = True, lateral_bool=(True, True, False, False), lateral_stride=(2, 2, 2, 2),
+                 pool_stride: int = 1, device="cuda", keep_taps: bool = False):
+        assert frames % 4 == 0 and height % 32 == 0 and width % 32 == 0, \
+            "T must be a multiple of 4 and H, W multiples of 32 (model_utils.py:506,566-570)"
+        self.sd = {k: v.detach().to(device) for k, v in sd.items()}
+        self.B, self.T, self.H, self.W = batch, frames, height, width
+        self.audio = audio
+        self.device = device
+        self.lateral_bool, self.lateral_stride, self.pool_stride = lateral_bool, lateral_stride, pool_stride
+        self.steps: List[Tuple[str, Callable[[], None]]] = []
+        self.flops = 0.0
+        self.bytes_alloc = 0
+        self.taps: Dict[str, Act] = {}
+        self.keep_taps = keep_taps
+        self._keep = []
+        self._inputs = {"clips": None, "audio": None}
+        self.graph = None
+        self._build()
+
+    # ------------------------------------------------------------------ small helpers
+    def P(self, name: str) -> torch.Tensor:
+        return self.sd[name]
+
+    def new(self, n, t, h, w, c, dtype=torch.bfloat16) -> Act:
+        a = Act.empty(n, t, h, w, c, dtype=dtype, device=self.device)
+        self.bytes_alloc += a.buf.numel() * a.buf.element_size()
+        return a
+
+    def add(self, name: str, fn: Callable[[], None]):
+        self.steps.append((name, fn))
+
+    def tap(self, name: str, a: Act):
+        if self.keep_taps:
+            self.taps[name] = a
+
+    def bn(self, prefix: str, eps: float, conv_bias: Optional[torch.Tensor] = None):
+        return fold_bn(self.P(prefix + ".weight"), self.P(prefix + ".bias"), self.P(prefix + ".running_mean"),
+                       self.P(prefix + ".running_var"), eps, conv_bias)
+
+    def conv(self, name: str, x: Act, w: torch.Tensor, scale=None, shift=None, stride=(1, 1, 1), pad=(0, 0, 0),
+             act=ACT_NONE, out: Optional[Act] = None, residual: Optional[Act] = None, res_after_act=False,
+             out_dtype=torch.bfloat16, dtype=torch.bfloat16) -> Act:
+        c = Conv(w, scale, shift, stride=stride, pad=pad, act=act, dtype=dtype, res_after_act=res_after_act,
+                 device=self.device, name=name)
+        if out is None:
+            ot, oh, ow = c.out_shape(x.t, x.h, x.w)
+            out = self.new(x.n, ot, oh, ow, c.cout, out_dtype)
+        self.add(name, c.plan(x, out, residual))
+        self.flops += c.flops(x)
+        self._keep.append(c)
+        return out
+
+    def conv_bn_relu(self, conv_key: str, bn_key: str, x: Act, eps: float, stride=(1, 1, 1), pad=(0, 0, 0),
+                     out: Optional[Act] = None, bias_key: Optional[str] = None, relu=True) -> Act:
+        bias = self.P(bias_key) if bias_key else None
+        sc, sh = self.bn(bn_key, eps, bias)
+        return self.conv(conv_key, x, self.P(conv_key + ".weight"), sc, sh, stride, pad,
+                         ACT_RELU if relu else ACT_NONE, out)
+
+    def pool(self, name: str, x: Act, k, s, p, out: Optional[Act] = None) -> Act:
+        o = [(d + 2 * pp - kk) // ss + 1 for d, kk, ss, pp in zip((x.t, x.h, x.w), k, s, p)]
+        if out is None:
+            out = self.new(x.n, *o, x.c)
+        self.add(name, ops.maxpool3d(x, out, k, s, p))
+        return out
+
+    def up(self, name: str, x: Act, k: int, out: Optional[Act] = None, accumulate=False, dtype=None) -> Act:
+        if out is None:
+            out = self.new(x.n, x.t, x.h * k, x.w * k, x.c, dtype or x.dtype)
+        self.add(name, ops.upsample(x, out, k, accumulate))
+        return out
+
+    def rows_act(self, t: torch.Tensor, c: Optional[int] = None) -> Act:
+        """View a [M, C] row-major tensor as an Act with N=T=H=1, W=M (flat GEMM operand)."""
+        m, cs = t.shape
+        return Act(t.view(1, 1, 1, m, cs), 0, cs if c is None else c)
+
+    def flat(self, a: Act) -> Act:
+        return Act(a.buf.view(1, 1, 1, a.pixels, a.cs), a.c0, a.c)
+
+    def linear(self, name: str, x: Act, w_key: str, b_key: Optional[str], act=ACT_NONE, out: Optional[Act] = None,
+               residual: Optional[Act] = None, out_dtype=torch.bfloat16, scale=None) -> Act:
+        w = self.P(w_key)
+        shift = self.P(b_key) if b_key else None
+        if scale is not None and shift is not None:
+            shift = shift * scale
+        return self.conv(name, x, w, scale, shift, act=act, out=out, residual=residual,
+                         res_after_act=residual is not None, out_dtype=out_dtype)
+
+    # ------------------------------------------------------------------ stems reading the fp32 NCDHW inputs
+    def stem_gemm(self, name: str, which: str, shape5, w: torch.Tensor, scale, shift, kernel, stride, pad, act,
+                  out_dtype=torch.bfloat16) -> Act:
+        """Patch-gather (fp32 NCDHW -> bf16 rows) + flat GEMM for the Cin<=3 stems."""
+        n, c, t, h, wd = shape5
+        cout = w.shape[0]
+        k = c * kernel[0] * kernel[1] * kernel[2]
+        k_pad = -(-k // 64) * 64
+        ot = (t + 2 * pad[0] - kernel[0]) // stride[0] + 1
+        oh = (h + 2 * pad[1] - kernel[1]) // stride[1] + 1
+        ow = (wd + 2 * pad[2] - kernel[2]) // stride[2] + 1
+        m = n * ot * oh * ow
+        patches = torch.empty((m, k_pad), dtype=torch.bfloat16, device=self.device)
+        self.bytes_alloc += patches.numel() * 2
+        lib = ops._lib.load()
+        pd = ops.PatchDesc()
+        pd.src_layout = 0
+        pd.n, pd.c, pd.t, pd.h, pd.w = n, c, t, h, wd
+        pd.kt, pd.kh, pd.kw = kernel
+        pd.st, pd.sh, pd.sw = stride
+        pd.pt, pd.ph, pd.pw = pad
+        pd.ot, pd.oh, pd.ow = ot, oh, ow
+        pd.k_pad = k_pad
+        holder = self._inputs
+        import ctypes as C
+
+        def gather(_keep=(patches, pd)):
+            src = holder[which]
+            ops._lib.check(lib.mspi_patch_gather(C.byref(pd), ops._ptr(src), ops._ptr(patches), ops._stream()),
+                           f"patch_gather[{name}]")
+
+        self.add(name + ".gather", gather)
+        w2 = torch.zeros((cout, k_pad), dtype=torch.float32, device=self.device)
+        w5 = w if w.dim() == 5 else w[:, :, None]
+        w2[:, :k] = w5.permute(0, 2, 3, 4, 1).reshape(cout, k)
+        out = self.new(n, ot, oh, ow, cout, out_dtype)
+        self.conv(name, self.rows_act(patches), w2, scale, shift, act=act, out=self.flat(out))
+        self.flops -= 2.0 * m * cout * (k_pad - k)  # count algorithmic flops only
+        return out
+
+    # ------------------------------------------------------------------ S3D  (backbones/s3d.py)
+    def sep(self, p: str, x: Act, k: int, stride: int, pad: int, out: Optional[Act] = None) -> Act:
+        """SepConv3d, s3d.py:95-116"""
+        y = self.conv_bn_relu(p + ".conv_s", p + ".bn_s", x, 1e-3, (1, stride, stride), (0, pad, pad))
+        return self.conv_bn_relu(p + ".conv_t", p + ".bn_t", y, 1e-3, (stride, 1, 1), (pad, 0, 0), out)
+
+    def basic(self, p: str, x: Act, out: Optional[Act] = None, stride=(1, 1, 1), pad=(0, 0, 0)) -> Act:
+        """BasicConv3d, s3d.py:41-52"""
+        return self.conv_bn_relu(p + ".conv", p + ".bn", x, 1e-3, stride, pad, out)
+
+    def mixed(self, p: str, x: Act, out: Optional[Act] = None) -> Act:
+        """Mixed_* / Inception block: four branches written straight into their slices of the
+        concatenated output.  s3d.py:118-376, model_utils.py:173-199"""
+        c0 = self.P(p + ".branch0.0.conv.weight").shape[0]
+        c1 = self.P(p + ".branch1.1.conv_t.weight").shape[0]
+        c2 = self.P(p + ".branch2.1.conv_t.weight").shape[0]
+        c3 = self.P(p + ".branch3.1.conv.weight").shape[0]
+        if out is None:
+            out = self.new(x.n, x.t, x.h, x.w, c0 + c1 + c2 + c3)
+        self.basic(p + ".branch0.0", x, out.slice(0, c0))
+        t1 = self.basic(p + ".branch1.0", x)
+        self.sep(p + ".branch1.1", t1, 3, 1, 1, out.slice(c0, c1))
+        t2 = self.basic(p + ".branch2.0", x)
+        self.sep(p + ".branch2.1", t2, 3, 1, 1, out.slice(c0 + c1, c2))
+        pooled = self.pool(p + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        self.basic(p + ".branch3.1", pooled, out.slice(c0 + c1 + c2, c3))
+        return out
+
+    def s3d(self, v4_out: Optional[Act]):
+        """S3D_features_only.forward, s3d.py:406-418"""
+        p = "visnet."
+        B, T, H, W = self.B, self.T, self.H, self.W
+        sc, sh = self.bn(p + "base1.0.bn_s", 1e-3)
+        x = self.stem_gemm(p + "base1.0.conv_s", "clips", (B, 3, T, H, W), self.P(p + "base1.0.conv_s.weight"), sc, sh,
+                           (1, 7, 7), (1, 2, 2), (0, 3, 3), ACT_RELU)
+        x = self.conv_bn_relu(p + "base1.0.conv_t", p + "base1.0.bn_t", x, 1e-3, (2, 1, 1), (3, 0, 0))
+        x = self.pool(p + "base1.1", x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        x = self.basic(p + "base1.2", x)
+        v1 = self.sep(p + "base1.3", x, 3, 1, 1)
+        x = self.pool(p + "maxpooling2", v1, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        x = self.mixed(p + "base2.0", x)
+        v2 = self.mixed(p + "base2.1", x)
+        x = self.pool(p + "maxpooling3", v2, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+        for i in range(5):
+            x = self.mixed(p + f"base3.{i}", x)
+        v3 = x
+        ps = self.pool_stride
+        x = self.pool(p + "maxpooling4", v3, (ps, 2, 2), (ps, 2, 2), (0, 0, 0))
+        x = self.mixed(p + "base4.0", x)
+        v4 = self.mixed(p + "base4.1", x, v4_out)
+        for i, v in enumerate((v1, v2, v3, v4)):
+            self.tap(f"visnet.base{i + 1}", v)
+        return v1, v2, v3, v4
+
+    # ------------------------------------------------------------------ ResNet18 audio (backbones/resnet.py)
+    def resnet18(self) -> Act:
+        p = "audnet."
+        B = self.B
+        sc, sh = self.bn(p + "bn1", 1e-5)
+        x = self.stem_gemm(p + "conv1", "audio", (B, 1, 1, 257, 111), self.P(p + "conv1.weight"), sc, sh,
+                           (1, 7, 7), (1, 2, 2), (0, 3, 3), ACT_RELU)
+        x = self.pool(p + "maxpool", x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        for li in range(1, 5):
+            for bi in range(2):
+                q = f"{p}layer{li}.{bi}"
+                s = 2 if (li > 1 and bi == 0) else 1
+                idn = x
+                if (q + ".downsample.0.weight") in self.sd:
+                    dsc, dsh = self.bn(q + ".downsample.1", 1e-5)
+                    idn = self.conv(q + ".downsample.0", x, self.P(q + ".downsample.0.weight"), dsc, dsh, (1, s, s))
+                sc1, sh1 = self.bn(q + ".bn1", 1e-5)
+                o = self.conv(q + ".conv1", x, self.P(q + ".conv1.weight"), sc1, sh1, (1, s, s), (0, 1, 1), ACT_RELU)
+                sc2, sh2 = self.bn(q + ".bn2", 1e-5)
+                x = self.conv(q + ".conv2", o, self.P(q + ".conv2.weight"), sc2, sh2, (1, 1, 1), (0, 1, 1), ACT_RELU,
+                              residual=idn)  # relu(bn2(conv2) + identity), resnet.py:44-52
+        self.tap("audnet", x)
+        return x
+
+    # ------------------------------------------------------------------ ConvNeXt-T image encoder
+    def convnext(self) -> Tuple[Act, Act]:
+        """timm convnext_tiny(features_only) on the B*T frames + smooth convs, model_utils.py:357-385.
+        Frames are the (b t) order of rearrange('b c t h w -> (b t) c h w'), i.e. exactly the
+        N,T-major rows of the clip tensor, so N=B*T, T=1 here."""
+        p = "image_encoder.encoder."
+        B, T, H, W = self.B, self.T, self.H, self.W
+        nf = B * T
+        x32 = self.stem_gemm(p + "stem_0", "clips", (B, 3, T, H, W), self.P(p + "stem_0.weight"), None,
+                             self.P(p + "stem_0.bias"), (1, 4, 4), (1, 4, 4), (0, 0, 0), ACT_NONE, out_dtype=torch.float32)
+        h, w = H // 4, W // 4
+        x = self.new(nf, 1, h, w, 96)
+        self.add(p + "stem_1", ops.layernorm(x32.buf, x.buf, nf * h * w, 96, self.P(p + "stem_1.weight"),
+                                             self.P(p + "stem_1.bias"), 1e-6))
+        dims, depths = (96, 192, 384, 768), (3, 3, 9, 3)
+        feats = []
+        for s, (d, depth) in enumerate(zip(dims, depths)):
+            q = f"{p}stages_{s}."
+            if s > 0:
+                xn = self.new(nf, 1, h, w, dims[s - 1])
+                self.add(q + "downsample.0", ops.layernorm(x.buf, xn.buf, nf * h * w, dims[s - 1],
+                                                           self.P(q + "downsample.0.weight"),
+                                                           self.P(q + "downsample.0.bias"), 1e-6))
+                x = self.conv(q + "downsample.1", xn, self.P(q + "downsample.1.weight"), None,
+                              self.P(q + "downsample.1.bias"), (1, 2, 2))
+                h, w = h // 2, w // 2
+            for j in range(depth):
+                b = f"{q}blocks.{j}."
+                y = self.new(nf, 1, h, w, d)
+                self.add(b + "conv_dw+norm", ops.dwconv_ln(x, y, self.P(b + "conv_dw.weight"), self.P(b + "conv_dw.bias"),
+                                                           self.P(b + "norm.weight"), self.P(b + "norm.bias"), 1e-6))
+                hid = self.linear(b + "mlp.fc1", y, b + "mlp.fc1.weight", b + "mlp.fc1.bias", ACT_GELU)
+                # x + gamma * (fc2(h) + bias): layer scale folded into the epilogue scale/shift
+                x = self.linear(b + "mlp.fc2", hid, b + "mlp.fc2.weight", b + "mlp.fc2.bias", residual=x,
+                                scale=self.P(b + "gamma"))
+            feats.append(x)
+        o1, o0 = feats[2], feats[3]
+        i = "image_encoder."
+        sc, sh = self.bn(i + "smooth_1.1", 1e-5, self.P(i + "smooth_1.0.bias"))
+        s1 = self.conv(i + "smooth_1.0", o1, self.P(i + "smooth_1.0.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU)
+        sc, sh = self.bn(i + "smooth_0.1", 1e-5, self.P(i + "smooth_0.0.bias"))
+        s0 = self.conv(i + "smooth_0.0", o0, self.P(i + "smooth_0.0.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU)
+        self.tap("image_encoder.o1", s1)
+        self.tap("image_encoder.o0", s0)
+        return s1, s0
+
+    def adapter(self, o1: Act, o0: Act) -> Act:
+        """Adapter.forward, model_utils.py:202-220"""
+        B, T = self.B, self.T
+        st = T // 4
+        o1 = Act(o1.buf.view(B, T, o1.h, o1.w, o1.cs))  # (b t) frames are already b-major, t-minor
+        o0 = Act(o0.buf.view(B, T, o0.h, o0.w, o0.cs))
+        cat = self.new(B, 4, o1.h, o1.w, o1.c + o0.c)
+        self.pool("adapter.pool_time.o3", o1, (st, 1, 1), (st, 1, 1), (0, 0, 0), cat.slice(0, o1.c))
+        p0 = self.pool("adapter.pool_time.o2", o0, (st, 1, 1), (st, 1, 1), (0, 0, 0))
+        self.up("adapter.up", p0, 2, cat.slice(o1.c, o0.c))
+        masks = self.mixed("adapter.conv", cat)
+        self.tap("adapter", masks)
+        return masks
+
+    # ------------------------------------------------------------------ SyncBlock + SimSiam heads
+    @staticmethod
+    def sinusoid(n: int, d: int) -> torch.Tensor:
+        """model_utils.py:18-29 (fp64 table cast to fp32)"""
+        pos = np.arange(n, dtype=np.float64)[:, None]
+        j = np.arange(d)[None, :]
+        tab = pos / np.power(10000, 2 * (j // 2) / d)
+        tab[:, 0::2] = np.sin(tab[:, 0::2])
+        tab[:, 1::2] = np.cos(tab[:, 1::2])
+        return torch.tensor(tab, dtype=torch.float32)
+
+    def sync_block(self, v4: Act, aud: Act, v4cat: Act):
+        """SyncBlock.forward + forward_encoder's token split and SimSiam loss, model_utils.py:257-282,540-552"""
+        p = "aud_vis_sync_block."
+        B = self.B
+        nv, na, c = v4.t * v4.h * v4.w, aud.h * aud.w, 512
+        n = nv + na
+        dev = self.device
+        stream = torch.empty((B, n, c), dtype=torch.float32, device=dev)  # residual stream, fp32
+        self._keep.append(stream)
+        vp = self.linear(p + "vis_proj", self.flat(v4), p + "vis_proj.weight", p + "vis_proj.bias", out_dtype=torch.float32)
+        pos_v, pos_a = self.sinusoid(nv, c).to(dev), self.sinusoid(na, c).to(dev)
+        self.add(p + "vis_norm", ops.layernorm(vp.buf, stream, B * nv, c, self.P(p + "vis_norm.weight"),
+                                               self.P(p + "vis_norm.bias"), 1e-5, pos=pos_v, rows_per_group=nv,
+                                               out_gstride=n * c))
+        assert aud.c0 == 0 and aud.cs == c
+        self.add(p + "aud_norm", ops.layernorm(aud.buf, stream, B * na, c, self.P(p + "aud_norm.weight"),
+                                               self.P(p + "aud_norm.bias"), 1e-5, pos=pos_a, rows_per_group=na,
+                                               out_gstride=n * c, y_off=nv * c))
+        s_act = self.rows_act(stream.view(B * n, c))
+        ln = torch.empty((B * n, c), dtype=torch.bfloat16, device=dev)
+        ln_act = self.rows_act(ln)
+        attn_out = torch.empty((B * n, c), dtype=torch.bfloat16, device=dev)
+        for i in range(3):
+            b = f"{p}blocks.{i}."
+            self.add(b + "norm1", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm1.weight"), self.P(b + "norm1.bias"), 1e-5))
+            qkv = self.linear(b + "attn.qkv", ln_act, b + "attn.qkv.weight", None)
+            self.add(b + "attn", ops.attention(qkv.buf, attn_out, B, n, 4, c // 4))
+            self.flops += 4.0 * B * n * n * c
+            self.linear(b + "attn.proj", self.rows_act(attn_out), b + "attn.proj.weight", b + "attn.proj.bias",
+                        out=s_act, residual=s_act)
+            self.add(b + "norm2", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm2.weight"), self.P(b + "norm2.bias"), 1e-5))
+            hid = self.linear(b + "mlp.fc1", ln_act, b + "mlp.fc1.weight", b + "mlp.fc1.bias", ACT_GELU)
+            self.linear(b + "mlp.fc2", hid, b + "mlp.fc2.weight", b + "mlp.fc2.bias", out=s_act, residual=s_act)
+        self.taps_stream = stream
+        # vis tokens -> channels [1024, 1536) of the concatenated v4 (torch.cat([v4, vis_sync]), :559)
+        self.add("vis_sync.cat", ops.cast_rows(stream, v4cat.buf, B, nv, c, c, n * c, v4cat.cs, nv * v4cat.cs,
+                                               dst_off=v4.c))
+        # SimSiam heads (:404-435, 545-552)
+        pooled_v = torch.empty((B, c), dtype=torch.float32, device=dev)
+        pooled_a = torch.empty((B, c), dtype=torch.float32, device=dev)
+        self.add("vis_pool", ops.token_mean(stream, pooled_v, B, n, 0, nv, c))
+        self.add("aud_pool", ops.token_mean(stream, pooled_a, B, n, nv, n, c))
+
+        def head(prefix: str, x32: torch.Tensor, idx, last_norm: bool) -> torch.Tensor:
+            cur32 = x32
+            for k, i in enumerate(idx):
+                cin = cur32.shape[1]
+                xb = torch.empty((B, cin), dtype=torch.bfloat16, device=dev)
+                self.add(f"{prefix}.{i}.cast", ops.cast_rows(cur32, xb, 1, B, cin, cin, 0, cin, 0))
+                y = self.linear(f"{prefix}.{i}", self.rows_act(xb), f"{prefix}.{i}.weight", f"{prefix}.{i}.bias",
+                                out_dtype=torch.float32)
+                cur32 = y.buf.view(B, -1)
+                last = k == len(idx) - 1
+                if not last or last_norm:
+                    cout = cur32.shape[1]
+                    z = torch.empty((B, cout), dtype=torch.float32, device=dev)
+                    self.add(f"{prefix}.{i + 1}", ops.layernorm(cur32, z, B, cout, self.P(f"{prefix}.{i + 1}.weight"),
+                                                                self.P(f"{prefix}.{i + 1}.bias"), 1e-5, relu=not last))
+                    cur32 = z
+            return cur32
+
+        zv = head("vis_projector", pooled_v, (0, 3, 6), True)
+        za = head("aud_projector", pooled_a, (0, 3, 6), True)
+        pv = head("mlp_vis", zv, (0, 3), False)
+        pa = head("mlp_aud", za, (0, 3), False)
+        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.add("simsiam", ops.simsiam_loss(pv, za, pa, zv, self.loss, B, zv.shape[1]))
+
+    # ------------------------------------------------------------------ decoder
+    def convnext_block3d(self, p: str, x: Act) -> Act:
+        """ConvNextBlock, model_utils.py:306-354"""
+        a = self.new(x.n, x.t, x.h, x.w, x.c)
+        self.add(p + ".dwconv_t", ops.dwconv_ln(x, a, self.P(p + ".dwconv_t.weight"), self.P(p + ".dwconv_t.bias")))
+        b = self.new(x.n, x.t, x.h, x.w, x.c)
+        self.add(p + ".dwconv_s+norm", ops.dwconv_ln(a, b, self.P(p + ".dwconv_s.weight"), self.P(p + ".dwconv_s.bias"),
+                                                     self.P(p + ".norm.norm.weight"), self.P(p + ".norm.norm.bias"), 1e-5))
+        hid = self.conv(p + ".pwconv1", b, self.P(p + ".pwconv1.weight"), None, self.P(p + ".pwconv1.bias"), act=ACT_GELU)
+        return self.conv(p + ".pwconv2", hid, self.P(p + ".pwconv2.weight"), None, self.P(p + ".pwconv2.bias"),
+                         residual=x, res_after_act=True)
+
+    def lateral(self, k: int, x: Act) -> Act:
+        """latlayer_k, model_utils.py:437-484"""
+        p = f"latlayer_{k}"
+        y = self.conv(p + ".0", x, self.P(p + ".0.weight"), None, self.P(p + ".0.bias"))
+        i = 1
+        if self.lateral_bool[k]:
+            s = self.lateral_stride[k]
+            y = self.conv(p + ".1", y, self.P(p + ".1.weight"), stride=(s, 1, 1))
+            i = 2
+        out = self.convnext_block3d(f"{p}.{i}", y)
+        self.tap(p, out)
+        return out
+
+    def sa_masks(self, masks: Act) -> Act:
+        """The three SA 512->32 3x3x3 BasicConv3d run on the same `masks` (model_utils.py:161, Appendix C.9):
+        one GEMM with the three weight sets stacked along N."""
+        ws, scs, shs = [], [], []
+        for k in range(3):
+            ws.append(self.P(f"sa_{k}.conv_mask.0.conv.weight"))
+            sc, sh = self.bn(f"sa_{k}.conv_mask.0.bn", 1e-3)
+            scs.append(sc), shs.append(sh)
+        return self.conv("sa_*.conv_mask.0", masks, torch.cat(ws, 0), torch.cat(scs), torch.cat(shs), pad=(1, 1, 1),
+                         act=ACT_RELU)
+
+    def sa_gate(self, k: int, x: Act, m96: Act, scale: int, out: Optional[Act] = None) -> Act:
+        """SA.forward, model_utils.py:167-170"""
+        p = f"sa_{k}"
+        m = m96.slice(32 * k, 32)
+        if scale != 1:
+            m = self.up(p + ".up", m, scale)
+        logit = self.conv(p + ".conv_mask.2", m, self.P(p + ".conv_mask.2.weight"), None, self.P(p + ".conv_mask.2.bias"),
+                          pad=(0, 1, 1), out_dtype=torch.float32)
+        if out is None:
+            out = self.new(x.n, x.t, x.h, x.w, x.c)
+        self.add(p + ".gate", ops.sa_gate(x, logit.buf.view(-1), out))
+        return out
+
+    def readout(self, cat: Act) -> torch.Tensor:
+        """readout Sequential + log-softmax, model_utils.py:490-504,571-572"""
+        p = "readout"
+        x = self.conv(p + ".0", cat, self.P(p + ".0.weight"), None, self.P(p + ".0.bias"))
+        sc, sh = self.bn(p + ".2", 1e-5, self.P(p + ".1.bias"))
+        x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU)
+        sc, sh = self.bn(p + ".5", 1e-5, self.P(p + ".4.bias"))
+        x = self.conv(p + ".4", x, self.P(p + ".4.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU)
+        x = self.up(p + ".7", x, 4)
+        x = self.conv(p + ".8", x, self.P(p + ".8.weight"), None, self.P(p + ".8.bias"), stride=(4, 1, 1), act=ACT_RELU)
+        x = self.conv(p + ".10", x, self.P(p + ".10.weight"), None, self.P(p + ".10.bias"), pad=(0, 1, 1), act=ACT_RELU)
+        x = self.conv(p + ".12", x, self.P(p + ".12.weight"), None, self.P(p + ".12.bias"), pad=(0, 1, 1),
+                      out_dtype=torch.float32)
+        assert x.t == 1 and x.c == 1
+        self.logits = x.buf.view(self.B, self.H * self.W)
+        self.out = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device)
+        self.add("log_softmax", ops.logsoftmax2d(self.logits, self.out, self.B, self.H * self.W))
+        return self.out
+
+    # ------------------------------------------------------------------ whole forward
+    def _build(self):
+        B = self.B
+        o1, o0 = self.convnext()
+        masks = self.adapter(o1, o0)
+        t4 = self.T // 4 if self.pool_stride == 1 else None
+        h32, w32 = self.H // 32, self.W // 32
+        if self.audio:
+            v4cat = self.new(B, self.T // 4, h32, w32, 1024 + 512)
+            v1, v2, v3, v4 = self.s3d(v4cat.slice(0, 1024))
+            aud = self.resnet18()
+            self.sync_block(v4, aud, v4cat)
+            v4in = v4cat
+        else:
+            v1, v2, v3, v4 = self.s3d(None)
+            v4in = v4
+            self.loss = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        s3 = self.lateral(3, v4in)
+        s0 = self.lateral(0, v1)
+        s1 = self.lateral(1, v2)
+        s2 = self.lateral(2, v3)
+        assert s0.t == s1.t == s2.t == s3.t == masks.t, "laterals must land on the adapter's 4 frames (model_utils.py:169)"
+        m96 = self.sa_masks(masks)
+        # top-down fusion, model_utils.py:566-570
+        g2 = self.sa_gate(2, s2, m96, 1)
+        self.up("fuse.s2+=up2(s3)", s3, 2, g2, accumulate=True)
+        g1 = self.sa_gate(1, s1, m96, 2)
+        self.up("fuse.s1+=up2(s2)", g2, 2, g1, accumulate=True)
+        self.up("fuse.s1+=up4(s3)", s3, 4, g1, accumulate=True)
+        cat = self.new(B, s0.t, s0.h, s0.w, 4 * s0.c)
+        g0 = self.sa_gate(0, s0, m96, 4, cat.slice(0, s0.c))
+        self.up("fuse.s0+=up2(s1)", g1, 2, g0, accumulate=True)
+        self.up("fuse.s0+=up4(s2)", g2, 4, g0, accumulate=True)
+        self.up("fuse.s0+=up8(s3)", s3, 8, g0, accumulate=True)
+        self.tap("fuse.s2", g2), self.tap("fuse.s1", g1), self.tap("fuse.s0", g0)
+        c = s0.c
+        self.up("cat.up2(s1)", g1, 2, cat.slice(c, c))
+        self.up("cat.up4(s2)", g2, 4, cat.slice(2 * c, c))
+        self.up("cat.up8(s3)", s3, 8, cat.slice(3 * c, c))
+        self.readout(cat)
+
+    # ------------------------------------------------------------------ execution
+    def bind(self, clips: torch.Tensor, audio: Optional[torch.Tensor]):
+        assert clips.is_cuda and clips.dtype == torch.float32 and clips.is_contiguous()
+        assert tuple(clips.shape) == (self.B, 3, self.T, self.H, self.W), f"plan is for {(self.B, 3, self.T, self.H, self.W)}"
+        self._inputs["clips"] = clips
+        if self.audio:
+            assert audio is not None and audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
+            assert tuple(audio.shape) == (self.B, 1, 257, 111), "audio must be [B,1,257,111] (inference.py:26)"
+            self._inputs["audio"] = audio
+
+    def run_eager(self):
+        for _name, fn in self.steps:
+            fn()
+
+    def capture(self):
+        """Capture the step list into a CUDA graph bound to static input buffers."""
+        dev = self.device
+        self.static_clips = torch.zeros((self.B, 3, self.T, self.H, self.W), dtype=torch.float32, device=dev)
+        self.static_audio = torch.zeros((self.B, 1, 257, 111), dtype=torch.float32, device=dev) if self.audio else None
+        self.bind(self.static_clips, self.static_audio)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.run_eager()  # warm-up (module loading, attribute setting) outside capture
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager()
+        self.graph = g
+
+    def run(self, clips: torch.Tensor, audio: Optional[torch.Tensor]):
+        if self.graph is not None:
+            self.static_clips.copy_(clips, non_blocking=True)
+            if self.audio:
+                self.static_audio.copy_(audio, non_blocking=True)
+            self.graph.replay()
+        else:
+            self.bind(clips, audio)
+            self.run_eager()
+        return self.out, self.loss
+
+    @property
+    def num_launches(self) -> int:
+        """Kernels per forward (patch-gather steps of non-stem convs launch two)."""
+        return getattr(self, "_launches", len(self.steps))

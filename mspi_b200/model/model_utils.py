@@ -1,0 +1,237 @@
+"""AudioVisualSaliencyModel / VisualSaliencyModel — drop-in nn.Module surface of the reference's
+model/model_utils.py:388-702, executed by the B200 kernels.
+
+Same constructor argument (`cfg`), same attribute / state_dict names (`audnet`, `image_encoder`,
+`visnet`, `aud_vis_sync_block`, `vis_projector`, `mlp_vis`, `aud_projector`, `mlp_aud`, `latlayer_k`,
+`readout`, `adapter`, `sa_k`), same `forward(clips[B,3,T,H,W] fp32, audios[B,1,257,111] fp32) ->
+(log_map[B,H,W] fp32, loss_av)`, same `frozen_encoder()`.  The forward is inference-only (eval-mode
+BatchNorm); the modules below hold parameters, the arithmetic runs in libmspi_b200.so.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from ..backbones.resnet import get_resnet18
+from ..backbones.s3d import declare_basic, declare_mixed
+from ..engine import ForwardPlan
+from ..params import ParamNode, conv_bn, layer_norm, linear
+from .get_video_backbones import video_motion_extractor
+
+CONVNEXT_DIMS, CONVNEXT_DEPTHS = (96, 192, 384, 768), (3, 3, 9, 3)
+
+
+class StaticSaliencyModelConvNext(ParamNode):
+    """model_utils.py:357-385; `encoder` uses timm==0.6.12 FeatureListNet key names (stem_0, stem_1,
+    stages_k.downsample.{0,1}, stages_k.blocks.j.{conv_dw,norm,mlp.fc1,mlp.fc2,gamma})."""
+
+    def __init__(self):
+        super().__init__()
+        e = "encoder."
+        conv_bn(self, e + "stem_0", None, 96, 3, (4, 4), bias=True, init="trunc")
+        layer_norm(self, e + "stem_1", 96)
+        prev = 96
+        for s, (d, n) in enumerate(zip(CONVNEXT_DIMS, CONVNEXT_DEPTHS)):
+            q = f"{e}stages_{s}."
+            if s > 0:
+                layer_norm(self, q + "downsample.0", prev)
+                conv_bn(self, q + "downsample.1", None, d, prev, (2, 2), bias=True, init="trunc")
+            for j in range(n):
+                b = f"{q}blocks.{j}."
+                self.put(b + "gamma", torch.full((d,), 1e-6))
+                conv_bn(self, b + "conv_dw", None, d, 1, (7, 7), bias=True, init="trunc")
+                layer_norm(self, b + "norm", d)
+                linear(self, b + "mlp.fc1", 4 * d, d, init="trunc")
+                linear(self, b + "mlp.fc2", d, 4 * d, init="trunc")
+            prev = d
+        conv_bn(self, "smooth_0.0", "smooth_0.1", 320, 768, (3, 3), bias=True)
+        conv_bn(self, "smooth_1.0", "smooth_1.1", 96, 384, (3, 3), bias=True)
+
+
+class SyncBlock(ParamNode):
+    """model_utils.py:223-282 (the sinusoid tables are not parameters and not in the state_dict)."""
+
+    def __init__(self, num_blocks=3, num_vis_tokens=336, num_aud_tokens=36, vis_in_embed=1024, embed_dim=512):
+        super().__init__()
+        self.num_vis_tokens, self.num_aud_tokens = num_vis_tokens, num_aud_tokens
+        linear(self, "vis_proj", 512, vis_in_embed, init="xavier")
+        layer_norm(self, "vis_norm", 512)
+        layer_norm(self, "aud_norm", 512)
+        for i in range(num_blocks):
+            b = f"blocks.{i}."
+            layer_norm(self, b + "norm1", embed_dim)
+            linear(self, b + "attn.qkv", 3 * embed_dim, embed_dim, bias=False, init="xavier")
+            linear(self, b + "attn.proj", embed_dim, embed_dim, init="xavier")
+            layer_norm(self, b + "norm2", embed_dim)
+            linear(self, b + "mlp.fc1", 4 * embed_dim, embed_dim, init="xavier")
+            linear(self, b + "mlp.fc2", embed_dim, 4 * embed_dim, init="xavier")
+
+
+def _projector(cin, hidden):
+    n = ParamNode()
+    dims = (cin, hidden, hidden, hidden)
+    for k, i in enumerate((0, 3, 6)):
+        linear(n, str(i), dims[k + 1], dims[k])
+        layer_norm(n, str(i + 1), dims[k + 1])
+    return n
+
+
+def _predictor(hidden, mid):
+    n = ParamNode()
+    linear(n, "0", mid, hidden)
+    layer_norm(n, "1", mid)
+    linear(n, "3", hidden, mid)
+    return n
+
+
+def _latlayer(cin, de, temporal_stride: Optional[int]):
+    """model_utils.py:437-484 + ConvNextBlock :306-337 (trunc_normal .02 weights, zero bias)."""
+    n = ParamNode()
+    conv_bn(n, "0", None, de, cin, (1, 1, 1), bias=True)
+    i = 1
+    if temporal_stride:
+        conv_bn(n, "1", None, de, de, (temporal_stride, 1, 1))
+        i = 2
+    q = str(i)
+    conv_bn(n, q + ".dwconv_t", None, de, 1, (7, 1, 1), bias=True, init="trunc")
+    conv_bn(n, q + ".dwconv_s", None, de, 1, (1, 7, 7), bias=True, init="trunc")
+    layer_norm(n, q + ".norm.norm", de)
+    conv_bn(n, q + ".pwconv1", None, 4 * de, de, (1, 1, 1), bias=True, init="trunc")
+    conv_bn(n, q + ".pwconv2", None, de, 4 * de, (1, 1, 1), bias=True, init="trunc")
+    return n
+
+
+def _readout(de):
+    n = ParamNode()
+    conv_bn(n, "0", None, de, 4 * de, (1, 1, 1), bias=True)
+    conv_bn(n, "1", "2", de, de, (3, 3, 3), bias=True)
+    conv_bn(n, "4", "5", 64, de, (1, 3, 3), bias=True)
+    conv_bn(n, "8", None, 32, 64, (4, 1, 1), bias=True)
+    conv_bn(n, "10", None, 32, 32, (1, 3, 3), bias=True)
+    conv_bn(n, "12", None, 1, 32, (1, 3, 3), bias=True)
+    return n
+
+
+def _sa(in_embed=512):
+    n = ParamNode()
+    declare_basic(n, "conv_mask.0", in_embed, in_embed // 16, (3, 3, 3))
+    conv_bn(n, "conv_mask.2", None, 1, in_embed // 16, (1, 3, 3), bias=True)
+    return n
+
+
+def _adapter():
+    n = ParamNode()
+    declare_mixed(n, "conv", 416, (192, 96, 208, 16, 48, 64))
+    return n
+
+
+class _SaliencyBase(nn.Module):
+    has_audio = True
+
+    def __init__(self, cfg, aud_embed_dim=512, de_embed_dim=192, load_pretrained: bool = True):
+        super().__init__()
+        print("Motion Encoder is {}.".format(cfg.MODEL.MOTION_ENCODER))
+        self.cfg = cfg
+        vis_embed_dims = cfg.MODEL.MOTION_ENCODER_EMBEDS[cfg.MODEL.MOTION_ENCODER]
+        num_vis_tokens = cfg.MODEL.NUM_VIS_TOKENS[cfg.MODEL.MOTION_ENCODER]
+        if self.has_audio:
+            self.audnet = get_resnet18(path=cfg.MODEL.AUDIO_ENCODER_WEIGHT, pretrained=load_pretrained)
+        self.image_encoder = StaticSaliencyModelConvNext()
+        self.visnet = video_motion_extractor(cfg)
+        if self.has_audio:
+            self.aud_vis_sync_block = SyncBlock(num_blocks=3, num_vis_tokens=num_vis_tokens,
+                                                vis_in_embed=vis_embed_dims[-1], embed_dim=aud_embed_dim)
+            hidden = 2048
+            self.vis_projector = _projector(aud_embed_dim, hidden)
+            self.mlp_vis = _predictor(hidden, 512)
+            self.aud_projector = _projector(aud_embed_dim, hidden)
+            self.mlp_aud = _predictor(hidden, 512)
+        lb, ls = cfg.MODEL.LATERAL_BOOL, cfg.MODEL.LATERAL_STRIDE
+        extra = aud_embed_dim if self.has_audio else 0
+        self.latlayer_0 = _latlayer(vis_embed_dims[0], de_embed_dim, ls[0] if lb[0] else None)
+        self.latlayer_1 = _latlayer(vis_embed_dims[1], de_embed_dim, ls[1] if lb[1] else None)
+        self.latlayer_2 = _latlayer(vis_embed_dims[2], de_embed_dim, ls[2] if lb[2] else None)
+        self.latlayer_3 = _latlayer(vis_embed_dims[3] + extra, de_embed_dim, ls[3] if lb[3] else None)
+        self.readout = _readout(de_embed_dim)
+        self.adapter = _adapter()
+        self.sa_0 = _sa(512)
+        self.sa_1 = _sa(512)
+        self.sa_2 = _sa(512)
+        self._plans: Dict[Tuple, ForwardPlan] = {}
+        self.use_cuda_graph = False
+        self.keep_taps = False
+        if load_pretrained:
+            # Load Pretrained Weights — same files, same failure mode as model_utils.py:512-514
+            self.visnet.load_weight(cfg.MODEL.MOTION_ENCODER_WEIGHT)
+            if self.has_audio:
+                self.audnet.load_state_dict(torch.load(cfg.MODEL.AUDIO_ENCODER_WEIGHT, map_location="cpu"))
+            self.image_encoder.load_state_dict(torch.load(cfg.MODEL.IMAGE_SALIENCY_ENCODER_WEIGHT, map_location="cpu"),
+                                               strict=False)
+
+    def frozen_encoder(self):
+        if self.has_audio:
+            self.audnet.eval()
+        self.image_encoder.eval()
+
+    # -- plan cache ---------------------------------------------------------------------------
+    def load_state_dict(self, *a, **k):
+        self._plans.clear()  # packed weights are derived from the parameters
+        return super().load_state_dict(*a, **k)
+
+    def invalidate_plans(self):
+        """Call after mutating parameters in place (the packed bf16 weights are cached per input shape)."""
+        self._plans.clear()
+
+    def plan_for(self, clips: torch.Tensor) -> ForwardPlan:
+        b, c, t, h, w = clips.shape
+        if c != 3:
+            raise RuntimeError(f"expected clips [B,3,T,H,W], got {tuple(clips.shape)}")
+        if t != self.cfg.DATA.NUM_FRAMES:
+            raise RuntimeError(f"clip has {t} frames, cfg.DATA.NUM_FRAMES is {self.cfg.DATA.NUM_FRAMES}")
+        key = (b, t, h, w, clips.device.index, self.use_cuda_graph, self.keep_taps)
+        plan = self._plans.get(key)
+        if plan is None:
+            m = self.cfg.MODEL
+            plan = ForwardPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL),
+                               lateral_stride=tuple(m.LATERAL_STRIDE), pool_stride=m.S3D.POOL_STRIDE,
+                               device=clips.device, keep_taps=self.keep_taps)
+            if self.use_cuda_graph:
+                plan.capture()
+            self._plans[key] = plan
+        return plan
+
+    def _forward(self, clips, audios):
+        if not clips.is_cuda:
+            raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only: move the model inputs to the GPU; "
+                               "there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("mspi_b200 implements the inference forward (eval-mode BatchNorm); call model.eval()")
+        clips = clips.contiguous().float()
+        if audios is not None:
+            audios = audios.contiguous().float()
+        with torch.cuda.device(clips.device):
+            plan = self.plan_for(clips)
+            out, loss = plan.run(clips, audios)
+            return out.clone(), loss[0].clone()
+
+
+class AudioVisualSaliencyModel(_SaliencyBase):
+    """model_utils.py:388-574"""
+    has_audio = True
+
+    @torch.no_grad()
+    def forward(self, clips, audios):
+        return self._forward(clips, audios)
+
+
+class VisualSaliencyModel(_SaliencyBase):
+    """model_utils.py:576-702; returns (log_map, 0)."""
+    has_audio = False
+
+    @torch.no_grad()
+    def forward(self, clips):
+        out, _ = self._forward(clips, None)
+        return out, 0

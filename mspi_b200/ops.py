@@ -438,11 +438,51 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, 
 
 def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
     lib = _lib.load()
-    assert x.c0 == 0 and x.cs == x.c and y.c0 == 0 and y.cs == y.c and mask_logits.dtype == torch.float32
+    assert mask_logits.dtype == torch.float32 and x.c == y.c
     pixels, c = x.pixels, x.c
-    assert mask_logits.numel() == pixels
+    assert mask_logits.numel() == pixels and y.pixels == pixels
+    xp, yp, xcs, ycs = x.ptr, y.ptr, x.cs, y.cs
 
     def run(_keep=(x.buf, y.buf, mask_logits)):
-        _lib.check(lib.mspi_sa_gate(x.ptr, _ptr(mask_logits), y.ptr, pixels, c, _stream()), "sa_gate")
+        _lib.check(lib.mspi_sa_gate(xp, xcs, _ptr(mask_logits), yp, ycs, pixels, c, _stream()), "sa_gate")
+
+    return run
+
+
+def token_mean(x: torch.Tensor, y: torch.Tensor, b: int, rows: int, r0: int, r1: int, c: int) -> Callable[[], None]:
+    lib = _lib.load()
+
+    def run(_keep=(x, y)):
+        _lib.check(lib.mspi_token_mean(_ptr(x), _DT[x.dtype], _ptr(y), b, rows, r0, r1, c, _stream()), "token_mean")
+
+    return run
+
+
+def cast_rows(src: torch.Tensor, dst: torch.Tensor, groups: int, rows: int, c: int, src_rstride: int, src_gstride: int,
+              dst_rstride: int, dst_gstride: int, src_off: int = 0, dst_off: int = 0) -> Callable[[], None]:
+    lib = _lib.load()
+    sp, dp = _ptr(src, src_off * _ES[src.dtype]), _ptr(dst, dst_off * _ES[dst.dtype])
+
+    def run(_keep=(src, dst)):
+        _lib.check(lib.mspi_cast_rows(sp, _DT[src.dtype], src_rstride, src_gstride, dp, _DT[dst.dtype], dst_rstride,
+                                      dst_gstride, groups, rows, c, _stream()), "cast_rows")
+
+    return run
+
+
+def simsiam_loss(pv, za, pa, zv, out, b: int, c: int) -> Callable[[], None]:
+    lib = _lib.load()
+
+    def run(_keep=(pv, za, pa, zv, out)):
+        _lib.check(lib.mspi_simsiam_loss(_ptr(pv), _ptr(za), _ptr(pa), _ptr(zv), _ptr(out), b, c, _stream()), "simsiam")
+
+    return run
+
+
+def logsoftmax2d(x: torch.Tensor, y: torch.Tensor, b: int, pixels: int) -> Callable[[], None]:
+    lib = _lib.load()
+
+    def run(_keep=(x, y)):
+        _lib.check(lib.mspi_logsoftmax2d(_ptr(x), _ptr(y), b, pixels, _stream()), "logsoftmax2d")
 
     return run

@@ -271,7 +271,8 @@ def test_sa_gate_token_mean_simsiam():
     t = torch.randn(3, 20, 512, generator=g).to(torch.bfloat16)
     y = torch.empty(3, 512, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.mspi_token_mean(C.c_void_p(t.cuda().data_ptr()), C.c_void_p(y.data_ptr()), 3, 20, 4, 17, 512, st))
+    td = t.cuda()
+    _lib.check(lib.mspi_token_mean(C.c_void_p(td.data_ptr()), 0, C.c_void_p(y.data_ptr()), 3, 20, 4, 17, 512, st))
     torch.cuda.synchronize()
     assert (y.cpu() - t.float()[:, 4:17].mean(1)).abs().max() < 1e-5
     # simsiam
