@@ -124,7 +124,9 @@ int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, void* stream);
 /* ------------------------------------------------------------------------------------------
  * Bilinear (1,k,k) upsample, align_corners=False, channels-last.  Replaces
  * nn.Upsample(mode='trilinear', scale_factor=(1,k,k)) at model_utils.py:158,208,486-488,498.
- *   y = up(x) (+ y if accumulate)        in/out dtype bf16 or fp32
+ *   y = act( up(x) (+ y if accumulate) )        in/out dtype bf16 or fp32; act NONE or RELU
+ * (the ReLU lets a temporal conv be applied BEFORE the upsample: both are linear, they commute,
+ *  and the non-linearity that followed the conv moves here — readout.7-9, model_utils.py:498-500)
  */
 typedef struct {
   int32_t nt;        /* N*T planes */
@@ -133,6 +135,7 @@ typedef struct {
   int64_t in_cstride, out_cstride;
   int32_t in_dtype, out_dtype;
   int32_t accumulate;
+  int32_t act;
 } MspiUpDesc;
 int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* y, void* stream);
 
@@ -148,6 +151,7 @@ typedef struct {
   int32_t kt, kh, kw; /* odd, "same" padding */
   float ln_eps;
   int32_t out_dtype;
+  int32_t in_dtype;
 } MspiDwDesc;
 int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias,
                    const float* ln_w, const float* ln_b, void* y, void* stream);
@@ -174,9 +178,9 @@ int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, 
                    void* stream);
 
 /* SA gating + top-down sums (model_utils.py:167-170,566-568):
- *   y = x * sigmoid_mask + x ; the mask logits are fp32 [N*T*H*W] (one channel). */
+ *   y = x * sigmoid_mask + x ; the mask logits are fp32 [N*T*H*W] (one channel); x, y bf16 or fp32 (`dtype`). */
 int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, void* y, int64_t y_cstride,
-                 int64_t pixels, int c, void* stream);
+                 int64_t pixels, int c, int dtype, void* stream);
 
 /* Elementwise y = a + b over bf16 (used for ViT residuals when not fused) */
 int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);

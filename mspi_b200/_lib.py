@@ -72,7 +72,7 @@ class UpDesc(C.Structure):
     _fields_ = [
         ("nt", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("k", C.c_int32),
         ("in_cstride", C.c_int64), ("out_cstride", C.c_int64),
-        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("accumulate", C.c_int32), ("act", C.c_int32),
     ]
 
 
@@ -80,7 +80,7 @@ class DwDesc(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
-        ("ln_eps", C.c_float), ("out_dtype", C.c_int32),
+        ("ln_eps", C.c_float), ("out_dtype", C.c_int32), ("in_dtype", C.c_int32),
     ]
 
 
@@ -109,7 +109,7 @@ _SIGNATURES = {
     "mspi_dwconv_ln": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_layernorm": (C.c_int, [C.POINTER(LnDesc), _P, _P, _P, _P, _P, _P]),
     "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
-    "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+    "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "mspi_add_bf16": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "mspi_token_mean": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_cast_rows": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),

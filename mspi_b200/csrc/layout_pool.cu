@@ -9,6 +9,35 @@ constexpr int kBlock = 256;
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[VEC]) {
+  if constexpr (sizeof(T) == 2) {
+    static_assert(VEC == 8, "bf16 vectors are 8 wide");
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+    unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
+      v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+    }
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const float (&v)[VEC]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = o;
+  } else {
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q)
+      reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
 // ------------------------------------------------------------------------- patch gather
 // bf16 NDHWC source, C % 8 == 0: one thread moves 8 channels of one tap (16 B).
 __global__ void patch_gather_nhwc_kernel(MspiPatchDesc d, const __nv_bfloat16* __restrict__ src,
@@ -177,41 +206,42 @@ __global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __re
     const float ly = sy - y0, lx = sx - x0;
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
     const long long base = plane * d.h * d.w;
-    const TI* p00 = x + (base + static_cast<long long>(y0) * d.w + x0) * d.in_cstride + cc * VEC;
-    const TI* p01 = x + (base + static_cast<long long>(y0) * d.w + x1) * d.in_cstride + cc * VEC;
-    const TI* p10 = x + (base + static_cast<long long>(y1) * d.w + x0) * d.in_cstride + cc * VEC;
-    const TI* p11 = x + (base + static_cast<long long>(y1) * d.w + x1) * d.in_cstride + cc * VEC;
-    float v[VEC];
+    float a[VEC], b[VEC], c[VEC], e[VEC], v[VEC];
+    load_vec<TI, VEC>(x + (base + static_cast<long long>(y0) * d.w + x0) * d.in_cstride + cc * VEC, a);
+    load_vec<TI, VEC>(x + (base + static_cast<long long>(y0) * d.w + x1) * d.in_cstride + cc * VEC, b);
+    load_vec<TI, VEC>(x + (base + static_cast<long long>(y1) * d.w + x0) * d.in_cstride + cc * VEC, c);
+    load_vec<TI, VEC>(x + (base + static_cast<long long>(y1) * d.w + x1) * d.in_cstride + cc * VEC, e);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e)
-      v[e] = w00 * static_cast<float>(p00[e]) + w01 * static_cast<float>(p01[e]) +
-             w10 * static_cast<float>(p10[e]) + w11 * static_cast<float>(p11[e]);
+    for (int j = 0; j < VEC; ++j) v[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * e[j];
     TO* yp = y + opix * d.out_cstride + cc * VEC;
     if (d.accumulate) {
+      float o[VEC];
+      load_vec<TO, VEC>(yp, o);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) v[e] += static_cast<float>(yp[e]);
+      for (int j = 0; j < VEC; ++j) v[j] += o[j];
     }
+    if (d.act == MSPI_ACT_RELU) {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) yp[e] = static_cast<TO>(v[e]);
+      for (int j = 0; j < VEC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    store_vec<TO, VEC>(yp, v);
   }
 }
 
 // ------------------------------------------------------------------------- SA gate, add
-__global__ void sa_gate_kernel(const __nv_bfloat16* __restrict__ x, long long xcs, const float* __restrict__ m,
-                               __nv_bfloat16* __restrict__ y, long long ycs, long long total, int c8) {
+template <typename T>
+__global__ void sa_gate_kernel(const T* __restrict__ x, long long xcs, const float* __restrict__ m, T* __restrict__ y,
+                               long long ycs, long long total, int c8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / c8;
     const int cc = static_cast<int>(i - pix * c8);
-    const float g = 1.f + 1.f / (1.f + __expf(-__ldg(m + pix)));  // x*mask + x
-    const uint4 v = ldg16(x + pix * xcs + cc * 8);
+    const float g = 1.f + 1.f / (1.f + expf(-__ldg(m + pix)));  // x*mask + x
     float f[8];
-    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
-    unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
-    uint4 o;
-    o.x = pack_bf16x2(f[0] * g, f[1] * g); o.y = pack_bf16x2(f[2] * g, f[3] * g);
-    o.z = pack_bf16x2(f[4] * g, f[5] * g); o.w = pack_bf16x2(f[6] * g, f[7] * g);
-    *reinterpret_cast<uint4*>(y + pix * ycs + cc * 8) = o;
+    load_vec<T, 8>(x + pix * xcs + cc * 8, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= g;
+    store_vec<T, 8>(y + pix * ycs + cc * 8, f);
   }
 }
 
@@ -319,7 +349,9 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
 extern "C" int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* y, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(d && x && y && d->k >= 1, "mspi_upsample_bilinear: bad argument");
-  MSPI_CHECK_ARG(d->c % 8 == 0, "channels must be a multiple of 8");
+  MSPI_CHECK_ARG(d->c % 8 == 0 && d->in_cstride % 8 == 0 && d->out_cstride % 8 == 0,
+                 "channels and pixel strides must be multiples of 8");
+  MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "16-byte alignment");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   constexpr int VEC = 8;
   const int cv = d->c / VEC;
@@ -339,14 +371,18 @@ extern "C" int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* 
 }
 
 extern "C" int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, void* y, int64_t y_cstride,
-                            int64_t pixels, int c, void* stream_) {
+                            int64_t pixels, int c, int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0,
                  "mspi_sa_gate: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const long long total = pixels * (c / 8);
-  sa_gate_kernel<<<grid_for(total), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_cstride, mask_logits,
-                                                         static_cast<__nv_bfloat16*>(y), y_cstride, total, c / 8);
+  if (dtype == MSPI_BF16)
+    sa_gate_kernel<__nv_bfloat16><<<grid_for(total), kBlock, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, mask_logits, static_cast<__nv_bfloat16*>(y), y_cstride, total, c / 8);
+  else
+    sa_gate_kernel<float><<<grid_for(total), kBlock, 0, stream>>>(static_cast<const float*>(x), x_cstride, mask_logits,
+                                                                  static_cast<float*>(y), y_cstride, total, c / 8);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -8,8 +8,13 @@ namespace {
 
 // ------------------------------------------------------------------------- depthwise conv (+LN)
 // MAXP = channel pairs per lane (C <= 64*MAXP).
-template <int MAXP>
-__global__ void dwconv_ln_kernel(MspiDwDesc d, const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* row, int p) {
+  return __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(row)[p]);
+}
+__device__ __forceinline__ float2 ld_pair(const float* row, int p) { return reinterpret_cast<const float2*>(row)[p]; }
+
+template <int MAXP, typename TI>
+__global__ void dwconv_ln_kernel(MspiDwDesc d, const TI* __restrict__ x, const float* __restrict__ wgt,
                                  const float* __restrict__ bias, const float* __restrict__ ln_w,
                                  const float* __restrict__ ln_b, void* __restrict__ y, long long pixels) {
   const int lane = threadIdx.x & 31;
@@ -41,14 +46,13 @@ __global__ void dwconv_ln_kernel(MspiDwDesc d, const __nv_bfloat16* __restrict__
           const int iw = ow + kw - pw;
           if (iw < 0 || iw >= d.w) continue;
           const int tap = (kt * d.kh + kh) * d.kw + kw;
-          const __nv_bfloat162* xp =
-              reinterpret_cast<const __nv_bfloat162*>(x + (((n * d.t + it) * d.h + ih) * d.w + iw) * c);
+          const TI* xp = x + (((n * d.t + it) * d.h + ih) * d.w + iw) * c;
           const float2* wp = reinterpret_cast<const float2*>(wgt + static_cast<long long>(tap) * c);
 #pragma unroll
           for (int i = 0; i < MAXP; ++i) {
             const int p = lane + 32 * i;
             if (p < pairs) {
-              const float2 xv = __bfloat1622float2(xp[p]);
+              const float2 xv = ld_pair(xp, p);
               const float2 wv = __ldg(wp + p);
               acc[2 * i] = fmaf(xv.x, wv.x, acc[2 * i]);
               acc[2 * i + 1] = fmaf(xv.y, wv.y, acc[2 * i + 1]);
@@ -267,16 +271,22 @@ extern "C" int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* w
   long long blocks = (pixels + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
-  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   const int pairs = d->c / 2;
-  if (pairs <= 96)
-    dwconv_ln_kernel<3><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
-  else if (pairs <= 192)
-    dwconv_ln_kernel<6><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
-  else if (pairs <= 384)
-    dwconv_ln_kernel<12><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
-  else
-    dwconv_ln_kernel<16><<<static_cast<int>(blocks), threads, 0, stream>>>(*d, xp, wgt, bias, ln_w, ln_b, y, pixels);
+  const int g = static_cast<int>(blocks);
+#define MSPI_DW_LAUNCH(MAXP)                                                                                         \
+  do {                                                                                                                 \
+    if (d->in_dtype == MSPI_BF16)                                                                                      \
+      dwconv_ln_kernel<MAXP, __nv_bfloat16><<<g, threads, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x), wgt,  \
+                                                                       bias, ln_w, ln_b, y, pixels);                   \
+    else                                                                                                               \
+      dwconv_ln_kernel<MAXP, float><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), wgt, bias, ln_w,      \
+                                                               ln_b, y, pixels);                                       \
+  } while (0)
+  if (pairs <= 96) MSPI_DW_LAUNCH(3);
+  else if (pairs <= 192) MSPI_DW_LAUNCH(6);
+  else if (pairs <= 384) MSPI_DW_LAUNCH(12);
+  else MSPI_DW_LAUNCH(16);
+#undef MSPI_DW_LAUNCH
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -66,9 +66,9 @@ class ForwardPlan:
 
     def conv(self, name: str, x: Act, w: torch.Tensor, scale=None, shift=None, stride=(1, 1, 1), pad=(0, 0, 0),
              act=ACT_NONE, out: Optional[Act] = None, residual: Optional[Act] = None, res_after_act=False,
-             out_dtype=torch.bfloat16, dtype=torch.bfloat16) -> Act:
+             out_dtype=torch.bfloat16, dtype=torch.bfloat16, split_weights=False) -> Act:
         c = Conv(w, scale, shift, stride=stride, pad=pad, act=act, dtype=dtype, res_after_act=res_after_act,
-                 device=self.device, name=name)
+                 device=self.device, name=name, split_weights=split_weights)
         if out is None:
             ot, oh, ow = c.out_shape(x.t, x.h, x.w)
             out = self.new(x.n, ot, oh, ow, c.cout, out_dtype)
@@ -91,10 +91,11 @@ class ForwardPlan:
         self.add(name, ops.maxpool3d(x, out, k, s, p))
         return out
 
-    def up(self, name: str, x: Act, k: int, out: Optional[Act] = None, accumulate=False, dtype=None) -> Act:
+    def up(self, name: str, x: Act, k: int, out: Optional[Act] = None, accumulate=False, dtype=None,
+           act=ACT_NONE) -> Act:
         if out is None:
             out = self.new(x.n, x.t, x.h * k, x.w * k, x.c, dtype or x.dtype)
-        self.add(name, ops.upsample(x, out, k, accumulate))
+        self.add(name, ops.upsample(x, out, k, accumulate, act))
         return out
 
     def rows_act(self, t: torch.Tensor, c: Optional[int] = None) -> Act:
@@ -372,26 +373,42 @@ class ForwardPlan:
         self.add("simsiam", ops.simsiam_loss(pv, za, pa, zv, self.loss, B, zv.shape[1]))
 
     # ------------------------------------------------------------------ decoder
+    # Precision: everything after the encoders is min-max normalised by its consumers (inference.py:88,
+    # compute_saliency_metrics.normalize_map) and, with freshly initialised weights, carries a pixel-to-pixel
+    # signal far smaller than its bias-dominated mean.  bf16 storage there costs 1.1e-2 of the normalised map
+    # (measured: DESIGN.md "precision"), over the 1e-2 budget, so the decoder keeps fp32 activations and runs
+    # its GEMMs as kind::tf32 (fp32 accumulate); the encoders (87% of the FLOPs) stay bf16.
     def convnext_block3d(self, p: str, x: Act) -> Act:
-        """ConvNextBlock, model_utils.py:306-354"""
-        a = self.new(x.n, x.t, x.h, x.w, x.c)
+        """ConvNextBlock, model_utils.py:306-354.  x: fp32."""
+        f32 = torch.float32
+        a = self.new(x.n, x.t, x.h, x.w, x.c, f32)
         self.add(p + ".dwconv_t", ops.dwconv_ln(x, a, self.P(p + ".dwconv_t.weight"), self.P(p + ".dwconv_t.bias")))
-        b = self.new(x.n, x.t, x.h, x.w, x.c)
+        b = self.new(x.n, x.t, x.h, x.w, x.c, f32)
         self.add(p + ".dwconv_s+norm", ops.dwconv_ln(a, b, self.P(p + ".dwconv_s.weight"), self.P(p + ".dwconv_s.bias"),
                                                      self.P(p + ".norm.norm.weight"), self.P(p + ".norm.norm.bias"), 1e-5))
-        hid = self.conv(p + ".pwconv1", b, self.P(p + ".pwconv1.weight"), None, self.P(p + ".pwconv1.bias"), act=ACT_GELU)
+        hid = self.conv(p + ".pwconv1", b, self.P(p + ".pwconv1.weight"), None, self.P(p + ".pwconv1.bias"), act=ACT_GELU,
+                        out_dtype=f32, dtype=f32)
         return self.conv(p + ".pwconv2", hid, self.P(p + ".pwconv2.weight"), None, self.P(p + ".pwconv2.bias"),
-                         residual=x, res_after_act=True)
+                         residual=x, res_after_act=True, out_dtype=f32, dtype=f32)
 
     def lateral(self, k: int, x: Act) -> Act:
-        """latlayer_k, model_utils.py:437-484"""
+        """latlayer_k, model_utils.py:437-484.  Conv1x1(+bias) followed by the bias-free (s,1,1)/s temporal conv
+        is one linear map: W[kt] = W1[:,:,kt] @ W0, b = sum_kt W1[:,:,kt] @ b0 — composed on the host in fp32 and
+        run as ONE strided conv on the bf16 encoder tap, with hi/lo-split bf16 weights and an fp32 result."""
         p = f"latlayer_{k}"
-        y = self.conv(p + ".0", x, self.P(p + ".0.weight"), None, self.P(p + ".0.bias"))
+        w0 = self.P(p + ".0.weight").float()[:, :, 0, 0, 0]  # [de, cin]
+        b0 = self.P(p + ".0.bias").float()
         i = 1
         if self.lateral_bool[k]:
             s = self.lateral_stride[k]
-            y = self.conv(p + ".1", y, self.P(p + ".1.weight"), stride=(s, 1, 1))
+            w1 = self.P(p + ".1.weight").float()[:, :, :, 0, 0]  # [de, de, s]
+            w = torch.einsum("omk,mi->oik", w1, w0)[:, :, :, None, None]  # [de, cin, s, 1, 1]
+            bias = torch.einsum("omk,m->o", w1, b0)
+            y = self.conv(p + ".0+1", x, w, None, bias, stride=(s, 1, 1), out_dtype=torch.float32, split_weights=True)
+            self.flops += 2.0 * y.pixels * w1.shape[0] * w1.shape[1] * s  # the reference's separate temporal conv
             i = 2
+        else:
+            y = self.conv(p + ".0", x, w0[:, :, None, None, None], None, b0, out_dtype=torch.float32, split_weights=True)
         out = self.convnext_block3d(f"{p}.{i}", y)
         self.tap(p, out)
         return out
@@ -416,23 +433,38 @@ class ForwardPlan:
         logit = self.conv(p + ".conv_mask.2", m, self.P(p + ".conv_mask.2.weight"), None, self.P(p + ".conv_mask.2.bias"),
                           pad=(0, 1, 1), out_dtype=torch.float32)
         if out is None:
-            out = self.new(x.n, x.t, x.h, x.w, x.c)
+            out = self.new(x.n, x.t, x.h, x.w, x.c, x.dtype)
         self.add(p + ".gate", ops.sa_gate(x, logit.buf.view(-1), out))
         return out
 
-    def readout(self, cat: Act) -> torch.Tensor:
-        """readout Sequential + log-softmax, model_utils.py:490-504,571-572"""
+    def readout(self, g0: Act, g1: Act, g2: Act, s3: Act) -> torch.Tensor:
+        """readout Sequential + log-softmax, model_utils.py:490-504,570-572.
+
+        readout.0 is a 1x1x1 conv over cat[s0, up2(s1), up4(s2), up8(s3)]: linear and pointwise in space, so it
+        commutes with the bilinear upsamples.  Each 192-channel group is multiplied by its slice of the weight at
+        its own resolution and the products are upsample-accumulated into one 192-channel map; the 768-channel
+        concatenation (66 MB per clip in fp32) is never materialised."""
         p = "readout"
-        x = self.conv(p + ".0", cat, self.P(p + ".0.weight"), None, self.P(p + ".0.bias"))
+        f32 = torch.float32
+        w0 = self.P(p + ".0.weight")
+        c = g0.c
+        x = self.conv(p + ".0[s0]", g0, w0[:, 0:c], None, self.P(p + ".0.bias"), out_dtype=f32, dtype=f32)
+        for i, (g, k) in enumerate(((g1, 2), (g2, 4), (s3, 8)), 1):
+            part = self.conv(f"{p}.0[s{i}]", g, w0[:, i * c:(i + 1) * c], out_dtype=f32, dtype=f32)
+            self.up(f"{p}.0+=up{k}", part, k, x, accumulate=True)
         sc, sh = self.bn(p + ".2", 1e-5, self.P(p + ".1.bias"))
-        x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU)
+        x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
         sc, sh = self.bn(p + ".5", 1e-5, self.P(p + ".4.bias"))
-        x = self.conv(p + ".4", x, self.P(p + ".4.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU)
-        x = self.up(p + ".7", x, 4)
-        x = self.conv(p + ".8", x, self.P(p + ".8.weight"), None, self.P(p + ".8.bias"), stride=(4, 1, 1), act=ACT_RELU)
-        x = self.conv(p + ".10", x, self.P(p + ".10.weight"), None, self.P(p + ".10.bias"), pad=(0, 1, 1), act=ACT_RELU)
+        x = self.conv(p + ".4", x, self.P(p + ".4.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
+        # readout.7-9: Upsample(1,4,4) -> Conv(4,1,1)/s4 -> ReLU.  The conv mixes T and C only, the upsample H and
+        # W only: both linear, so conv first (16x fewer pixels, no 64ch full-resolution tensor), ReLU after.
+        x = self.conv(p + ".8", x, self.P(p + ".8.weight"), None, self.P(p + ".8.bias"), stride=(4, 1, 1),
+                      out_dtype=f32, dtype=f32)
+        x = self.up(p + ".7", x, 4, act=ACT_RELU)
+        x = self.conv(p + ".10", x, self.P(p + ".10.weight"), None, self.P(p + ".10.bias"), pad=(0, 1, 1), act=ACT_RELU,
+                      out_dtype=f32, dtype=f32)
         x = self.conv(p + ".12", x, self.P(p + ".12.weight"), None, self.P(p + ".12.bias"), pad=(0, 1, 1),
-                      out_dtype=torch.float32)
+                      out_dtype=f32, dtype=f32)
         assert x.t == 1 and x.c == 1
         self.logits = x.buf.view(self.B, self.H * self.W)
         self.out = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device)
@@ -444,7 +476,6 @@ class ForwardPlan:
         B = self.B
         o1, o0 = self.convnext()
         masks = self.adapter(o1, o0)
-        t4 = self.T // 4 if self.pool_stride == 1 else None
         h32, w32 = self.H // 32, self.W // 32
         if self.audio:
             v4cat = self.new(B, self.T // 4, h32, w32, 1024 + 512)
@@ -462,23 +493,18 @@ class ForwardPlan:
         s2 = self.lateral(2, v3)
         assert s0.t == s1.t == s2.t == s3.t == masks.t, "laterals must land on the adapter's 4 frames (model_utils.py:169)"
         m96 = self.sa_masks(masks)
-        # top-down fusion, model_utils.py:566-570
+        # top-down fusion, model_utils.py:566-568 (fp32)
         g2 = self.sa_gate(2, s2, m96, 1)
         self.up("fuse.s2+=up2(s3)", s3, 2, g2, accumulate=True)
         g1 = self.sa_gate(1, s1, m96, 2)
         self.up("fuse.s1+=up2(s2)", g2, 2, g1, accumulate=True)
         self.up("fuse.s1+=up4(s3)", s3, 4, g1, accumulate=True)
-        cat = self.new(B, s0.t, s0.h, s0.w, 4 * s0.c)
-        g0 = self.sa_gate(0, s0, m96, 4, cat.slice(0, s0.c))
+        g0 = self.sa_gate(0, s0, m96, 4)
         self.up("fuse.s0+=up2(s1)", g1, 2, g0, accumulate=True)
         self.up("fuse.s0+=up4(s2)", g2, 4, g0, accumulate=True)
         self.up("fuse.s0+=up8(s3)", s3, 8, g0, accumulate=True)
         self.tap("fuse.s2", g2), self.tap("fuse.s1", g1), self.tap("fuse.s0", g0)
-        c = s0.c
-        self.up("cat.up2(s1)", g1, 2, cat.slice(c, c))
-        self.up("cat.up4(s2)", g2, 4, cat.slice(2 * c, c))
-        self.up("cat.up8(s3)", s3, 8, cat.slice(3 * c, c))
-        self.readout(cat)
+        self.readout(g0, g1, g2, s3)
 
     # ------------------------------------------------------------------ execution
     def bind(self, clips: torch.Tensor, audio: Optional[torch.Tensor]):

@@ -164,7 +164,8 @@ class Conv:
 
     def __init__(self, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
                  shift: Optional[torch.Tensor] = None, stride=(1, 1, 1), pad=(0, 0, 0), act: int = ACT_NONE,
-                 dtype: torch.dtype = torch.bfloat16, res_after_act: bool = False, device="cuda", name: str = ""):
+                 dtype: torch.dtype = torch.bfloat16, res_after_act: bool = False, device="cuda", name: str = "",
+                 split_weights: bool = False):
         w = weight.detach().float()
         if w.dim() == 2:
             w = w[:, :, None, None, None]
@@ -177,6 +178,10 @@ class Conv:
         self.act = act
         self.dtype = dtype
         self.res_after_act = res_after_act
+        # split_weights: W = bf16(W) + bf16(W - bf16(W)); the low half rides along as a second set of taps at the
+        # same offsets, so a bf16 activation meets ~16-bit-mantissa weights at 2x the MMA work (used where the
+        # result is min-max normalised downstream and the input is already exact in bf16).
+        self.split = split_weights and dtype == torch.bfloat16
         self.device = device
         self.w_raw = w
         self.packed = None  # built lazily, the packing depends on the execution mode
@@ -200,8 +205,13 @@ class Conv:
         return "gather"
 
     def _pack(self, w5: torch.Tensor):
-        packed, taps, cin_pad = pack_conv_weight(w5.to(self.device), self.dtype)
-        return packed, taps, cin_pad
+        w5 = w5.to(self.device)
+        if not self.split:
+            return pack_conv_weight(w5, self.dtype)
+        hi = w5.to(torch.bfloat16).float()
+        p_hi, taps, cin_pad = pack_conv_weight(hi, self.dtype)
+        p_lo, _, _ = pack_conv_weight(w5 - hi, self.dtype)
+        return torch.cat([p_hi, p_lo], 1).contiguous(), 2 * taps, cin_pad
 
     def plan(self, x: Act, y: Act, residual: Optional[Act] = None) -> Callable[[], None]:
         """Build the descriptor(s) for this input/output pair; returns a closure that enqueues the kernels."""
@@ -273,6 +283,8 @@ class Conv:
             ostr = lambda a: (a.cs, 0, 0, 0)
             x_ptr = _ptr(patches)
             self._patches = patches
+        if self.split:
+            offs = offs + offs
         box = choose_box(tuple(o_dims))
         for j in range(5):
             d.a_dims[j] = a_dims[j]
@@ -358,13 +370,14 @@ def maxpool3d(x: Act, y: Act, kernel, stride, pad) -> Callable[[], None]:
     return run
 
 
-def upsample(x: Act, y: Act, k: int, accumulate: bool = False) -> Callable[[], None]:
+def upsample(x: Act, y: Act, k: int, accumulate: bool = False, act: int = ACT_NONE) -> Callable[[], None]:
     lib = _lib.load()
     d = UpDesc()
     d.nt, d.h, d.w, d.c, d.k = x.n * x.t, x.h, x.w, x.c, k
     d.in_cstride, d.out_cstride = x.cs, y.cs
     d.in_dtype, d.out_dtype = _DT[x.dtype], _DT[y.dtype]
     d.accumulate = 1 if accumulate else 0
+    d.act = act
     assert (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h * k, x.w * k, x.c)
     xp, yp = x.ptr, y.ptr
 
@@ -392,6 +405,7 @@ def dwconv_ln(x: Act, y: Act, weight: torch.Tensor, bias: torch.Tensor, ln_w=Non
     d.kt, d.kh, d.kw = kt, kh, kw
     d.ln_eps = eps
     d.out_dtype = _DT[y.dtype]
+    d.in_dtype = _DT[x.dtype]
     xp, yp = x.ptr, y.ptr
 
     def run(_keep=(x.buf, y.buf, wt, b, lw, lb, d)):
@@ -438,13 +452,14 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, 
 
 def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
     lib = _lib.load()
-    assert mask_logits.dtype == torch.float32 and x.c == y.c
+    assert mask_logits.dtype == torch.float32 and x.c == y.c and x.dtype == y.dtype
     pixels, c = x.pixels, x.c
+    dt = _DT[x.dtype]
     assert mask_logits.numel() == pixels and y.pixels == pixels
     xp, yp, xcs, ycs = x.ptr, y.ptr, x.cs, y.cs
 
     def run(_keep=(x.buf, y.buf, mask_logits)):
-        _lib.check(lib.mspi_sa_gate(xp, xcs, _ptr(mask_logits), yp, ycs, pixels, c, _stream()), "sa_gate")
+        _lib.check(lib.mspi_sa_gate(xp, xcs, _ptr(mask_logits), yp, ycs, pixels, c, dt, _stream()), "sa_gate")
 
     return run
 

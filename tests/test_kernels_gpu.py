@@ -283,3 +283,46 @@ def test_sa_gate_token_mean_simsiam():
     torch.cuda.synchronize()
     ref = -0.5 * (F.cosine_similarity(pv, za, dim=-1).mean() + F.cosine_similarity(pa, zv, dim=-1).mean())
     assert abs(o.item() - ref.item()) < 1e-5
+
+
+def test_metrics_kernel_against_golden_and_oracle():
+    """Metric kernel on identical fp32 maps: KATs produced by the reference's own functions (tests/golden/metrics.pt)
+    within 1e-5 relative, far inside the 1e-3 budget."""
+    import os
+    from mspi_b200.utils import compute_saliency_metrics as m
+    from mspi_b200.utils.loss import SalLoss
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.pt"), weights_only=False)
+    for nm, c in cases.items():
+        s, g, f = c["s"].cuda(), c["gt"].cuda(), c["fix"].cuda()
+        for key, val in (("kld", m.kldiv(s, g)), ("cc", m.cc(s, g)), ("sim", m.similarity(s, g)), ("nss", m.nss(s, f))):
+            assert abs(val.item() - c[key]) <= 1e-5 * max(1.0, abs(c[key])), (nm, key, val.item(), c[key])
+        logp = torch.log(c["s"] / c["s"].sum((1, 2), keepdim=True)).cuda()
+        crit = SalLoss()
+        assert abs(crit(logp, g).item() - c["loss"]) <= 2e-5 * max(1.0, abs(c["loss"]))
+        assert abs(crit(logp, g, f).item() - c["loss_fix"]) <= 2e-5 * max(1.0, abs(c["loss_fix"]))
+        assert crit.log["loss"].count == 2
+
+
+def test_logsoftmax_full_size():
+    from mspi_b200 import ops
+    x = torch.randn(3, 224 * 384, generator=torch.Generator().manual_seed(8)) * 3
+    y = torch.empty(3, 224 * 384, device="cuda")
+    ops.logsoftmax2d(x.cuda(), y, 3, 224 * 384)()
+    torch.cuda.synchronize()
+    ref = x - torch.logsumexp(x, 1, keepdim=True)
+    assert (y.cpu() - ref).abs().max() < 2e-5
+
+
+def test_logspec_against_reference_fixtures():
+    import os
+    from mspi_b200.audio import log_spectrogram
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "audio.pt"), weights_only=False)
+    for nm, c in fx.items():
+        got = log_spectrogram(c["wave"].cuda())[0].cpu()
+        assert got.shape == c["feat"].shape
+        # fp32 direct DFT vs torch's fp32 FFT, after log and standardisation: 2e-3 absolute on O(1) values
+        assert (got - c["feat"]).abs().max().item() < 2e-3, (nm, (got - c["feat"]).abs().max().item())
+    # ragged / edge cases: a batch, a signal shorter than one hop beyond the half window
+    w = torch.randn(3, 400, generator=torch.Generator().manual_seed(4))
+    from oracle import mspi_oracle as orc
+    assert (log_spectrogram(w.cuda()).cpu() - orc.log_spectrogram(w)).abs().max() < 2e-3
