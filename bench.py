@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: MSPI-S3D clip forward, clips/s on N x B200 (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One process per GPU (the driver launches N>1 under torch.distributed.run).  A "step" is one forward of
+`--batch` synthetic clips [B,3,16,224,384] + spectrograms [B,1,257,111] per GPU through the C-ABI kernels,
+followed (N>1) by the NCCL all-gather of the saliency maps.  Rank 0 prints ONE JSON line.
+
+  value      clips/s, whole job, inputs resident in HBM before the timed region (CUDA-event timed, max over ranks)
+  e2e        clips/s through the public nn.Module API with HOST inputs: pinned fp32 clips are copied H2D every
+             step and the [B,H,W] maps are copied back D2H every step, inside the timed region
+  roofline   dominant kernel = the tcgen05 implicit-GEMM conv kernel (bf16 instance): algorithmic FLOPs of its
+             launches / their CUDA-event durations, against the measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (CPU port of the reference forward) timed on this box's host cores, rank 0, N=1
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import copy
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T, H, W = 16, 224, 384
+ALGO_GFLOP_PER_CLIP = 416.05  # 2xMAC of the reference forward at 16x224x384 (FlopCounterMode)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(seconds_budget: float = 20.0):
+    """The oracle (CPU fp32 port of the reference forward) on the host cores: B=1 at the default shape."""
+    import torch
+    from oracle import mspi_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.make_state_dict(1, "default")
+    clips, aud = orc.make_inputs(1, H, W, 2023)
+    orc.forward(sd, clips, aud)  # warm-up
+    times = []
+    t_end = time.time() + seconds_budget
+    while len(times) < 3 or (time.time() < t_end and len(times) < 10):
+        t0 = time.perf_counter()
+        orc.forward(sd, clips, aud)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"B=1 clip 16x{H}x{W} + audio, fp32, oracle port of the reference forward, best of {len(times)} "
+                      f"({best:.3f} s/clip, torch {torch.__version__} CPU, {torch.get_num_threads()} threads)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and cannot
+    travel to the GPU box, so its CPU port (oracle/, pinned to the live reference by tests/golden) is timed."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import mspi_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.make_state_dict(1, "default")
+    clips, aud = orc.make_inputs(1, H, W, 2023)
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.forward(sd, clips, aud)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward(sd, clips, aud)
+    dt = (time.perf_counter() - t0) / steps
+    v = 1.0 / dt
+    line = {"impl": "reference", "metric": "clips/sec MSPI-S3D inference", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"MSPI-S3D clip forward, bounded sample: B=1 clip 16x{H}x{W} per step on host cores"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"B=1 clip per step, {steps} steps, oracle port of the reference forward"},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--impl", default="mspi_b200", choices=["mspi_b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="replay the kernel list eagerly instead of a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this file")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(3, args.warmup)
+    K, B = args.steps, args.batch
+
+    from mspi_b200 import _lib
+    from mspi_b200.config import cfg as base_cfg
+    from mspi_b200.model.model_utils import AudioVisualSaliencyModel
+    torch.manual_seed(2023)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = AudioVisualSaliencyModel(copy.deepcopy(base_cfg), load_pretrained=False)  # random init, synthetic data
+    model = model.to(dev).eval()
+    model.use_cuda_graph = not args.no_graph
+
+    g = torch.Generator(device=dev).manual_seed(2023 + rank)
+    n_sets = 2  # rotate input sets; each set (B*16.5 MB) is already larger than... see config.l2
+    clips_sets = [torch.randn(B, 3, T, H, W, device=dev, generator=g) for _ in range(n_sets)]
+    audio_sets = [torch.randn(B, 1, 257, 111, device=dev, generator=g) for _ in range(n_sets)]
+    gathered = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(i):
+        out, loss = model(clips_sets[i % n_sets], audio_sets[i % n_sets])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return out, loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.load()
+    l0 = lib.mspi_launch_count()
+    step(0)  # builds the plan (and captures the graph)
+    torch.cuda.synchronize()
+    plan = next(iter(model._plans.values()))
+    # launches per forward, counted on an eager replay of the plan's step list
+    l0 = lib.mspi_launch_count()
+    plan.bind(clips_sets[0], audio_sets[0])
+    plan.run_eager()
+    torch.cuda.synchronize()
+    launches_per_fwd = int(lib.mspi_launch_count() - l0)
+    for i in range(W_):
+        step(i)
+    barrier()
+
+    # ------------------------------------------------------------------ timed region: device-resident inputs
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(K):
+            step(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * K / (ms / 1e3)
+
+    # ------------------------------------------------------------------ e2e: host inputs through the public API
+    pin = [torch.randn(B, 3, T, H, W).pin_memory() for _ in range(2)]
+    pin_a = [torch.randn(B, 1, 257, 111).pin_memory() for _ in range(2)]
+    host_out = [torch.empty(B, H, W).pin_memory() for _ in range(2)]
+    dclips = [torch.empty(B, 3, T, H, W, device=dev) for _ in range(2)]
+    daud = [torch.empty(B, 1, 257, 111, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    main_stream = torch.cuda.current_stream()
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            dclips[s].copy_(pin[s], non_blocking=True)
+            daud[s].copy_(pin_a[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_run(n):
+        for s in range(2):
+            freed[s].record(main_stream)
+        upload(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                upload(i + 1)  # overlaps the H2D of the next step's inputs with this step's kernels
+            main_stream.wait_event(ready[s])
+            out, loss = model(dclips[s], daud[s])
+            freed[s].record(main_stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out)
+            host_out[s].copy_(out, non_blocking=True)  # D2H of this step's maps
+        torch.cuda.synchronize()
+
+    e2e_run(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(K)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (t2.item() / 1e3)
+    h2d = B * (3 * T * H * W + 257 * 111) * 4
+    d2h = B * H * W * 4
+
+    # ------------------------------------------------------------------ per-kernel breakdown (CUDA events, eager replay)
+    roofline, tf32_info, breakdown = None, None, None
+    if rank == 0:
+        peaks = read_peaks()
+        plan.bind(clips_sets[0], audio_sets[0])
+        reps = 2
+        acc = {}
+        for rep in range(reps + 1):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.steps) + 1)]
+            evs[0].record()
+            for j, (_name, fn) in enumerate(plan.steps):
+                fn()
+                evs[j + 1].record()
+            torch.cuda.synchronize()
+            if rep == 0:
+                continue  # warm
+            for j, (name, fn) in enumerate(plan.steps):
+                acc.setdefault(j, []).append(evs[j].elapsed_time(evs[j + 1]))
+        rows = []
+        for j, (name, fn) in enumerate(plan.steps):
+            d = getattr(fn, "desc", None)
+            kind = "other"
+            flops = 0.0
+            if d is not None:
+                kind = "conv_gemm_bf16" if d.a_dtype == 0 else "conv_gemm_tf32"
+                flops = getattr(fn, "flops", 0.0)
+            rows.append({"step": name, "kind": kind, "ms": sum(acc[j]) / len(acc[j]), "gflop": flops / 1e9})
+        tot = sum(r["ms"] for r in rows)
+        for kind in ("conv_gemm_bf16", "conv_gemm_tf32"):
+            sel = [r for r in rows if r["kind"] == kind]
+            ms_k, gf_k = sum(r["ms"] for r in sel), sum(r["gflop"] for r in sel)
+            info = {"launches": len(sel), "ms": ms_k, "share_of_step": ms_k / tot if tot else None,
+                    "gflop": gf_k, "tflops": gf_k / ms_k if ms_k else None}
+            if kind == "conv_gemm_bf16":
+                peak = peaks["bf16_sustained"]
+                roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<bf16> (tcgen05 implicit GEMM)",
+                            "achieved": info["tflops"], "peak": peak, "unit": "TFLOP/s",
+                            "frac": (info["tflops"] / peak) if info["tflops"] else None, "traffic": None,
+                            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                            "launches_per_step": info["launches"], "share_of_step": info["share_of_step"],
+                            "algorithmic_gflop_per_step": gf_k}
+            else:
+                tf32_info = info
+        breakdown = {"total_ms_eager_sum": tot, "rows": sorted(rows, key=lambda r: -r["ms"])[:40]}
+        if args.breakdown:
+            with open(args.breakdown, "w") as f:
+                json.dump({"rows": rows, "total_ms": tot}, f, indent=1)
+
+    if rank == 0:
+        peaks = read_peaks()
+        line = {
+            "metric": "clips/sec MSPI-S3D inference", "value": value, "unit": "clips/s", "n_gpus": world, "steps": K,
+            "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"MSPI-S3D (S3D + ResNet18 audio + ConvNeXt-T image encoder + fusion decoder) inference, "
+                                   f"{B} clips/GPU/step of 16x{H}x{W} fp32 + [1,257,111] spectrograms, random init",
+                       "batch_per_gpu": B, "clip": [3, T, H, W], "parallelism": f"dp{world} (clip sharding, NCCL all-gather of maps)",
+                       "precision": "bf16 tensor cores (encoders), tf32 tensor cores + fp32 storage (fusion/decoder), fp32 accumulate",
+                       "cuda_graph": bool(model.use_cuda_graph),
+                       "l2": f"inputs larger than L2: {B * 3 * T * H * W * 4 / 2**20:.0f} MiB of clips per step, {n_sets} rotating sets"},
+            "tensor_frac_of_peak_whole_step": value / world * ALGO_GFLOP_PER_CLIP / 1e3 / peaks["bf16_sustained"],
+            "algorithmic_gflop_per_clip": ALGO_GFLOP_PER_CLIP,
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned host fp32 inputs, H2D of step i+1 overlapped with step i on a copy stream"},
+            "gpu_launches": launches_per_fwd * K,
+            "launches_per_step": launches_per_fwd,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "tf32_kernel": tf32_info,
+            "activation_bytes_allocated": plan.bytes_alloc,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

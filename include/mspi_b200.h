@@ -172,9 +172,9 @@ typedef struct {
 int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w, const float* b,
                    const float* pos, void* y, void* stream);
 
-/* Multi-head self attention over short sequences (model_utils.py:97-109): qkv bf16
- * [B][N][3][heads][hd] -> out bf16 [B][N][heads*hd]; softmax(q k^T * scale) v in fp32. */
-int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, float scale,
+/* Multi-head self attention over short sequences (model_utils.py:97-109): qkv (bf16 or fp32, `dtype`)
+ * [B][N][3][heads][hd] -> out (same dtype) [B][N][heads*hd]; softmax(q k^T * scale) v in fp32. */
+int mspi_attention(const void* qkv, void* out, int dtype, int b, int n, int heads, int hd, float scale,
                    void* stream);
 
 /* SA gating + top-down sums (model_utils.py:167-170,566-568):

@@ -108,7 +108,7 @@ _SIGNATURES = {
     "mspi_upsample_bilinear": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P]),
     "mspi_dwconv_ln": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_layernorm": (C.c_int, [C.POINTER(LnDesc), _P, _P, _P, _P, _P, _P]),
-    "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "mspi_add_bf16": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "mspi_token_mean": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

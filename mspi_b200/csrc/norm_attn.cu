@@ -139,9 +139,19 @@ __global__ void layernorm_kernel(MspiLnDesc d, const TI* __restrict__ x, const f
 constexpr int kQT = 16;
 constexpr int kAttnThreads = 128;
 
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+  unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kAttnThreads)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n, int heads, int hd,
-                 float scale, int n_pad) {
+attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int heads, int hd, float scale, int n_pad) {
   extern __shared__ float sm[];
   float* q_s = sm;                 // [kQT][hd]
   float* s_s = sm + kQT * hd;      // [kQT][n_pad]
@@ -149,24 +159,22 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int q0 = blockIdx.y * kQT;
   const int tid = threadIdx.x;
   const long long row_stride = 3ll * heads * hd;
-  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * n * row_stride + h * hd;
+  const T* base = qkv + static_cast<long long>(b) * n * row_stride + h * hd;
   for (int i = tid; i < kQT * hd; i += kAttnThreads) {
     const int qi = i / hd, dd = i % hd;
     const int qr = q0 + qi;
-    q_s[i] = qr < n ? bf2f(base[static_cast<long long>(qr) * row_stride + dd]) * scale : 0.f;
+    q_s[i] = qr < n ? static_cast<float>(base[static_cast<long long>(qr) * row_stride + dd]) * scale : 0.f;
   }
   __syncthreads();
   // phase 1: scores
   for (int k = tid; k < n; k += kAttnThreads) {
-    const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<long long>(k) * row_stride + heads * hd);
+    const T* kp = base + static_cast<long long>(k) * row_stride + heads * hd;
     float acc[kQT];
 #pragma unroll
     for (int qi = 0; qi < kQT; ++qi) acc[qi] = 0.f;
     for (int d8 = 0; d8 < hd / 8; ++d8) {
-      const uint4 kv = __ldg(kp + d8);
       float kf[8];
-      unpack_bf16x2(kv.x, kf[0], kf[1]); unpack_bf16x2(kv.y, kf[2], kf[3]);
-      unpack_bf16x2(kv.z, kf[4], kf[5]); unpack_bf16x2(kv.w, kf[6], kf[7]);
+      load8(kp + d8 * 8, kf);
 #pragma unroll
       for (int qi = 0; qi < kQT; ++qi) {
         const float* qq = q_s + qi * hd + d8 * 8;
@@ -200,17 +208,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     float acc[kQT];
 #pragma unroll
     for (int qi = 0; qi < kQT; ++qi) acc[qi] = 0.f;
-    const __nv_bfloat16* vp = base + 2ll * heads * hd + dd;
+    const T* vp = base + 2ll * heads * hd + dd;
     for (int k = 0; k < n; ++k) {
-      const float v = bf2f(vp[static_cast<long long>(k) * row_stride]);
+      const float v = static_cast<float>(vp[static_cast<long long>(k) * row_stride]);
 #pragma unroll
       for (int qi = 0; qi < kQT; ++qi) acc[qi] = fmaf(s_s[qi * n_pad + k], v, acc[qi]);
     }
 #pragma unroll
     for (int qi = 0; qi < kQT; ++qi) {
       const int qr = q0 + qi;
-      if (qr < n)
-        out[(static_cast<long long>(b) * n + qr) * (heads * hd) + h * hd + dd] = __float2bfloat16_rn(acc[qi]);
+      if (qr < n) out[(static_cast<long long>(b) * n + qr) * (heads * hd) + h * hd + dd] = static_cast<T>(acc[qi]);
     }
   }
 }
@@ -317,22 +324,28 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
   return MSPI_OK;
 }
 
-extern "C" int mspi_attention(const void* qkv, void* out, int b, int n, int heads, int hd, float scale, void* stream_) {
+extern "C" int mspi_attention(const void* qkv, void* out, int dtype, int b, int n, int heads, int hd, float scale,
+                              void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(qkv && out && b > 0 && n > 0 && heads > 0, "mspi_attention: bad argument");
   MSPI_CHECK_ARG(hd % 8 == 0 && n <= 1024, "hd %d / n %d unsupported", hd, n);
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const int n_pad = n + 1;  // odd-ish stride: rows of the score tile land in different banks
   const size_t smem = static_cast<size_t>(kQT) * (hd + n_pad) * sizeof(float);
+  MSPI_CHECK_ARG(smem <= 100 * 1024, "attention tile needs %zu bytes of shared memory", smem);
   static bool attr = false;
   if (!attr) {
-    MSPI_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MSPI_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MSPI_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  MSPI_CHECK_ARG(smem <= 100 * 1024, "attention tile needs %zu bytes of shared memory", smem);
   dim3 grid(b * heads, (n + kQT - 1) / kQT);
-  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                         static_cast<__nv_bfloat16*>(out), n, heads, hd, scale, n_pad);
+  if (dtype == MSPI_BF16)
+    attention_kernel<__nv_bfloat16><<<grid, kAttnThreads, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads, hd, scale, n_pad);
+  else
+    attention_kernel<float><<<grid, kAttnThreads, smem, stream>>>(static_cast<const float*>(qkv),
+                                                                  static_cast<float*>(out), n, heads, hd, scale, n_pad);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -311,9 +311,13 @@ class ForwardPlan:
         nv, na, c = v4.t * v4.h * v4.w, aud.h * aud.w, 512
         n = nv + na
         dev = self.device
-        stream = torch.empty((B, n, c), dtype=torch.float32, device=dev)  # residual stream, fp32
+        f32 = torch.float32
+        stream = torch.empty((B, n, c), dtype=f32, device=dev)  # residual stream, fp32
         self._keep.append(stream)
-        vp = self.linear(p + "vis_proj", self.flat(v4), p + "vis_proj.weight", p + "vis_proj.bias", out_dtype=torch.float32)
+        # v4 arrives in fp32 (the S3D head writes it that way, see _build) and the block runs in tf32: the fused
+        # tokens go straight back into the decoder, which is precision critical (see "decoder" below).
+        vp = self.conv(p + "vis_proj", self.flat(v4), self.P(p + "vis_proj.weight"), None, self.P(p + "vis_proj.bias"),
+                       out_dtype=f32, dtype=v4.dtype)
         pos_v, pos_a = self.sinusoid(nv, c).to(dev), self.sinusoid(na, c).to(dev)
         self.add(p + "vis_norm", ops.layernorm(vp.buf, stream, B * nv, c, self.P(p + "vis_norm.weight"),
                                                self.P(p + "vis_norm.bias"), 1e-5, pos=pos_v, rows_per_group=nv,
@@ -323,20 +327,24 @@ class ForwardPlan:
                                                self.P(p + "aud_norm.bias"), 1e-5, pos=pos_a, rows_per_group=na,
                                                out_gstride=n * c, y_off=nv * c))
         s_act = self.rows_act(stream.view(B * n, c))
-        ln = torch.empty((B * n, c), dtype=torch.bfloat16, device=dev)
+        ln = torch.empty((B * n, c), dtype=f32, device=dev)
         ln_act = self.rows_act(ln)
-        attn_out = torch.empty((B * n, c), dtype=torch.bfloat16, device=dev)
+        attn_out = torch.empty((B * n, c), dtype=f32, device=dev)
+
+        def lin(name, x, wk, bk, act=ACT_NONE, out=None, residual=None):
+            return self.conv(name, x, self.P(wk), None, self.P(bk) if bk else None, act=act, out=out, residual=residual,
+                             res_after_act=residual is not None, out_dtype=f32, dtype=f32)
+
         for i in range(3):
             b = f"{p}blocks.{i}."
             self.add(b + "norm1", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm1.weight"), self.P(b + "norm1.bias"), 1e-5))
-            qkv = self.linear(b + "attn.qkv", ln_act, b + "attn.qkv.weight", None)
+            qkv = lin(b + "attn.qkv", ln_act, b + "attn.qkv.weight", None)
             self.add(b + "attn", ops.attention(qkv.buf, attn_out, B, n, 4, c // 4))
             self.flops += 4.0 * B * n * n * c
-            self.linear(b + "attn.proj", self.rows_act(attn_out), b + "attn.proj.weight", b + "attn.proj.bias",
-                        out=s_act, residual=s_act)
+            lin(b + "attn.proj", self.rows_act(attn_out), b + "attn.proj.weight", b + "attn.proj.bias", out=s_act, residual=s_act)
             self.add(b + "norm2", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm2.weight"), self.P(b + "norm2.bias"), 1e-5))
-            hid = self.linear(b + "mlp.fc1", ln_act, b + "mlp.fc1.weight", b + "mlp.fc1.bias", ACT_GELU)
-            self.linear(b + "mlp.fc2", hid, b + "mlp.fc2.weight", b + "mlp.fc2.bias", out=s_act, residual=s_act)
+            hid = lin(b + "mlp.fc1", ln_act, b + "mlp.fc1.weight", b + "mlp.fc1.bias", ACT_GELU)
+            lin(b + "mlp.fc2", hid, b + "mlp.fc2.weight", b + "mlp.fc2.bias", out=s_act, residual=s_act)
         self.taps_stream = stream
         # vis tokens -> channels [1024, 1536) of the concatenated v4 (torch.cat([v4, vis_sync]), :559)
         self.add("vis_sync.cat", ops.cast_rows(stream, v4cat.buf, B, nv, c, c, n * c, v4cat.cs, nv * v4cat.cs,
@@ -407,6 +415,8 @@ class ForwardPlan:
             y = self.conv(p + ".0+1", x, w, None, bias, stride=(s, 1, 1), out_dtype=torch.float32, split_weights=True)
             self.flops += 2.0 * y.pixels * w1.shape[0] * w1.shape[1] * s  # the reference's separate temporal conv
             i = 2
+        elif x.dtype == torch.float32:
+            y = self.conv(p + ".0", x, w0[:, :, None, None, None], None, b0, out_dtype=torch.float32, dtype=torch.float32)
         else:
             y = self.conv(p + ".0", x, w0[:, :, None, None, None], None, b0, out_dtype=torch.float32, split_weights=True)
         out = self.convnext_block3d(f"{p}.{i}", y)
@@ -478,7 +488,7 @@ class ForwardPlan:
         masks = self.adapter(o1, o0)
         h32, w32 = self.H // 32, self.W // 32
         if self.audio:
-            v4cat = self.new(B, self.T // 4, h32, w32, 1024 + 512)
+            v4cat = self.new(B, self.T // 4, h32, w32, 1024 + 512, torch.float32)  # cat([v4, vis_sync]) feeds the decoder
             v1, v2, v3, v4 = self.s3d(v4cat.slice(0, 1024))
             aud = self.resnet18()
             self.sync_block(v4, aud, v4cat)

@@ -317,6 +317,7 @@ class Conv:
 
         run.mode = mode
         run.desc = d
+        run.flops = self.flops(x)
         return run
 
     def flops(self, x: Act) -> float:
@@ -445,7 +446,7 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, 
     scale = float(hd) ** -0.5
 
     def run(_keep=(qkv, out)):
-        _lib.check(lib.mspi_attention(_ptr(qkv), _ptr(out), b, n, heads, hd, scale, _stream()), "attention")
+        _lib.check(lib.mspi_attention(_ptr(qkv), _ptr(out), _DT[qkv.dtype], b, n, heads, hd, scale, _stream()), "attention")
 
     return run
 
