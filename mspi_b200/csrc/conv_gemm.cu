@@ -7,7 +7,7 @@
 // One CTA per SM, persistent over output tiles, warp specialised:
 //   warp 0     : TMA producer (one elected lane)
 //   warp 1     : TMEM allocation + MMA issue (one elected lane)
-//   warps 2..5 : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31
+//   warps 2..9 : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 and every second 32-column chunk
 //
 // The convolution is never materialised as an im2col matrix: an M-tile is a box of output positions in
 // the (d1,d2,d3,d4) view of the NDHWC activation, and for filter tap `tap` the A operand is the same box
@@ -22,7 +22,8 @@
 namespace mspi {
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: they split the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // producer warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
 constexpr int kRowBytes = 128;               // one K chunk of one row: 64 bf16 or 32 tf32
 constexpr int kABytes = kTileM * kRowBytes;  // 16 KB
@@ -47,6 +48,7 @@ struct GemmParams {
   void* y;
   uint32_t idesc;
   int num_stages, b_bytes, a_tx_bytes, tmem_cols;
+  int ss_floats;  // staged scale/shift length (n_tiles * bn)
 };
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -125,7 +127,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue activation.  GELU uses Abramowitz-Stegun 7.1.26 for erf (|err| < 1.5e-7, branch free, two MUFU ops):
+// the epilogue of the small-K layers is ALU bound, and erff() costs about twice as many instructions.
+__device__ __forceinline__ float epi_act(float x, int act) {
+  if (act == MSPI_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == MSPI_ACT_GELU) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = fmaf(-poly * t, __expf(-z * z), 1.f);
+    return 0.5f * x * (1.f + copysignf(e, x));
+  }
+  if (act == MSPI_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -151,7 +182,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t bar_tfull = smem_base + 16 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t tiles_base = smem_base + kBarrierBytes;
+  // staged epilogue vectors: scale[ss_floats], shift[ss_floats] (fp32), then the operand ring (1024 B aligned)
+  float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kBarrierBytes);
+  float* s_shift = s_scale + p.ss_floats;
+  const uint32_t tiles_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
   const uint32_t stage_bytes = kABytes + p.b_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -166,7 +200,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,6 +209,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                  "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.ss_floats; i += kThreads) {
+    s_scale[i] = (p.scale != nullptr && i < p.cout) ? __ldg(p.scale + i) : 1.f;
+    s_shift[i] = (p.shift != nullptr && i < p.cout) ? __ldg(p.shift + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -244,11 +282,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================================================================== epilogue warps
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;          // TMEM lanes this warp may read: 32*(warp_id % 4) ..
+    const int half = (warp - 2) >> 2;      // which of the two warps sharing this lane quarter
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
     const bool out_bf16 = p.o_dtype == MSPI_BF16;
+    const int nchunks = (p.bn + 31) >> 5;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
@@ -272,74 +312,91 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * p.bn);
       const int n_base = nt * p.bn;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t acc[16];
+      for (int ch = half; ch < nchunks; ch += 2) {
+        const int c0 = ch << 5;
+        const int width = min(32, p.bn - c0);  // 32, or 16 for the last chunk of an odd multiple of 16
+        uint32_t acc[32];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
-        tmem_ld16(taddr + c0, acc);
+        if (width == 32) {
+          tmem_ld32(taddr + c0, acc);
+        } else {
+          uint32_t lo[16];
+          tmem_ld16(taddr + c0, lo);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { acc[j] = lo[j]; acc[16 + j] = 0u; }
+        }
         tmem_ld_wait();
         const int n0 = n_base + c0;
         if (!valid || n0 >= p.cout) continue;
-        float v[16];
-        const bool full16 = (n0 + 16 <= p.cout);
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + n0);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + n0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = full16 ? (n0 + j) : min(n0 + j, p.cout - 1);
-          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
-          const float sh = p.shift ? __ldg(p.shift + n) : 0.f;
-          v[j] = fmaf(__uint_as_float(acc[j]), sc, sh);
-        }
-        float res[16];
-        if (p.has_res) {
-          if (full16 && p.r_dtype == MSPI_BF16) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + n0);
-            const uint4 a = __ldg(rp), b = __ldg(rp + 1);
-            unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
-            unpack_bf16x2(a.z, res[4], res[5]); unpack_bf16x2(a.w, res[6], res[7]);
-            unpack_bf16x2(b.x, res[8], res[9]); unpack_bf16x2(b.y, res[10], res[11]);
-            unpack_bf16x2(b.z, res[12], res[13]); unpack_bf16x2(b.w, res[14], res[15]);
-          } else {
+        for (int g = 0; g < 4; ++g) {  // four groups of 8 columns (16 B of bf16 output each)
+          const int ng = n0 + 8 * g;
+          if (8 * g >= width || ng >= p.cout) break;
+          float v[8];
+          {
+            const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
+            v[0] = fmaf(__uint_as_float(acc[8 * g + 0]), s0.x, h0.x);
+            v[1] = fmaf(__uint_as_float(acc[8 * g + 1]), s0.y, h0.y);
+            v[2] = fmaf(__uint_as_float(acc[8 * g + 2]), s0.z, h0.z);
+            v[3] = fmaf(__uint_as_float(acc[8 * g + 3]), s0.w, h0.w);
+            v[4] = fmaf(__uint_as_float(acc[8 * g + 4]), s1.x, h1.x);
+            v[5] = fmaf(__uint_as_float(acc[8 * g + 5]), s1.y, h1.y);
+            v[6] = fmaf(__uint_as_float(acc[8 * g + 6]), s1.z, h1.z);
+            v[7] = fmaf(__uint_as_float(acc[8 * g + 7]), s1.w, h1.w);
+          }
+          const bool full8 = (ng + 8 <= p.cout);
+          float res[8];
+          if (p.has_res) {
+            if (full8 && p.r_dtype == MSPI_BF16) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + ng));
+              unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
+              unpack_bf16x2(a.z, res[4], res[5]); unpack_bf16x2(a.w, res[6], res[7]);
+            } else if (full8) {
+              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + roff + ng);
+              const float4 a = __ldg(rp), b = __ldg(rp + 1);
+              res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
+              res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = min(n0 + j, p.cout - 1);
-              res[j] = p.r_dtype == MSPI_BF16
-                           ? bf2f(static_cast<const __nv_bfloat16*>(p.residual)[roff + n])
-                           : static_cast<const float*>(p.residual)[roff + n];
+              for (int j = 0; j < 8; ++j) {
+                const int n = min(ng + j, p.cout - 1);
+                res[j] = p.r_dtype == MSPI_BF16 ? bf2f(static_cast<const __nv_bfloat16*>(p.residual)[roff + n])
+                                                : static_cast<const float*>(p.residual)[roff + n];
+              }
             }
           }
-        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[j];
-          if (p.has_res && !p.res_after_act) x += res[j];
-          x = apply_act(x, p.act);
-          if (p.has_res && p.res_after_act) x += res[j];
-          v[j] = x;
-        }
-        if (out_bf16) {
-          __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) + yoff + n0;
-          if (full16) {
-            uint4 a, b;
-            a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
-            a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
-            b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]);
-            b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-            reinterpret_cast<uint4*>(yp)[0] = a;
-            reinterpret_cast<uint4*>(yp)[1] = b;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
+          for (int j = 0; j < 8; ++j) {
+            float x = v[j];
+            if (p.has_res && !p.res_after_act) x += res[j];
+            x = epi_act(x, p.act);
+            if (p.has_res && p.res_after_act) x += res[j];
+            v[j] = x;
           }
-        } else {
-          float* yp = static_cast<float*>(p.y) + yoff + n0;
-          if (full16 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+          if (out_bf16) {
+            __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) + yoff + ng;
+            if (full8) {
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(yp) = o;
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<float4*>(yp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int j = 0; j < 8; ++j)
+                if (ng + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
+            }
           } else {
+            float* yp = static_cast<float*>(p.y) + yoff + ng;
+            if (full8 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+              reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+              reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < p.cout) yp[j] = v[j];
+              for (int j = 0; j < 8; ++j)
+                if (ng + j < p.cout) yp[j] = v[j];
+            }
           }
         }
       }
@@ -482,12 +539,15 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.b_bytes = d->bn * kRowBytes;
   p.a_tx_bytes = static_cast<int>(rows) * kRowBytes;
   const int stage_bytes = kABytes + p.b_bytes;
-  p.num_stages = (kSmemBudget - kBarrierBytes - 1024) / stage_bytes;
+  p.ss_floats = p.n_tiles * d->bn;
+  const int ss_bytes = (8 * p.ss_floats + 1023) & ~1023;
+  MSPI_CHECK_ARG(ss_bytes <= 64 * 1024, "cout %d too large for the staged epilogue vectors", d->cout);
+  p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   int cols = 32;
   while (cols < 2 * d->bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = 1024 + kBarrierBytes + static_cast<size_t>(p.num_stages) * stage_bytes;
+  const size_t smem = 1024 + kBarrierBytes + ss_bytes + static_cast<size_t>(p.num_stages) * stage_bytes;
 
   auto kern = d->a_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16> : conv_gemm_kernel<MSPI_F32>;
   static bool attr_set[2] = {false, false};
