@@ -7,7 +7,11 @@
 // One CTA per SM, persistent over output tiles, warp specialised:
 //   warp 0     : TMA producer (one elected lane)
 //   warp 1     : TMEM allocation + MMA issue (one elected lane)
-//   warps 2..9 : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 and every second 32-column chunk
+//   warps 2..9 : epilogue, two groups of four warps; warp w owns TMEM lanes 32*(w%4) .. +31, each group
+//                takes every second 128-byte column chunk of the tile, stages it (swizzled) in shared
+//                memory and one thread TMA-stores it (cp.async.bulk.tensor ... bulk_group).  Per-thread
+//                row stores would write half sectors from 32 different lines per instruction, which
+//                the memory system sustains at < 0.5 TB/s; the bulk store writes whole lines.
 //
 // The convolution is never materialised as an im2col matrix: an M-tile is a box of output positions in
 // the (d1,d2,d3,d4) view of the NDHWC activation, and for filter tap `tap` the A operand is the same box
@@ -49,6 +53,7 @@ struct GemmParams {
   uint32_t idesc;
   int num_stages, b_bytes, a_tx_bytes, tmem_cols;
   int ss_floats;  // staged scale/shift length (n_tiles * bn)
+  int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
 };
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -140,19 +145,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Epilogue activation.  GELU uses Abramowitz-Stegun 7.1.26 for erf (|err| < 1.5e-7, branch free, two MUFU ops):
-// the epilogue of the small-K layers is ALU bound, and erff() costs about twice as many instructions.
+// Epilogue activation.
+// GELU, fp32 outputs: Abramowitz-Stegun 7.1.26 for erf (|err| < 1.5e-7, branch free).
+// GELU, bf16 outputs: 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715x^3))) with the hardware tanh (one MUFU op).  Against the
+//   exact erf form its error is < 4e-4 absolute and < 2^-10 relative, below the half-ulp (2^-9) of the bf16 result it is
+//   rounded to; the epilogue of the small-K MLP layers is issue bound, and this form is a third of the instructions.
+template <bool OUT_BF16>
 __device__ __forceinline__ float epi_act(float x, int act) {
   if (act == MSPI_ACT_RELU) return fmaxf(x, 0.f);
   if (act == MSPI_ACT_GELU) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = fmaf(-poly * t, __expf(-z * z), 1.f);
-    return 0.5f * x * (1.f + copysignf(e, x));
+    if constexpr (OUT_BF16) {
+      const float u = x * x;
+      const float t = x * fmaf(u, 0.0356774081f, 0.7978845608f);
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+      const float hx = 0.5f * x;
+      return fmaf(hx, th, hx);
+    } else {
+      const float z = fabsf(x) * 0.70710678118654752440f;
+      const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+      float poly = fmaf(t, 1.061405429f, -1.453152027f);
+      poly = fmaf(poly, t, 1.421413741f);
+      poly = fmaf(poly, t, -0.284496736f);
+      poly = fmaf(poly, t, 0.254829592f);
+      const float e = fmaf(-poly * t, __expf(-z * z), 1.f);
+      return 0.5f * x * (1.f + copysignf(e, x));
+    }
   }
   if (act == MSPI_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
   return x;
@@ -170,10 +188,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------ kernel
-template <int KIND>
+// ACT / RES are compile-time for the layer types the model uses (ACT: MSPI_ACT_*, RES: 0 none, 1 added before
+// the activation, 2 added after it); -1 selects the run-time value from the parameters (generic instance).
+template <int KIND, int OUT, int ACT, int RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ GemmParams p) {
+                 const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barrier block: full[8] empty[8] tmem_full[2] tmem_empty[2] tmem_ptr
@@ -182,10 +202,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t bar_tfull = smem_base + 16 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  // staged epilogue vectors: scale[ss_floats], shift[ss_floats] (fp32), then the operand ring (1024 B aligned)
+  // staged epilogue vectors: scale[ss_floats], shift[ss_floats] (fp32); then, 1024 B aligned, the two output
+  // staging buffers (TMA-store path) and the operand ring
   float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kBarrierBytes);
   float* s_shift = s_scale + p.ss_floats;
-  const uint32_t tiles_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
+  const uint32_t stage_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
+  const uint32_t tiles_base = stage_base + (p.tma_store ? 2u * kABytes : 0u);
   const uint32_t stage_bytes = kABytes + p.b_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -194,6 +216,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_y) : "memory");
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -282,24 +305,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================================================================== epilogue warps
-    const int quarter = warp & 3;          // TMEM lanes this warp may read: 32*(warp_id % 4) ..
-    const int half = (warp - 2) >> 2;      // which of the two warps sharing this lane quarter
+    // All eight warps work on the same 128-byte column chunk of the tile (64 bf16 / 32 fp32 columns): warp w reads
+    // TMEM lanes 32*(w%4).. (its rows) and the half of the chunk given by its group, HC columns.
+    const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
+    const bool leader = warp == 2 && lane == 0;
     int as = 0;
     uint32_t aphase = 0;
-    const bool out_bf16 = p.o_dtype == MSPI_BF16;
-    const int nchunks = (p.bn + 31) >> 5;
+    constexpr bool out_bf16 = OUT == MSPI_BF16;
+    constexpr int HC = out_bf16 ? 32 : 16;  // columns per thread per chunk (16 packed registers either way)
+    constexpr int CH = 2 * HC;
+    const int act = ACT >= 0 ? ACT : p.act;
+    const bool has_res = RES >= 0 ? RES != 0 : p.has_res != 0;
+    const bool res_after = RES >= 0 ? RES == 2 : p.res_after_act != 0;
+    const int nchunks = (p.bn + CH - 1) / CH;
+    uint32_t store_seq = 0;  // bulk stores issued so far: chunk k of the kernel uses staging buffer k & 1
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       int r = row;
       bool valid = true;
       long long yoff = 0, roff = 0;
+      int org[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int org = (mt % p.tiles_d[j]) * p.box[j];
+        org[j] = (mt % p.tiles_d[j]) * p.box[j];
         mt /= p.tiles_d[j];
-        const int c = org + (r % p.box[j]);
+        const int c = org[j] + (r % p.box[j]);
         r /= p.box[j];
         valid = valid && (c < p.o_dims[j]);
         yoff += static_cast<long long>(c) * p.o_strides[j];
@@ -312,28 +345,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * p.bn);
       const int n_base = nt * p.bn;
-      for (int ch = half; ch < nchunks; ch += 2) {
-        const int c0 = ch << 5;
-        const int width = min(32, p.bn - c0);  // 32, or 16 for the last chunk of an odd multiple of 16
-        uint32_t acc[32];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
-        if (width == 32) {
-          tmem_ld32(taddr + c0, acc);
-        } else {
-          uint32_t lo[16];
-          tmem_ld16(taddr + c0, lo);
+#pragma unroll 1
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * CH + group * HC;
+        const int width = min(HC, p.bn - c0);  // HC, 16 (bf16, odd multiple of 16), or <= 0 past the tile
+        const int n0 = n_base + c0;
+        uint32_t acc[HC];
+        __syncwarp();  // tcgen05.ld is warp-collective
+        if constexpr (out_bf16) {
+          if (width >= 32) {
+            tmem_ld32(taddr + c0, reinterpret_cast<uint32_t(&)[32]>(acc));
+          } else if (width > 0) {
+            uint32_t lo[16];
+            tmem_ld16(taddr + c0, lo);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { acc[j] = lo[j]; acc[16 + j] = 0u; }
+            for (int j = 0; j < 16; ++j) { acc[j] = lo[j]; acc[HC - 16 + j] = 0u; }
+          }
+        } else {
+          if (width > 0) tmem_ld16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(acc));
         }
         tmem_ld_wait();
-        const int n0 = n_base + c0;
-        if (!valid || n0 >= p.cout) continue;
-        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + n0);
-        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + n0);
+        if (width <= 0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // four groups of 8 columns (16 B of bf16 output each)
+          for (int j = 0; j < HC; ++j) acc[j] = 0u;
+        }
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + n0);  // staged vectors are padded by 64
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + n0);
+        uint32_t packed[16];
+#pragma unroll
+        for (int g = 0; g < HC / 8; ++g) {  // groups of 8 columns
           const int ng = n0 + 8 * g;
-          if (8 * g >= width || ng >= p.cout) break;
+          const bool live = (8 * g < width) && (ng < p.cout);
           float v[8];
           {
             const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
@@ -348,7 +390,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           const bool full8 = (ng + 8 <= p.cout);
           float res[8];
-          if (p.has_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = 0.f;
+          if (has_res && valid && live) {
             if (full8 && p.r_dtype == MSPI_BF16) {
               const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + ng));
               unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
@@ -370,41 +414,82 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float x = v[j];
-            if (p.has_res && !p.res_after_act) x += res[j];
-            x = epi_act(x, p.act);
-            if (p.has_res && p.res_after_act) x += res[j];
+            if (has_res && !res_after) x += res[j];
+            x = epi_act<out_bf16>(x, act);
+            if (has_res && res_after) x += res[j];
             v[j] = x;
           }
-          if (out_bf16) {
-            __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) + yoff + ng;
-            if (full8) {
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(yp) = o;
+          if (p.tma_store) {
+            if (out_bf16) {
+              packed[4 * g + 0] = pack_bf16x2(v[0], v[1]);
+              packed[4 * g + 1] = pack_bf16x2(v[2], v[3]);
+              packed[4 * g + 2] = pack_bf16x2(v[4], v[5]);
+              packed[4 * g + 3] = pack_bf16x2(v[6], v[7]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (ng + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
+              for (int j = 0; j < 8; ++j) packed[8 * g + j] = __float_as_uint(v[j]);
             }
-          } else {
-            float* yp = static_cast<float*>(p.y) + yoff + ng;
-            if (full8 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-              reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
-              reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
+          } else if (valid && live) {
+            if (out_bf16) {
+              __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) + yoff + ng;
+              if (full8) {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(yp) = o;
+              } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (ng + j < p.cout) yp[j] = v[j];
+                for (int j = 0; j < 8; ++j)
+                  if (ng + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
+              }
+            } else {
+              float* yp = static_cast<float*>(p.y) + yoff + ng;
+              if (full8 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+                reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (ng + j < p.cout) yp[j] = v[j];
+              }
             }
           }
         }
+        if (ch == nchunks - 1) {
+          // every TMEM read of this tile is done: hand the accumulator buffer back to the MMA warp now,
+          // before the last chunk is staged and stored
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+        if (p.tma_store) {
+          // staging buffer (store_seq & 1) is free once the bulk store issued two chunks ago has finished READING it
+          const uint32_t stage_row = stage_base + (store_seq & 1u) * kABytes + row * kRowBytes;
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // this thread's four 16-byte pieces, 128B-swizzled like the tensor map expects
+            const uint32_t dst = stage_row + (static_cast<uint32_t>((4 * group + j) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]), "r"(packed[4 * j + 1]),
+                         "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tma_y),
+                "r"(stage_base + (store_seq & 1u) * kABytes), "r"(n_base + ch * CH), "r"(org[0]), "r"(org[1]), "r"(org[2]),
+                "r"(org[3])
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++store_seq;
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (p.tma_store && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -539,28 +624,80 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.b_bytes = d->bn * kRowBytes;
   p.a_tx_bytes = static_cast<int>(rows) * kRowBytes;
   const int stage_bytes = kABytes + p.b_bytes;
-  p.ss_floats = p.n_tiles * d->bn;
+  p.ss_floats = p.n_tiles * d->bn + 64;  // padded: the last staged chunk may run past the tile
   const int ss_bytes = (8 * p.ss_floats + 1023) & ~1023;
   MSPI_CHECK_ARG(ss_bytes <= 64 * 1024, "cout %d too large for the staged epilogue vectors", d->cout);
-  p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes) / stage_bytes;
+
+  // Output path: bulk tensor stores need 16-byte aligned row strides and N tiles that end on a 128-byte chunk.
+  const int o_es = d->o_dtype == MSPI_BF16 ? 2 : 4;
+  const int chunk_cols = kRowBytes / o_es;
+  p.tma_store = (p.n_tiles == 1 || d->bn % chunk_cols == 0) ? 1 : 0;
+  for (int j = 0; j < 4; ++j)
+    if (d->o_dims[j] > 1 && (d->o_strides[j] * o_es) % 16 != 0) p.tma_store = 0;
+  CUtensorMap map_y = map_a;
+  if (p.tma_store) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
+    gdim[0] = static_cast<cuuint64_t>(d->cout);
+    bdim[0] = static_cast<cuuint32_t>(chunk_cols);
+    cuuint64_t span = static_cast<cuuint64_t>((d->cout * o_es + 15) / 16 * 16);
+    for (int j = 0; j < 4; ++j) {
+      gdim[j + 1] = static_cast<cuuint64_t>(d->o_dims[j]);
+      bdim[j + 1] = static_cast<cuuint32_t>(d->box[j + 1]);
+      cuuint64_t st = static_cast<cuuint64_t>(d->o_strides[j]) * o_es;
+      if (d->o_dims[j] == 1 && (st == 0 || st % 16 != 0)) st = span;  // never dereferenced: any legal stride
+      gstr[j] = st;
+      if (st * gdim[j + 1] > span) span = st * gdim[j + 1];
+    }
+    CUresult r = encode(&map_y, d->o_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        5, y, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled(Y) failed: %d cout=%d dims=[%d,%d,%d,%d] strides=[%lld,%lld,%lld,%lld]",
+                       (int)r, d->cout, d->o_dims[0], d->o_dims[1], d->o_dims[2], d->o_dims[3], (long long)d->o_strides[0],
+                       (long long)d->o_strides[1], (long long)d->o_strides[2], (long long)d->o_strides[3]);
+  }
+  const int out_stage_bytes = p.tma_store ? 2 * kABytes : 0;
+  p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes - out_stage_bytes) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   int cols = 32;
   while (cols < 2 * d->bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = 1024 + kBarrierBytes + ss_bytes + static_cast<size_t>(p.num_stages) * stage_bytes;
+  MSPI_CHECK_ARG(p.num_stages >= 2, "shared memory budget leaves %d pipeline stages", p.num_stages);
+  const size_t smem = 1024 + kBarrierBytes + ss_bytes + out_stage_bytes + static_cast<size_t>(p.num_stages) * stage_bytes;
 
-  auto kern = d->a_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16> : conv_gemm_kernel<MSPI_F32>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[d->a_dtype]) {
-    MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[d->a_dtype] = true;
+  // Specialised instances for the (operand kind, output dtype, activation, residual) combinations the model
+  // uses; anything else runs the generic instance that reads activation / residual mode at run time.
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+  const int res_mode = d->has_residual ? (d->res_after_act ? 2 : 1) : 0;
+  Kern kern = nullptr;
+#define MSPI_PICK(K, O, A, R) \
+  if (d->a_dtype == K && d->o_dtype == O && d->act == A && res_mode == R) kern = conv_gemm_kernel<K, O, A, R>;
+  MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_RELU, 0)
+  MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_NONE, 0)
+  MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_GELU, 0)
+  MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_NONE, 2)
+  MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_RELU, 1)
+  MSPI_PICK(MSPI_BF16, MSPI_F32, MSPI_ACT_NONE, 0)
+  MSPI_PICK(MSPI_BF16, MSPI_F32, MSPI_ACT_RELU, 0)
+  MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_NONE, 0)
+  MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_RELU, 0)
+  MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_GELU, 0)
+  MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_NONE, 2)
+#undef MSPI_PICK
+  if (kern == nullptr) {
+    if (d->a_dtype == MSPI_BF16) kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, -1, -1>
+                                                                : conv_gemm_kernel<MSPI_BF16, MSPI_F32, -1, -1>;
+    else kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_F32, MSPI_BF16, -1, -1>
+                                        : conv_gemm_kernel<MSPI_F32, MSPI_F32, -1, -1>;
   }
+  MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
   MSPI_CHECK_ARG(total < (1ll << 31), "too many tiles");
   int grid = num_sms();
   if (grid <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   if (total < grid) grid = static_cast<int>(total);
-  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, p);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -127,10 +127,17 @@ def choose_box(dims: Tuple[int, int, int, int], max_rows: int = 128) -> Tuple[in
     return best
 
 
-def choose_bn(cout: int) -> int:
-    n_tiles = -(-cout // 256)
-    bn = -(-cout // n_tiles)
-    return max(16, -(-bn // 16) * 16)
+def choose_bn(cout: int, chunk: int = 64) -> int:
+    """N tile of the UMMA (multiple of 16, <= 256).  With several N tiles every tile must end on a 128-byte
+    output chunk (`chunk` columns: 64 bf16 / 32 fp32) so the epilogue can bulk-store whole chunks."""
+    if cout <= 256:
+        return max(16, -(-cout // 16) * 16)
+    best = None
+    for bn in range(256, 127, -chunk):
+        key = (-(-cout // bn) * bn, -bn)  # least padded work, then the widest tile
+        if best is None or key < best[0]:
+            best = (key, bn)
+    return best[1]
 
 
 def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype) -> Tuple[torch.Tensor, int, int]:
@@ -187,7 +194,6 @@ class Conv:
         self.packed = None  # built lazily, the packing depends on the execution mode
         self.scale = None if scale is None else scale.detach().float().contiguous().to(device)
         self.shift = None if shift is None else shift.detach().float().contiguous().to(device)
-        self.bn = choose_bn(self.cout)
 
     # -- geometry ---------------------------------------------------------------------------
     def out_shape(self, t, h, w):
@@ -222,6 +228,7 @@ class Conv:
         mode = self._mode(x)
         d = ConvDesc()
         d.a_dtype = _DT[self.dtype]
+        self.bn = choose_bn(self.cout, 64 if y.dtype == torch.bfloat16 else 32)
         d.cout, d.bn = self.cout, self.bn
         d.o_dtype = _DT[y.dtype]
         d.act = self.act
