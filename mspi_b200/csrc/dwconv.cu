@@ -1,0 +1,276 @@
+// Depthwise 7x7 convolution + LayerNorm over channels (ConvNeXt block front half), and the (7,1,1)
+// temporal depthwise convolution of the decoder's ConvNextBlock.  Channels-last, fp32 arithmetic.
+//
+// Replaces timm ConvNeXt conv_dw + norm (model_utils.py:361) and ConvNextBlock.dwconv_t / dwconv_s +
+// LayerNorm3d (model_utils.py:293-303,321-323).
+//
+// The 7x7 stencil is FMA bound (49 FMA per output element against 4 bytes of HBM traffic), so the
+// kernel is built around on-chip reuse:
+//   1. the block copies its input tile, (S+6) x (P+6) pixels x C channels with a zero halo, into
+//      shared memory with 16-byte cp.async (every load of the tile in flight at once);
+//   2. a thread owns 4 channels of a horizontal strip of P output pixels: each input value it reads
+//      from shared memory feeds up to 7 accumulators, the 7 taps of the current filter row sit in
+//      registers (49 x 4 FMA per 1/P.. of a load);
+//   3. the strip results (+bias) are parked in shared memory as fp32 (re-using the tile buffer) and
+//      warps normalise one pixel at a time (two-pass mean / variance in registers), writing whole
+//      channel rows.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace mspi {
+namespace {
+
+template <typename T>
+struct Ld4;
+template <>
+struct Ld4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 cvt(uint2 u) {
+    float4 f;
+    unpack_bf16x2(u.x, f.x, f.y);
+    unpack_bf16x2(u.y, f.z, f.w);
+    return f;
+  }
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) { return cvt(__ldg(reinterpret_cast<const uint2*>(p))); }
+  static __device__ __forceinline__ float4 lds(const __nv_bfloat16* p) { return cvt(*reinterpret_cast<const uint2*>(p)); }
+};
+template <>
+struct Ld4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ float4 lds(const float* p) { return *reinterpret_cast<const float4*>(p); }
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = pred ? 16 : 0;  // src-size 0: the 16 destination bytes are zero filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// CQ = C/4 threads per strip, S strips (rows) per block, P output pixels per strip.
+template <typename TI, int CQ, int S, int P>
+__global__ void __launch_bounds__(CQ * S)
+dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                const float* __restrict__ ln_w, const float* __restrict__ ln_b, void* __restrict__ y, int out_bf16,
+                int H, int W, int tiles_x, int tiles_y, float eps) {
+  constexpr int C = 4 * CQ;
+  constexpr int TW = P + 6, TH = S + 6;
+  constexpr int kThreads = CQ * S;
+  constexpr int kVec = 16 / sizeof(TI);            // elements per 16-byte copy
+  constexpr int kRowVecs = C / kVec;               // 16-byte copies per pixel
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  TI* tile_s = reinterpret_cast<TI*>(dw_smem);        // [TH][TW][C] input tile, zero halo
+  float* out_s = reinterpret_cast<float*>(dw_smem);   // [S*P][C] results; re-uses the tile buffer after the stencil
+
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y; tile /= tiles_y;
+  const int n = tile;
+  const int x0 = tx * P, y0 = ty * S;
+  const TI* xin = x + static_cast<long long>(n) * H * W * C;
+
+  for (int i = threadIdx.x; i < TH * TW * kRowVecs; i += kThreads) {
+    const int cv = i % kRowVecs, pix = i / kRowVecs;
+    const int tc = pix % TW, tr = pix / TW;
+    const int gy = y0 + tr - 3, gx = x0 + tc - 3;
+    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const TI* src = xin + (static_cast<long long>(in ? gy : 0) * W + (in ? gx : 0)) * C + cv * kVec;
+    cp_async16_zfill(tile_s + static_cast<size_t>(pix) * C + cv * kVec, src, in);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  const int q = threadIdx.x % CQ;
+  const int s = threadIdx.x / CQ;
+  float4 acc[P];
+  {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = b;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+#pragma unroll 1
+  for (int kh = 0; kh < 7; ++kh) {
+    float4 w[7];
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) w[kw] = __ldg(reinterpret_cast<const float4*>(wgt + (kh * 7 + kw) * C) + q);
+    const TI* trow = tile_s + static_cast<size_t>(s + kh) * TW * C + 4 * q;
+#pragma unroll
+    for (int ix = 0; ix < TW; ++ix) {
+      const float4 v = Ld4<TI>::lds(trow + ix * C);
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        const int j = ix - kw;  // output pixel fed by this input through tap kw
+        if (j >= 0 && j < P) {
+          acc[j].x = fmaf(v.x, w[kw].x, acc[j].x);
+          acc[j].y = fmaf(v.y, w[kw].y, acc[j].y);
+          acc[j].z = fmaf(v.z, w[kw].z, acc[j].z);
+          acc[j].w = fmaf(v.w, w[kw].w, acc[j].w);
+        }
+      }
+    }
+  }
+  __syncthreads();  // everyone is done reading the tile: its memory becomes the result buffer
+#pragma unroll
+  for (int j = 0; j < P; ++j) reinterpret_cast<float4*>(out_s + static_cast<size_t>(s * P + j) * C)[q] = acc[j];
+  __syncthreads();
+
+  // ---- LayerNorm over C, one warp per pixel; lane owns channel pairs lane, lane+32, ...
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = kThreads / 32;
+  constexpr int pairs = C / 2;
+  constexpr int MAXI = (pairs + 31) / 32;
+  for (int pix = warp; pix < S * P; pix += nwarps) {
+    const int py = y0 + pix / P, px = x0 + pix % P;
+    if (py >= H || px >= W) continue;
+    const float2* src = reinterpret_cast<const float2*>(out_s + static_cast<size_t>(pix) * C);
+    float2 v[MAXI];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int p = lane + 32 * i;
+      v[i] = p < pairs ? src[p] : make_float2(0.f, 0.f);
+      sum += v[i].x + v[i].y;
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (ln_w != nullptr) {
+      mean = warp_sum(sum) * (1.f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int p = lane + 32 * i;
+        if (p < pairs) {
+          const float a = v[i].x - mean, b = v[i].y - mean;
+          sq += a * a + b * b;
+        }
+      }
+      rstd = rsqrtf(warp_sum(sq) * (1.f / C) + eps);
+    }
+    const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * C;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pairs) {
+        float a = v[i].x, b = v[i].y;
+        if (ln_w != nullptr) {
+          const float2 g = __ldg(reinterpret_cast<const float2*>(ln_w) + p);
+          const float2 sh = __ldg(reinterpret_cast<const float2*>(ln_b) + p);
+          a = (a - mean) * rstd * g.x + sh.x;
+          b = (b - mean) * rstd * g.y + sh.y;
+        }
+        if (out_bf16)
+          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
+        else
+          reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
+      }
+    }
+  }
+}
+
+// (kt,1,1) temporal depthwise conv, T <= 8 frames: a thread owns 4 channels of one (h,w) position for all T
+// frames of one sample; every input is read once.  HBM bound.
+template <typename TI, int MAXT>
+__global__ void dwt_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                           void* __restrict__ y, int out_bf16, long long n_hw, int T, int HW, int C, int kt) {
+  const int cq = C >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_hw * cq) return;
+  const int q = static_cast<int>(idx % cq);
+  const long long pos = idx / cq;  // n*HW + hw
+  const long long n = pos / HW, hw = pos % HW;
+  const long long base = (n * T * HW + hw) * C + 4 * q;
+  const long long tstride = static_cast<long long>(HW) * C;
+  float4 v[MAXT];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t)
+    if (t < T) v[t] = Ld4<TI>::ld(x + base + t * tstride);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+  const int pt = kt / 2;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t >= T) break;
+    float4 a = b;
+#pragma unroll
+    for (int u = 0; u < MAXT; ++u) {
+      const int k = u - t + pt;  // tap that connects input frame u to output frame t
+      if (u < T && k >= 0 && k < kt) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wgt + k * C) + q);
+        a.x = fmaf(v[u].x, w.x, a.x);
+        a.y = fmaf(v[u].y, w.y, a.y);
+        a.z = fmaf(v[u].z, w.z, a.z);
+        a.w = fmaf(v[u].w, w.w, a.w);
+      }
+    }
+    if (out_bf16) {
+      uint2 o;
+      o.x = pack_bf16x2(a.x, a.y);
+      o.y = pack_bf16x2(a.z, a.w);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + base + t * tstride) = o;
+    } else {
+      *reinterpret_cast<float4*>(static_cast<float*>(y) + base + t * tstride) = a;
+    }
+  }
+}
+
+template <typename TI, int CQ, int S, int P>
+int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
+                 const float* ln_b, void* y, cudaStream_t stream) {
+  constexpr int C = 4 * CQ;
+  constexpr size_t tile_bytes = static_cast<size_t>(S + 6) * (P + 6) * C * sizeof(TI);
+  constexpr size_t out_bytes = static_cast<size_t>(S) * P * C * sizeof(float);
+  constexpr size_t smem = tile_bytes > out_bytes ? tile_bytes : out_bytes;
+  static_assert(smem <= 113 * 1024, "two blocks per SM must fit");
+  const int tiles_x = (d->w + P - 1) / P, tiles_y = (d->h + S - 1) / S;
+  const long long blocks = static_cast<long long>(d->n) * d->t * tiles_x * tiles_y;
+  MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv 7x7: grid out of range");
+  auto kern = dw7x7_ln_kernel<TI, CQ, S, P>;
+  MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<static_cast<int>(blocks), CQ * S, smem, stream>>>(static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y,
+                                                            d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
+                                                            d->ln_eps);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+}  // namespace
+
+// Fast paths of mspi_dwconv_ln (norm_attn.cu holds the generic kernel).  Returns 1 if the shape is not covered.
+int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
+                     const float* ln_b, void* y, cudaStream_t stream) {
+  const bool aligned = d->c % 8 == 0 && d->c <= 768;
+  if (!aligned) return 1;
+  if (d->kt == 1 && d->kh == 7 && d->kw == 7) {
+    using bf = __nv_bfloat16;
+    const bool wide = d->w % 16 == 0;  // strip of 16 where it tiles the row, else 8 (P+6 loads feed 7P FMA groups)
+    if (d->in_dtype == MSPI_BF16) {
+      if (d->c == 96) return wide ? launch_dw7x7<bf, 24, 8, 16>(d, x, wgt, bias, ln_w, ln_b, y, stream)
+                                  : launch_dw7x7<bf, 24, 8, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+      if (d->c == 192) return wide ? launch_dw7x7<bf, 48, 4, 16>(d, x, wgt, bias, ln_w, ln_b, y, stream)
+                                   : launch_dw7x7<bf, 48, 4, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+      if (d->c == 384) return launch_dw7x7<bf, 96, 2, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+    } else {
+      if (d->c == 192) return launch_dw7x7<float, 48, 4, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+    }
+    return 1;
+  }
+  if (d->kh == 1 && d->kw == 1 && d->t <= 8 && ln_w == nullptr) {
+    const int HW = d->h * d->w;
+    const long long n_hw = static_cast<long long>(d->n) * HW;
+    const long long total = n_hw * (d->c / 4);
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv_t: grid out of range");
+    const int ob = d->out_dtype == MSPI_BF16 ? 1 : 0;
+    if (d->in_dtype == MSPI_BF16)
+      dwt_kernel<__nv_bfloat16, 8><<<static_cast<int>(blocks), threads, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt);
+    else
+      dwt_kernel<float, 8><<<static_cast<int>(blocks), threads, 0, stream>>>(static_cast<const float*>(x), wgt, bias, y,
+                                                                            ob, n_hw, d->t, HW, d->c, d->kt);
+    MSPI_LAUNCH_CHECK();
+    return MSPI_OK;
+  }
+  return 1;
+}
+
+}  // namespace mspi

@@ -263,6 +263,10 @@ __global__ void simsiam_kernel(const float* __restrict__ pv, const float* __rest
 }  // namespace
 }  // namespace mspi
 
+namespace mspi {
+int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
+                     const float* ln_b, void* y, cudaStream_t stream);  // dwconv.cu
+}
 using namespace mspi;
 
 extern "C" int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias,
@@ -273,6 +277,10 @@ extern "C" int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* w
   MSPI_CHECK_ARG((d->kt & 1) && (d->kh & 1) && (d->kw & 1), "kernel extents must be odd");
   MSPI_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "ln_w / ln_b must both be given or both null");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  {
+    const int rc = dwconv_fast_path(d, x, wgt, bias, ln_w, ln_b, y, stream);
+    if (rc <= 0) return rc;  // handled (or failed) by a specialised kernel; 1 = not covered, use the generic one
+  }
   const long long pixels = static_cast<long long>(d->n) * d->t * d->h * d->w;
   const int threads = 256, warps = threads / 32;
   long long blocks = (pixels + warps - 1) / warps;

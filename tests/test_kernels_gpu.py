@@ -225,6 +225,31 @@ def test_dwconv_ln(c, kern):
     assert (ya.to_ncdhw().cpu() - ref).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("c,h,w,dt", [(96, 16, 32, torch.bfloat16), (384, 6, 24, torch.bfloat16), (192, 7, 12, torch.float32),
+                                      (40, 5, 16, torch.float32)])
+def test_dwconv7x7_ln_strip_kernel(c, h, w, dt):
+    """Register-tiled 7x7 depthwise + LayerNorm (dwconv.cu): strip lengths 16/12/8, bf16 and fp32 inputs, bf16 output."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(3, c, 1, h, w, generator=g)
+    wgt = torch.randn(c, 1, 7, 7, generator=g) * 0.2
+    b = torch.randn(c, generator=g) * 0.1
+    lw, lb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    xa = _act_from_ncdhw(x, dtype=dt)
+    xr = _bf(x) if dt == torch.bfloat16 else x
+    conv = F.conv3d(xr, wgt[:, :, None], b, padding=(0, 3, 3), groups=c)
+    ref = F.layer_norm(conv.permute(0, 2, 3, 4, 1), (c,), lw, lb, 1e-6).permute(0, 4, 1, 2, 3)
+    y32 = Act.empty(3, 1, h, w, c, dtype=torch.float32)
+    ops.dwconv_ln(xa, y32, wgt, b, lw, lb, eps=1e-6)()
+    torch.cuda.synchronize()
+    assert (y32.to_ncdhw().cpu() - ref).abs().max() < 2e-4  # fp32 math, summation order only
+    y16 = Act.empty(3, 1, h, w, c, dtype=torch.bfloat16)
+    ops.dwconv_ln(xa, y16, wgt, b, lw, lb, eps=1e-6)()
+    torch.cuda.synchronize()
+    assert (y16.to_ncdhw().cpu() - ref).abs().max() < 4e-2  # one bf16 rounding of values up to ~5
+
+
 def test_layernorm_pos_groups():
     from mspi_b200 import ops
     g = torch.Generator().manual_seed(5)
