@@ -78,6 +78,10 @@ typedef struct {
   int32_t act;          /* MSPI_ACT_* */
   int32_t has_residual;
   int32_t res_after_act; /* 0: act(v + res)   1: act(v) + res */
+  int32_t k_row_bytes;  /* 0 = 128.  Bytes of K fetched per row per step (one TMA box, one swizzled smem tile): 128, 64 or
+                           32.  The small sizes serve the Cin=3 stems, where one filter row over the padded 4-channel
+                           frames of mspi_clip_to_padded_nhwc4 is a 64-byte (S3D, 8 px) or 32-byte (ConvNeXt, 4 px)
+                           contiguous run; cin_pad is then a multiple of k_row_bytes / elsize. */
 } MspiConvDesc;
 
 int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
@@ -105,6 +109,14 @@ int mspi_patch_gather(const MspiPatchDesc* d, const void* src, void* dst, void* 
 /* fp32 NCDHW -> bf16 NDHWC (clips, model_utils.py:557 rearrange; audio [B,1,F,T]) */
 int mspi_ncdhw_to_ndhwc(const float* src, void* dst, int n, int c, int thw, int64_t dst_cstride,
                         void* stream);
+/* fp32 NCDHW clip [N][3][T][H][W] (the forward's input contract, model_utils.py:556) -> bf16 frames
+ * [N*T][hp][wp][4] with the image at rows pad_t.., columns pad_l.. and channel 3 = 0.  Only the interior is
+ * written; the caller zeroes the buffer once.  With 8-byte pixels every row of a stem filter (7 taps at stride 2
+ * for S3D, s3d.py:383; 4 taps at stride 4 for ConvNeXt, model_utils.py:361) is one contiguous, 16-byte aligned
+ * run of the padded frame, which is what lets the stems run as implicit GEMMs straight off TMA loads
+ * (MspiConvDesc.k_row_bytes).  w % 4 == 0, pad_l and wp even. */
+int mspi_clip_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
+                              int hp, int wp, void* stream);
 /* bf16/fp32 NDHWC (channel slice) -> fp32 NCDHW, used to hand taps back to PyTorch callers */
 int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n,
                         int c, int thw, void* stream);

@@ -41,6 +41,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32),
         ("has_residual", C.c_int32),
         ("res_after_act", C.c_int32),
+        ("k_row_bytes", C.c_int32),
     ]
 
 
@@ -103,6 +104,7 @@ _SIGNATURES = {
     "mspi_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_patch_gather": (C.c_int, [C.POINTER(PatchDesc), _P, _P, _P]),
     "mspi_ncdhw_to_ndhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
+    "mspi_clip_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_ndhwc_to_ncdhw": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_maxpool3d": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P]),
     "mspi_upsample_bilinear": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P]),

@@ -51,7 +51,8 @@ struct GemmParams {
   const void* residual;
   void* y;
   uint32_t idesc;
-  int num_stages, b_bytes, a_tx_bytes, tmem_cols;
+  int num_stages, a_bytes, b_bytes, a_tx_bytes, tmem_cols;
+  int row_bytes;  // K chunk of one row: 128 (default), 64 or 32 bytes; selects the swizzle mode of the operand tiles
   int ss_floats;  // staged scale/shift length (n_tiles * bn)
   int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
 };
@@ -177,13 +178,14 @@ __device__ __forceinline__ float epi_act(float x, int act) {
 }
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// row_bytes = 128 / 64 / 32 -> SWIZZLE_128B / 64B / 32B (layout codes 2 / 4 / 6), 8-row groups 8*row_bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset (unused for SW128 K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;  // stride byte offset: 8 rows
   d |= static_cast<uint64_t>(1) << 46;                  // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
 
@@ -208,7 +210,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   float* s_shift = s_scale + p.ss_floats;
   const uint32_t stage_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
   const uint32_t tiles_base = stage_base + (p.tma_store ? 2u * kABytes : 0u);
-  const uint32_t stage_bytes = kABytes + p.b_bytes;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -269,7 +271,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
             const uint32_t sa = tiles_base + stage * stage_bytes;
             tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
-            tma_load_2d(sa + kABytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+            tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -290,10 +292,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = tiles_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K * elsize = 32 B) per 128 B swizzle row
+          const uint64_t adesc = make_smem_desc(sa, p.row_bytes);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.row_bytes);
+          const int mmas = p.row_bytes >> 5;  // one UMMA consumes 32 bytes of K per row
+#pragma unroll 4
+          for (int k = 0; k < mmas; ++k) {
             tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
           }
           tc_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
@@ -533,7 +536,9 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   MSPI_CHECK_ARG(d && x && w && y, "mspi_conv_gemm: null argument");
   MSPI_CHECK_ARG(d->a_dtype == MSPI_BF16 || d->a_dtype == MSPI_F32, "a_dtype %d", d->a_dtype);
   const int elsize = d->a_dtype == MSPI_BF16 ? 2 : 4;
-  const int bk = kRowBytes / elsize;
+  const int row_bytes = d->k_row_bytes > 0 ? d->k_row_bytes : kRowBytes;
+  MSPI_CHECK_ARG(row_bytes == 128 || row_bytes == 64 || row_bytes == 32, "k_row_bytes %d", row_bytes);
+  const int bk = row_bytes / elsize;
   MSPI_CHECK_ARG(d->a_strides[0] == 1, "channel stride must be 1");
   MSPI_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= MSPI_MAX_TAPS, "ntaps %d", d->ntaps);
   MSPI_CHECK_ARG(d->bn >= 16 && d->bn <= 256 && d->bn % 16 == 0, "bn %d", d->bn);
@@ -559,6 +564,8 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   if (!encode) return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
 
   CUtensorMap map_a, map_b;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
@@ -568,7 +575,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     for (int j = 1; j < 5; ++j) bdim[j] = d->box[j];
     CUresult r = encode(&map_a, d->a_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
                         5, const_cast<void*>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d dims=[%d,%d,%d,%d,%d] box=[%d,%d,%d,%d,%d]",
@@ -582,7 +589,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_b, d->a_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
                         2, const_cast<void*>(w), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d K=%llu rows=%d bn=%d", (int)r,
@@ -594,9 +601,9 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.m_tiles = 1;
   for (int j = 0; j < 4; ++j) {
     p.box[j] = d->box[j + 1];
-    p.tiles_d[j] = (d->o_dims[j] + p.box[j] - 1) / p.box[j];
-    p.m_tiles *= p.tiles_d[j];
     p.o_dims[j] = d->o_dims[j];
+    p.tiles_d[j] = (p.o_dims[j] + p.box[j] - 1) / p.box[j];
+    p.m_tiles *= p.tiles_d[j];
     p.o_strides[j] = d->o_strides[j];
     p.r_strides[j] = d->r_strides[j];
   }
@@ -621,9 +628,11 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   const uint32_t fmt = d->a_dtype == MSPI_BF16 ? 1u : 2u;  // UMMA F16F32Format: BF16 = 1, TF32 = 2
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(d->bn >> 3) << 17) |
             (static_cast<uint32_t>(kTileM >> 4) << 24);
-  p.b_bytes = d->bn * kRowBytes;
-  p.a_tx_bytes = static_cast<int>(rows) * kRowBytes;
-  const int stage_bytes = kABytes + p.b_bytes;
+  p.row_bytes = row_bytes;
+  p.a_bytes = kTileM * row_bytes;
+  p.b_bytes = d->bn * row_bytes;
+  p.a_tx_bytes = static_cast<int>(rows) * row_bytes;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
   p.ss_floats = p.n_tiles * d->bn + 64;  // padded: the last staged chunk may run past the tile
   const int ss_bytes = (8 * p.ss_floats + 1023) & ~1023;
   MSPI_CHECK_ARG(ss_bytes <= 64 * 1024, "cout %d too large for the staged epilogue vectors", d->cout);
@@ -633,7 +642,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   const int chunk_cols = kRowBytes / o_es;
   p.tma_store = (p.n_tiles == 1 || d->bn % chunk_cols == 0) ? 1 : 0;
   for (int j = 0; j < 4; ++j)
-    if (d->o_dims[j] > 1 && (d->o_strides[j] * o_es) % 16 != 0) p.tma_store = 0;
+    if (p.o_dims[j] > 1 && (p.o_strides[j] * o_es) % 16 != 0) p.tma_store = 0;
   CUtensorMap map_y = map_a;
   if (p.tma_store) {
     cuuint64_t gdim[5], gstr[4];
@@ -642,10 +651,10 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     bdim[0] = static_cast<cuuint32_t>(chunk_cols);
     cuuint64_t span = static_cast<cuuint64_t>((d->cout * o_es + 15) / 16 * 16);
     for (int j = 0; j < 4; ++j) {
-      gdim[j + 1] = static_cast<cuuint64_t>(d->o_dims[j]);
-      bdim[j + 1] = static_cast<cuuint32_t>(d->box[j + 1]);
-      cuuint64_t st = static_cast<cuuint64_t>(d->o_strides[j]) * o_es;
-      if (d->o_dims[j] == 1 && (st == 0 || st % 16 != 0)) st = span;  // never dereferenced: any legal stride
+      gdim[j + 1] = static_cast<cuuint64_t>(p.o_dims[j]);
+      bdim[j + 1] = static_cast<cuuint32_t>(p.box[j]);
+      cuuint64_t st = static_cast<cuuint64_t>(p.o_strides[j]) * o_es;
+      if (p.o_dims[j] == 1 && (st == 0 || st % 16 != 0)) st = span;  // never dereferenced: any legal stride
       gstr[j] = st;
       if (st * gdim[j + 1] > span) span = st * gdim[j + 1];
     }

@@ -116,6 +116,24 @@ class ForwardPlan:
                          res_after_act=residual is not None, out_dtype=out_dtype)
 
     # ------------------------------------------------------------------ stems reading the fp32 NCDHW inputs
+    def padded_frames(self) -> torch.Tensor:
+        """The clip as bf16 zero-padded 4-channel frames, converted once per forward and shared by both video stems."""
+        if getattr(self, "_frames", None) is None:
+            B, T, H, W = self.B, self.T, self.H, self.W
+            self._frames = torch.zeros((B * T, H + ops.PAD_EXTRA, W + ops.PAD_EXTRA, 4), dtype=torch.bfloat16,
+                                       device=self.device)
+            self.bytes_alloc += self._frames.numel() * 2
+            self.add("clips.to_padded_nhwc4", ops.clip_to_padded(self._inputs, "clips", self._frames, B, T, H, W))
+        return self._frames
+
+    def stem_direct(self, name: str, w: torch.Tensor, scale, shift, k: int, stride: int, pad: int, act,
+                    out: Act) -> Act:
+        fr = self.padded_frames()
+        run = ops.stem_conv(fr, self.H, self.W, w, scale, shift, k, stride, pad, act, out, name)
+        self.add(name, run)
+        self.flops += run.flops
+        return out
+
     def stem_gemm(self, name: str, which: str, shape5, w: torch.Tensor, scale, shift, kernel, stride, pad, act,
                   out_dtype=torch.bfloat16) -> Act:
         """Patch-gather (fp32 NCDHW -> bf16 rows) + flat GEMM for the Cin<=3 stems."""
@@ -188,8 +206,8 @@ class ForwardPlan:
         p = "visnet."
         B, T, H, W = self.B, self.T, self.H, self.W
         sc, sh = self.bn(p + "base1.0.bn_s", 1e-3)
-        x = self.stem_gemm(p + "base1.0.conv_s", "clips", (B, 3, T, H, W), self.P(p + "base1.0.conv_s.weight"), sc, sh,
-                           (1, 7, 7), (1, 2, 2), (0, 3, 3), ACT_RELU)
+        x = self.stem_direct(p + "base1.0.conv_s", self.P(p + "base1.0.conv_s.weight"), sc, sh, 7, 2, 3, ACT_RELU,
+                             self.new(B, T, H // 2, W // 2, 64))
         x = self.conv_bn_relu(p + "base1.0.conv_t", p + "base1.0.bn_t", x, 1e-3, (2, 1, 1), (3, 0, 0))
         x = self.pool(p + "base1.1", x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
         x = self.basic(p + "base1.2", x)
@@ -241,9 +259,9 @@ class ForwardPlan:
         p = "image_encoder.encoder."
         B, T, H, W = self.B, self.T, self.H, self.W
         nf = B * T
-        x32 = self.stem_gemm(p + "stem_0", "clips", (B, 3, T, H, W), self.P(p + "stem_0.weight"), None,
-                             self.P(p + "stem_0.bias"), (1, 4, 4), (1, 4, 4), (0, 0, 0), ACT_NONE, out_dtype=torch.float32)
         h, w = H // 4, W // 4
+        x32 = self.stem_direct(p + "stem_0", self.P(p + "stem_0.weight"), None, self.P(p + "stem_0.bias"), 4, 4, 0,
+                               ACT_NONE, self.new(nf, 1, h, w, 96, torch.float32))
         x = self.new(nf, 1, h, w, 96)
         self.add(p + "stem_1", ops.layernorm(x32.buf, x.buf, nf * h * w, 96, self.P(p + "stem_1.weight"),
                                              self.P(p + "stem_1.bias"), 1e-6))

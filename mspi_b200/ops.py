@@ -332,6 +332,102 @@ class Conv:
         return 2.0 * x.n * ot * oh * ow * self.cout * self.cin * self.kt * self.kh * self.kw
 
 
+# ------------------------------------------------------------------------------------------ Cin=3 stems
+PAD_T, PAD_L, PAD_EXTRA = 3, 4, 8   # padded frame: rows 3 above / 5 below, columns 4 left / 4 right (ops.stem_conv)
+
+
+def clip_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int, h: int, w: int) -> Callable[[], None]:
+    """fp32 NCDHW clip (looked up as holder[key] at run time) -> bf16 zero-padded [N*T, H+8, W+8, 4] frames."""
+    lib = _lib.load()
+    hp, wp = h + PAD_EXTRA, w + PAD_EXTRA
+    assert tuple(frames.shape) == (n * t, hp, wp, 4) and frames.dtype == torch.bfloat16
+    fp = _ptr(frames)
+
+    def run(_keep=(frames,)):
+        _lib.check(lib.mspi_clip_to_padded_nhwc4(_ptr(holder[key]), fp, n, t, h, w, PAD_T, PAD_L, hp, wp, _stream()),
+                   "clip_to_padded_nhwc4")
+
+    return run
+
+
+def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale, shift, k: int, stride: int, pad: int,
+              act: int, y: "Act", name: str = "stem") -> Callable[[], None]:
+    """(1,k,k)/stride conv with Cin=3 straight off the padded 4-channel frames (no im2col buffer).
+
+    One row of the filter (k taps x 4 channels, at most 8 pixels) is a contiguous 16-byte aligned run of the frame;
+    the filter rows are the GEMM's taps and each is fetched by one TMA box whose inner extent is that run
+    (MspiConvDesc.k_row_bytes = 64 or 32: 64B / 32B-swizzled operand tiles).
+      S3D   conv_s 7x7/s2 p3 (s3d.py:383):  run = 8 px starting at 2*ow-4 (+PAD_L), 7 taps, frame row 2*(oh+j)+r for
+                                            filter row kh = 2j+r: the row parity r is its own tensor axis
+      ConvNeXt stem 4x4/s4 p0 (timm):       run = 4 px starting at 4*ow   (+PAD_L), 4 taps, frame row 4*oh+kh
+    """
+    lib = _lib.load()
+    nf, hp, wp, _ = frames.shape
+    cout = weight.shape[0]
+    w5 = weight.detach().float().to(frames.device)
+    if w5.dim() == 5:
+        w5 = w5[:, :, 0]
+    assert w5.shape[1] == 3 and w5.shape[2] == w5.shape[3] == k
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    if (k, stride, pad) == (7, 2, 3):
+        run_px, x_lead = 8, 1     # window starts one pixel before tap 0 (alignment)
+        row0, col0 = PAD_T - pad, PAD_L - pad - x_lead
+    elif (k, stride, pad) == (4, 4, 0):
+        run_px, x_lead = 4, 0
+        row0, col0 = PAD_T, PAD_L
+    else:
+        raise ValueError(f"stem_conv: unsupported geometry k={k} stride={stride} pad={pad}")
+    run_el = run_px * 4
+    assert (col0 * 4 * 2) % 16 == 0 and (stride * 4 * 2) % 16 == 0 and row0 >= 0 and col0 >= 0
+    # weight matrix [cout16][k taps][run_px][4]
+    rows16 = -(-cout // 16) * 16
+    wm = torch.zeros((rows16, k, run_px, 4), dtype=torch.float32, device=frames.device)
+    wm[:cout, :, x_lead:x_lead + k, :3] = w5.permute(0, 2, 3, 1)
+    packed = wm.reshape(rows16, k * run_el).to(torch.bfloat16).contiguous()
+    # frame row of (oh, kh) = row0 + stride*oh + kh = row0 + stride*(oh + kh // stride) + kh % stride
+    n_r, n_j = min(stride, k), (k - 1) // stride + 1
+    assert row0 + stride * (oh - 1) + k - 1 < hp and col0 + stride * (ow - 1) + run_px - 1 < wp
+    d = ConvDesc()
+    d.a_dtype = MSPI_BF16
+    d.k_row_bytes = run_el * 2
+    a_dims = (run_el, n_r, ow, oh + n_j - 1, nf)
+    a_str = (1, wp * 4, stride * 4, stride * wp * 4, hp * wp * 4)
+    for j in range(5):
+        d.a_dims[j] = a_dims[j]
+        d.a_strides[j] = a_str[j]
+    o_dims = (1, ow, oh, nf)
+    box = (1,) + choose_box((ow, oh, nf, 1))[:3]
+    ostr = (0, y.cs, y.w * y.cs, y.h * y.w * y.cs)  # frames (n, t) are contiguous in y
+    d.box[0] = 0
+    for j in range(4):
+        d.box[j + 1] = box[j]
+        d.o_dims[j] = o_dims[j]
+        d.o_strides[j] = ostr[j]
+        d.r_strides[j] = 0
+    d.ntaps = k
+    for kh in range(k):
+        d.tap_off[kh][0], d.tap_off[kh][1], d.tap_off[kh][2], d.tap_off[kh][3] = kh % stride, 0, kh // stride, 0
+    d.cin_pad = run_el
+    d.cout, d.w_rows = cout, rows16
+    d.bn = choose_bn(cout, 64 if y.dtype == torch.bfloat16 else 32)
+    d.o_dtype = _DT[y.dtype]
+    d.act = act
+    sc = None if scale is None else scale.detach().float().contiguous().to(frames.device)
+    sh = None if shift is None else shift.detach().float().contiguous().to(frames.device)
+    x_ptr = _ptr(frames, (row0 * wp + col0) * 4 * 2)
+    w_ptr, y_ptr = _ptr(packed), y.ptr
+    assert y.pixels == nf * oh * ow and y.c == cout
+
+    def run(_keep=(frames, packed, sc, sh, y.buf, d)):
+        _lib.check(lib.mspi_conv_gemm(C.byref(d), x_ptr, w_ptr, _ptr(sc), _ptr(sh), C.c_void_p(0), y_ptr, _stream()),
+                   f"conv_gemm[{name}]")
+
+    run.mode = "stem"
+    run.desc = d
+    run.flops = 2.0 * nf * oh * ow * cout * 3 * k * k
+    return run
+
+
 # ------------------------------------------------------------------------------------------ other ops
 def patch_gather_ncdhw(src: torch.Tensor, kernel, stride, pad, k_pad: int, out: torch.Tensor) -> Callable[[], None]:
     """fp32 NCDHW input (the model's input contract) -> bf16 patch rows [M, k_pad]."""

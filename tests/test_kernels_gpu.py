@@ -168,6 +168,36 @@ def test_patch_gather_from_ncdhw_stem():
     assert (got[:, kk:] == 0).all()
 
 
+@pytest.mark.parametrize("k,stride,pad,cout,odt", [(7, 2, 3, 64, torch.bfloat16), (4, 4, 0, 96, torch.float32)])
+def test_stem_conv_on_padded_frames(k, stride, pad, cout, odt):
+    """Cin=3 stems as implicit GEMMs off the padded 4-channel frames (MspiConvDesc.k_rows): S3D conv_s 7x7/s2
+    (s3d.py:383) and the ConvNeXt 4x4/s4 stem, against F.conv2d on the bf16-rounded clip."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(21)
+    b, t, h, w = 2, 3, 32, 64
+    clip = torch.randn(b, 3, t, h, w, generator=g)
+    wgt = torch.randn(cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    frames = torch.zeros(b * t, h + ops.PAD_EXTRA, w + ops.PAD_EXTRA, 4, dtype=torch.bfloat16, device="cuda")
+    holder = {"clips": clip.cuda()}
+    ops.clip_to_padded(holder, "clips", frames, b, t, h, w)()
+    torch.cuda.synchronize()
+    inner = frames[:, ops.PAD_T:ops.PAD_T + h, ops.PAD_L:ops.PAD_L + w].float().cpu()
+    want = _bf(clip).permute(0, 2, 3, 4, 1).reshape(b * t, h, w, 3)
+    assert torch.equal(inner[..., :3], want) and (inner[..., 3] == 0).all()
+    assert frames.float().abs().sum().item() == pytest.approx(inner.abs().sum().item(), rel=1e-6)  # borders stay zero
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    y = Act.empty(b, t, oh, ow, cout, dtype=odt)
+    ops.stem_conv(frames, h, w, wgt, scale, shift, k, stride, pad, 1, y)()
+    torch.cuda.synchronize()
+    x2 = _bf(clip).permute(0, 2, 1, 3, 4).reshape(b * t, 3, h, w)
+    ref = F.conv2d(x2, _bf(wgt), None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = ref.relu().view(b, t, cout, oh, ow).permute(0, 2, 1, 3, 4)
+    got = y.to_ncdhw().cpu()
+    assert _rel(got, ref) < (BF16_TOL if odt == torch.bfloat16 else 1e-4)
+
+
 def test_maxpool_variants():
     from mspi_b200 import ops
     from mspi_b200.ops import Act
