@@ -93,6 +93,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def read_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu pass (profiles/r01_roofline_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def cpu_baseline(seconds_budget: float = 20.0):
     """The oracle (CPU fp32 port of the reference forward) on the host cores: B=1 at the default shape."""
     import torch
@@ -185,12 +194,12 @@ def main():
     n_sets = 2  # rotate input sets; each set (B*16.5 MB) is already larger than... see config.l2
     clips_sets = [torch.randn(B, 3, T, H, W, device=dev, generator=g) for _ in range(n_sets)]
     audio_sets = [torch.randn(B, 1, 257, 111, device=dev, generator=g) for _ in range(n_sets)]
-    gathered = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
+    from mspi_b200.distributed import gather_maps
 
     def step(i):
         out, loss = model(clips_sets[i % n_sets], audio_sets[i % n_sets])
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            out = gather_maps(out, world * B)  # NCCL all-gather of the [B,H,W] maps, global clip order
         return out, loss
 
     def barrier():
@@ -260,7 +269,7 @@ def main():
             out, loss = model(dclips[s], daud[s])
             freed[s].record(main_stream)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, out)
+                gather_maps(out, world * B)
             host_out[s].copy_(out, non_blocking=True)  # D2H of this step's maps
         torch.cuda.synchronize()
 
@@ -313,9 +322,15 @@ def main():
                     "gflop": gf_k, "tflops": gf_k / ms_k if ms_k else None}
             if kind == "conv_gemm_bf16":
                 peak = peaks["bf16_sustained"]
+                tr = read_traffic()
+                traffic = tr["conv_gemm_bf16"]["dram_bytes_per_launch"] if tr else None
                 roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<bf16> (tcgen05 implicit GEMM)",
                             "achieved": info["tflops"], "peak": peak, "unit": "TFLOP/s",
-                            "frac": (info["tflops"] / peak) if info["tflops"] else None, "traffic": None,
+                            "frac": (info["tflops"] / peak) if info["tflops"] else None, "traffic": traffic,
+                            "traffic_note": "dram read+write bytes per launch, mean over the 164 bf16 launches of one step "
+                                            "(ncu, profiles/r01_launches.csv)" if tr else None,
+                            "hbm_gbs_from_traffic": (tr["conv_gemm_bf16"]["dram_bytes_per_step"] / ms_k / 1e6) if tr else None,
+                            "hbm_peak_gbs": peaks["hbm"],
                             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                             "launches_per_step": info["launches"], "share_of_step": info["share_of_step"],
                             "algorithmic_gflop_per_step": gf_k}

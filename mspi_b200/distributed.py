@@ -1,0 +1,73 @@
+"""Clip sharding across GPUs (one process per GPU, torch.distributed).
+
+Clips are independent in inference (eval-mode BatchNorm, model_utils.py:556-574 has no cross-sample op except the
+batch mean inside loss_av), so the global batch is split contiguously by rank and the weights are replicated; there
+is no data-path collective.  The only exchange is the gather of the [B_local, H, W] fp32 saliency maps (344 KB per
+clip at 224x384) and the mean of the scalar loss_av — NCCL on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of the global batch owned by `rank`; the first (global_batch % world) ranks get one
+    extra clip, so any batch size (including fewer clips than ranks) is covered exactly once."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(global_batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def max_shard(global_batch: int, world: int) -> int:
+    return -(-global_batch // world)
+
+
+def gather_maps(local_maps: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank [b_local, H, W] maps into [global_batch, H, W] in global clip order.
+
+    Ragged shards are padded to the largest shard for the collective (all_gather_into_tensor needs equal sizes)
+    and the padding rows are dropped afterwards."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(global_batch, rank, world)
+    if local_maps.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} holds {local_maps.shape[0]} maps, its shard is [{lo},{hi})")
+    m = max_shard(global_batch, world)
+    h, w = local_maps.shape[1:]
+    send = local_maps
+    if send.shape[0] != m:
+        send = torch.zeros((m, h, w), dtype=local_maps.dtype, device=local_maps.device)
+        send[: hi - lo] = local_maps
+    recv = torch.empty((world * m, h, w), dtype=local_maps.dtype, device=local_maps.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if global_batch == world * m:
+        return recv
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(global_batch, r, world)
+        parts.append(recv[r * m: r * m + (b - a)])
+    return torch.cat(parts, 0)
+
+
+def forward_sharded(forward: Callable, clips: torch.Tensor, audios: Optional[torch.Tensor], group=None):
+    """Run `forward(clips_local, audios_local) -> (maps_local, loss_local)` on this rank's shard of a replicated
+    global batch and return (all maps in global order, batch-mean loss).  The loss is the clip-weighted mean of the
+    per-rank means, which equals the reference's mean over the global batch (model_utils.py:551)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = clips.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    if hi > lo:
+        maps, loss = forward(clips[lo:hi], None if audios is None else audios[lo:hi])
+        loss = torch.as_tensor(loss, dtype=torch.float32, device=maps.device).reshape(1) * (hi - lo)
+    else:  # more ranks than clips: this rank contributes nothing
+        h, w = clips.shape[-2:]
+        maps = torch.empty((0, h, w), dtype=torch.float32, device=clips.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=clips.device)
+    full = gather_maps(maps, n, group)
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    return full, loss[0] / n

@@ -1,0 +1,76 @@
+"""world_size-2 (and 3) gloo tests of the clip-sharding host logic (mspi_b200/distributed.py) on CPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mspi_b200.distributed import forward_sharded, gather_maps, max_shard, shard_bounds
+
+
+def test_shard_bounds_cover_batch_exactly_once():
+    for n in (0, 1, 2, 5, 32, 33):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_bounds(n, r, world)
+                assert 0 <= lo <= hi <= n and hi - lo <= max_shard(n, world)
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_forward(clips, audios):
+    """A per-clip function (no cross-sample coupling), like the eval-mode model: map = mean over (c,t) + audio mean."""
+    m = clips.mean((1, 2))
+    if audios is not None:
+        m = m + audios.mean((1, 2, 3)).view(-1, 1, 1)
+    return m, m.mean((1, 2)).mean()
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)  # same global batch on every rank
+        clips = torch.randn(n, 3, 4, 8, 12, generator=g)
+        aud = torch.randn(n, 1, 5, 7, generator=g)
+        full, loss = forward_sharded(_fake_forward, clips, aud)
+        ref_maps, _ = _fake_forward(clips, aud)
+        ref_loss = ref_maps.mean((1, 2)).mean() if n else torch.tensor(0.0)
+        ok = torch.allclose(full, ref_maps, atol=1e-6) and abs(float(loss) - float(ref_loss)) < 1e-6
+        # gather_maps rejects a shard of the wrong size
+        lo, hi = shard_bounds(n, rank, world)
+        try:
+            gather_maps(torch.zeros(hi - lo + 1, 8, 12), n)
+            ok = False
+        except ValueError:
+            pass
+        q.put((rank, bool(ok), tuple(full.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 4), (2, 5), (3, 2), (2, 1)])
+def test_forward_sharded_gloo(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (n, 8, 12) for _, _, shape in res)
