@@ -115,53 +115,76 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   for (int j = 0; j < P; ++j) reinterpret_cast<float4*>(out_s + static_cast<size_t>(s * P + j) * C)[q] = acc[j];
   __syncthreads();
 
-  // ---- LayerNorm over C, one warp per pixel; lane owns channel pairs lane, lane+32, ...
+  // ---- LayerNorm over C.  A warp normalises G pixels at a time (lane owns channel pairs lane, lane+32, ... of
+  // each): the G butterfly reductions are independent, so their shuffle latencies overlap.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kThreads / 32;
   constexpr int pairs = C / 2;
   constexpr int MAXI = (pairs + 31) / 32;
-  for (int pix = warp; pix < S * P; pix += nwarps) {
-    const int py = y0 + pix / P, px = x0 + pix % P;
-    if (py >= H || px >= W) continue;
-    const float2* src = reinterpret_cast<const float2*>(out_s + static_cast<size_t>(pix) * C);
-    float2 v[MAXI];
-    float sum = 0.f;
+  constexpr int G = 4;
+  static_assert((S * P) % G == 0, "pixel groups");
+  for (int p0 = warp * G; p0 < S * P; p0 += nwarps * G) {
+    float2 v[G][MAXI];
+    float sum[G], sq[G];
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const int p = lane + 32 * i;
-      v[i] = p < pairs ? src[p] : make_float2(0.f, 0.f);
-      sum += v[i].x + v[i].y;
+    for (int g = 0; g < G; ++g) {
+      const float2* src = reinterpret_cast<const float2*>(out_s + static_cast<size_t>(p0 + g) * C);
+      sum[g] = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int p = lane + 32 * i;
+        v[g][i] = p < pairs ? src[p] : make_float2(0.f, 0.f);
+        sum[g] += v[g][i].x + v[g][i].y;
+      }
     }
-    float mean = 0.f, rstd = 1.f;
     if (ln_w != nullptr) {
-      mean = warp_sum(sum) * (1.f / C);
-      float sq = 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], o);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        sum[g] *= (1.f / C);  // mean
+        sq[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i) {
+          if (lane + 32 * i < pairs) {
+            const float a = v[g][i].x - sum[g], b = v[g][i].y - sum[g];
+            sq[g] += a * a + b * b;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], o);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) sq[g] = rsqrtf(sq[g] * (1.f / C) + eps);  // rstd
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int pix = p0 + g;
+      const int py = y0 + pix / P, px = x0 + pix % P;
+      if (py >= H || px >= W) continue;
+      const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * C;
 #pragma unroll
       for (int i = 0; i < MAXI; ++i) {
         const int p = lane + 32 * i;
         if (p < pairs) {
-          const float a = v[i].x - mean, b = v[i].y - mean;
-          sq += a * a + b * b;
+          float a = v[g][i].x, b = v[g][i].y;
+          if (ln_w != nullptr) {
+            const float2 gm = __ldg(reinterpret_cast<const float2*>(ln_w) + p);
+            const float2 sh = __ldg(reinterpret_cast<const float2*>(ln_b) + p);
+            a = (a - sum[g]) * sq[g] * gm.x + sh.x;
+            b = (b - sum[g]) * sq[g] * gm.y + sh.y;
+          }
+          if (out_bf16)
+            reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
+          else
+            reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
         }
-      }
-      rstd = rsqrtf(warp_sum(sq) * (1.f / C) + eps);
-    }
-    const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * C;
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const int p = lane + 32 * i;
-      if (p < pairs) {
-        float a = v[i].x, b = v[i].y;
-        if (ln_w != nullptr) {
-          const float2 g = __ldg(reinterpret_cast<const float2*>(ln_w) + p);
-          const float2 sh = __ldg(reinterpret_cast<const float2*>(ln_b) + p);
-          a = (a - mean) * rstd * g.x + sh.x;
-          b = (b - mean) * rstd * g.y + sh.y;
-        }
-        if (out_bf16)
-          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
-        else
-          reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
       }
     }
   }

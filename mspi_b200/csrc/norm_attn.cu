@@ -133,6 +133,81 @@ __global__ void layernorm_kernel(MspiLnDesc d, const TI* __restrict__ x, const f
   }
 }
 
+// Vectorised variant for C % 4 == 0, C <= 128*NI: a warp owns a row, each lane keeps its 4-element chunks in
+// registers (one global read of the row), 8/16-byte accesses, two-pass statistics in registers.
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  float4 f;
+  unpack_bf16x2(u.x, f.x, f.y);
+  unpack_bf16x2(u.y, f.z, f.w);
+  return f;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TI, typename TO, int NI>
+__global__ void layernorm_vec_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ b, const float* __restrict__ pos, TO* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int c4 = d.c >> 2;
+  const float inv_c = 1.f / d.c;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < d.rows;
+       row += static_cast<long long>(gridDim.x) * warps) {
+    const TI* xr = x + row * d.in_rstride;
+    float4 v[NI];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = lane + 32 * i;
+      v[i] = q < c4 ? ld4<TI>(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (lane + 32 * i < c4) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_c + d.eps);
+    const long long g = row / d.rows_per_group, within = row - g * d.rows_per_group;
+    TO* yr = y + g * d.out_gstride + within * d.out_rstride;
+    const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c : nullptr;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = lane + 32 * i;
+      if (q < c4) {
+        const float4 gw = __ldg(reinterpret_cast<const float4*>(w) + q);
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(b) + q);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * gw.x + gb.x;
+        o.y = (v[i].y - mean) * rstd * gw.y + gb.y;
+        o.z = (v[i].z - mean) * rstd * gw.z + gb.z;
+        o.w = (v[i].w - mean) * rstd * gw.w + gb.w;
+        if (d.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (pr) {
+          const float4 pp = __ldg(reinterpret_cast<const float4*>(pr) + q);
+          o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+        }
+        st4(yr + 4 * q, o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- attention
 // qkv: [B][N][3][H][HD] bf16.  Block = (b*H + h, query tile of QT rows).  Scores for the whole
 // key range live in shared memory (N <= 1024), softmax in fp32, then P·V.
@@ -320,6 +395,30 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
   if (blocks < 1) blocks = 1;
   using bf = __nv_bfloat16;
   const int g = static_cast<int>(blocks);
+  const int ies = d->in_dtype == MSPI_BF16 ? 2 : 4, oes = d->out_dtype == MSPI_BF16 ? 2 : 4;
+  const bool vec_ok = d->c % 4 == 0 && d->c <= 1024 && (d->in_rstride * ies) % (4 * ies) == 0 &&
+                      (d->out_rstride * oes) % (4 * oes) == 0 && (d->out_gstride * oes) % (4 * oes) == 0 &&
+                      (reinterpret_cast<uintptr_t>(x) % (4 * ies)) == 0 && (reinterpret_cast<uintptr_t>(y) % (4 * oes)) == 0 &&
+                      (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
+                      (pos == nullptr || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
+  if (vec_ok) {
+#define MSPI_LN_VEC(TI, TO)                                                                                              \
+  do {                                                                                                                   \
+    if (d->c <= 256)                                                                                                     \
+      layernorm_vec_kernel<TI, TO, 2><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+    else if (d->c <= 512)                                                                                                \
+      layernorm_vec_kernel<TI, TO, 4><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+    else                                                                                                                 \
+      layernorm_vec_kernel<TI, TO, 8><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+  } while (0)
+    if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16) MSPI_LN_VEC(bf, bf);
+    else if (d->in_dtype == MSPI_BF16) MSPI_LN_VEC(bf, float);
+    else if (d->out_dtype == MSPI_BF16) MSPI_LN_VEC(float, bf);
+    else MSPI_LN_VEC(float, float);
+#undef MSPI_LN_VEC
+    MSPI_LAUNCH_CHECK();
+    return MSPI_OK;
+  }
   if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16)
     layernorm_kernel<bf, bf><<<g, threads, 0, stream>>>(*d, static_cast<const bf*>(x), w, b, pos, static_cast<bf*>(y));
   else if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_F32)
