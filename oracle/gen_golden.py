@@ -21,8 +21,12 @@ from oracle import ref_shim  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# (name, audio, B, H, W, init, weight seed, input seed)
+# (name, audio, B, H, W, init, weight seed, input seed[, encoder])
 CASES = [
+    ("x3dl_av_64x64_b1_cal", True, 1, 64, 64, "calibrated", 3, 2023, "x3dl"),
+    ("x3dl_av_64x96_b1_def", True, 1, 64, 96, "default", 4, 2023, "x3dl"),
+    ("sf_av_64x64_b1_cal", True, 1, 64, 64, "calibrated", 5, 2023, "slowfast4x16"),
+    ("sf_av_64x96_b1_def", True, 1, 64, 96, "default", 6, 2023, "slowfast4x16"),
     ("s3d_av_64x64_b2_cal", True, 2, 64, 64, "calibrated", 0, 2023),
     ("s3d_av_64x96_b1_def", True, 1, 64, 96, "default", 1, 2023),
     ("s3d_v_64x64_b1_cal", False, 1, 64, 64, "calibrated", 2, 2023),
@@ -41,10 +45,10 @@ def summarize(t: torch.Tensor, n_samples: int = 256) -> dict:
             "absmax": flat.abs().max().item(), "stride": stride, "samples": flat[::stride][:n_samples].clone()}
 
 
-def run_case(name, audio, b, h, w, init, wseed, iseed):
-    sd = orc.make_state_dict(wseed, init, audio=audio)
-    tokens = 4 * (h // 32) * (w // 32)
-    model = ref_shim.build_reference_model(sd, "s3d", num_vis_tokens=tokens, audio=audio)
+def run_case(name, audio, b, h, w, init, wseed, iseed, encoder="s3d"):
+    sd = orc.make_state_dict(wseed, init, audio=audio, encoder=encoder)
+    tokens = (16 if encoder == "x3dl" else 4) * (h // 32) * (w // 32)
+    model = ref_shim.build_reference_model(sd, encoder, num_vis_tokens=tokens, audio=audio)
     ref_sd = model.state_dict()
     assert list(ref_sd.keys()) == list(sd.keys()), "param_spec order/names differ from the reference state_dict"
     for k in sd:
@@ -65,11 +69,20 @@ def run_case(name, audio, b, h, w, init, wseed, iseed):
     for nm in TAP_MODULES + ["visnet", "image_encoder"]:
         if hasattr(model, nm):
             hooks.append(getattr(model, nm).register_forward_hook(hook(nm)))
+    if encoder != "s3d":  # the PySlowFast-style encoders return lists per stage: tap the four feature maps
+        orig = model.visnet.forward
+
+        def wrapped(x, _o=orig):
+            feats = _o(x)
+            for i, f in enumerate(feats):
+                taps[f"visnet.base{i + 1}"] = summarize(f)
+            return feats
+        model.visnet.forward = wrapped
     with torch.no_grad():
         out, loss = model(clips, aud) if audio else model(clips)
     for hk in hooks:
         hk.remove()
-    fix = {"case": dict(name=name, audio=audio, b=b, h=h, w=w, init=init, wseed=wseed, iseed=iseed),
+    fix = {"case": dict(name=name, audio=audio, b=b, h=h, w=w, init=init, wseed=wseed, iseed=iseed, encoder=encoder),
            "out": out.clone(), "loss": float(loss), "taps": taps}
     torch.save(fix, os.path.join(GOLDEN, name + ".pt"))
     print(f"{name}: out range [{out.min():.4f}, {out.max():.4f}] loss {float(loss):.6f} taps {len(taps)}")
@@ -128,10 +141,13 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
-    run_metrics()
-    run_audio()
+    only = sys.argv[1:]
+    if not only:
+        run_metrics()
+        run_audio()
     for c in CASES:
-        run_case(*c)
+        if not only or any(o in c[0] for o in only):
+            run_case(*c)
 
 
 if __name__ == "__main__":

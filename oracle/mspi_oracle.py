@@ -96,6 +96,110 @@ def s3d_features(sd: SD, p: str, x, pool: int = 1) -> List[torch.Tensor]:
     return [v1, v2, v3, v4]
 
 
+# ------------------------------------------------------------------ PySlowFast-style ResNet pieces
+# (vendored SlowFast/resnet_helper.py, SlowFast/stem_helper.py; all BatchNorm eps 1e-5)
+X3D_DEPTHS, X3D_OUT, X3D_INNER = (5, 10, 25, 15), (24, 48, 96, 192), (54, 108, 216, 432)  # X3D_L.yaml + X3D.py:139-163
+
+
+def _se_width(dim_in: int, ratio: float = 0.0625, divisor: int = 8) -> int:
+    """SE._round_width, resnet_helper.py:26-45"""
+    w = dim_in * ratio
+    out = max(divisor, int(w + divisor / 2) // divisor * divisor)
+    if out < 0.9 * w:
+        out += divisor
+    return int(out)
+
+
+def _se(sd: SD, p: str, x):
+    """SE: avg-pool -> fc1 -> ReLU -> fc2 -> sigmoid -> scale.  resnet_helper.py:47-73"""
+    s = x.mean((2, 3, 4), keepdim=True)
+    s = F.relu(F.conv3d(s, sd[p + ".fc1.weight"], sd[p + ".fc1.bias"]))
+    s = torch.sigmoid(F.conv3d(s, sd[p + ".fc2.weight"], sd[p + ".fc2.bias"]))
+    return x * s
+
+
+def _res_block(sd: SD, p: str, x, stride: int, transform):
+    """ResBlock.forward: relu(shortcut + branch2(x)); projection shortcut when present.  resnet_helper.py:580-590"""
+    f = transform(sd, p + ".branch2", x, stride)
+    if (p + ".branch1.weight") in sd:
+        x = _bn(sd, p + ".branch1_bn", F.conv3d(x, sd[p + ".branch1.weight"], None, (1, stride, stride)), 1e-5)
+    return F.relu(x + f)
+
+
+def _x3d_transform(use_se: bool):
+    def tr(sd: SD, p: str, x, stride: int):
+        """X3DTransform: 1x1x1+BN+ReLU -> depthwise 3x3x3 (stride on H,W)+BN -> [SE] -> Swish -> 1x1x1+BN.
+        resnet_helper.py:213-351 (children() order)"""
+        c = sd[p + ".b.weight"].shape[0]
+        x = F.relu(_bn(sd, p + ".a_bn", F.conv3d(x, sd[p + ".a.weight"]), 1e-5))
+        x = _bn(sd, p + ".b_bn", F.conv3d(x, sd[p + ".b.weight"], None, (1, stride, stride), (1, 1, 1), 1, c), 1e-5)
+        if use_se:
+            x = _se(sd, p + ".se", x)
+        x = x * torch.sigmoid(x)
+        return _bn(sd, p + ".c_bn", F.conv3d(x, sd[p + ".c.weight"]), 1e-5)
+    return tr
+
+
+def x3d_features(sd: SD, p: str, x) -> List[torch.Tensor]:
+    """X3D(features_only).forward for X3D-L: stem conv_xy (1,3,3)/s(1,2,2) -> depthwise (5,1,1) -> BN -> ReLU; four
+    stages of 5/10/25/15 ResBlocks (first of each stage has spatial stride 2), SE on every other block.
+    backbones/X3D.py:111-250, stem_helper.py:207-290"""
+    q = p + "s1.pathway0_stem"
+    x = F.conv3d(x, sd[q + ".conv_xy.weight"], None, (1, 2, 2), (0, 1, 1))
+    x = F.conv3d(x, sd[q + ".conv.weight"], None, 1, (2, 0, 0), 1, x.shape[1])
+    x = F.relu(_bn(sd, q + ".bn", x, 1e-5))
+    feats = []
+    for si, depth in enumerate(X3D_DEPTHS):
+        for i in range(depth):
+            x = _res_block(sd, f"{p}s{si + 2}.pathway0_res{i}", x, 2 if i == 0 else 1, _x3d_transform((i + 1) % 2 == 1))
+        feats.append(x)
+    return feats
+
+
+SF_DEPTHS = (3, 4, 6, 3)                       # ResNet-50, SLOWFAST_4x16_R50.yaml
+SF_TK_SLOW, SF_TK_FAST = (1, 1, 3, 3), (3, 3, 3, 3)   # _TEMPORAL_KERNEL_BASIS["slowfast"], sf.py:31-100
+SF_SLOW_FRAMES = (0, 4, 12, -1)                # model_utils.py:523
+
+
+def _bottleneck(tk: int):
+    def tr(sd: SD, p: str, x, stride: int):
+        """BottleneckTransform: (tk,1,1)+BN+ReLU -> (1,3,3)/stride+BN+ReLU -> 1x1x1+BN.  resnet_helper.py:354-487"""
+        x = F.relu(_bn(sd, p + ".a_bn", F.conv3d(x, sd[p + ".a.weight"], None, 1, (tk // 2, 0, 0)), 1e-5))
+        x = F.relu(_bn(sd, p + ".b_bn", F.conv3d(x, sd[p + ".b.weight"], None, (1, stride, stride), (0, 1, 1)), 1e-5))
+        return _bn(sd, p + ".c_bn", F.conv3d(x, sd[p + ".c.weight"]), 1e-5)
+    return tr
+
+
+def slowfast_features(sd: SD, p: str, clips) -> List[torch.Tensor]:
+    """SlowFast 4x16 R50 features: slow pathway = frames [0,4,12,-1], fast = all 16.  Stems (k,7,7)/s(1,2,2)+BN+ReLU+
+    MaxPool(1,3,3)/s(1,2,2); FuseFastToSlow = (5,1,1)/s(4,1,1) conv + BN + ReLU concatenated to the slow pathway
+    after the stem and after res2..res4.  backbones/sf.py:101-389, model_utils.py:521-524"""
+    xs = torch.stack([clips[:, :, i] for i in SF_SLOW_FRAMES], 2)
+    xf = clips
+
+    def stem(q, x, kt):
+        x = F.relu(_bn(sd, q + ".bn", F.conv3d(x, sd[q + ".conv.weight"], None, (1, 2, 2), (kt // 2, 3, 3)), 1e-5))
+        return F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+
+    def fuse(q, xs, xf):
+        f = F.relu(_bn(sd, q + ".bn", F.conv3d(xf, sd[q + ".conv_f2s.weight"], None, (4, 1, 1), (2, 0, 0)), 1e-5))
+        return torch.cat([xs, f], 1)
+
+    xs, xf = stem(p + "s1.pathway0_stem", xs, 1), stem(p + "s1.pathway1_stem", xf, 5)
+    xs = fuse(p + "s1_fuse", xs, xf)
+    feats = []
+    for si, depth in enumerate(SF_DEPTHS):
+        stride = 1 if si == 0 else 2
+        for i in range(depth):
+            st = stride if i == 0 else 1
+            xs = _res_block(sd, f"{p}s{si + 2}.pathway0_res{i}", xs, st, _bottleneck(SF_TK_SLOW[si]))
+            xf = _res_block(sd, f"{p}s{si + 2}.pathway1_res{i}", xf, st, _bottleneck(SF_TK_FAST[si]))
+        if si < 3:
+            xs = fuse(f"{p}s{si + 2}_fuse", xs, xf)
+        feats.append(xs)
+    return feats
+
+
 def resnet18_audio(sd: SD, p: str, x):
     """ResNet18 trunk without pool/fc on a 1-channel spectrogram.  backbones/resnet.py:17-54,131-143"""
     x = F.conv2d(x, sd[p + "conv1.weight"], None, 2, 3)
@@ -281,12 +385,31 @@ def readout(sd: SD, p: str, x):
 # ================================================================================== the model
 LATERAL_BOOL_S3D = (True, True, False, False)  # config.py:41
 LATERAL_STRIDE = 2                             # config.py:63
+# per motion encoder: tap channels (config.py:65-74), lateral temporal convs (config.py:38-47) and their stride (:63)
+ENCODERS = {
+    "s3d": {"embeds": S3D_EMBEDS, "lateral_bool": LATERAL_BOOL_S3D, "lateral_stride": 2},
+    "x3dl": {"embeds": (24, 48, 96, 192), "lateral_bool": (True, True, True, True), "lateral_stride": 4},
+    "slowfast4x16": {"embeds": (320, 640, 1280, 2048), "lateral_bool": (False, False, False, False), "lateral_stride": 2},
+}
+
+
+def motion_features(sd: SD, encoder: str, clips):
+    if encoder == "s3d":
+        return s3d_features(sd, "visnet.", clips)
+    if encoder == "x3dl":
+        return x3d_features(sd, "visnet.", clips)
+    if encoder == "slowfast4x16":
+        return slowfast_features(sd, "visnet.", clips)
+    raise Exception("Invalid Motion Encoder!")  # get_video_backbones.py:28-29
 
 
 @torch.no_grad()
-def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: Optional[dict] = None):
-    """AudioVisualSaliencyModel.forward (audios given) / VisualSaliencyModel.forward (audios None), S3D
-    motion encoder.  model_utils.py:520-574, 685-702.  Returns (log_map [B,H,W], loss_av)."""
+def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: Optional[dict] = None,
+            encoder: str = "s3d"):
+    """AudioVisualSaliencyModel.forward (audios given) / VisualSaliencyModel.forward (audios None) for the motion
+    encoders s3d / x3dl / slowfast4x16.  model_utils.py:520-574, 685-702.  Returns (log_map [B,H,W], loss_av)."""
+    enc = ENCODERS[encoder]
+    lat = lambda k: enc["lateral_stride"] if enc["lateral_bool"][k] else None
     rec = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
     b, _, t, h, w = clips.shape
     frames = clips.permute(0, 2, 1, 3, 4).reshape(b * t, 3, h, w)
@@ -294,7 +417,7 @@ def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: O
     rec("image_encoder.o1", o1), rec("image_encoder.o0", o0)
     masks = adapter(sd, "adapter.", o1, o0, t)
     rec("adapter", masks)
-    v1, v2, v3, v4 = s3d_features(sd, "visnet.", clips)
+    v1, v2, v3, v4 = motion_features(sd, encoder, clips)
     for i, v in enumerate((v1, v2, v3, v4)):
         rec(f"visnet.base{i + 1}", v)
     loss = torch.zeros(())
@@ -308,10 +431,10 @@ def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: O
         loss = simsiam_loss(sd, vis_tok, aud_tok)
         vis_sync = vis_tok.transpose(1, 2).reshape(b, 512, *v4.shape[2:])
         v4 = torch.cat([v4, vis_sync], 1)
-    s3 = lateral(sd, "latlayer_3", v4, LATERAL_STRIDE if LATERAL_BOOL_S3D[3] else None)
-    s0 = lateral(sd, "latlayer_0", v1, LATERAL_STRIDE if LATERAL_BOOL_S3D[0] else None)
-    s1 = lateral(sd, "latlayer_1", v2, LATERAL_STRIDE if LATERAL_BOOL_S3D[1] else None)
-    s2 = lateral(sd, "latlayer_2", v3, LATERAL_STRIDE if LATERAL_BOOL_S3D[2] else None)
+    s3 = lateral(sd, "latlayer_3", v4, lat(3))
+    s0 = lateral(sd, "latlayer_0", v1, lat(0))
+    s1 = lateral(sd, "latlayer_1", v2, lat(1))
+    s2 = lateral(sd, "latlayer_2", v3, lat(2))
     for i, s in enumerate((s0, s1, s2, s3)):
         rec(f"latlayer_{i}", s)
     s2 = sa_gate(sd, "sa_2", s2, masks, 1) + up_hw(s3, 2)
@@ -437,9 +560,61 @@ def _spec_ln(spec, p, c):
     spec[p + ".bias"] = ("ln_b", (c,))
 
 
-def param_spec(audio: bool = True) -> Dict[str, Tuple[str, tuple]]:
-    """Every state_dict entry of the reference's S3D model variant: name -> (kind, shape).
+def _spec_res_block(sp, q, cin, cout, inner, tk_a, k_b, groups_b, first, se_dim=0):
+    """ResBlock keys in module-registration order (resnet_helper.py:540-578, 270-351, 400-487)."""
+    if first:
+        _spec_conv_bn(sp, q + ".branch1", cout, cin, (1, 1, 1), q + ".branch1_bn")
+    _spec_conv_bn(sp, q + ".branch2.a", inner, cin, (tk_a, 1, 1), q + ".branch2.a_bn")
+    if groups_b == inner:
+        sp[q + ".branch2.b.weight"] = ("dw", (inner, 1) + tuple(k_b))
+        for s_, kind in (("weight", "bn_w"), ("bias", "bn_b"), ("running_mean", "bn_m"), ("running_var", "bn_v")):
+            sp[f"{q}.branch2.b_bn.{s_}"] = (kind, (inner,))
+        sp[q + ".branch2.b_bn.num_batches_tracked"] = ("count", ())
+    else:
+        _spec_conv_bn(sp, q + ".branch2.b", inner, inner, k_b, q + ".branch2.b_bn")
+    if se_dim:
+        _spec_conv_bn(sp, q + ".branch2.se.fc1", se_dim, inner, (1, 1, 1), None, bias=True)
+        _spec_conv_bn(sp, q + ".branch2.se.fc2", inner, se_dim, (1, 1, 1), None, bias=True)
+    _spec_conv_bn(sp, q + ".branch2.c", cout, inner, (1, 1, 1), q + ".branch2.c_bn")
+
+
+def _spec_x3d(sp, v):
+    _spec_conv_bn(sp, v + "s1.pathway0_stem.conv_xy", 24, 3, (1, 3, 3), None)
+    sp[v + "s1.pathway0_stem.conv.weight"] = ("dw", (24, 1, 5, 1, 1))
+    for s_, kind in (("weight", "bn_w"), ("bias", "bn_b"), ("running_mean", "bn_m"), ("running_var", "bn_v")):
+        sp[f"{v}s1.pathway0_stem.bn.{s_}"] = (kind, (24,))
+    sp[v + "s1.pathway0_stem.bn.num_batches_tracked"] = ("count", ())
+    cin = 24
+    for si, (depth, cout, inner) in enumerate(zip(X3D_DEPTHS, X3D_OUT, X3D_INNER)):
+        for i in range(depth):
+            _spec_res_block(sp, f"{v}s{si + 2}.pathway0_res{i}", cin, cout, inner, 1, (3, 3, 3), inner, i == 0,
+                            _se_width(inner) if (i + 1) % 2 == 1 else 0)
+            cin = cout
+
+
+def _spec_slowfast(sp, v):
+    _spec_conv_bn(sp, v + "s1.pathway0_stem.conv", 64, 3, (1, 7, 7), v + "s1.pathway0_stem.bn")
+    _spec_conv_bn(sp, v + "s1.pathway1_stem.conv", 8, 3, (5, 7, 7), v + "s1.pathway1_stem.bn")
+    _spec_conv_bn(sp, v + "s1_fuse.conv_f2s", 16, 8, (5, 1, 1), v + "s1_fuse.bn")
+    cs, cf = 64 + 16, 8
+    for si, depth in enumerate(SF_DEPTHS):
+        outs, outf = 256 * 2 ** si, 32 * 2 ** si
+        ins, inf_ = 64 * 2 ** si, 8 * 2 ** si
+        for pw, (cin, cout, inner, tk) in enumerate(((cs, outs, ins, SF_TK_SLOW[si]), (cf, outf, inf_, SF_TK_FAST[si]))):
+            c = cin
+            for i in range(depth):
+                _spec_res_block(sp, f"{v}s{si + 2}.pathway{pw}_res{i}", c, cout, inner, tk, (1, 3, 3), 1, i == 0)
+                c = cout
+        if si < 3:
+            _spec_conv_bn(sp, f"{v}s{si + 2}_fuse.conv_f2s", 2 * outf, outf, (5, 1, 1), f"{v}s{si + 2}_fuse.bn")
+        cs, cf = outs + (2 * outf if si < 3 else 0), outf
+
+
+def param_spec(audio: bool = True, encoder: str = "s3d") -> Dict[str, Tuple[str, tuple]]:
+    """Every state_dict entry of the reference model for the given motion encoder: name -> (kind, shape).
     Order and names follow the reference module tree (model_utils.py:388-514)."""
+    enc = ENCODERS[encoder]
+    embeds = enc["embeds"]
     sp: Dict[str, Tuple[str, tuple]] = {}
     if audio:
         _spec_conv_bn(sp, "audnet.conv1", 64, 1, (7, 7), "audnet.bn1")
@@ -473,14 +648,19 @@ def param_spec(audio: bool = True) -> Dict[str, Tuple[str, tuple]]:
     _spec_conv_bn(sp, "image_encoder.smooth_0.0", 320, 768, (3, 3), "image_encoder.smooth_0.1", bias=True)
     _spec_conv_bn(sp, "image_encoder.smooth_1.0", 96, 384, (3, 3), "image_encoder.smooth_1.1", bias=True)
     v = "visnet."
-    _spec_sep(sp, v + "base1.0", 3, 64, 7)
-    _spec_basic(sp, v + "base1.2", 64, 64, (1, 1, 1))
-    _spec_sep(sp, v + "base1.3", 64, 192, 3)
-    for name, (cin, plan) in S3D_MIXED.items():
-        _spec_mixed(sp, v + name, cin, plan)
+    if encoder == "s3d":
+        _spec_sep(sp, v + "base1.0", 3, 64, 7)
+        _spec_basic(sp, v + "base1.2", 64, 64, (1, 1, 1))
+        _spec_sep(sp, v + "base1.3", 64, 192, 3)
+        for name, (cin, plan) in S3D_MIXED.items():
+            _spec_mixed(sp, v + name, cin, plan)
+    elif encoder == "x3dl":
+        _spec_x3d(sp, v)
+    else:
+        _spec_slowfast(sp, v)
     if audio:
         a = "aud_vis_sync_block."
-        _spec_linear(sp, a + "vis_proj", 512, S3D_EMBEDS[3])
+        _spec_linear(sp, a + "vis_proj", 512, embeds[3])
         _spec_ln(sp, a + "vis_norm", 512)
         _spec_ln(sp, a + "aud_norm", 512)
         for i in range(3):
@@ -501,12 +681,12 @@ def param_spec(audio: bool = True) -> Dict[str, Tuple[str, tuple]]:
             _spec_ln(sp, f"{pred}.1", 512)
             _spec_linear(sp, f"{pred}.3", 2048, 512)
     for k in range(4):
-        cin = S3D_EMBEDS[k] + (512 if (k == 3 and audio) else 0)
+        cin = embeds[k] + (512 if (k == 3 and audio) else 0)
         p = f"latlayer_{k}"
         _spec_conv_bn(sp, p + ".0", DE, cin, (1, 1, 1), None, bias=True)
         i = 1
-        if LATERAL_BOOL_S3D[k]:
-            _spec_conv_bn(sp, p + ".1", DE, DE, (LATERAL_STRIDE, 1, 1), None)
+        if enc["lateral_bool"][k]:
+            _spec_conv_bn(sp, p + ".1", DE, DE, (enc["lateral_stride"], 1, 1), None)
             i = 2
         q = f"{p}.{i}"
         sp[q + ".dwconv_t.weight"] = ("dw", (DE, 1, 7, 1, 1))
@@ -530,7 +710,7 @@ def param_spec(audio: bool = True) -> Dict[str, Tuple[str, tuple]]:
     return sp
 
 
-def make_state_dict(seed: int = 0, init: str = "calibrated", audio: bool = True) -> SD:
+def make_state_dict(seed: int = 0, init: str = "calibrated", audio: bool = True, encoder: str = "s3d") -> SD:
     """Deterministic random-init weights for every entry of param_spec().
 
     init='default'    mimics PyTorch's default init scale (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) convs/linears,
@@ -540,7 +720,7 @@ def make_state_dict(seed: int = 0, init: str = "calibrated", audio: bool = True)
     g = torch.Generator().manual_seed(seed)
     sd: SD = {}
     cal = init == "calibrated"
-    for name, (kind, shape) in param_spec(audio).items():
+    for name, (kind, shape) in param_spec(audio, encoder).items():
         if kind in ("conv", "linear", "dw"):
             fan_in = int(np.prod(shape[1:]))
             if cal:
@@ -555,6 +735,8 @@ def make_state_dict(seed: int = 0, init: str = "calibrated", audio: bool = True)
             t = torch.randn(shape, generator=g) * (0.05 if cal else 0.01)
         elif kind in ("bn_w", "ln_w"):
             t = 1.0 + (torch.rand(shape, generator=g) - 0.5) * (0.4 if cal else 0.0)
+            if cal and name.endswith("branch2.c_bn.weight"):
+                t = t * 0.25  # residual branches of the 16..55-block ResNets: keeps the trunk O(1) (cf. zero-init final BN)
         elif kind in ("bn_b", "ln_b"):
             t = torch.randn(shape, generator=g) * (0.1 if cal else 0.0)
         elif kind == "bn_m":

@@ -340,6 +340,12 @@ def build_reference_model(state_dict, encoder="s3d", num_vis_tokens=None, audio=
 
         if encoder == "s3d":
             torch.save(sub("visnet."), cfg.MODEL.MOTION_ENCODER_WEIGHT)
+        elif encoder == "x3dl":       # X3D.load_weight: torch.load(path)['model_state'], strict=False (X3D.py:248-250)
+            torch.save({"model_state": sub("visnet.")}, cfg.MODEL.MOTION_ENCODER_WEIGHT)
+        elif encoder == "slowfast4x16":  # caffe2 pickle path of load_checkpoint (checkpoint.py:226-233): empty blobs
+            import pickle
+            with open(cfg.MODEL.MOTION_ENCODER_WEIGHT, "wb") as f:
+                pickle.dump({"blobs": {}}, f)
         else:
             raise NotImplementedError(encoder)
         torch.save(sub("audnet."), cfg.MODEL.AUDIO_ENCODER_WEIGHT)

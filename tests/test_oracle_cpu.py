@@ -21,6 +21,8 @@ def _tap_samples(t, summ):
 
 
 TAP_MAP = {  # reference module hook name -> oracle tap name
+    "visnet.base1": "visnet.base1", "visnet.base2": "visnet.base2", "visnet.base3": "visnet.base3",
+    "visnet.base4": "visnet.base4",
     "visnet.0": "visnet.base1", "visnet.1": "visnet.base2", "visnet.2": "visnet.base3", "visnet.3": "visnet.base4",
     "image_encoder.0": "image_encoder.o1", "image_encoder.1": "image_encoder.o0", "audnet": "audnet",
     "adapter": "adapter", "aud_vis_sync_block": "aud_vis_sync_block", "latlayer_0": "latlayer_0",
@@ -28,14 +30,17 @@ TAP_MAP = {  # reference module hook name -> oracle tap name
 }
 
 
-@pytest.mark.parametrize("name", ["s3d_av_64x64_b2_cal", "s3d_av_64x96_b1_def", "s3d_v_64x64_b1_cal"])
+@pytest.mark.parametrize("name", ["s3d_av_64x64_b2_cal", "s3d_av_64x96_b1_def", "s3d_v_64x64_b1_cal",
+                                  "x3dl_av_64x64_b1_cal", "x3dl_av_64x96_b1_def", "sf_av_64x64_b1_cal", "sf_av_64x96_b1_def"])
 def test_forward_matches_reference_small(name):
+    """S3D, X3D-L (BASELINE config 3) and SlowFast 4x16 R50 (config 4) model variants vs the live reference."""
     fx = _load(name + ".pt")
     c = fx["case"]
-    sd = orc.make_state_dict(c["wseed"], c["init"], audio=c["audio"])
+    enc = c.get("encoder", "s3d")
+    sd = orc.make_state_dict(c["wseed"], c["init"], audio=c["audio"], encoder=enc)
     clips, aud = orc.make_inputs(c["b"], c["h"], c["w"], c["iseed"])
     taps = {}
-    out, loss = orc.forward(sd, clips, aud if c["audio"] else None, taps)
+    out, loss = orc.forward(sd, clips, aud if c["audio"] else None, taps, encoder=enc)
     # same fp32 arithmetic, different kernels/summation order: 1e-4 on O(10) log-probabilities
     assert (out - fx["out"]).abs().max().item() < 2e-4 * max(1.0, fx["out"].abs().max().item())
     assert abs(float(loss) - fx["loss"]) < 1e-5
@@ -116,6 +121,11 @@ def test_convnext_restatement_matches_torchvision():
         mine = orc.convnext_tiny_features(sd, p, x)
     for a, b in zip(mine, feats):
         assert (a - b).abs().max().item() < 1e-4 * max(1.0, b.abs().max().item())
+
+
+def test_param_spec_other_encoders():
+    assert len(orc.param_spec(True, "x3dl")) == 1670 and len(orc.param_spec(True, "slowfast4x16")) == 1189
+    assert orc._se_width(54) == 8 and orc._se_width(216) == 16 and orc._se_width(432) == 32
 
 
 def test_param_spec_counts():
