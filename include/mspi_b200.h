@@ -34,8 +34,9 @@ extern "C" {
 #define MSPI_ACT_RELU 1
 #define MSPI_ACT_GELU 2    /* exact erf GELU, nn.GELU() default (model_utils.py:325) */
 #define MSPI_ACT_SIGMOID 3 /* nn.Sigmoid (model_utils.py:164) */
+#define MSPI_ACT_SWISH 4   /* x * sigmoid(x), SlowFast/resnet_helper.py:76-101 (X3D); not an epilogue of mspi_conv_gemm */
 
-#define MSPI_MAX_TAPS 32
+#define MSPI_MAX_TAPS 64
 
 const char* mspi_last_error(void);
 /* Library/ABI version and the SM architecture the kernels were compiled for ("sm_100a"). */
@@ -117,6 +118,13 @@ int mspi_ncdhw_to_ndhwc(const float* src, void* dst, int n, int c, int thw, int6
  * (MspiConvDesc.k_row_bytes).  w % 4 == 0, pad_l and wp even. */
 int mspi_clip_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
                               int hp, int wp, void* stream);
+/* Same, for a subset / re-ordering of the frames and a time-padded destination: destination frame
+ * b*dst_frames_per_clip + dst_frame0 + j (j < t_out) receives source frame frame_map[j] (HOST array).  Serves the
+ * SlowFast pathways: slow = frames [0,4,12,T-1] (model_utils.py:523); fast = all frames with two zero frames at
+ * either end of every clip, the temporal padding of its (5,7,7) stem (stem_helper.py:128-204). */
+int mspi_clip_frames_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
+                                     int hp, int wp, const int32_t* frame_map, int t_out, int dst_frames_per_clip,
+                                     int dst_frame0, void* stream);
 /* bf16/fp32 NDHWC (channel slice) -> fp32 NCDHW, used to hand taps back to PyTorch callers */
 int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n,
                         int c, int thw, void* stream);
@@ -167,6 +175,27 @@ typedef struct {
 } MspiDwDesc;
 int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias,
                    const float* ln_w, const float* ln_b, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * X3D-L blocks (backbones/X3D.py:111-250, SlowFast/resnet_helper.py:47-73,213-351, stem_helper.py:207-290).
+ * Depthwise (kt,kh,kw) convolution with "same" padding, spatial stride (sh,sw), BatchNorm folded into the weights
+ * (wgt fp32 [kt*kh*kw][c] = w * bn_scale) and `shift` (fp32 [c]), then act (NONE / RELU / SWISH); bf16 NDHWC in/out.
+ * Serves X3DTransform.b + b_bn (3x3x3, stride (1,s,s)) and the stem's depthwise (5,1,1) conv + bn + relu. */
+typedef struct {
+  int32_t n, t, h, w, c;
+  int64_t in_cstride, out_cstride;
+  int32_t kt, kh, kw, sh, sw;
+  int32_t oh, ow;
+  int32_t act;
+} MspiDw3dDesc;
+int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y, void* stream);
+/* Squeeze-Excitation (resnet_helper.py:47-73): out[n][c] = mean over rows of x[n][rows][c] (bf16, pixel stride cstride); */
+int mspi_channel_mean(const void* x, float* out, int n, int64_t rows, int c, int64_t cstride, void* stream);
+/* gate[n][c] = sigmoid(w2 relu(w1 mean[n] + b1) + b2), w1 fp32 [cfc][c], w2 fp32 [c][cfc]; */
+int mspi_se_gate(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
+                 int n, int c, int cfc, void* stream);
+/* y = act(x * gate[n][c]) over bf16 [n][rows][c] (x == y allowed): the SE scaling fused with the Swish that follows it. */
+int mspi_scale_act(const void* x, const float* gate, void* y, int n, int64_t rows, int c, int act, void* stream);
 
 /* LayerNorm over the last dim of [rows][c]; in/out dtype selectable; optional ReLU and an
  * optional additive table pos[(row % pos_rows)][c] (sinusoid position table, model_utils.py:18-29,

@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmspi_b200.so")
 
 MSPI_BF16, MSPI_F32 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
-MAX_TAPS = 32
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID, ACT_SWISH = 0, 1, 2, 3, 4
+MAX_TAPS = 64
 
 
 class MspiError(RuntimeError):
@@ -85,6 +85,15 @@ class DwDesc(C.Structure):
     ]
 
 
+class Dw3dDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("in_cstride", C.c_int64), ("out_cstride", C.c_int64),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("oh", C.c_int32), ("ow", C.c_int32), ("act", C.c_int32),
+    ]
+
+
 class LnDesc(C.Structure):
     _fields_ = [
         ("rows", C.c_int64), ("c", C.c_int32),
@@ -105,10 +114,16 @@ _SIGNATURES = {
     "mspi_patch_gather": (C.c_int, [C.POINTER(PatchDesc), _P, _P, _P]),
     "mspi_ncdhw_to_ndhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "mspi_clip_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mspi_clip_frames_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   _P, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_ndhwc_to_ncdhw": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_maxpool3d": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P]),
     "mspi_upsample_bilinear": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P]),
     "mspi_dwconv_ln": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "mspi_dwconv3d_bn": (C.c_int, [C.POINTER(Dw3dDesc), _P, _P, _P, _P, _P]),
+    "mspi_channel_mean": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int64, _P]),
+    "mspi_se_gate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mspi_scale_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
     "mspi_layernorm": (C.c_int, [C.POINTER(LnDesc), _P, _P, _P, _P, _P, _P]),
     "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),

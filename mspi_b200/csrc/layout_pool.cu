@@ -125,18 +125,23 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat
 // fp32 NCDHW clip [N][3][T][H][W] -> bf16 zero-padded frames [N*T][Hp][Wp][4] (channel 3 = 0).  A thread converts 4
 // consecutive pixels of a row: three coalesced float4 loads (one per colour plane), two 16-byte stores.  The borders
 // of the destination are never written (the buffer is zeroed once when it is allocated).
+struct ClipMap {  // destination frame j of clip b <- source frame map[j]; dst frame index = b*dst_fpc + dst_f0 + j
+  int t_out, dst_fpc, dst_f0;
+  int map[32];
+};
 __global__ void clip_to_padded_nhwc4_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int t,
-                                            int h, int w, int pad_t, int pad_l, int hp, int wp) {
+                                            int h, int w, int pad_t, int pad_l, int hp, int wp, ClipMap m) {
   const int w4 = w >> 2;
-  const long long total = static_cast<long long>(n) * t * h * w4;
+  const long long total = static_cast<long long>(n) * m.t_out * h * w4;
   const long long plane = static_cast<long long>(t) * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int xq = static_cast<int>(i % w4);
     long long r = i / w4;
     const int yy = static_cast<int>(r % h); r /= h;
-    const int tt = static_cast<int>(r % t);
-    const long long b = r / t;
+    const int j = static_cast<int>(r % m.t_out);
+    const long long b = r / m.t_out;
+    const int tt = m.map[j];
     const float* sp = src + (b * 3 * t + tt) * static_cast<long long>(h) * w + static_cast<long long>(yy) * w + 4 * xq;
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(sp));
     const float4 c1 = __ldg(reinterpret_cast<const float4*>(sp + plane));
@@ -146,7 +151,8 @@ __global__ void clip_to_padded_nhwc4_kernel(const float* __restrict__ src, __nv_
     o0.z = pack_bf16x2(c0.y, c1.y); o0.w = pack_bf16x2(c2.y, 0.f);
     o1.x = pack_bf16x2(c0.z, c1.z); o1.y = pack_bf16x2(c2.z, 0.f);
     o1.z = pack_bf16x2(c0.w, c1.w); o1.w = pack_bf16x2(c2.w, 0.f);
-    __nv_bfloat16* dp = dst + (((b * t + tt) * hp + (yy + pad_t)) * static_cast<long long>(wp) + pad_l + 4 * xq) * 4;
+    const long long f = b * m.dst_fpc + m.dst_f0 + j;
+    __nv_bfloat16* dp = dst + ((f * hp + (yy + pad_t)) * static_cast<long long>(wp) + pad_l + 4 * xq) * 4;
     reinterpret_cast<uint4*>(dp)[0] = o0;
     reinterpret_cast<uint4*>(dp)[1] = o1;
   }
@@ -347,19 +353,41 @@ extern "C" int mspi_ncdhw_to_ndhwc(const float* src, void* dst, int n, int c, in
   return MSPI_OK;
 }
 
-extern "C" int mspi_clip_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
-                                         int hp, int wp, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int clip_to_padded(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l, int hp, int wp,
+                          const ClipMap& m, cudaStream_t stream) {
   MSPI_CHECK_ARG(src && dst && n > 0 && t > 0 && h > 0 && w > 0, "mspi_clip_to_padded_nhwc4: bad argument");
   MSPI_CHECK_ARG(w % 4 == 0 && pad_l % 2 == 0 && wp % 2 == 0 && hp >= h + pad_t && wp >= w + pad_l,
                  "mspi_clip_to_padded_nhwc4: w %% 4, even pad_l / wp and hp >= h+pad_t, wp >= w+pad_l required");
   MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "16-byte alignment");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  const long long total = static_cast<long long>(n) * t * h * (w / 4);
+  const long long total = static_cast<long long>(n) * m.t_out * h * (w / 4);
   clip_to_padded_nhwc4_kernel<<<grid_for(total), kBlock, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n, t, h, w,
-                                                                      pad_t, pad_l, hp, wp);
+                                                                      pad_t, pad_l, hp, wp, m);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
+}
+
+extern "C" int mspi_clip_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
+                                         int hp, int wp, void* stream_) {
+  MSPI_CHECK_ARG(t <= 32, "at most 32 frames per clip");
+  ClipMap m;
+  m.t_out = t; m.dst_fpc = t; m.dst_f0 = 0;
+  for (int j = 0; j < 32; ++j) m.map[j] = j < t ? j : 0;
+  return clip_to_padded(src, dst, n, t, h, w, pad_t, pad_l, hp, wp, m, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mspi_clip_frames_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
+                                                int hp, int wp, const int32_t* frame_map, int t_out,
+                                                int dst_frames_per_clip, int dst_frame0, void* stream_) {
+  MSPI_CHECK_ARG(frame_map && t_out >= 1 && t_out <= 32 && dst_frame0 >= 0 && dst_frame0 + t_out <= dst_frames_per_clip,
+                 "mspi_clip_frames_to_padded_nhwc4: bad frame map");
+  ClipMap m;
+  m.t_out = t_out; m.dst_fpc = dst_frames_per_clip; m.dst_f0 = dst_frame0;
+  for (int j = 0; j < 32; ++j) {
+    m.map[j] = j < t_out ? frame_map[j] : 0;
+    MSPI_CHECK_ARG(m.map[j] >= 0 && m.map[j] < t, "frame_map[%d] = %d outside the clip", j, m.map[j]);
+  }
+  return clip_to_padded(src, dst, n, t, h, w, pad_t, pad_l, hp, wp, m, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n, int c,

@@ -435,7 +435,7 @@ extern "C" int mspi_attention(const void* qkv, void* out, int dtype, int b, int 
                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(qkv && out && b > 0 && n > 0 && heads > 0, "mspi_attention: bad argument");
-  MSPI_CHECK_ARG(hd % 8 == 0 && n <= 1024, "hd %d / n %d unsupported", hd, n);
+  MSPI_CHECK_ARG(hd % 8 == 0 && n <= 4096, "hd %d / n %d unsupported", hd, n);
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const int n_pad = n + 1;  // odd-ish stride: rows of the score tile land in different banks
   const size_t smem = static_cast<size_t>(kQT) * (hd + n_pad) * sizeof(float);

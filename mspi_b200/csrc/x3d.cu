@@ -1,0 +1,275 @@
+// Kernels specific to the X3D-L motion encoder (backbones/X3D.py, SlowFast/resnet_helper.py:213-351):
+//   * depthwise 3x3x3 convolution with spatial stride, folded BatchNorm and optional ReLU / Swish,
+//   * the Squeeze-Excitation path: per-(sample, channel) mean, the two tiny FC layers + sigmoid,
+//     and the gate * Swish applied to the activation,
+//   * the stem's depthwise temporal (5,1,1) conv + BN + ReLU for 16-frame clips.
+// All are HBM-bound elementwise / stencil / reduction kernels: channels-last bf16, 16-byte accesses,
+// fp32 arithmetic.
+#include "common.cuh"
+
+namespace mspi {
+namespace {
+
+__device__ __forceinline__ float act_f(float v, int act) {
+  if (act == MSPI_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MSPI_ACT_SWISH) return v / (1.f + __expf(-v));
+  if (act == MSPI_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+  unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// thread = (output position, 8 channels).  wgt: fp32 [kt*kh*kw][C] with the BatchNorm scale folded in, shift fp32 [C].
+__global__ void dw3d_kernel(MspiDw3dDesc d, const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long total, int c8) {
+  const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long r = i / c8;
+    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
+    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
+    const int ot = static_cast<int>(r % d.t);
+    const long long n = r / d.t;
+    float acc[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg), b = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg + 1);
+      acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
+    }
+    for (int kt = 0; kt < d.kt; ++kt) {
+      const int it = ot + kt - pt;
+      if (it < 0 || it >= d.t) continue;
+      for (int kh = 0; kh < d.kh; ++kh) {
+        const int ih = oh * d.sh + kh - ph;
+        if (ih < 0 || ih >= d.h) continue;
+        for (int kw = 0; kw < d.kw; ++kw) {
+          const int iw = ow * d.sw + kw - pw;
+          if (iw < 0 || iw >= d.w) continue;
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((n * d.t + it) * d.h + ih) * d.w + iw) * d.in_cstride) + cg);
+          float f[8];
+          unpack8(u, f);
+          const float4* wp = reinterpret_cast<const float4*>(wgt + static_cast<long long>((kt * d.kh + kh) * d.kw + kw) * d.c) + 2 * cg;
+          const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+          acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+          acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+          acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j], d.act);
+    reinterpret_cast<uint4*>(y + (((n * d.t + ot) * d.oh + oh) * d.ow + ow) * d.out_cstride)[cg] = pack8(acc);
+  }
+}
+
+// Depthwise (kt,1,1) conv over up to 16 frames + shift + activation: a thread owns 8 channels of one (h,w) position for
+// all frames of a sample, every input is read once.
+template <int MAXT>
+__global__ void dwt_bn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ shift,
+                              __nv_bfloat16* __restrict__ y, long long n_hw, int T, int HW, int C, int kt, int act) {
+  const int c8 = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_hw * c8) return;
+  const int cg = static_cast<int>(idx % c8);
+  const long long pos = idx / c8;
+  const long long n = pos / HW, hw = pos % HW;
+  const long long base = (n * T * HW + hw) * C + 8 * cg;
+  const long long tstride = static_cast<long long>(HW) * C;
+  uint4 v[MAXT];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t)
+    if (t < T) v[t] = __ldg(reinterpret_cast<const uint4*>(x + base + t * tstride));
+  float sh[8];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg), b = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg + 1);
+    sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = b.x; sh[5] = b.y; sh[6] = b.z; sh[7] = b.w;
+  }
+  const int pt = kt / 2;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t >= T) break;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sh[j];
+#pragma unroll
+    for (int u = 0; u < MAXT; ++u) {
+      const int k = u - t + pt;
+      if (u < T && k >= 0 && k < kt) {
+        float f[8];
+        unpack8(v[u], f);
+        const float4* wp = reinterpret_cast<const float4*>(wgt + static_cast<long long>(k) * C) + 2 * cg;
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+        acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+        acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+        acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j], act);
+    *reinterpret_cast<uint4*>(y + base + t * tstride) = pack8(acc);
+  }
+}
+
+// Per-(sample, channel) sum over `rows` positions: grid (chunks, N); a block reduces its chunk of rows (threads: channel
+// pair x row lane) and adds its partial sums to out[n][c] (fp32 atomics; out is zeroed by the caller's memset node).
+__global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int c,
+                                   long long cstride, long long rows_per_block, float scale) {
+  extern __shared__ float part[];  // [blockDim.y][c]
+  const int n = blockIdx.y;
+  const long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const int pairs = c >> 1;
+  for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(x + (static_cast<long long>(n) * rows + r) * cstride)[p];
+      s0 += __bfloat162float(v.x);
+      s1 += __bfloat162float(v.y);
+    }
+    part[threadIdx.y * c + 2 * p] = s0;
+    part[threadIdx.y * c + 2 * p + 1] = s1;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y) {
+    float s = 0.f;
+    for (int j = 0; j < blockDim.y; ++j) s += part[j * c + ch];
+    atomicAdd(out + static_cast<long long>(n) * c + ch, s * scale);
+  }
+}
+
+// SE gate: gate[n][c] = sigmoid(W2 relu(W1 mean[n] + b1) + b2).  One block per sample.  resnet_helper.py:47-73
+__global__ void se_gate_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
+                               const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate, int c,
+                               int cfc) {
+  extern __shared__ float sm[];  // mean[c] + hidden[cfc]
+  float* m_s = sm;
+  float* h_s = sm + c;
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) m_s[i] = mean[static_cast<long long>(n) * c + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < cfc; j += nw) {
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s = fmaf(w1[static_cast<long long>(j) * c + i], m_s[i], s);
+    s = warp_sum(s);
+    if (lane == 0) h_s[j] = fmaxf(s + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float s = b2[i];
+    for (int j = 0; j < cfc; ++j) s = fmaf(w2[static_cast<long long>(i) * cfc + j], h_s[j], s);
+    gate[static_cast<long long>(n) * c + i] = 1.f / (1.f + __expf(-s));
+  }
+}
+
+// y = act(x * gate[n][c]) over [N][rows][C] bf16 (in place allowed).
+__global__ void scale_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate, __nv_bfloat16* __restrict__ y,
+                                 long long rows, int c8, long long total, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    const long long n = (i / c8) / rows;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    float f[8];
+    unpack8(u, f);
+    const float4* gp = reinterpret_cast<const float4*>(gate + n * (8ll * c8)) + 2 * cg;
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+    f[0] = act_f(f[0] * g0.x, act); f[1] = act_f(f[1] * g0.y, act); f[2] = act_f(f[2] * g0.z, act); f[3] = act_f(f[3] * g0.w, act);
+    f[4] = act_f(f[4] * g1.x, act); f[5] = act_f(f[5] * g1.y, act); f[6] = act_f(f[6] * g1.z, act); f[7] = act_f(f[7] * g1.w, act);
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+
+inline int grid_for(long long total, int block = 256) {
+  long long b = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+
+}  // namespace
+}  // namespace mspi
+
+using namespace mspi;
+
+extern "C" int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && wgt && shift && y, "mspi_dwconv3d_bn: null argument");
+  MSPI_CHECK_ARG(d->c % 8 == 0 && d->in_cstride % 8 == 0 && d->out_cstride % 8 == 0, "channels / strides must be multiples of 8");
+  MSPI_CHECK_ARG((d->kt & 1) && (d->kh & 1) && (d->kw & 1) && d->sh >= 1 && d->sw >= 1, "odd kernel, positive strides");
+  MSPI_CHECK_ARG(d->oh == (d->h + 2 * (d->kh / 2) - d->kh) / d->sh + 1 && d->ow == (d->w + 2 * (d->kw / 2) - d->kw) / d->sw + 1,
+                 "output extents do not match the geometry");
+  MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(wgt) |
+                   reinterpret_cast<uintptr_t>(shift)) & 15) == 0, "16-byte alignment");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int c8 = d->c / 8;
+  const long long total = static_cast<long long>(d->n) * d->t * d->oh * d->ow * c8;
+  if (d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1 && d->t <= 16 && d->in_cstride == d->c && d->out_cstride == d->c) {
+    const int HW = d->h * d->w;
+    const long long n_hw = static_cast<long long>(d->n) * HW;
+    const long long blocks = (n_hw * c8 + 127) / 128;
+    MSPI_CHECK_ARG(blocks < (1ll << 31), "grid out of range");
+    dwt_bn_kernel<16><<<static_cast<int>(blocks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), wgt, shift,
+                                                                    static_cast<__nv_bfloat16*>(y), n_hw, d->t, HW, d->c,
+                                                                    d->kt, d->act);
+  } else {
+    dw3d_kernel<<<grid_for(total), 256, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x), wgt, shift,
+                                                     static_cast<__nv_bfloat16*>(y), total, c8);
+  }
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_channel_mean(const void* x, float* out, int n, int64_t rows, int c, int64_t cstride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && out && n > 0 && rows > 0 && c > 0 && c % 2 == 0 && cstride >= c && cstride % 2 == 0 && c <= 2048,
+                 "mspi_channel_mean: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  MSPI_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n * c, stream));
+  const int ty = 8, tx = 32;
+  long long chunks = (static_cast<long long>(num_sms()) * 4 + n - 1) / n;  // ~4 blocks per SM over the batch
+  const long long max_chunks = (rows + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const long long rpb = (rows + chunks - 1) / chunks;
+  dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), n), block(tx, ty);
+  channel_sum_kernel<<<grid, block, sizeof(float) * ty * c, stream>>>(static_cast<const __nv_bfloat16*>(x), out, rows, c,
+                                                                      cstride, rpb, 1.f / static_cast<float>(rows));
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_se_gate(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                            float* gate, int n, int c, int cfc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(mean && w1 && b1 && w2 && b2 && gate && n > 0 && c > 0 && cfc > 0 && c + cfc <= 8192, "mspi_se_gate: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  se_gate_kernel<<<n, 256, sizeof(float) * (c + cfc), stream>>>(mean, w1, b1, w2, b2, gate, c, cfc);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_scale_act(const void* x, const float* gate, void* y, int n, int64_t rows, int c, int act, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && gate && y && n > 0 && rows > 0 && c > 0 && c % 8 == 0, "mspi_scale_act: bad argument");
+  MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0,
+                 "16-byte alignment");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int c8 = c / 8;
+  const long long total = static_cast<long long>(n) * rows * c8;
+  scale_act_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), gate,
+                                                        static_cast<__nv_bfloat16*>(y), rows, c8, total, act);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}

@@ -26,7 +26,7 @@ from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Act, Conv, fold_bn
 class ForwardPlan:
     def __init__(self, sd: Dict[str, torch.Tensor], batch: int, frames: int, height: int, width: int,
                  audio: bool = True, lateral_bool=(True, True, False, False), lateral_stride=(2, 2, 2, 2),
-                 pool_stride: int = 1, device="cuda", keep_taps: bool = False):
+                 pool_stride: int = 1, device="cuda", keep_taps: bool = False, encoder: str = "s3d"):
         assert frames % 4 == 0 and height % 32 == 0 and width % 32 == 0, \
             "T must be a multiple of 4 and H, W multiples of 32 (model_utils.py:506,566-570)"
         self.sd = {k: v.detach().to(device) for k, v in sd.items()}
@@ -34,6 +34,9 @@ class ForwardPlan:
         self.audio = audio
         self.device = device
         self.lateral_bool, self.lateral_stride, self.pool_stride = lateral_bool, lateral_stride, pool_stride
+        if encoder not in ("s3d", "x3dl", "slowfast4x16"):
+            raise Exception("Invalid Motion Encoder!")  # get_video_backbones.py:28-29
+        self.encoder = encoder
         self.steps: List[Tuple[str, Callable[[], None]]] = []
         self.flops = 0.0
         self.bytes_alloc = 0
@@ -126,10 +129,20 @@ class ForwardPlan:
             self.add("clips.to_padded_nhwc4", ops.clip_to_padded(self._inputs, "clips", self._frames, B, T, H, W))
         return self._frames
 
+    def padded_frames_variant(self, tag: str, frame_map, t_pad: int) -> torch.Tensor:
+        """Frame-selected / time-padded copies of the clip for the SlowFast stems (ops.clip_to_padded)."""
+        B, T, H, W = self.B, self.T, self.H, self.W
+        t_out = len(frame_map) if frame_map is not None else T
+        fr = torch.zeros((B * (t_out + 2 * t_pad), H + ops.PAD_EXTRA, W + ops.PAD_EXTRA, 4), dtype=torch.bfloat16,
+                         device=self.device)
+        self.bytes_alloc += fr.numel() * 2
+        self.add(f"clips.to_padded_nhwc4[{tag}]", ops.clip_to_padded(self._inputs, "clips", fr, B, T, H, W, frame_map, t_pad))
+        return fr
+
     def stem_direct(self, name: str, w: torch.Tensor, scale, shift, k: int, stride: int, pad: int, act,
-                    out: Act) -> Act:
-        fr = self.padded_frames()
-        run = ops.stem_conv(fr, self.H, self.W, w, scale, shift, k, stride, pad, act, out, name)
+                    out: Act, frames: Optional[torch.Tensor] = None, clips: int = 0) -> Act:
+        fr = self.padded_frames() if frames is None else frames
+        run = ops.stem_conv(fr, self.H, self.W, w, scale, shift, k, stride, pad, act, out, name, clips=clips)
         self.add(name, run)
         self.flops += run.flops
         return out
@@ -226,6 +239,142 @@ class ForwardPlan:
         for i, v in enumerate((v1, v2, v3, v4)):
             self.tap(f"visnet.base{i + 1}", v)
         return v1, v2, v3, v4
+
+    # ------------------------------------------------------------------ PySlowFast-style ResNets (X3D-L, SlowFast)
+    @staticmethod
+    def _pad_rows(t: torch.Tensor, n: int) -> torch.Tensor:
+        if t.shape[0] == n:
+            return t
+        out = torch.zeros((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[: t.shape[0]] = t
+        return out
+
+    @staticmethod
+    def _pad_cin(w: torch.Tensor, n: int) -> torch.Tensor:
+        if w.shape[1] == n:
+            return w
+        out = torch.zeros((w.shape[0], n) + tuple(w.shape[2:]), dtype=w.dtype, device=w.device)
+        out[:, : w.shape[1]] = w
+        return out
+
+    def res_shortcut(self, q: str, x: Act, stride: int) -> Act:
+        """ResBlock projection shortcut: 1x1x1 conv with spatial stride + BN (resnet_helper.py:556-570, 586-587)."""
+        if (q + ".branch1.weight") not in self.sd:
+            return x
+        sc, sh = self.bn(q + ".branch1_bn", 1e-5)
+        return self.conv(q + ".branch1", x, self.P(q + ".branch1.weight"), sc, sh, stride=(1, stride, stride))
+
+    def x3d_block(self, q: str, x: Act, stride: int, out: Optional[Act] = None) -> Act:
+        """ResBlock(X3DTransform): a 1x1x1+BN+ReLU -> b depthwise 3x3x3 (stride s)+BN -> [SE] -> Swish -> c 1x1x1+BN;
+        relu(shortcut + .).  resnet_helper.py:213-351, 580-590.  The inner width (54/108) is padded to a multiple of 8
+        with zero weights so every tensor keeps 16-byte channel vectors."""
+        inner = self.P(q + ".branch2.a.weight").shape[0]
+        ip = -(-inner // 8) * 8
+        sc, sh = self.bn(q + ".branch2.a_bn", 1e-5)
+        a = self.conv(q + ".branch2.a", x, self._pad_rows(self.P(q + ".branch2.a.weight"), ip), self._pad_rows(sc, ip),
+                      self._pad_rows(sh, ip), act=ACT_RELU)
+        has_se = (q + ".branch2.se.fc1.weight") in self.sd
+        sc, sh = self.bn(q + ".branch2.b_bn", 1e-5)
+        b = self.new(x.n, x.t, x.h // stride, x.w // stride, ip)
+        self.add(q + ".branch2.b", ops.dwconv3d_bn(a, b, self.P(q + ".branch2.b.weight"), sc, sh, stride,
+                                                   ops.ACT_NONE if has_se else ops.ACT_SWISH))
+        self.flops += 2.0 * b.pixels * inner * 27
+        if has_se:
+            se = q + ".branch2.se."
+            for nm, fn in zip(("mean", "fc", "scale+swish"),
+                              ops.se_block(b, self.P(se + "fc1.weight"), self.P(se + "fc1.bias"), self.P(se + "fc2.weight"),
+                                           self.P(se + "fc2.bias"))):
+                self.add(se + nm, fn)
+        short = self.res_shortcut(q, x, stride)
+        sc, sh = self.bn(q + ".branch2.c_bn", 1e-5)
+        return self.conv(q + ".branch2.c", b, self._pad_cin(self.P(q + ".branch2.c.weight"), ip), sc, sh, act=ACT_RELU,
+                         out=out, residual=short, out_dtype=out.dtype if out is not None else torch.bfloat16)
+
+    def x3d(self, v4_out: Optional[Act]):
+        """X3D(features_only).forward, backbones/X3D.py:232-246; stem: stem_helper.py:207-290."""
+        from .backbones.X3D import DEPTHS
+        p = "visnet."
+        B, T, H, W = self.B, self.T, self.H, self.W
+        q = p + "s1.pathway0_stem"
+        xy = self.stem_direct(q + ".conv_xy", self.P(q + ".conv_xy.weight"), None, None, 3, 2, 1, ACT_NONE,
+                              self.new(B, T, H // 2, W // 2, 24))
+        sc, sh = self.bn(q + ".bn", 1e-5)
+        x = self.new(B, T, H // 2, W // 2, 24)
+        self.add(q + ".conv+bn", ops.dwconv3d_bn(xy, x, self.P(q + ".conv.weight"), sc, sh, 1, ACT_RELU))
+        self.flops += 2.0 * x.pixels * 24 * 5
+        feats = []
+        for si, depth in enumerate(DEPTHS):
+            for i in range(depth):
+                last = si == 3 and i == depth - 1
+                x = self.x3d_block(f"{p}s{si + 2}.pathway0_res{i}", x, 2 if i == 0 else 1, v4_out if last else None)
+            feats.append(x)
+            self.tap(f"visnet.base{si + 1}", x)
+        return feats
+
+    def bottleneck_block(self, q: str, x: Act, stride: int, tk: int, out: Optional[Act] = None) -> Act:
+        """ResBlock(BottleneckTransform): (tk,1,1)+BN+ReLU -> (1,3,3)/s+BN+ReLU -> 1x1x1+BN; relu(shortcut + .).
+        resnet_helper.py:354-487, 580-590"""
+        sc, sh = self.bn(q + ".branch2.a_bn", 1e-5)
+        a = self.conv(q + ".branch2.a", x, self.P(q + ".branch2.a.weight"), sc, sh, pad=(tk // 2, 0, 0), act=ACT_RELU)
+        sc, sh = self.bn(q + ".branch2.b_bn", 1e-5)
+        b = self.conv(q + ".branch2.b", a, self.P(q + ".branch2.b.weight"), sc, sh, stride=(1, stride, stride), pad=(0, 1, 1),
+                      act=ACT_RELU)
+        short = self.res_shortcut(q, x, stride)
+        sc, sh = self.bn(q + ".branch2.c_bn", 1e-5)
+        return self.conv(q + ".branch2.c", b, self.P(q + ".branch2.c.weight"), sc, sh, act=ACT_RELU, out=out, residual=short,
+                         out_dtype=out.dtype if out is not None else torch.bfloat16)
+
+    def slowfast(self, v4_out: Optional[Act]):
+        """SlowFast.forward (backbones/sf.py:364-385) on [slow = frames 0,4,12,T-1 ; fast = all frames]
+        (model_utils.py:521-524)."""
+        from .backbones.sf import DEPTHS, SLOW_FRAMES, TK_FAST, TK_SLOW
+        p = "visnet."
+        B, T, H, W = self.B, self.T, self.H, self.W
+        ts = len(SLOW_FRAMES)
+        # stems: (k,7,7)/s(1,2,2) + BN + ReLU + MaxPool(1,3,3)/s(1,2,2)   stem_helper.py:128-204
+        fr_s = self.padded_frames_variant("slow", SLOW_FRAMES, 0)
+        sc, sh = self.bn(p + "s1.pathway0_stem.bn", 1e-5)
+        xs = self.stem_direct(p + "s1.pathway0_stem.conv", self.P(p + "s1.pathway0_stem.conv.weight"), sc, sh, 7, 2, 3,
+                              ACT_RELU, self.new(B, ts, H // 2, W // 2, 64), frames=fr_s)
+        fr_f = self.padded_frames_variant("fast", None, 2)
+        sc, sh = self.bn(p + "s1.pathway1_stem.bn", 1e-5)
+        xf = self.stem_direct(p + "s1.pathway1_stem.conv", self.P(p + "s1.pathway1_stem.conv.weight"), sc, sh, 7, 2, 3,
+                              ACT_RELU, self.new(B, T, H // 2, W // 2, 8), frames=fr_f, clips=B)
+        cat = self.new(B, ts, H // 4, W // 4, 64 + 16)
+        self.pool(p + "s1.pathway0_stem.pool", xs, (1, 3, 3), (1, 2, 2), (0, 1, 1), cat.slice(0, 64))
+        xf = self.pool(p + "s1.pathway1_stem.pool", xf, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+
+        def fuse(q: str, xf: Act, dst: Act):
+            """FuseFastToSlow: (5,1,1)/s(4,1,1) conv + BN + ReLU written next to the slow features (sf.py:101-159)."""
+            sc, sh = self.bn(q + ".bn", 1e-5)
+            self.conv(q + ".conv_f2s", xf, self.P(q + ".conv_f2s.weight"), sc, sh, stride=(4, 1, 1), pad=(2, 0, 0),
+                      act=ACT_RELU, out=dst)
+
+        fuse(p + "s1_fuse", xf, cat.slice(64, 16))
+        xs = cat
+        feats = []
+        for si, depth in enumerate(DEPTHS):
+            outs, outf = 256 * 2 ** si, 32 * 2 ** si
+            stride = 1 if si == 0 else 2
+            nxt = None
+            for i in range(depth):
+                st = stride if i == 0 else 1
+                lastb = i == depth - 1
+                dst = None
+                if lastb and si < 3:
+                    nxt = self.new(B, ts, xs.h // st, xs.w // st, outs + 2 * outf)
+                    dst = nxt.slice(0, outs)
+                elif lastb and si == 3:
+                    dst = v4_out
+                xs = self.bottleneck_block(f"{p}s{si + 2}.pathway0_res{i}", xs, st, TK_SLOW[si], dst)
+                if si < 3 or not lastb or True:
+                    xf = self.bottleneck_block(f"{p}s{si + 2}.pathway1_res{i}", xf, st, TK_FAST[si])
+            if si < 3:
+                fuse(f"{p}s{si + 2}_fuse", xf, nxt.slice(outs, 2 * outf))
+                xs = nxt
+            feats.append(xs)
+            self.tap(f"visnet.base{si + 1}", xs)
+        return feats
 
     # ------------------------------------------------------------------ ResNet18 audio (backbones/resnet.py)
     def resnet18(self) -> Act:
@@ -430,7 +579,8 @@ class ForwardPlan:
             w1 = self.P(p + ".1.weight").float()[:, :, :, 0, 0]  # [de, de, s]
             w = torch.einsum("omk,mi->oik", w1, w0)[:, :, :, None, None]  # [de, cin, s, 1, 1]
             bias = torch.einsum("omk,m->o", w1, b0)
-            y = self.conv(p + ".0+1", x, w, None, bias, stride=(s, 1, 1), out_dtype=torch.float32, split_weights=True)
+            y = self.conv(p + ".0+1", x, w, None, bias, stride=(s, 1, 1), out_dtype=torch.float32, dtype=x.dtype,
+                          split_weights=x.dtype == torch.bfloat16)
             self.flops += 2.0 * y.pixels * w1.shape[0] * w1.shape[1] * s  # the reference's separate temporal conv
             i = 2
         elif x.dtype == torch.float32:
@@ -505,14 +655,17 @@ class ForwardPlan:
         o1, o0 = self.convnext()
         masks = self.adapter(o1, o0)
         h32, w32 = self.H // 32, self.W // 32
+        visnet = {"s3d": self.s3d, "x3dl": self.x3d, "slowfast4x16": self.slowfast}[self.encoder]
+        c4 = {"s3d": 1024, "x3dl": 192, "slowfast4x16": 2048}[self.encoder]
+        t4 = self.T if self.encoder == "x3dl" else self.T // 4   # X3D keeps all 16 frames (X3D.py), the others end on 4
         if self.audio:
-            v4cat = self.new(B, self.T // 4, h32, w32, 1024 + 512, torch.float32)  # cat([v4, vis_sync]) feeds the decoder
-            v1, v2, v3, v4 = self.s3d(v4cat.slice(0, 1024))
+            v4cat = self.new(B, t4, h32, w32, c4 + 512, torch.float32)  # cat([v4, vis_sync]) feeds the decoder
+            v1, v2, v3, v4 = visnet(v4cat.slice(0, c4))
             aud = self.resnet18()
             self.sync_block(v4, aud, v4cat)
             v4in = v4cat
         else:
-            v1, v2, v3, v4 = self.s3d(None)
+            v1, v2, v3, v4 = visnet(None)
             v4in = v4
             self.loss = torch.zeros((1,), dtype=torch.float32, device=self.device)
         s3 = self.lateral(3, v4in)

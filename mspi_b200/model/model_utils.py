@@ -197,7 +197,7 @@ class _SaliencyBase(nn.Module):
             m = self.cfg.MODEL
             plan = ForwardPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL),
                                lateral_stride=tuple(m.LATERAL_STRIDE), pool_stride=m.S3D.POOL_STRIDE,
-                               device=clips.device, keep_taps=self.keep_taps)
+                               device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER)
             if self.use_cuda_graph:
                 plan.capture()
             self._plans[key] = plan

@@ -16,7 +16,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MSPI_BF16, MSPI_F32, ConvDesc, DwDesc,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, MSPI_BF16, MSPI_F32, ConvDesc, Dw3dDesc, DwDesc,
                    LnDesc, PatchDesc, PoolDesc, UpDesc)
 
 _DT = {torch.bfloat16: MSPI_BF16, torch.float32: MSPI_F32}
@@ -208,6 +208,8 @@ class Conv:
             return "shift"
         if sh == 1 and sw == 1 and self.kh == 1 and self.kw == 1 and x.t % st == 0:
             return "tstride"
+        if (self.kt, self.kh, self.kw) == (1, 1, 1) and st == 1 and self.pad == (0, 0, 0):
+            return "pick"  # 1x1x1 conv with spatial stride (ResBlock.branch1, resnet_helper.py:556-566): a strided view
         return "gather"
 
     def _pack(self, w5: torch.Tensor):
@@ -244,6 +246,14 @@ class Conv:
             a_str = (1, x.cs, x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
             o_dims = (ow, oh, ot, x.n)
             offs = [(kw - pw, kh - ph, kt - pt, 0) for kt in range(self.kt) for kh in range(self.kh) for kw in range(self.kw)]
+            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+            x_ptr = x.ptr
+        elif mode == "pick":
+            packed, taps, cin_pad = self._pack(self.w_raw)
+            a_dims = (x.c, ow, oh, x.t, x.n)
+            a_str = (1, sw * x.cs, sh * x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
+            o_dims = (ow, oh, ot, x.n)
+            offs = [(0, 0, 0, 0)]
             ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
             x_ptr = x.ptr
         elif mode == "tstride":
@@ -336,22 +346,33 @@ class Conv:
 PAD_T, PAD_L, PAD_EXTRA = 3, 4, 8   # padded frame: rows 3 above / 5 below, columns 4 left / 4 right (ops.stem_conv)
 
 
-def clip_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int, h: int, w: int) -> Callable[[], None]:
-    """fp32 NCDHW clip (looked up as holder[key] at run time) -> bf16 zero-padded [N*T, H+8, W+8, 4] frames."""
+def clip_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int, h: int, w: int,
+                   frame_map: Optional[Sequence[int]] = None, t_pad: int = 0) -> Callable[[], None]:
+    """fp32 NCDHW clip (looked up as holder[key] at run time) -> bf16 zero-padded [N*T', H+8, W+8, 4] frames.
+    frame_map selects / re-orders source frames (SlowFast slow pathway); t_pad leaves that many zero frames at both
+    ends of every clip (temporal padding of the SlowFast fast stem): T' = len(frame_map or range(t)) + 2*t_pad."""
     lib = _lib.load()
     hp, wp = h + PAD_EXTRA, w + PAD_EXTRA
-    assert tuple(frames.shape) == (n * t, hp, wp, 4) and frames.dtype == torch.bfloat16
+    fm = list(range(t)) if frame_map is None else [f % t for f in frame_map]
+    t_out = len(fm)
+    fpc = t_out + 2 * t_pad
+    assert tuple(frames.shape) == (n * fpc, hp, wp, 4) and frames.dtype == torch.bfloat16
     fp = _ptr(frames)
+    arr = (C.c_int32 * t_out)(*fm)
 
-    def run(_keep=(frames,)):
-        _lib.check(lib.mspi_clip_to_padded_nhwc4(_ptr(holder[key]), fp, n, t, h, w, PAD_T, PAD_L, hp, wp, _stream()),
-                   "clip_to_padded_nhwc4")
+    def run(_keep=(frames, arr)):
+        if frame_map is None and t_pad == 0:
+            rc = lib.mspi_clip_to_padded_nhwc4(_ptr(holder[key]), fp, n, t, h, w, PAD_T, PAD_L, hp, wp, _stream())
+        else:
+            rc = lib.mspi_clip_frames_to_padded_nhwc4(_ptr(holder[key]), fp, n, t, h, w, PAD_T, PAD_L, hp, wp,
+                                                      C.cast(arr, C.c_void_p), t_out, fpc, t_pad, _stream())
+        _lib.check(rc, "clip_to_padded_nhwc4")
 
     return run
 
 
 def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale, shift, k: int, stride: int, pad: int,
-              act: int, y: "Act", name: str = "stem") -> Callable[[], None]:
+              act: int, y: "Act", name: str = "stem", clips: int = 0) -> Callable[[], None]:
     """(1,k,k)/stride conv with Cin=3 straight off the padded 4-channel frames (no im2col buffer).
 
     One row of the filter (k taps x 4 channels, at most 8 pixels) is a contiguous 16-byte aligned run of the frame;
@@ -365,9 +386,15 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     nf, hp, wp, _ = frames.shape
     cout = weight.shape[0]
     w5 = weight.detach().float().to(frames.device)
-    if w5.dim() == 5:
-        w5 = w5[:, :, 0]
-    assert w5.shape[1] == 3 and w5.shape[2] == w5.shape[3] == k
+    if w5.dim() == 4:
+        w5 = w5[:, :, None]
+    kt = w5.shape[2]
+    # kt > 1 (SlowFast fast stem, (5,7,7)): `frames` holds kt//2 zero frames at both ends of each of the `clips` clips
+    # and the conv runs once per clip, so a temporal tap is a plain offset along the clip's own frame axis.
+    assert w5.shape[1] == 3 and w5.shape[3] == w5.shape[4] == k and (kt == 1 or clips > 0)
+    if kt > 1:
+        fpc = nf // clips
+        nf = fpc - (kt - 1)  # frames produced per launch
     oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     if (k, stride, pad) == (7, 2, 3):
         run_px, x_lead = 8, 1     # window starts one pixel before tap 0 (alignment)
@@ -375,22 +402,25 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     elif (k, stride, pad) == (4, 4, 0):
         run_px, x_lead = 4, 0
         row0, col0 = PAD_T, PAD_L
+    elif (k, stride, pad) == (3, 2, 1):   # X3D stem conv_xy (stem_helper.py:262-270): 4-px window from 2*ow-2
+        run_px, x_lead = 4, 1
+        row0, col0 = PAD_T - pad, PAD_L - pad - x_lead
     else:
         raise ValueError(f"stem_conv: unsupported geometry k={k} stride={stride} pad={pad}")
     run_el = run_px * 4
     assert (col0 * 4 * 2) % 16 == 0 and (stride * 4 * 2) % 16 == 0 and row0 >= 0 and col0 >= 0
     # weight matrix [cout16][k taps][run_px][4]
     rows16 = -(-cout // 16) * 16
-    wm = torch.zeros((rows16, k, run_px, 4), dtype=torch.float32, device=frames.device)
-    wm[:cout, :, x_lead:x_lead + k, :3] = w5.permute(0, 2, 3, 1)
-    packed = wm.reshape(rows16, k * run_el).to(torch.bfloat16).contiguous()
+    wm = torch.zeros((rows16, kt, k, run_px, 4), dtype=torch.float32, device=frames.device)
+    wm[:cout, :, :, x_lead:x_lead + k, :3] = w5.permute(0, 2, 3, 4, 1)
+    packed = wm.reshape(rows16, kt * k * run_el).to(torch.bfloat16).contiguous()
     # frame row of (oh, kh) = row0 + stride*oh + kh = row0 + stride*(oh + kh // stride) + kh % stride
     n_r, n_j = min(stride, k), (k - 1) // stride + 1
     assert row0 + stride * (oh - 1) + k - 1 < hp and col0 + stride * (ow - 1) + run_px - 1 < wp
     d = ConvDesc()
     d.a_dtype = MSPI_BF16
     d.k_row_bytes = run_el * 2
-    a_dims = (run_el, n_r, ow, oh + n_j - 1, nf)
+    a_dims = (run_el, n_r, ow, oh + n_j - 1, nf + kt - 1)
     a_str = (1, wp * 4, stride * 4, stride * wp * 4, hp * wp * 4)
     for j in range(5):
         d.a_dims[j] = a_dims[j]
@@ -404,9 +434,12 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
         d.o_dims[j] = o_dims[j]
         d.o_strides[j] = ostr[j]
         d.r_strides[j] = 0
-    d.ntaps = k
-    for kh in range(k):
-        d.tap_off[kh][0], d.tap_off[kh][1], d.tap_off[kh][2], d.tap_off[kh][3] = kh % stride, 0, kh // stride, 0
+    d.ntaps = kt * k
+    assert d.ntaps <= _lib.MAX_TAPS
+    for it in range(kt):
+        for kh in range(k):
+            i = it * k + kh
+            d.tap_off[i][0], d.tap_off[i][1], d.tap_off[i][2], d.tap_off[i][3] = kh % stride, 0, kh // stride, it
     d.cin_pad = run_el
     d.cout, d.w_rows = cout, rows16
     d.bn = choose_bn(cout, 64 if y.dtype == torch.bfloat16 else 32)
@@ -414,18 +447,90 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     d.act = act
     sc = None if scale is None else scale.detach().float().contiguous().to(frames.device)
     sh = None if shift is None else shift.detach().float().contiguous().to(frames.device)
-    x_ptr = _ptr(frames, (row0 * wp + col0) * 4 * 2)
-    w_ptr, y_ptr = _ptr(packed), y.ptr
-    assert y.pixels == nf * oh * ow and y.c == cout
+    launches = 1 if kt == 1 else clips
+    x_ptrs = [_ptr(frames, ((b * (nf + kt - 1) * hp + row0) * wp + col0) * 4 * 2) for b in range(launches)]
+    es_y = _ES[y.dtype]
+    y_ptrs = [_ptr(y.buf, (b * nf * oh * ow * y.cs + y.c0) * es_y) for b in range(launches)]
+    w_ptr = _ptr(packed)
+    assert y.pixels == launches * nf * oh * ow and y.c == cout
 
     def run(_keep=(frames, packed, sc, sh, y.buf, d)):
-        _lib.check(lib.mspi_conv_gemm(C.byref(d), x_ptr, w_ptr, _ptr(sc), _ptr(sh), C.c_void_p(0), y_ptr, _stream()),
-                   f"conv_gemm[{name}]")
+        for xp_, yp_ in zip(x_ptrs, y_ptrs):
+            _lib.check(lib.mspi_conv_gemm(C.byref(d), xp_, w_ptr, _ptr(sc), _ptr(sh), C.c_void_p(0), yp_, _stream()),
+                       f"conv_gemm[{name}]")
 
     run.mode = "stem"
     run.desc = d
-    run.flops = 2.0 * nf * oh * ow * cout * 3 * k * k
+    run.flops = 2.0 * launches * nf * oh * ow * cout * 3 * kt * k * k
     return run
+
+
+# ------------------------------------------------------------------------------------------ X3D pieces
+def dwconv3d_bn(x: Act, y: Act, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                stride_hw: int = 1, act: int = ACT_NONE) -> Callable[[], None]:
+    """Depthwise Conv3d [C,1,kt,kh,kw] ("same" padding, stride (1,s,s)) + per-channel scale/shift + activation.
+    The channel count of x / y may exceed the weight's (buffers padded to a multiple of 8): extra channels get zero
+    weights and zero shift, so they stay zero."""
+    lib = _lib.load()
+    w = weight.detach().float()
+    c, _, kt, kh, kw = w.shape
+    cp = x.c
+    assert cp >= c and cp % 8 == 0 and y.c == cp and x.dtype == y.dtype == torch.bfloat16
+    dev = x.buf.device
+    wt = torch.zeros((kt * kh * kw, cp), dtype=torch.float32, device=dev)
+    sc = torch.ones(c, device=dev) if scale is None else scale.detach().float().to(dev)
+    wt[:, :c] = (w.reshape(c, -1).to(dev) * sc[:, None]).t()
+    sh = torch.zeros(cp, dtype=torch.float32, device=dev)
+    if shift is not None:
+        sh[:c] = shift.detach().float().to(dev)
+    d = Dw3dDesc()
+    d.n, d.t, d.h, d.w, d.c = x.n, x.t, x.h, x.w, cp
+    d.in_cstride, d.out_cstride = x.cs, y.cs
+    d.kt, d.kh, d.kw, d.sh, d.sw = kt, kh, kw, stride_hw, stride_hw
+    d.oh, d.ow = y.h, y.w
+    d.act = act
+    assert (y.n, y.t) == (x.n, x.t) and x.c0 % 8 == 0 and y.c0 % 8 == 0
+    xp, yp = x.ptr, y.ptr
+
+    def run(_keep=(x.buf, y.buf, wt, sh, d)):
+        _lib.check(lib.mspi_dwconv3d_bn(C.byref(d), xp, _ptr(wt), _ptr(sh), yp, _stream()), "dwconv3d_bn")
+
+    return run
+
+
+def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH) -> List[Callable[[], None]]:
+    """SE (+ the Swish that follows it in X3DTransform): x <- act(x * sigmoid(fc2(relu(fc1(mean_thw(x)))))), in place.
+    resnet_helper.py:47-73,327-333.  Three launches: channel mean, the two FCs, scale+act."""
+    lib = _lib.load()
+    dev = x.buf.device
+    cp, n = x.c, x.n
+    assert x.c0 == 0 and x.cs == cp and x.dtype == torch.bfloat16
+    w1 = fc1_w.detach().float().reshape(fc1_w.shape[0], -1).to(dev)
+    cfc, c = w1.shape
+    w1p = torch.zeros((cfc, cp), dtype=torch.float32, device=dev)
+    w1p[:, :c] = w1
+    w2p = torch.zeros((cp, cfc), dtype=torch.float32, device=dev)
+    w2p[:c] = fc2_w.detach().float().reshape(c, cfc).to(dev)
+    b1 = fc1_b.detach().float().contiguous().to(dev)
+    b2 = torch.zeros(cp, dtype=torch.float32, device=dev)
+    b2[:c] = fc2_b.detach().float().to(dev)
+    mean = torch.empty((n, cp), dtype=torch.float32, device=dev)
+    gate = torch.empty((n, cp), dtype=torch.float32, device=dev)
+    rows = x.t * x.h * x.w
+    xp = x.ptr
+    keep = (x.buf, w1p, w2p, b1, b2, mean, gate)
+
+    def k_mean(_keep=keep):
+        _lib.check(lib.mspi_channel_mean(xp, _ptr(mean), n, rows, cp, cp, _stream()), "channel_mean")
+
+    def k_gate(_keep=keep):
+        _lib.check(lib.mspi_se_gate(_ptr(mean), _ptr(w1p), _ptr(b1), _ptr(w2p), _ptr(b2), _ptr(gate), n, cp, cfc, _stream()),
+                   "se_gate")
+
+    def k_scale(_keep=keep):
+        _lib.check(lib.mspi_scale_act(xp, _ptr(gate), xp, n, rows, cp, act, _stream()), "scale_act")
+
+    return [k_mean, k_gate, k_scale]
 
 
 # ------------------------------------------------------------------------------------------ other ops

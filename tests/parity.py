@@ -13,10 +13,10 @@ import torch
 from oracle import mspi_oracle as orc
 
 
-def build_product_model(sd, audio=True, height=None):
-    from mspi_b200.config import cfg as base_cfg
+def build_product_model(sd, audio=True, height=None, encoder="s3d"):
+    from mspi_b200.config import cfg as base_cfg, select_motion_encoder
     from mspi_b200.model.model_utils import AudioVisualSaliencyModel, VisualSaliencyModel
-    cfg = copy.deepcopy(base_cfg)
+    cfg = select_motion_encoder(encoder, copy.deepcopy(base_cfg))
     cls = AudioVisualSaliencyModel if audio else VisualSaliencyModel
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cfg, load_pretrained=False)
@@ -36,14 +36,14 @@ def rel_l2(a, b):
 
 
 def run_forward_parity(height=64, width=64, batch=1, init="calibrated", seed=0, audio=True, input_seed=2023,
-                       tap_tol=3e-2, map_tol=1e-2, verbose=False):
-    sd = orc.make_state_dict(seed, init, audio=audio)
+                       tap_tol=3e-2, map_tol=1e-2, verbose=False, encoder="s3d"):
+    sd = orc.make_state_dict(seed, init, audio=audio, encoder=encoder)
     clips, aud = orc.make_inputs(batch, height, width, input_seed)
     taps_ref = {}
     t0 = time.time()
-    ref_out, ref_loss = orc.forward(sd, clips, aud if audio else None, taps_ref)
+    ref_out, ref_loss = orc.forward(sd, clips, aud if audio else None, taps_ref, encoder=encoder)
     t_cpu = time.time() - t0
-    model = build_product_model(sd, audio)
+    model = build_product_model(sd, audio, encoder=encoder)
     model.keep_taps = True
     if audio:
         out, loss = model(clips.cuda(), aud.cuda())

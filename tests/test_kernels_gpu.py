@@ -198,6 +198,89 @@ def test_stem_conv_on_padded_frames(k, stride, pad, cout, odt):
     assert _rel(got, ref) < (BF16_TOL if odt == torch.bfloat16 else 1e-4)
 
 
+def test_conv_1x1_spatial_stride_pick_mode():
+    """ResBlock.branch1 (1x1x1 conv, stride (1,2,2), resnet_helper.py:556-566) as a strided TMA view, no gather."""
+    got, ref, mode = _run_conv(24, 48, (1, 1, 1), (1, 2, 2), (0, 0, 0), (2, 3, 12, 20), seed=31)
+    assert mode == "pick" and _rel(got, ref) < BF16_TOL
+
+
+def test_clip_frame_map_and_time_padding():
+    """SlowFast inputs: slow pathway = frames [0,4,12,T-1] (model_utils.py:523); fast pathway time-padded by 2."""
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(22)
+    b, t, h, w = 2, 16, 8, 12
+    clip = torch.randn(b, 3, t, h, w, generator=g)
+    fm = (0, 4, 12, -1)
+    fr = torch.zeros(b * 4, h + 8, w + 8, 4, dtype=torch.bfloat16, device="cuda")
+    ops.clip_to_padded({"c": clip.cuda()}, "c", fr, b, t, h, w, fm, 0)()
+    fr2 = torch.zeros(b * (t + 4), h + 8, w + 8, 4, dtype=torch.bfloat16, device="cuda")
+    ops.clip_to_padded({"c": clip.cuda()}, "c", fr2, b, t, h, w, None, 2)()
+    torch.cuda.synchronize()
+    inner = fr[:, ops.PAD_T:ops.PAD_T + h, ops.PAD_L:ops.PAD_L + w, :3].float().cpu().view(b, 4, h, w, 3)
+    want = _bf(clip)[:, :, [0, 4, 12, 15]].permute(0, 2, 3, 4, 1)
+    assert torch.equal(inner, want)
+    v = fr2.view(b, t + 4, h + 8, w + 8, 4).float().cpu()
+    assert (v[:, :2] == 0).all() and (v[:, -2:] == 0).all()
+    assert torch.equal(v[:, 2:-2, ops.PAD_T:ops.PAD_T + h, ops.PAD_L:ops.PAD_L + w, :3], _bf(clip).permute(0, 2, 3, 4, 1))
+
+
+def test_stem_conv_temporal_taps_per_clip():
+    """SlowFast fast stem (5,7,7)/s(1,2,2) p(2,3,3), 3->8 (stem_helper.py:128-204): 35 taps, one launch per clip."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(23)
+    b, t, h, w, cout = 2, 16, 32, 64, 8
+    clip = torch.randn(b, 3, t, h, w, generator=g)
+    wgt = torch.randn(cout, 3, 5, 7, 7, generator=g) / (3 * 5 * 49) ** 0.5
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    fr = torch.zeros(b * (t + 4), h + 8, w + 8, 4, dtype=torch.bfloat16, device="cuda")
+    ops.clip_to_padded({"c": clip.cuda()}, "c", fr, b, t, h, w, None, 2)()
+    y = Act.empty(b, t, h // 2, w // 2, cout)
+    ops.stem_conv(fr, h, w, wgt, scale, shift, 7, 2, 3, 1, y, clips=b)()
+    torch.cuda.synchronize()
+    ref = F.conv3d(_bf(clip), _bf(wgt), None, (1, 2, 2), (2, 3, 3)) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    assert _rel(y.to_ncdhw().cpu(), ref.relu()) < BF16_TOL
+
+
+@pytest.mark.parametrize("c,stride,act", [(56, 2, 4), (112, 1, 0), (24, 1, 1)])
+def test_x3d_depthwise_and_se(c, stride, act):
+    """X3DTransform.b + b_bn (+Swish) and the SE path (resnet_helper.py:47-73,213-351) against PyTorch."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(24)
+    creal = c - 2 if c % 8 == 0 and c > 24 else c          # weights narrower than the padded buffers (54 -> 56)
+    n, t, h, w = 2, 4, 10, 12
+    x = torch.zeros(n, c, t, h, w)
+    x[:, :creal] = torch.randn(n, creal, t, h, w, generator=g)
+    k = (5, 1, 1) if c == 24 else (3, 3, 3)
+    wgt = torch.randn(creal, 1, *k, generator=g) * 0.3
+    scale, shift = torch.rand(creal, generator=g) + 0.5, torch.randn(creal, generator=g) * 0.1
+    xa = _act_from_ncdhw(x)
+    oh, ow = (h - 1) // stride + 1 if k[1] == 3 else h, (w - 1) // stride + 1 if k[2] == 3 else w
+    ya = Act.empty(n, t, oh, ow, c)
+    ops.dwconv3d_bn(xa, ya, wgt, scale, shift, stride, act)()
+    torch.cuda.synchronize()
+    ref = F.conv3d(_bf(x[:, :creal]), wgt, None, (1, stride, stride) if k[1] == 3 else 1, tuple(kk // 2 for kk in k), 1, creal)
+    ref = ref * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    ref = ref * torch.sigmoid(ref) if act == 4 else (ref.relu() if act == 1 else ref)
+    got = ya.to_ncdhw().cpu()
+    assert _rel(got[:, :creal], ref) < BF16_TOL and (got[:, creal:] == 0).all()
+    # SE + Swish in place on the conv output
+    cfc = 8
+    w1, b1 = torch.randn(cfc, creal, 1, 1, 1, generator=g) * 0.3, torch.randn(cfc, generator=g) * 0.1
+    w2, b2 = torch.randn(creal, cfc, 1, 1, 1, generator=g) * 0.3, torch.randn(creal, generator=g) * 0.1
+    for fn in ops.se_block(ya, w1, b1, w2, b2):
+        fn()
+    torch.cuda.synchronize()
+    y0 = got[:, :creal]
+    s = y0.mean((2, 3, 4), keepdim=True)
+    s = torch.sigmoid(F.conv3d(F.relu(F.conv3d(s, w1, b1)), w2, b2))
+    z = y0 * s
+    z = z * torch.sigmoid(z)
+    got2 = ya.to_ncdhw().cpu()
+    assert _rel(got2[:, :creal], z) < BF16_TOL and (got2[:, creal:] == 0).all()
+
+
 def test_maxpool_variants():
     from mspi_b200 import ops
     from mspi_b200.ops import Act

@@ -58,3 +58,20 @@ def test_forward_default_shape_and_metrics():
         r = ref[k].item()
         assert abs(v - r) <= 1e-3 * abs(r), (k, v, r)
     assert abs(loss.item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+
+
+@pytest.mark.parametrize("encoder,init,seed", [("x3dl", "calibrated", 3), ("x3dl", "default", 4),
+                                               ("slowfast4x16", "calibrated", 5), ("slowfast4x16", "default", 6)])
+def test_forward_parity_other_motion_encoders(encoder, init, seed):
+    """BASELINE configs 3 and 4: MSPI with the X3D-L and SlowFast 4x16 R50 motion encoders (config.py:29-74),
+    CUDA path vs the oracle (itself pinned to the live reference by tests/golden/{x3dl,sf}_*.pt)."""
+    from tests.parity import run_forward_parity
+    res = run_forward_parity(64, 96 if init == "default" else 64, 1, init=init, seed=seed, encoder=encoder, verbose=True)
+    print({k: v for k, v in res.items() if k not in ("ref_out", "out", "taps")})
+    assert res["worst_tap"] < 3e-2, res["taps"]
+    assert res["loss_abs"] < 1e-3
+    if init == "default":
+        assert res["map_maxabs_minmax"] < 1e-2
+    else:
+        rng = (res["ref_out"].max() - res["ref_out"].min()).item()
+        assert res["logit_maxabs"] / rng < 5e-2
