@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 T, H, W = 16, 224, 384
 ALGO_GFLOP_PER_CLIP = 416.05  # 2xMAC of the reference forward at 16x224x384 (FlopCounterMode)
+ALGO_GFLOP = {"s3d": 416.05, "x3dl": 414.75, "slowfast4x16": 434.61}
+ENC_NAME = {"s3d": "MSPI-S3D", "x3dl": "MSPI-X3D-L", "slowfast4x16": "MSPI-SlowFast4x16-R50"}
 
 
 def read_peaks():
@@ -159,6 +161,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
     ap.add_argument("--impl", default="mspi_b200", choices=["mspi_b200", "reference"])
+    ap.add_argument("--encoder", default="s3d", choices=["s3d", "x3dl", "slowfast4x16"],
+                    help="motion encoder (BASELINE configs: s3d = headline, x3dl = config 3, slowfast4x16 = config 4)")
     ap.add_argument("--no-graph", action="store_true", help="replay the kernel list eagerly instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this file")
@@ -182,11 +186,13 @@ def main():
     K, B = args.steps, args.batch
 
     from mspi_b200 import _lib
-    from mspi_b200.config import cfg as base_cfg
+    from mspi_b200.config import cfg as base_cfg, select_motion_encoder
     from mspi_b200.model.model_utils import AudioVisualSaliencyModel
     torch.manual_seed(2023)
+    algo_gflop = ALGO_GFLOP[args.encoder]
     with contextlib.redirect_stdout(io.StringIO()):
-        model = AudioVisualSaliencyModel(copy.deepcopy(base_cfg), load_pretrained=False)  # random init, synthetic data
+        model = AudioVisualSaliencyModel(select_motion_encoder(args.encoder, copy.deepcopy(base_cfg)),
+                                         load_pretrained=False)  # random init, synthetic data
     model = model.to(dev).eval()
     model.use_cuda_graph = not args.no_graph
 
@@ -344,17 +350,17 @@ def main():
     if rank == 0:
         peaks = read_peaks()
         line = {
-            "metric": "clips/sec MSPI-S3D inference", "value": value, "unit": "clips/s", "n_gpus": world, "steps": K,
+            "metric": f"clips/sec {ENC_NAME[args.encoder]} inference", "value": value, "unit": "clips/s", "n_gpus": world, "steps": K,
             "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"MSPI-S3D (S3D + ResNet18 audio + ConvNeXt-T image encoder + fusion decoder) inference, "
+            "config": {"workload": f"{ENC_NAME[args.encoder]} ({args.encoder} motion encoder + ResNet18 audio + ConvNeXt-T image encoder + fusion decoder) inference, "
                                    f"{B} clips/GPU/step of 16x{H}x{W} fp32 + [1,257,111] spectrograms, random init",
                        "batch_per_gpu": B, "clip": [3, T, H, W], "parallelism": f"dp{world} (clip sharding, NCCL all-gather of maps)",
                        "precision": "bf16 tensor cores (encoders), tf32 tensor cores + fp32 storage (fusion/decoder), fp32 accumulate",
                        "cuda_graph": bool(model.use_cuda_graph),
                        "l2": f"inputs larger than L2: {B * 3 * T * H * W * 4 / 2**20:.0f} MiB of clips per step, {n_sets} rotating sets"},
-            "tensor_frac_of_peak_whole_step": value / world * ALGO_GFLOP_PER_CLIP / 1e3 / peaks["bf16_sustained"],
-            "algorithmic_gflop_per_clip": ALGO_GFLOP_PER_CLIP,
+            "tensor_frac_of_peak_whole_step": value / world * algo_gflop / 1e3 / peaks["bf16_sustained"],
+            "algorithmic_gflop_per_clip": algo_gflop,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host fp32 inputs, H2D of step i+1 overlapped with step i on a copy stream"},
             "gpu_launches": launches_per_fwd * K,

@@ -253,6 +253,12 @@ int mspi_logsoftmax2d(const float* x, float* y, int b, int64_t pixels, void* str
 int mspi_saliency_metrics(const float* pred, int pred_is_log, const float* gt, const float* fix,
                           float* out, float* work, int b, int64_t pixels, void* stream);
 
+/* Post-processing of the inference driver (inference.py:65-91): 11x11 Gaussian blur (sigma 2.0, reflect-101) of the LOG map
+ * -> exp -> bilinear resize to (oh, ow) (cv2 INTER_LINEAR) -> per-map min-max -> round(255 x) -> uint8 [b][oh][ow].
+ * work: fp32 scratch of b*h*w + b*oh*ow + 2*b elements. */
+int mspi_postprocess_maps(const float* log_maps, uint8_t* out, float* work, int b, int h, int w, int oh, int ow,
+                          void* stream);
+
 /* Log power spectrogram front end (inference.py:24-63, avsp_dataloader.py:51-80):
  * wave fp32 [B][n] -> out fp32 [B][257][frames_out]; STFT n_fft=512, hop=160, periodic Hann,
  * center=True reflect pad, |.|^2, log(x+1e-6), per-frame standardise over the 257 bins

@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""Inference entry point — same command line, dataset layout and output files as the reference's inference.py
+(`python inference.py --weight W --path_data D --dataset AVAD --split 2 --clip_size 16 --save_path out`),
+driving the B200 kernels.
+
+What is kept (reference inference.py line numbers):
+  * the fold-list format and directory layout (:97-118), the sliding window with stride one frame (:120-150), the
+    time-flipped clips that cover the first clip_size-1 frames (:142-149), the audio window of len_snippet=32 frames
+    (:24, quirk C.4), the forced 640x480 output (:127), blur-of-the-log-map post-processing (:85-91), one 8-bit image
+    per input frame named like the frame (:91).
+What is done differently (same results, fewer passes):
+  * windows are batched (`--batch`, default 8) instead of one forward per frame;
+  * the wav is decoded and resampled once per video, not once per frame (:28-30 re-reads the whole file every step);
+    the spectrogram of each window is computed on the GPU (mspi_logspec);
+  * blur / exp / resize / min-max / uint8 run on the GPU (mspi_postprocess_maps); only uint8 images cross PCIe.
+There is no CPU fallback: a CUDA device (sm_100a) is required.
+"""
+import argparse
+import glob
+import os
+
+import numpy as np
+import torch
+
+from mspi_b200.audio import log_spectrogram
+from mspi_b200.config import cfg
+from mspi_b200.model.model_utils import AudioVisualSaliencyModel as SalModel
+from mspi_b200.postprocess import postprocess_maps
+
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)  # timm.data.constants, inference.py:8
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+SAMPLE_RATE = 16000
+SPECTRO_FRAMES = 111
+
+
+def torch_transform(path, resolution=(224, 384)):
+    """Resize((224,384)) -> ToTensor -> Normalize(ImageNet), inference.py:154-165.  Returns (tensor[3,H,W], (w,h))."""
+    from PIL import Image
+    img = Image.open(path).convert('RGB')
+    sz = img.size
+    img = img.resize((resolution[1], resolution[0]), Image.BILINEAR)
+    x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1)
+    mean = torch.tensor(IMAGENET_DEFAULT_MEAN).view(3, 1, 1)
+    std = torch.tensor(IMAGENET_DEFAULT_STD).view(3, 1, 1)
+    return (x - mean) / std, sz
+
+
+def load_audio(audio_path):
+    """torchaudio.load + Resample(sr -> 16 kHz) + stereo mean (inference.py:28-32), once per video.
+    Returns a mono float32 tensor [n] or None when the file does not exist (the reference then feeds 0.02)."""
+    if not os.path.exists(audio_path):
+        return None
+    import torchaudio
+    try:
+        audio, sr = torchaudio.load(audio_path)
+    except (ImportError, RuntimeError):  # torchaudio >= 2.9 decodes through torchcodec; plain PCM wav needs neither
+        from scipy.io import wavfile
+        sr, data = wavfile.read(audio_path)
+        data = np.asarray(data)
+        scale = float(np.iinfo(data.dtype).max) if np.issubdtype(data.dtype, np.integer) else 1.0
+        audio = torch.from_numpy(data.astype(np.float32) / scale)
+        audio = audio.t().contiguous() if audio.dim() == 2 else audio.unsqueeze(0)
+    audio = torchaudio.transforms.Resample(orig_freq=sr, new_freq=SAMPLE_RATE)(audio)
+    if audio.shape[0] == 2:
+        audio = torch.mean(audio, dim=0).unsqueeze(0)
+    return audio[0].contiguous()
+
+
+def audio_window(audio, start_idx, fps, len_snippet=32, flip=False):
+    """The waveform slice get_audio_feature takes for a window (inference.py:38-43)."""
+    start = int(np.round((start_idx / float(fps)) * SAMPLE_RATE))
+    end = int(np.round(((start_idx + len_snippet + 1) / float(fps)) * SAMPLE_RATE))
+    w = audio[start:end]
+    return torch.flip(w, [0]) if flip else w
+
+
+def audio_features(audio, windows, fps, device):
+    """[B,1,257,111] spectrogram features for a list of (start_idx, flip) windows; GPU STFT per distinct slice length."""
+    out = torch.full((len(windows), 1, 257, SPECTRO_FRAMES), 0.02, dtype=torch.float32, device=device)
+    if audio is None:
+        return out
+    slices = [audio_window(audio, s, fps, flip=f) for s, f in windows]
+    by_len = {}
+    for i, w in enumerate(slices):
+        by_len.setdefault(w.numel(), []).append(i)
+    for n, idx in by_len.items():
+        if n < 512:  # shorter than one STFT frame after the clip's end: the reference would fail; keep the pad value
+            continue
+        batch = torch.stack([slices[i] for i in idx]).to(device, non_blocking=True)
+        out[idx] = log_spectrogram(batch, SPECTRO_FRAMES)
+    return out
+
+
+@torch.no_grad()
+def process_batch(model, clips, feats, names, vname, img_size, args):
+    """Forward + GPU post-processing of a batch of windows; writes one image per window (inference.py:72-91)."""
+    import cv2
+    if args.use_sound:
+        pred = model(clips, feats)[0]
+    else:
+        pred = model(clips)[0]
+    imgs = postprocess_maps(pred, img_size).cpu().numpy()
+    out_dir = os.path.join(args.save_path, vname)
+    os.makedirs(out_dir, exist_ok=True)
+    for img, name in zip(imgs, names):
+        cv2.imwrite(os.path.join(out_dir, name), img)
+
+
+def inference_dataset(model, args, device):
+    len_temporal = args.clip_size
+    if args.dataset == 'DIEM':
+        file_name = 'DIEM_list_test_fps.txt'
+    else:
+        file_name = '{}_list_test_{}_fps.txt'.format(args.dataset, args.split)
+    list_data, videos_fps = [], {}
+    with open(os.path.join(args.path_data, 'fold_lists', file_name), 'r') as f:
+        for line in f.readlines():
+            if not line.strip():
+                continue
+            name, _frame_num, fps = line.split(' ')
+            list_data.append(name)
+            videos_fps[name] = float(fps)
+    list_data.sort()
+    print(list_data)
+    for vname in list_data:
+        print("Processing: " + vname)
+        audio_path = os.path.join(args.path_data, 'video_audio', args.dataset, vname, vname + ".wav")
+        list_frames = glob.glob(os.path.join(args.path_data, 'video_frames', args.dataset, vname, "*.jpg"))
+        list_frames.sort(key=lambda x: int(os.path.basename(x).split('.')[0].split('_')[1]))
+        os.makedirs(os.path.join(args.save_path, vname), exist_ok=True)
+        if len(list_frames) < 2 * len_temporal - 1:
+            print('More frames are needed')
+            continue
+        audio = load_audio(audio_path) if args.use_sound else None
+        fps = videos_fps[vname]
+        img_size = (640, 480)  # inference.py:127
+        frames = torch.stack([torch_transform(p, cfg.DATA.RESOLUTION)[0] for p in list_frames])  # [N,3,H,W], host
+        # every window as (first frame, flipped?, output frame name) in the reference's order (:125-150)
+        jobs = []
+        for i in range(len_temporal - 1, len(list_frames)):
+            s = i - len_temporal + 1
+            jobs.append((s, False, os.path.basename(list_frames[i])))
+            if i < 2 * len_temporal - 2:
+                jobs.append((s, True, os.path.basename(list_frames[s])))
+        for j0 in range(0, len(jobs), args.batch):
+            chunk = jobs[j0:j0 + args.batch]
+            clips = []
+            for s, flip, _ in chunk:
+                c = frames[s:s + len_temporal].permute(1, 0, 2, 3)  # [3,T,H,W]
+                clips.append(torch.flip(c, [1]) if flip else c)
+            clips = torch.stack(clips).contiguous().to(device, non_blocking=True)
+            feats = audio_features(audio, [(s, flip) for s, flip, _ in chunk], fps, device) if args.use_sound else None
+            process_batch(model, clips, feats, [n for _, _, n in chunk], vname, img_size, args)
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--weight', default="./output/mvitv2_small_224_384_16_s2.pt", type=str)
+    parser.add_argument('--save_path', default='./output', type=str)
+    parser.add_argument('--split', default=2, type=int)
+    parser.add_argument('--path_data', default='./AuViDataset', type=str)
+    parser.add_argument('--dataset', default='AVAD', type=str)
+    parser.add_argument('--clip_size', default=16, type=int)
+    parser.add_argument('--use_sound', default=True, type=bool)
+    parser.add_argument('--batch', default=8, type=int, help="sliding windows per forward (the reference uses 1)")
+    parser.add_argument('--random_init', action='store_true', help="skip checkpoint loading (smoke tests)")
+    args = parser.parse_args(argv)
+    print(args)
+    os.makedirs(args.save_path, exist_ok=True)
+    if not torch.cuda.is_available():
+        raise RuntimeError("inference.py needs a CUDA device: mspi_b200 has no CPU path")
+    device = torch.device('cuda')
+    model = SalModel(cfg=cfg, load_pretrained=not args.random_init)
+    if not args.random_init:
+        model.load_state_dict(torch.load(args.weight, map_location="cpu"), strict=False)
+    model = model.to(device)
+    model.eval()
+    inference_dataset(model, args, device)
+
+
+if __name__ == "__main__":
+    main()

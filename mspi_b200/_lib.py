@@ -133,6 +133,7 @@ _SIGNATURES = {
     "mspi_simsiam_loss": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "mspi_logsoftmax2d": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "mspi_saliency_metrics": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int64, _P]),
+    "mspi_postprocess_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_logspec": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
 }
 

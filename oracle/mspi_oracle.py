@@ -519,6 +519,19 @@ def log_spectrogram(wave: torch.Tensor, frames_out: int = 111) -> torch.Tensor:
     return out.unsqueeze(1)
 
 
+# ================================================================================ post-processing
+def postprocess(pred_map, img_size=(640, 480)):
+    """process() after the forward, verbatim (cv2 is the reference's own dependency): blur the LOG map, exp, resize,
+    min-max, round to uint8.  inference.py:65-91.  pred_map: [H,W] float32 numpy / tensor -> uint8 [h,w] numpy."""
+    import cv2
+    m = np.asarray(pred_map, dtype=np.float32)
+    m = cv2.GaussianBlur(m, (11, 11), 0)
+    m = np.exp(m)
+    m = cv2.resize(m, img_size)
+    m = (m - m.min()) / (m.max() - m.min())
+    return np.round(m * 255).astype(np.uint8)
+
+
 # ============================================================== seeded weights and inputs (shared)
 def _spec_conv_bn(spec, p, cout, cin, k, bn_prefix=None, bias=False):
     spec[p + ".weight"] = ("conv", (cout, cin) + tuple(k))

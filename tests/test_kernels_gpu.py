@@ -464,3 +464,29 @@ def test_logspec_against_reference_fixtures():
     w = torch.randn(3, 400, generator=torch.Generator().manual_seed(4))
     from oracle import mspi_oracle as orc
     assert (log_spectrogram(w.cuda()).cpu() - orc.log_spectrogram(w)).abs().max() < 2e-3
+
+
+def test_postprocess_maps_against_cv2():
+    """GPU blur/exp/resize/normalise/uint8 vs the reference's cv2 + numpy sequence (inference.py:84-91).  uint8 output:
+    float summation order can flip a rounding at an exact .5 boundary, so at most 1 LSB on a small fraction of pixels."""
+    pytest.importorskip("cv2")
+    from oracle import mspi_oracle as orc
+    from mspi_b200.postprocess import postprocess_maps
+    g = torch.Generator().manual_seed(33)
+    yy, xx = torch.meshgrid(torch.arange(224.), torch.arange(384.), indexing="ij")
+    maps = []
+    for i in range(3):
+        m = torch.zeros(224, 384)
+        for _ in range(4):
+            cy, cx = torch.rand(1, generator=g) * 224, torch.rand(1, generator=g) * 384
+            m += torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 25.0 ** 2))
+        m = m + 0.05 * torch.rand(224, 384, generator=g)
+        maps.append(torch.log(m / m.sum()))
+    x = torch.stack(maps)
+    got = postprocess_maps(x.cuda(), (640, 480)).cpu().numpy()
+    assert got.shape == (3, 480, 640) and got.dtype.name == "uint8"
+    for i in range(3):
+        ref = orc.postprocess(x[i].numpy(), (640, 480))
+        d = abs(got[i].astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02, (d.max(), (d > 0).mean())
+        assert got[i].max() == 255 and got[i].min() == 0

@@ -4,6 +4,8 @@ Tolerances (north_star): saliency maps within 1e-2 max-abs after min-max normali
 CC/NSS/KLD/SIM within 1e-3 relative.  Intermediate taps are held to rel-L2 <= 3e-2 (bf16 operands with
 fp32 accumulation give 4e-3..9e-3); they are checked because with the default init the
 S3D activations vanish and the final map alone would not exercise those kernels."""
+import os
+
 import pytest
 import torch
 
@@ -75,3 +77,45 @@ def test_forward_parity_other_motion_encoders(encoder, init, seed):
     else:
         rng = (res["ref_out"].max() - res["ref_out"].min()).item()
         assert res["logit_maxabs"] / rng < 5e-2
+
+
+def test_inference_entry_point_on_synthetic_dataset(tmp_path):
+    """inference.py (the reference's entry point, same CLI / dataset layout / output naming) end to end on a tiny
+    synthetic AVAD-style dataset: 33 frames -> 18 forward windows + 15 time-flipped ones = one image per frame."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from scipy.io import wavfile
+    import inference
+    root, vname = tmp_path / "data", "V01"
+    (root / "fold_lists").mkdir(parents=True)
+    (root / "video_frames" / "AVAD" / vname).mkdir(parents=True)
+    (root / "video_audio" / "AVAD" / vname).mkdir(parents=True)
+    n = 33
+    rng = np.random.default_rng(0)
+    for i in range(n):
+        img = (rng.random((90, 120, 3)) * 255).astype(np.uint8)
+        cv2.imwrite(str(root / "video_frames" / "AVAD" / vname / f"img_{i + 1:05d}.jpg"), img)
+    wavfile.write(str(root / "video_audio" / "AVAD" / vname / f"{vname}.wav"), 22050,
+                  (rng.standard_normal(22050 * 3) * 0.1).astype(np.float32))
+    (root / "fold_lists" / "AVAD_list_test_2_fps.txt").write_text(f"{vname} {n} 25\n")
+    out = tmp_path / "out"
+    inference.main(["--path_data", str(root), "--save_path", str(out), "--dataset", "AVAD", "--split", "2",
+                    "--random_init", "--batch", "6"])
+    files = sorted(os.listdir(out / vname))
+    assert files == [f"img_{i + 1:05d}.jpg" for i in range(n)]
+    img = cv2.imread(str(out / vname / files[20]), cv2.IMREAD_GRAYSCALE)
+    assert img.shape == (480, 640) and img.max() > 200 and img.min() < 30
+
+
+def test_inference_audio_features_match_oracle():
+    """Per-window spectrograms of the driver (GPU STFT on slices of a once-resampled wav) vs the oracle front end."""
+    import inference
+    from oracle import mspi_oracle as orc
+    g = torch.Generator().manual_seed(8)
+    audio = torch.randn(16000 * 4, generator=g) * 0.1
+    wins = [(0, False), (3, False), (3, True), (40, False)]
+    feats = inference.audio_features(audio, wins, 25.0, torch.device("cuda")).cpu()
+    for k, (s, flip) in enumerate(wins):
+        w = inference.audio_window(audio, s, 25.0, flip=flip)
+        ref = orc.log_spectrogram(w[None])[0]
+        assert (feats[k] - ref).abs().max() < 2e-3
