@@ -693,6 +693,9 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_RELU, 0)
   MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_GELU, 0)
   MSPI_PICK(MSPI_F32, MSPI_F32, MSPI_ACT_NONE, 2)
+  MSPI_PICK(MSPI_F32, MSPI_BF16, MSPI_ACT_GELU, 0)
+  MSPI_PICK(MSPI_BF16, MSPI_F32, MSPI_ACT_NONE, 2)
+  MSPI_PICK(MSPI_BF16, MSPI_F32, MSPI_ACT_RELU, 1)
 #undef MSPI_PICK
   if (kern == nullptr) {
     if (d->a_dtype == MSPI_BF16) kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, -1, -1>

@@ -561,10 +561,13 @@ class ForwardPlan:
         b = self.new(x.n, x.t, x.h, x.w, x.c, f32)
         self.add(p + ".dwconv_s+norm", ops.dwconv_ln(a, b, self.P(p + ".dwconv_s.weight"), self.P(p + ".dwconv_s.bias"),
                                                      self.P(p + ".norm.norm.weight"), self.P(p + ".norm.norm.bias"), 1e-5))
+        # the 4C hidden tensor is the block's largest (2.1 GB per step at latlayer_0): it is stored in bf16 (one rounding,
+        # like every hidden activation of the encoders) and multiplied by hi/lo-split bf16 weights; the LayerNorm output,
+        # the residual stream and the block output stay fp32.
         hid = self.conv(p + ".pwconv1", b, self.P(p + ".pwconv1.weight"), None, self.P(p + ".pwconv1.bias"), act=ACT_GELU,
-                        out_dtype=f32, dtype=f32)
+                        out_dtype=torch.bfloat16, dtype=f32)
         return self.conv(p + ".pwconv2", hid, self.P(p + ".pwconv2.weight"), None, self.P(p + ".pwconv2.bias"),
-                         residual=x, res_after_act=True, out_dtype=f32, dtype=f32)
+                         residual=x, res_after_act=True, out_dtype=f32, split_weights=True)
 
     def lateral(self, k: int, x: Act) -> Act:
         """latlayer_k, model_utils.py:437-484.  Conv1x1(+bias) followed by the bias-free (s,1,1)/s temporal conv
