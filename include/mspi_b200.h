@@ -83,6 +83,12 @@ typedef struct {
                            32.  The small sizes serve the Cin=3 stems, where one filter row over the padded 4-channel
                            frames of mspi_clip_to_padded_nhwc4 is a 64-byte (S3D, 8 px) or 32-byte (ConvNeXt, 4 px)
                            contiguous run; cin_pad is then a multiple of k_row_bytes / elsize. */
+  int32_t w_batch_dims[2]; /* {0,0}: one weight matrix (normal).  {D3, D4} (== o_dims[2], o_dims[3]): batched GEMM — the B
+                              operand of an M tile at (d3, d4) is matrix (d3, d4) of a [D4][D3][w_rows][K] family addressed
+                              by w_strides (elements): [0] between rows, [1] between d3 matrices, [2] between d4 matrices;
+                              K = a_dims[0], ntaps = 1, box[3] = box[4] = 1.  Used for attention (model_utils.py:97-109):
+                              scores = Q K^T per (head, sample) and out = P V. */
+  int64_t w_strides[3];
 } MspiConvDesc;
 
 int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
@@ -217,6 +223,13 @@ int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w, const flo
  * [B][N][3][heads][hd] -> out (same dtype) [B][N][heads*hd]; softmax(q k^T * scale) v in fp32. */
 int mspi_attention(const void* qkv, void* out, int dtype, int b, int n, int heads, int hd, float scale,
                    void* stream);
+
+/* Attention as two batched tensor-core GEMMs (MspiConvDesc.w_batch_dims) plus this glue, fp32:
+ *   scores[b][h][q][k] = scale * Q K^T  (mspi_conv_gemm)  ->  mspi_softmax_rows in place  ->  out = P V (mspi_conv_gemm)
+ * mspi_transpose_v writes the K-major copy of V the second GEMM needs: qkv [B][N][3][heads][hd] -> vt [B][heads][hd][n_pad]
+ * (columns >= n are written as zero). */
+int mspi_softmax_rows(float* s, int64_t rows, int n, int64_t stride, void* stream);
+int mspi_transpose_v(const float* qkv, float* vt, int b, int n, int heads, int hd, int n_pad, void* stream);
 
 /* SA gating + top-down sums (model_utils.py:167-170,566-568):
  *   y = x * sigmoid_mask + x ; the mask logits are fp32 [N*T*H*W] (one channel); x, y bf16 or fp32 (`dtype`). */

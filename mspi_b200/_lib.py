@@ -42,6 +42,8 @@ class ConvDesc(C.Structure):
         ("has_residual", C.c_int32),
         ("res_after_act", C.c_int32),
         ("k_row_bytes", C.c_int32),
+        ("w_batch_dims", C.c_int32 * 2),
+        ("w_strides", C.c_int64 * 3),
     ]
 
 
@@ -126,6 +128,8 @@ _SIGNATURES = {
     "mspi_scale_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
     "mspi_layernorm": (C.c_int, [C.POINTER(LnDesc), _P, _P, _P, _P, _P, _P]),
     "mspi_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "mspi_softmax_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P]),
+    "mspi_transpose_v": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "mspi_add_bf16": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "mspi_token_mean": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

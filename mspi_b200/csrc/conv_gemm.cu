@@ -54,6 +54,7 @@ struct GemmParams {
   int num_stages, a_bytes, b_bytes, a_tx_bytes, tmem_cols;
   int row_bytes;  // K chunk of one row: 128 (default), 64 or 32 bytes; selects the swizzle mode of the operand tiles
   int ss_floats;  // staged scale/shift length (n_tiles * bn)
+  int w_batched;  // 1: the B operand has its own matrix per (d3, d4) index of the M tile (batched GEMM, attention)
   int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
 };
 
@@ -102,6 +103,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -271,7 +280,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
             const uint32_t sa = tiles_base + stage * stage_bytes;
             tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
-            tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+            if (p.w_batched)
+              tma_load_4d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn, org[2], org[3]);
+            else
+              tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -582,13 +594,27 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
                        (int)r, d->a_dims[0], d->a_dims[1], d->a_dims[2], d->a_dims[3], d->a_dims[4], bk,
                        d->box[1], d->box[2], d->box[3], d->box[4]);
   }
+  const bool w_batched = d->w_batch_dims[0] > 0;
+  if (w_batched) {
+    MSPI_CHECK_ARG(d->ntaps == 1 && d->w_batch_dims[0] == d->o_dims[2] && d->w_batch_dims[1] == d->o_dims[3] &&
+                       d->box[3] == 1 && d->box[4] == 1,
+                   "batched weights: one matrix per (d3, d4) index, boxes of 1 along d3/d4, a single tap");
+    for (int j = 0; j < 3; ++j)
+      MSPI_CHECK_ARG(d->w_strides[j] > 0 && (d->w_strides[j] * elsize) % 16 == 0, "w_strides[%d] not 16B aligned", j);
+  }
   {
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d->ntaps) * d->cin_pad, static_cast<cuuint64_t>(d->w_rows)};
-    cuuint64_t gstr[1] = {gdim[0] * elsize};
-    cuuint32_t bdim[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->bn)};
-    cuuint32_t estr[2] = {1, 1};
+    cuuint64_t gdim[4] = {w_batched ? static_cast<cuuint64_t>(d->a_dims[0]) : static_cast<cuuint64_t>(d->ntaps) * d->cin_pad,
+                          static_cast<cuuint64_t>(d->w_rows), 1, 1};
+    cuuint64_t gstr[3] = {gdim[0] * elsize, 0, 0};
+    cuuint32_t bdim[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->bn), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (w_batched) {
+      gdim[2] = static_cast<cuuint64_t>(d->w_batch_dims[0]);
+      gdim[3] = static_cast<cuuint64_t>(d->w_batch_dims[1]);
+      for (int j = 0; j < 3; ++j) gstr[j] = static_cast<cuuint64_t>(d->w_strides[j]) * elsize;
+    }
     CUresult r = encode(&map_b, d->a_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
-                        2, const_cast<void*>(w), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        w_batched ? 4 : 2, const_cast<void*>(w), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -629,6 +655,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(d->bn >> 3) << 17) |
             (static_cast<uint32_t>(kTileM >> 4) << 24);
   p.row_bytes = row_bytes;
+  p.w_batched = w_batched ? 1 : 0;
   p.a_bytes = kTileM * row_bytes;
   p.b_bytes = d->bn * row_bytes;
   p.a_tx_bytes = static_cast<int>(rows) * row_bytes;

@@ -297,6 +297,49 @@ attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int head
   }
 }
 
+// ------------------------------------------------------------------------- attention as two batched GEMMs
+// (mspi_conv_gemm with batched weights computes scores = Q K^T * scale and out = P V on the tensor cores; these two
+//  kernels are the glue: the row softmax and the K-major copy of V the second GEMM needs.)
+// One warp per score row: max, exp / sum, normalise; fp32 in place.
+__global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int n, long long stride) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * warps) {
+    float* r = s + row * stride;
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, r[i]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float e = __expf(r[i] - m);
+      r[i] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    for (int i = lane; i < n; i += 32) r[i] *= inv;
+  }
+}
+
+// qkv [B][N][3][H][HD] (v = index 2) -> vt [B][H][HD][n_pad] (keys contiguous), 32x32 tiles through shared memory.
+__global__ void transpose_v_kernel(const float* __restrict__ qkv, float* __restrict__ vt, int n, int heads, int hd, int n_pad) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z, b = bh / heads, h = bh % heads;
+  const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const long long row_stride = 3ll * heads * hd;
+  const float* src = qkv + static_cast<long long>(b) * n * row_stride + 2ll * heads * hd + h * hd;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, dd = d0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < n && dd < hd) ? src[static_cast<long long>(k) * row_stride + dd] : 0.f;
+  }
+  __syncthreads();
+  float* dst = vt + (static_cast<long long>(bh) * hd) * n_pad;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int dd = d0 + r, k = k0 + threadIdx.x;
+    if (dd < hd && k < n_pad) dst[static_cast<long long>(dd) * n_pad + k] = tile[threadIdx.x][r];
+  }
+}
+
 // ------------------------------------------------------------------------- token mean
 template <typename T>
 __global__ void token_mean_kernel(const T* __restrict__ x, float* __restrict__ y, int rows, int r0, int r1, int c) {
@@ -453,6 +496,29 @@ extern "C" int mspi_attention(const void* qkv, void* out, int dtype, int b, int 
   else
     attention_kernel<float><<<grid, kAttnThreads, smem, stream>>>(static_cast<const float*>(qkv),
                                                                   static_cast<float*>(out), n, heads, hd, scale, n_pad);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_softmax_rows(float* s, int64_t rows, int n, int64_t stride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(s && rows > 0 && n > 0 && stride >= n, "mspi_softmax_rows: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int threads = 256, warps = threads / 32;
+  long long blocks = (rows + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  softmax_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(s, rows, n, stride);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_transpose_v(const float* qkv, float* vt, int b, int n, int heads, int hd, int n_pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(qkv && vt && b > 0 && n > 0 && heads > 0 && hd > 0 && n_pad >= n, "mspi_transpose_v: bad argument");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  dim3 grid((n_pad + 31) / 32, (hd + 31) / 32, b * heads), block(32, 8);
+  transpose_v_kernel<<<grid, block, 0, stream>>>(qkv, vt, n, heads, hd, n_pad);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

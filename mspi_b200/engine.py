@@ -506,7 +506,8 @@ class ForwardPlan:
             b = f"{p}blocks.{i}."
             self.add(b + "norm1", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm1.weight"), self.P(b + "norm1.bias"), 1e-5))
             qkv = lin(b + "attn.qkv", ln_act, b + "attn.qkv.weight", None)
-            self.add(b + "attn", ops.attention(qkv.buf, attn_out, B, n, 4, c // 4))
+            for nm, fn in ops.attention_gemm(qkv.buf.view(B * n, 3 * c), attn_out, B, n, 4, c // 4):
+                self.add(b + "attn." + nm, fn)
             self.flops += 4.0 * B * n * n * c
             lin(b + "attn.proj", self.rows_act(attn_out), b + "attn.proj.weight", b + "attn.proj.bias", out=s_act, residual=s_act)
             self.add(b + "norm2", ops.layernorm(stream, ln, B * n, c, self.P(b + "norm2.weight"), self.P(b + "norm2.bias"), 1e-5))

@@ -659,6 +659,64 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, 
     return run
 
 
+def attention_gemm(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: int, hd: int) -> List[Tuple[str, Callable[[], None]]]:
+    """Multi-head self-attention (model_utils.py:97-109) as tensor-core work: scores = scale * Q K^T and out = P V are
+    batched kind::tf32 GEMMs (one weight matrix per (head, sample), MspiConvDesc.w_batch_dims); softmax and the K-major
+    copy of V are small fp32 kernels.  qkv fp32 [B*N, 3*heads*hd] (layout [3][heads][hd] per token), out fp32 [B*N, heads*hd].
+    Returns the four launches as (name, closure)."""
+    lib = _lib.load()
+    assert qkv.dtype == torch.float32 and out.dtype == torch.float32 and hd % 32 == 0
+    dev = qkv.device
+    c = heads * hd
+    n_pad = -(-n // 4) * 4                      # fp32 rows must start 16-byte aligned
+    scores = torch.empty((b, heads, n, n_pad), dtype=torch.float32, device=dev)
+    vt = torch.zeros((b, heads, hd, n_pad), dtype=torch.float32, device=dev)
+    scale = torch.full((n,), float(hd) ** -0.5, dtype=torch.float32, device=dev)
+    row = 3 * c                                  # elements between consecutive tokens of qkv
+
+    def desc(k, m_stride, h_stride, b_stride, w_rows, w_strides, cout, o_strides):
+        d = ConvDesc()
+        d.a_dtype = MSPI_F32
+        for j, (dim, st) in enumerate(zip((k, n, 1, heads, b), (1, m_stride, m_stride * n, h_stride, b_stride))):
+            d.a_dims[j], d.a_strides[j] = dim, st
+        d.box[0], d.box[1], d.box[2], d.box[3], d.box[4] = 0, min(n, 128), 1, 1, 1
+        d.ntaps = 1
+        d.cin_pad = -(-k // 32) * 32
+        d.cout, d.w_rows = cout, w_rows
+        d.bn = choose_bn(cout, 32)
+        for j, (dim, st) in enumerate(zip((n, 1, heads, b), o_strides)):
+            d.o_dims[j], d.o_strides[j], d.r_strides[j] = dim, st, 0
+        d.o_dtype = MSPI_F32
+        d.w_batch_dims[0], d.w_batch_dims[1] = heads, b
+        for j in range(3):
+            d.w_strides[j] = w_strides[j]
+        return d
+
+    # scores[b][h][q][k] = scale * sum_d Q[b,q,h,d] K[b,k,h,d]
+    d1 = desc(hd, row, hd, n * row, n, (row, hd, n * row), n, (n_pad, 0, n * n_pad, heads * n * n_pad))
+    # out[b,q,h,:] = sum_k P[b][h][q][k] Vt[b][h][:, k]
+    d2 = desc(n, n_pad, n * n_pad, heads * n * n_pad, hd, (n_pad, hd * n_pad, heads * hd * n_pad), hd, (c, 0, hd, n * c))
+    q_ptr, k_ptr = _ptr(qkv), _ptr(qkv, c * 4)
+    keep = (qkv, out, scores, vt, scale, d1, d2)
+    null = C.c_void_p(0)
+
+    def k_scores(_keep=keep):
+        _lib.check(lib.mspi_conv_gemm(C.byref(d1), q_ptr, k_ptr, _ptr(scale), null, null, _ptr(scores), _stream()), "attn.scores")
+
+    def k_softmax(_keep=keep):
+        _lib.check(lib.mspi_softmax_rows(_ptr(scores), b * heads * n, n, n_pad, _stream()), "attn.softmax")
+
+    def k_vt(_keep=keep):
+        _lib.check(lib.mspi_transpose_v(_ptr(qkv), _ptr(vt), b, n, heads, hd, n_pad, _stream()), "attn.transpose_v")
+
+    def k_out(_keep=keep):
+        _lib.check(lib.mspi_conv_gemm(C.byref(d2), _ptr(scores), _ptr(vt), null, null, null, _ptr(out), _stream()), "attn.out")
+
+    k_scores.desc, k_scores.flops = d1, 2.0 * b * heads * n * n * hd
+    k_out.desc, k_out.flops = d2, 2.0 * b * heads * n * n * hd
+    return [("scores", k_scores), ("softmax", k_softmax), ("transpose_v", k_vt), ("out", k_out)]
+
+
 def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
     lib = _lib.load()
     assert mask_logits.dtype == torch.float32 and x.c == y.c and x.dtype == y.dtype

@@ -392,6 +392,24 @@ def test_attention_small():
     assert (out.float().cpu() - ref).abs().max() < 2e-2  # bf16 output rounding
 
 
+@pytest.mark.parametrize("b,n", [(2, 52), (1, 372), (1, 1380)])
+def test_attention_as_batched_gemms(b, n):
+    """scores = scale Q K^T and out = P V as batched kind::tf32 GEMMs + row softmax (model_utils.py:97-109); N = 372 is
+    the S3D/SlowFast token count at 224x384, 1380 the X3D-L one.  tf32 operands (10-bit mantissa), fp32 accumulate."""
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(16)
+    heads, hd = 4, 128
+    qkv = torch.randn(b, n, 3, heads, hd, generator=g)
+    out = torch.empty(b * n, heads * hd, dtype=torch.float32, device="cuda")
+    for _nm, fn in ops.attention_gemm(qkv.view(b * n, -1).cuda(), out, b, n, heads, hd):
+        fn()
+    torch.cuda.synchronize()
+    q, k, v = qkv.permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v
+    ref = ref.transpose(1, 2).reshape(b * n, heads * hd)
+    assert _rel(out.cpu(), ref) < 5e-3
+
+
 def test_sa_gate_token_mean_simsiam():
     from mspi_b200 import _lib, ops
     from mspi_b200.ops import Act
