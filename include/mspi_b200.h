@@ -95,6 +95,16 @@ int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const fl
                    const float* shift, const void* residual, void* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused ConvNeXt MLP (timm convnext Mlp + layer scale + residual, model_utils.py:361), C = 96 or 192:
+ *   y[m][:] = residual[m][:] + scale * ( W2 . gelu(W1 . x[m][:] + b1) ) + shift        (scale = gamma, shift = gamma*b2)
+ * x bf16 [m][c] (row stride c), w1 bf16 [4c][c_pad] (K zero padded to c_pad = multiple of 64), w2 bf16 [c][4c],
+ * b1 fp32 [4c], scale/shift fp32 [c], residual / y bf16 with row strides res_stride / y_stride (elements).
+ * Two chained tcgen05 GEMMs per 128-row tile; the 4c-wide hidden tile lives in TMEM / shared memory only. */
+int mspi_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                   const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                   int64_t res_stride, int64_t y_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Patch gather (explicit im2col) for the layers whose input has too few channels for a TMA
  * K-chunk (Cin = 3 or 1) or an odd-size strided grid: S3D stem conv_s (backbones/s3d.py:383),
  * ConvNeXt stem 4x4/s4 (timm convnext_tiny, model_utils.py:361), ResNet conv1 and its stride-2

@@ -1,0 +1,367 @@
+// Fused ConvNeXt MLP for sm_100a:   y = r + gamma * ( W2 . gelu(W1 . x + b1) + b2 )
+//
+// Replaces timm ConvNeXt Mlp (fc1 -> GELU -> fc2) + layer scale + residual (model_utils.py:361; stages 0 and 1,
+// C = 96 / 192) with ONE kernel.  Unfused, the 4C-wide hidden activation is written to and re-read from HBM (2.1 GB
+// per layer at stage 0, four times the layer's input + output), which makes those layers HBM/epilogue bound; here the
+// hidden tile never leaves the SM:
+//
+//   TMA:   x tile [128 x C] -> smem (double buffered across tiles); W1 / W2 pieces stream through a smem ring
+//   MMA1:  H_j [128 x 128] = x . W1_j^T          tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 buffers)
+//   epi:   H_j -> +b1 -> GELU -> bf16 -> smem, written in the 128B-swizzled K-major layout MMA2 reads as its A operand
+//   MMA2:  Y [128 x C] += gelu(H_j) . W2_j^T      accumulators in TMEM columns 256..
+//   epi:   Y -> gamma * (. + b2) + residual -> bf16 -> global
+//
+// One persistent CTA per SM, warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue
+// (the kernel is bound by the GELU epilogue: 16 warps give the schedulers four independent instruction streams each).
+// The MMA warp runs one software-pipelined stream over all (tile, hidden chunk) pairs: MMA1(g) is issued before
+// MMA2(g-1), so the tensor pipe always has a GEMM to run while the epilogue warps apply GELU to the previous chunk.
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mspi {
+namespace {
+
+using namespace tc;
+
+constexpr int kHC = 128;                       // hidden columns per chunk
+constexpr int kEpiWarps = 16;                  // four per TMEM lane quarter: each takes 32 of a chunk's 128 columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kChunkBytes = 128 * 128;         // one K chunk of a 128-row operand tile: 16 KB
+constexpr int kMaxRing = 8;
+constexpr uint32_t kTmemY = 2 * kHC;           // Y accumulators start after the two H buffers
+
+struct MlpParams {
+  int m_rows, c, kc1, nh, m_tiles, x_bufs;
+  int ring_stages, ring_stage_bytes;
+  const float* b1;      // [4C]
+  const float* scale;   // [C]  layer scale gamma
+  const float* shift;   // [C]  gamma * b2
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  long long res_stride, y_stride;
+  uint32_t idesc1, idesc2;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // barrier block
+  const uint32_t ring_full = base, ring_empty = base + 8 * kMaxRing;
+  const uint32_t x_full = base + 16 * kMaxRing, x_empty = x_full + 16;
+  const uint32_t h_full = x_empty + 16, h_empty = h_full + 16;
+  const uint32_t a2_full = h_empty + 16, a2_empty = a2_full + 16;
+  const uint32_t y_full = a2_empty + 16, y_empty = y_full + 8;
+  const uint32_t tmem_slot = y_empty + 8;
+  float* s_b1 = reinterpret_cast<float*>(base_ptr + 1024);       // [4C]
+  float* s_scale = s_b1 + 4 * p.c;                               // [C]
+  float* s_shift = s_scale + p.c;                                // [C]
+  const uint32_t x_base = base + 1024 + 8192;                    // 2 x kc1 chunks
+  const uint32_t a2_base = x_base + static_cast<uint32_t>(p.x_bufs) * p.kc1 * kChunkBytes;  // 2 buffers x 2 chunks
+  const uint32_t ring_base = a2_base + 4u * kChunkBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    for (int s = 0; s < p.ring_stages; ++s) {
+      mbar_init(ring_full + 8 * s, 1);
+      mbar_init(ring_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(x_full + 8 * s, 1);
+      mbar_init(x_empty + 8 * s, 1);
+      mbar_init(h_full + 8 * s, 1);
+      mbar_init(h_empty + 8 * s, kEpiWarps);
+      mbar_init(a2_full + 8 * s, kEpiWarps);
+      mbar_init(a2_empty + 8 * s, 1);
+    }
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, kEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * p.c; i += kThreads) s_b1[i] = __ldg(p.b1 + i);
+  for (int i = threadIdx.x; i < p.c; i += kThreads) {
+    s_scale[i] = __ldg(p.scale + i);
+    s_shift[i] = __ldg(p.shift + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int x_buf_bytes = p.kc1 * kChunkBytes;
+  const int w2_bytes = p.c * 128;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int xs = 0;
+      uint32_t xph = 0;
+      auto load_x = [&](int tile) {
+        mbar_wait(x_empty + 8 * xs, xph ^ 1u);
+        mbar_expect_tx(x_full + 8 * xs, static_cast<uint32_t>(x_buf_bytes));
+        for (int kc = 0; kc < p.kc1; ++kc)
+          tma_load_2d(x_base + xs * x_buf_bytes + kc * kChunkBytes, &map_x, x_full + 8 * xs, kc * 64, tile * 128);
+        if (++xs == p.x_bufs) { xs = 0; xph ^= 1u; }
+      };
+      auto load_w1 = [&](int j) {
+        for (int kc = 0; kc < p.kc1; ++kc) {
+          mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
+          mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
+          tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w1, ring_full + 8 * stage, kc * 64, j * kHC);
+          if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
+        }
+      };
+      auto load_w2 = [&](int j) {
+        for (int kc2 = 0; kc2 < 2; ++kc2) {
+          mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
+          mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
+          tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w2, ring_full + 8 * stage, j * kHC + kc2 * 64, 0);
+          if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
+        }
+      };
+      // with two x buffers the tile after the current one is requested before the current tile's weights
+      if (p.x_bufs == 2 && static_cast<int>(blockIdx.x) < p.m_tiles) load_x(blockIdx.x);
+      int prev_j = -1;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        if (p.x_bufs == 1) load_x(tile);
+        else if (tile + static_cast<int>(gridDim.x) < p.m_tiles) load_x(tile + gridDim.x);
+        for (int j = 0; j < p.nh; ++j) {
+          load_w1(j);
+          if (prev_j >= 0) load_w2(prev_j);
+          prev_j = j;
+        }
+      }
+      if (prev_j >= 0) load_w2(prev_j);
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int xs = 0;
+      uint32_t xph = 0;
+      uint32_t g = 0, ytile = 0;
+      int prev_j = -1;
+      uint32_t prev_g = 0;
+      auto mma2 = [&](int pj, uint32_t pg) {
+        const uint32_t pb = pg & 1u;
+        mbar_wait(a2_full + 8 * pb, (pg >> 1) & 1u);
+        if (pj == 0) mbar_wait(y_empty, (ytile & 1u) ^ 1u);  // the previous tile's Y has been read out
+        tc_fence_after();
+        for (int kc2 = 0; kc2 < 2; ++kc2) {
+          mbar_wait(ring_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(a2_base + (pb * 2 + kc2) * kChunkBytes, 128);
+          const uint64_t bdesc = make_smem_desc(ring_base + stage * p.ring_stage_bytes, 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma<MSPI_BF16>(tmem_base + kTmemY, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (pj | kc2 | k) != 0 ? 1u : 0u);
+          tc_commit(ring_empty + 8 * stage);
+          if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(a2_empty + 8 * pb);
+        if (pj == p.nh - 1) {
+          tc_commit(y_full);
+          ++ytile;
+        }
+      };
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        mbar_wait(x_full + 8 * xs, xph);
+        tc_fence_after();
+        for (int j = 0; j < p.nh; ++j) {
+          const uint32_t b = g & 1u;
+          mbar_wait(h_empty + 8 * b, ((g >> 1) & 1u) ^ 1u);  // the epilogue has read H[b] of chunk g-2
+          tc_fence_after();
+          for (int kc = 0; kc < p.kc1; ++kc) {
+            mbar_wait(ring_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(x_base + xs * x_buf_bytes + kc * kChunkBytes, 128);
+            const uint64_t bdesc = make_smem_desc(ring_base + stage * p.ring_stage_bytes, 128);
+            const int ksteps = min(4, (p.c - kc * 64 + 15) >> 4);  // skip the zero-padded K tail
+            for (int k = 0; k < ksteps; ++k)
+              tc_mma<MSPI_BF16>(tmem_base + b * kHC, adesc + 2u * k, bdesc + 2u * k, p.idesc1, (kc | k) != 0 ? 1u : 0u);
+            tc_commit(ring_empty + 8 * stage);
+            if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit(h_full + 8 * b);
+          if (j == p.nh - 1) tc_commit(x_empty + 8 * xs);  // x tile free once these MMAs have read it
+          if (prev_j >= 0) mma2(prev_j, prev_g);
+          prev_j = j;
+          prev_g = g;
+          ++g;
+        }
+        if (++xs == p.x_bufs) { xs = 0; xph ^= 1u; }
+      }
+      if (prev_j >= 0) mma2(prev_j, prev_g);
+    }
+  } else {
+    // ================================================================== epilogue warps
+    const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 = this warp's rows
+    const int colgrp = (warp - 2) >> 2;      // which 32 of a chunk's 128 hidden columns
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t g = 0, ytile = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      const long long grow = static_cast<long long>(tile) * 128 + row;
+      const bool valid = grow < p.m_rows;
+      for (int j = 0; j < p.nh; ++j) {
+        const uint32_t b = g & 1u, ph = (g >> 1) & 1u;
+        mbar_wait(h_full + 8 * b, ph);
+        mbar_wait(a2_empty + 8 * b, ph ^ 1u);  // MMA2 of chunk g-2 has finished reading this staging buffer
+        tc_fence_after();
+        uint32_t packed[16];
+        const float* b1 = s_b1 + j * kHC + colgrp * 32;
+        {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld32(lane_addr + b * kHC + colgrp * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * q);
+            const float v0 = gelu_bf16(__uint_as_float(acc[4 * q + 0]) + bb.x);
+            const float v1 = gelu_bf16(__uint_as_float(acc[4 * q + 1]) + bb.y);
+            const float v2 = gelu_bf16(__uint_as_float(acc[4 * q + 2]) + bb.z);
+            const float v3 = gelu_bf16(__uint_as_float(acc[4 * q + 3]) + bb.w);
+            packed[2 * q] = pack_bf16x2(v0, v1);
+            packed[2 * q + 1] = pack_bf16x2(v2, v3);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_empty + 8 * b);  // H[b] may be overwritten by MMA1 of chunk g+2
+        // 32 columns = four 16-byte pieces of K chunk (colgrp >> 1), pieces 4*(colgrp & 1) ..
+        const uint32_t dst_row = a2_base + (b * 2 + (colgrp >> 1)) * kChunkBytes + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int piece = 4 * (colgrp & 1) + i;
+          const uint32_t dst = dst_row + (static_cast<uint32_t>(piece ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * i]), "r"(packed[4 * i + 1]),
+                       "r"(packed[4 * i + 2]), "r"(packed[4 * i + 3])
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full + 8 * b);
+        ++g;
+      }
+      // ---- Y tile: gamma * (acc + b2) + residual -> bf16; this thread's row, 16-column units colgrp, colgrp+4, ...
+      mbar_wait(y_full, ytile & 1u);
+      tc_fence_after();
+      for (int c0 = 16 * colgrp; c0 < p.c; c0 += 64) {
+        uint32_t acc[16];
+        __syncwarp();
+        tmem_ld16(lane_addr + kTmemY + c0, acc);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int col = c0 + 8 * h8;
+            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + col));
+            float res[8];
+            unpack_bf16x2(rr.x, res[0], res[1]); unpack_bf16x2(rr.y, res[2], res[3]);
+            unpack_bf16x2(rr.z, res[4], res[5]); unpack_bf16x2(rr.w, res[6], res[7]);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = fmaf(__uint_as_float(acc[8 * h8 + e]), s_scale[col + e], s_shift[col + e]) + res[e];
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(p.y + grow * p.y_stride + col) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(y_empty);
+      ++ytile;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+}  // namespace mspi
+
+using namespace mspi;
+
+extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                              const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                              int64_t res_stride, int64_t y_stride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && w1 && b1 && w2 && scale && shift && residual && y && m > 0, "mspi_mlp_fused: null argument");
+  MSPI_CHECK_ARG((c == 96 || c == 192) && c_pad % 64 == 0 && c_pad >= c && c_pad < c + 64, "mspi_mlp_fused: C %d / pad %d unsupported", c, c_pad);
+  MSPI_CHECK_ARG(res_stride % 8 == 0 && y_stride % 8 == 0, "row strides must be multiples of 8 elements");
+  MSPI_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2) |
+                   reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "16-byte alignment");
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  if (!encode) return set_error(MSPI_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int hidden = 4 * c;
+  auto make2d = [&](CUtensorMap* map, const void* ptr, uint64_t k, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+    cuuint64_t gdim[2] = {k, rows};
+    cuuint64_t gstr[1] = {row_stride_elems * 2};
+    cuuint32_t bdim[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUtensorMap map_x, map_w1, map_w2;
+  CUresult r1 = make2d(&map_x, x, c, static_cast<uint64_t>(m), c, 128);
+  CUresult r2 = make2d(&map_w1, w1, c_pad, hidden, c_pad, 128);
+  CUresult r3 = make2d(&map_w2, w2, hidden, c, hidden, c);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS)
+    return set_error(MSPI_ERR_CUDA, "mspi_mlp_fused: cuTensorMapEncodeTiled failed (%d, %d, %d)", (int)r1, (int)r2, (int)r3);
+
+  MlpParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_rows = static_cast<int>(m);
+  p.c = c;
+  p.kc1 = c_pad / 64;
+  p.nh = hidden / kHC;
+  p.m_tiles = static_cast<int>((m + 127) / 128);
+  p.ring_stage_bytes = (c > 128 ? c : 128) * 128;
+  p.b1 = b1;
+  p.scale = scale;
+  p.shift = shift;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.res_stride = res_stride;
+  p.y_stride = y_stride;
+  p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kHC >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(c >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  p.x_bufs = c <= 96 ? 2 : 1;  // C = 192: the weight ring needs the room (30 pieces per tile, each one L2 round trip)
+  const int fixed = 1024 + 1024 + 8192 + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes;
+  p.ring_stages = (225 * 1024 - fixed) / p.ring_stage_bytes;
+  if (p.ring_stages > kMaxRing) p.ring_stages = kMaxRing;
+  MSPI_CHECK_ARG(p.ring_stages >= 2, "mspi_mlp_fused: shared memory leaves %d ring stages", p.ring_stages);
+  const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.ring_stages) * p.ring_stage_bytes;
+  MSPI_CUDA(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int grid = num_sms();
+  if (p.m_tiles < grid) grid = p.m_tiles;
+  fused_mlp_kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w1, map_w2, p);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}

@@ -1,0 +1,176 @@
+// tcgen05 / TMA / mbarrier PTX wrappers shared by the tensor-core kernels (conv_gemm.cu, fused_mlp.cu).  sm_100a only.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mspi {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > (1ll << 32)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (KIND == MSPI_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// GELU for bf16 results: the tanh form 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715x^3))) with the hardware tanh (one MUFU
+// op, six FMA-pipe ops).  Against the exact erf form it differs by < 5e-4 absolute and < 2^-10 relative, below the half-ulp
+// (2^-9) of the bf16 value it is rounded to.  (Measured alternative: x / (1 + 2^(x (k0 + k1 x^2))) with ex2 + rcp — two
+// MUFU ops — is 23 % slower on the stage-0 fc1 layer: the epilogue is bound by MUFU + issue slots.)
+__device__ __forceinline__ float gelu_bf16(float x) {
+  const float u = x * x;
+  const float t = x * fmaf(u, 0.0356774081f, 0.7978845608f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
+// Epilogue activation.
+// GELU, fp32 outputs: Abramowitz-Stegun 7.1.26 for erf (|err| < 1.5e-7, branch free).
+// GELU, bf16 outputs: gelu_bf16 above.
+template <bool OUT_BF16>
+__device__ __forceinline__ float epi_act(float x, int act) {
+  if (act == MSPI_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == MSPI_ACT_GELU) {
+    if constexpr (OUT_BF16) {
+      return gelu_bf16(x);
+    } else {
+      const float z = fabsf(x) * 0.70710678118654752440f;
+      const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+      float poly = fmaf(t, 1.061405429f, -1.453152027f);
+      poly = fmaf(poly, t, 1.421413741f);
+      poly = fmaf(poly, t, -0.284496736f);
+      poly = fmaf(poly, t, 0.254829592f);
+      const float e = fmaf(-poly * t, __expf(-z * z), 1.f);
+      return 0.5f * x * (1.f + copysignf(e, x));
+    }
+  }
+  if (act == MSPI_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+// row_bytes = 128 / 64 / 32 -> SWIZZLE_128B / 64B / 32B (layout codes 2 / 4 / 6), 8-row groups 8*row_bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;  // stride byte offset: 8 rows
+  d |= static_cast<uint64_t>(1) << 46;                  // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
+  return d;
+}
+
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+}  // namespace tc
+}  // namespace mspi

@@ -14,6 +14,7 @@ path; PyTorch only owns the memory.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -37,6 +38,7 @@ class ForwardPlan:
         if encoder not in ("s3d", "x3dl", "slowfast4x16"):
             raise Exception("Invalid Motion Encoder!")  # get_video_backbones.py:28-29
         self.encoder = encoder
+        self.fuse_mlp = os.environ.get("MSPI_FUSE_MLP", "1") != "0"
         self.steps: List[Tuple[str, Callable[[], None]]] = []
         self.flops = 0.0
         self.bytes_alloc = 0
@@ -431,6 +433,15 @@ class ForwardPlan:
                 y = self.new(nf, 1, h, w, d)
                 self.add(b + "conv_dw+norm", ops.dwconv_ln(x, y, self.P(b + "conv_dw.weight"), self.P(b + "conv_dw.bias"),
                                                            self.P(b + "norm.weight"), self.P(b + "norm.bias"), 1e-6))
+                if d in (96, 192) and self.fuse_mlp:
+                    # stages 0 and 1: fc1 + GELU + fc2 + layer scale + residual in one kernel, hidden tile on chip
+                    out = self.new(nf, 1, h, w, d)
+                    run = ops.mlp_fused(y, out, x, self.P(b + "mlp.fc1.weight"), self.P(b + "mlp.fc1.bias"),
+                                        self.P(b + "mlp.fc2.weight"), self.P(b + "mlp.fc2.bias"), self.P(b + "gamma"))
+                    self.add(b + "mlp(fused)", run)
+                    self.flops += run.flops
+                    x = out
+                    continue
                 hid = self.linear(b + "mlp.fc1", y, b + "mlp.fc1.weight", b + "mlp.fc1.bias", ACT_GELU)
                 # x + gamma * (fc2(h) + bias): layer scale folded into the epilogue scale/shift
                 x = self.linear(b + "mlp.fc2", hid, b + "mlp.fc2.weight", b + "mlp.fc2.bias", residual=x,

@@ -465,6 +465,34 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     return run
 
 
+# ------------------------------------------------------------------------------------------ fused ConvNeXt MLP
+def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma) -> Callable[[], None]:
+    """y = residual + gamma * (fc2(gelu(fc1(x)))) in one kernel (mspi_mlp_fused); C = 96 / 192, bf16."""
+    lib = _lib.load()
+    dev = x.buf.device
+    c = x.c
+    assert c in (96, 192) and x.c0 == 0 and x.cs == c and x.dtype == y.dtype == residual.dtype == torch.bfloat16
+    assert y.c == c and residual.c == c and y.pixels == x.pixels == residual.pixels
+    c_pad = -(-c // 64) * 64
+    w1 = torch.zeros((4 * c, c_pad), dtype=torch.float32, device=dev)
+    w1[:, :c] = fc1_w.detach().float().to(dev)
+    w1 = w1.to(torch.bfloat16).contiguous()
+    w2 = fc2_w.detach().float().to(dev).to(torch.bfloat16).contiguous()      # [c, 4c], K contiguous
+    b1 = fc1_b.detach().float().contiguous().to(dev)
+    g = gamma.detach().float().contiguous().to(dev)
+    sh = (g * fc2_b.detach().float().to(dev)).contiguous()
+    m = x.pixels
+    xp, yp, rp = x.ptr, y.ptr, residual.ptr
+    rs, ys = residual.cs, y.cs
+
+    def run(_keep=(x.buf, y.buf, residual.buf, w1, w2, b1, g, sh)):
+        _lib.check(lib.mspi_mlp_fused(xp, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(sh), rp, yp, m, c, c_pad, rs, ys,
+                                      _stream()), "mlp_fused")
+
+    run.flops = 2.0 * m * c * 4 * c * 2
+    return run
+
+
 # ------------------------------------------------------------------------------------------ X3D pieces
 def dwconv3d_bn(x: Act, y: Act, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                 stride_hw: int = 1, act: int = ACT_NONE) -> Callable[[], None]:

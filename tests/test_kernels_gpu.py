@@ -410,6 +410,31 @@ def test_attention_as_batched_gemms(b, n):
     assert _rel(out.cpu(), ref) < 5e-3
 
 
+@pytest.mark.parametrize("c,m", [(96, 128 * 5 + 37), (192, 128 * 3 + 5), (96, 128 * 300)])
+def test_mlp_fused(c, m):
+    """Fused ConvNeXt MLP (fc1 + GELU + fc2 + layer scale + residual, hidden tile on chip) against PyTorch on
+    bf16-rounded operands; the hidden activation is rounded to bf16 exactly like the unfused path does."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(m, c, generator=g)
+    r = torch.randn(m, c, generator=g)
+    w1 = torch.randn(4 * c, c, generator=g) / c ** 0.5
+    b1 = torch.randn(4 * c, generator=g) * 0.1
+    w2 = torch.randn(c, 4 * c, generator=g) / (4 * c) ** 0.5
+    b2 = torch.randn(c, generator=g) * 0.1
+    gamma = torch.rand(c, generator=g) + 0.5
+    xa = Act(x.to(torch.bfloat16).cuda().view(1, 1, 1, m, c))
+    ra = Act(r.to(torch.bfloat16).cuda().view(1, 1, 1, m, c))
+    ya = Act(torch.full((1, 1, 1, m, c), 7.0, dtype=torch.bfloat16, device="cuda"))
+    ops.mlp_fused(xa, ya, ra, w1, b1, w2, b2, gamma)()
+    torch.cuda.synchronize()
+    h = _bf(F.gelu(_bf(x) @ _bf(w1).t() + b1))
+    ref = _bf(r) + gamma * (h @ _bf(w2).t() + b2)
+    got = ya.buf.view(m, c).float().cpu()
+    assert _rel(got, ref) < BF16_TOL
+
+
 def test_sa_gate_token_mean_simsiam():
     from mspi_b200 import _lib, ops
     from mspi_b200.ops import Act

@@ -64,5 +64,31 @@ def main():
               f"elems/s={y.buf.numel() / ms / 1e6:.0f}G", flush=True)
 
 
+def fused():
+    """Fused MLP vs fc1 + fc2 on the ConvNeXt stage-0 / stage-1 shapes."""
+    import torch.nn.functional as F  # noqa: F401
+    for name, nf, h, w, c in (("s0.mlp.fused C96", 512, 56, 96, 96), ("s1.mlp.fused C192", 512, 28, 48, 192)):
+        m = nf * h * w
+        x = Act(torch.randn(1, 1, 1, m, c, device="cuda").to(torch.bfloat16))
+        r = Act(torch.randn(1, 1, 1, m, c, device="cuda").to(torch.bfloat16))
+        y = Act(torch.empty(1, 1, 1, m, c, device="cuda", dtype=torch.bfloat16))
+        run = ops.mlp_fused(x, y, r, torch.randn(4 * c, c) / c ** 0.5, torch.zeros(4 * c), torch.randn(c, 4 * c) / (4 * c) ** 0.5,
+                            torch.zeros(c), torch.ones(c))
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"{name:18s} {ms:8.3f} ms  {run.flops / ms / 1e9:8.1f} TF/s  {3 * m * c * 2 / ms / 1e6:8.1f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--fused" in sys.argv:
+        fused()
+    else:
+        main()
