@@ -122,7 +122,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    // Warp-uniform control flow (all lanes wait on the barriers), one elected lane issues: with `if (lane == 0)` ptxas
+    // wraps every uniform-datapath instruction (TMA, tcgen05) in a per-lane loop, and the single issuing thread's
+    // instruction latency — not the tensor pipe — bounds the small-N / small-K layers (profiles/r01: fused MLP study).
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -139,14 +143,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int c3 = org[2] + p.tap_off[tap][2], c4 = org[3] + p.tap_off[tap][3];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            const uint32_t full = bar_full + 8 * stage;
-            mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
-            const uint32_t sa = tiles_base + stage * stage_bytes;
-            tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
-            if (p.w_batched)
-              tma_load_4d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn, org[2], org[3]);
-            else
-              tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+            if (issuer) {
+              const uint32_t full = bar_full + 8 * stage;
+              mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
+              const uint32_t sa = tiles_base + stage * stage_bytes;
+              tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
+              if (p.w_batched)
+                tma_load_4d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn, org[2], org[3]);
+              else
+                tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+            }
+            __syncwarp();
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -154,11 +161,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const int mmas = p.row_bytes >> 5;  // one UMMA consumes 32 bytes of K per row
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
         tc_fence_after();
@@ -166,18 +175,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = tiles_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa, p.row_bytes);
-          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.row_bytes);
-          const int mmas = p.row_bytes >> 5;  // one UMMA consumes 32 bytes of K per row
-#pragma unroll 4
-          for (int k = 0; k < mmas; ++k) {
-            tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+          if (issuer) {
+            const uint32_t sa = tiles_base + stage * stage_bytes;
+            const uint64_t adesc = make_smem_desc(sa, p.row_bytes);
+            const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.row_bytes);
+            if (mmas == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+            } else {
+              for (int k = 0; k < mmas; ++k) tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
           }
-          tc_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(bar_tfull + 8 * as);  // accumulator complete
+        if (issuer) tc_commit(bar_tfull + 8 * as);  // accumulator complete
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -289,13 +303,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               }
             }
           }
+          if (out_bf16 && act == MSPI_ACT_GELU) {  // two elements per MUFU op (tc_ptx.cuh: gelu_pair)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = v[j];
-            if (has_res && !res_after) x += res[j];
-            x = epi_act<out_bf16>(x, act);
-            if (has_res && res_after) x += res[j];
-            v[j] = x;
+            for (int j = 0; j < 8; j += 2) {
+              if (has_res && !res_after) { v[j] += res[j]; v[j + 1] += res[j + 1]; }
+              gelu_pair(v[j], v[j + 1]);
+              if (has_res && res_after) { v[j] += res[j]; v[j + 1] += res[j + 1]; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = v[j];
+              if (has_res && !res_after) x += res[j];
+              x = epi_act<out_bf16>(x, act);
+              if (has_res && res_after) x += res[j];
+              v[j] = x;
+            }
           }
           if (p.tma_store) {
             if (out_bf16) {

@@ -13,8 +13,13 @@
 //
 // One persistent CTA per SM, warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue
 // (the kernel is bound by the GELU epilogue: 16 warps give the schedulers four independent instruction streams each).
+// Weight pieces are identical for every M tile, so the CTAs of a thread-block cluster (4 by default) stream them
+// TOGETHER: each CTA fetches 1/CL of every piece and TMA-multicasts it into the ring of all CL CTAs, and a ring slot
+// is released by a multicast tcgen05.commit from every consumer.  Without this the kernel is bound by re-reading the
+// 147 KB (C=96) / 590 KB (C=192) of weights per tile from L2 (measured 3.9 TB/s L2->SM, profiles/r01_fused_mlp*).
 // The MMA warp runs one software-pipelined stream over all (tile, hidden chunk) pairs: MMA1(g) is issued before
 // MMA2(g-1), so the tensor pipe always has a GEMM to run while the epilogue warps apply GELU to the previous chunk.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -30,10 +35,13 @@ constexpr int kEpiWarps = 16;                  // four per TMEM lane quarter: ea
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kChunkBytes = 128 * 128;         // one K chunk of a 128-row operand tile: 16 KB
 constexpr int kMaxRing = 8;
-constexpr uint32_t kTmemY = 2 * kHC;           // Y accumulators start after the two H buffers
+constexpr int kMaxHBuf = 3;
 
 struct MlpParams {
   int m_rows, c, kc1, nh, m_tiles, x_bufs;
+  int debug;            // tuning aid (MSPI_MLP_DEBUG bit mask): 1 skip GELU math, 2 skip TMEM loads, 4 skip A2 stores
+  int hbufs;            // TMEM buffers for the hidden chunk accumulators (3 when 3*128 + C <= 512, else 2)
+  int cl;               // cluster size (CTAs sharing the weight stream); cluster_tiles = ceil(m_tiles / cl)
   int ring_stages, ring_stage_bytes;
   const float* b1;      // [4C]
   const float* scale;   // [C]  layer scale gamma
@@ -44,6 +52,38 @@ struct MlpParams {
   uint32_t idesc1, idesc2;
 };
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ MlpParams p) {
@@ -53,8 +93,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   // barrier block
   const uint32_t ring_full = base, ring_empty = base + 8 * kMaxRing;
   const uint32_t x_full = base + 16 * kMaxRing, x_empty = x_full + 16;
-  const uint32_t h_full = x_empty + 16, h_empty = h_full + 16;
-  const uint32_t a2_full = h_empty + 16, a2_empty = a2_full + 16;
+  const uint32_t h_full = x_empty + 16, h_empty = h_full + 8 * kMaxHBuf;
+  const uint32_t a2_full = h_empty + 8 * kMaxHBuf, a2_empty = a2_full + 16;
   const uint32_t y_full = a2_empty + 16, y_empty = y_full + 8;
   const uint32_t tmem_slot = y_empty + 8;
   float* s_b1 = reinterpret_cast<float*>(base_ptr + 1024);       // [4C]
@@ -71,15 +111,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     for (int s = 0; s < p.ring_stages; ++s) {
       mbar_init(ring_full + 8 * s, 1);
-      mbar_init(ring_empty + 8 * s, 1);
+      mbar_init(ring_empty + 8 * s, static_cast<uint32_t>(p.cl));  // one multicast commit from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(x_full + 8 * s, 1);
       mbar_init(x_empty + 8 * s, 1);
-      mbar_init(h_full + 8 * s, 1);
-      mbar_init(h_empty + 8 * s, kEpiWarps);
       mbar_init(a2_full + 8 * s, kEpiWarps);
       mbar_init(a2_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < kMaxHBuf; ++s) {
+      mbar_init(h_full + 8 * s, 1);
+      mbar_init(h_empty + 8 * s, kEpiWarps);
     }
     mbar_init(y_full, 1);
     mbar_init(y_empty, kEpiWarps);
@@ -100,8 +142,18 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  const uint32_t tmem_y = tmem_base + static_cast<uint32_t>(p.hbufs * kHC);  // Y accumulators follow the H buffers
   const int x_buf_bytes = p.kc1 * kChunkBytes;
   const int w2_bytes = p.c * 128;
+  const uint32_t rank = p.cl > 1 ? cluster_ctarank() : 0u;
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cl) - 1u);
+  // tile schedule: cluster `cid` takes tile groups cid, cid + ncl, ...; CTA `rank` owns tile group*cl + rank.  Every CTA of
+  // a cluster runs the same number of iterations (a tile index past the end is a dummy: loads zero-fill, stores are
+  // masked), because all of them must consume every multicast weight piece.
+  const int cid = p.cl > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int ncl = p.cl > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
+  const int groups = (p.m_tiles + p.cl - 1) / p.cl;
+  if (p.cl > 1) cluster_sync_all();  // barrier inits of every CTA are visible before anyone multicasts
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -121,7 +173,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int kc = 0; kc < p.kc1; ++kc) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
           mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
-          tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w1, ring_full + 8 * stage, kc * 64, j * kHC);
+          if (p.cl > 1) {
+            const int share = kHC / p.cl;  // rows of the piece this CTA fetches for the whole cluster
+            tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w1, ring_full + 8 * stage,
+                           kc * 64, j * kHC + rank * share, mc_mask);
+          } else {
+            tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w1, ring_full + 8 * stage, kc * 64, j * kHC);
+          }
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
       };
@@ -129,16 +187,22 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
           mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
-          tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w2, ring_full + 8 * stage, j * kHC + kc2 * 64, 0);
+          if (p.cl > 1) {
+            const int share = p.c / p.cl;
+            tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w2, ring_full + 8 * stage,
+                           j * kHC + kc2 * 64, rank * share, mc_mask);
+          } else {
+            tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w2, ring_full + 8 * stage, j * kHC + kc2 * 64, 0);
+          }
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
       };
       // with two x buffers the tile after the current one is requested before the current tile's weights
-      if (p.x_bufs == 2 && static_cast<int>(blockIdx.x) < p.m_tiles) load_x(blockIdx.x);
+      if (p.x_bufs == 2 && cid < groups) load_x(cid * p.cl + rank);
       int prev_j = -1;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-        if (p.x_bufs == 1) load_x(tile);
-        else if (tile + static_cast<int>(gridDim.x) < p.m_tiles) load_x(tile + gridDim.x);
+      for (int grp = cid; grp < groups; grp += ncl) {
+        if (p.x_bufs == 1) load_x(grp * p.cl + rank);
+        else if (grp + ncl < groups) load_x((grp + ncl) * p.cl + rank);
         for (int j = 0; j < p.nh; ++j) {
           load_w1(j);
           if (prev_j >= 0) load_w2(prev_j);
@@ -149,7 +213,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the control flow (barrier waits are warp-uniform); one elected lane issues tcgen05 ops.
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int xs = 0;
@@ -167,24 +233,28 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(a2_base + (pb * 2 + kc2) * kChunkBytes, 128);
           const uint64_t bdesc = make_smem_desc(ring_base + stage * p.ring_stage_bytes, 128);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma<MSPI_BF16>(tmem_base + kTmemY, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (pj | kc2 | k) != 0 ? 1u : 0u);
-          tc_commit(ring_empty + 8 * stage);
+            for (int k = 0; k < 4; ++k)
+              tc_mma<MSPI_BF16>(tmem_y, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (pj | kc2 | k) != 0 ? 1u : 0u);
+            if (p.cl > 1) tc_commit_mc(ring_empty + 8 * stage, mc_mask); else tc_commit(ring_empty + 8 * stage);
+          }
+          __syncwarp();
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(a2_empty + 8 * pb);
-        if (pj == p.nh - 1) {
-          tc_commit(y_full);
-          ++ytile;
+        if (issuer) {
+          tc_commit(a2_empty + 8 * pb);
+          if (pj == p.nh - 1) tc_commit(y_full);
         }
+        __syncwarp();
+        if (pj == p.nh - 1) ++ytile;
       };
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      for (int grp = cid; grp < groups; grp += ncl) {
         mbar_wait(x_full + 8 * xs, xph);
         tc_fence_after();
         for (int j = 0; j < p.nh; ++j) {
-          const uint32_t b = g & 1u;
-          mbar_wait(h_empty + 8 * b, ((g >> 1) & 1u) ^ 1u);  // the epilogue has read H[b] of chunk g-2
+          const uint32_t b = g % static_cast<uint32_t>(p.hbufs);
+          mbar_wait(h_empty + 8 * b, ((g / p.hbufs) & 1u) ^ 1u);  // the epilogue has read H[b] of chunk g - hbufs
           tc_fence_after();
           for (int kc = 0; kc < p.kc1; ++kc) {
             mbar_wait(ring_full + 8 * stage, phase);
@@ -192,13 +262,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const uint64_t adesc = make_smem_desc(x_base + xs * x_buf_bytes + kc * kChunkBytes, 128);
             const uint64_t bdesc = make_smem_desc(ring_base + stage * p.ring_stage_bytes, 128);
             const int ksteps = min(4, (p.c - kc * 64 + 15) >> 4);  // skip the zero-padded K tail
-            for (int k = 0; k < ksteps; ++k)
-              tc_mma<MSPI_BF16>(tmem_base + b * kHC, adesc + 2u * k, bdesc + 2u * k, p.idesc1, (kc | k) != 0 ? 1u : 0u);
-            tc_commit(ring_empty + 8 * stage);
+            if (issuer) {
+              for (int k = 0; k < ksteps; ++k)
+                tc_mma<MSPI_BF16>(tmem_base + b * kHC, adesc + 2u * k, bdesc + 2u * k, p.idesc1, (kc | k) != 0 ? 1u : 0u);
+              if (p.cl > 1) tc_commit_mc(ring_empty + 8 * stage, mc_mask); else tc_commit(ring_empty + 8 * stage);
+            }
+            __syncwarp();
             if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(h_full + 8 * b);
-          if (j == p.nh - 1) tc_commit(x_empty + 8 * xs);  // x tile free once these MMAs have read it
+          if (issuer) {
+            tc_commit(h_full + 8 * b);
+            if (j == p.nh - 1) tc_commit(x_empty + 8 * xs);  // x tile free once these MMAs have read it
+          }
+          __syncwarp();
           if (prev_j >= 0) mma2(prev_j, prev_g);
           prev_j = j;
           prev_g = g;
@@ -214,64 +290,30 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int colgrp = (warp - 2) >> 2;      // which 32 of a chunk's 128 hidden columns
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t lane_y = tmem_y + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t g = 0, ytile = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const long long grow = static_cast<long long>(tile) * 128 + row;
-      const bool valid = grow < p.m_rows;
-      for (int j = 0; j < p.nh; ++j) {
-        const uint32_t b = g & 1u, ph = (g >> 1) & 1u;
-        mbar_wait(h_full + 8 * b, ph);
-        mbar_wait(a2_empty + 8 * b, ph ^ 1u);  // MMA2 of chunk g-2 has finished reading this staging buffer
-        tc_fence_after();
-        uint32_t packed[16];
-        const float* b1 = s_b1 + j * kHC + colgrp * 32;
-        {
-          uint32_t acc[32];
-          __syncwarp();
-          tmem_ld32(lane_addr + b * kHC + colgrp * 32, acc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * q);
-            const float v0 = gelu_bf16(__uint_as_float(acc[4 * q + 0]) + bb.x);
-            const float v1 = gelu_bf16(__uint_as_float(acc[4 * q + 1]) + bb.y);
-            const float v2 = gelu_bf16(__uint_as_float(acc[4 * q + 2]) + bb.z);
-            const float v3 = gelu_bf16(__uint_as_float(acc[4 * q + 3]) + bb.w);
-            packed[2 * q] = pack_bf16x2(v0, v1);
-            packed[2 * q + 1] = pack_bf16x2(v2, v3);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_empty + 8 * b);  // H[b] may be overwritten by MMA1 of chunk g+2
-        // 32 columns = four 16-byte pieces of K chunk (colgrp >> 1), pieces 4*(colgrp & 1) ..
-        const uint32_t dst_row = a2_base + (b * 2 + (colgrp >> 1)) * kChunkBytes + row * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int piece = 4 * (colgrp & 1) + i;
-          const uint32_t dst = dst_row + (static_cast<uint32_t>(piece ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * i]), "r"(packed[4 * i + 1]),
-                       "r"(packed[4 * i + 2]), "r"(packed[4 * i + 3])
-                       : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a2_full + 8 * b);
-        ++g;
-      }
-      // ---- Y tile: gamma * (acc + b2) + residual -> bf16; this thread's row, 16-column units colgrp, colgrp+4, ...
+    // The Y tile of a finished M tile is written one hidden chunk LATE (after the next tile's first GELU chunk): MMA2 of the
+    // last chunk then has time to finish, and the residual rows requested right after the last GELU chunk have arrived.
+    bool pend = false;
+    long long pgrow = 0;
+    bool pvalid = false;
+    uint4 resq[3][2];
+    auto y_epilogue = [&]() {
       mbar_wait(y_full, ytile & 1u);
       tc_fence_after();
-      for (int c0 = 16 * colgrp; c0 < p.c; c0 += 64) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int c0 = 16 * colgrp + 64 * u;
+        if (c0 >= p.c) break;
         uint32_t acc[16];
         __syncwarp();
-        tmem_ld16(lane_addr + kTmemY + c0, acc);
+        tmem_ld16(lane_y + c0, acc);
         tmem_ld_wait();
-        if (valid) {
+        if (pvalid) {
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             const int col = c0 + 8 * h8;
-            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + col));
+            const uint4 rr = resq[u][h8];
             float res[8];
             unpack_bf16x2(rr.x, res[0], res[1]); unpack_bf16x2(rr.y, res[2], res[3]);
             unpack_bf16x2(rr.z, res[4], res[5]); unpack_bf16x2(rr.w, res[6], res[7]);
@@ -282,7 +324,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.y + grow * p.y_stride + col) = o;
+            *reinterpret_cast<uint4*>(p.y + pgrow * p.y_stride + col) = o;
           }
         }
       }
@@ -290,11 +332,88 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(y_empty);
       ++ytile;
+    };
+    for (int grp = cid; grp < groups; grp += ncl) {
+      const long long grow = (static_cast<long long>(grp) * p.cl + rank) * 128 + row;
+      const bool valid = grow < p.m_rows;
+      for (int j = 0; j < p.nh; ++j) {
+        const uint32_t hb = g % static_cast<uint32_t>(p.hbufs), hph = (g / p.hbufs) & 1u;
+        const uint32_t ab = g & 1u, aph = (g >> 1) & 1u;
+        mbar_wait(h_full + 8 * hb, hph);
+        mbar_wait(a2_empty + 8 * ab, aph ^ 1u);  // MMA2 of chunk g-2 has finished reading this staging buffer
+        tc_fence_after();
+        uint32_t packed[16];
+        const float* b1 = s_b1 + j * kHC + colgrp * 32;
+        {
+          uint32_t acc[32];
+          __syncwarp();
+          if (!(p.debug & 2)) {
+            tmem_ld32(lane_addr + hb * kHC + colgrp * 32, acc);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[q] = 0x3f800000u + q + lane;
+          }
+          if (p.debug & 1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) packed[q] = pack_bf16x2(__uint_as_float(acc[2 * q]), __uint_as_float(acc[2 * q + 1]));
+          } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * q);
+            const float v0 = gelu_bf16(__uint_as_float(acc[4 * q + 0]) + bb.x);
+            const float v1 = gelu_bf16(__uint_as_float(acc[4 * q + 1]) + bb.y);
+            const float v2 = gelu_bf16(__uint_as_float(acc[4 * q + 2]) + bb.z);
+            const float v3 = gelu_bf16(__uint_as_float(acc[4 * q + 3]) + bb.w);
+            packed[2 * q] = pack_bf16x2(v0, v1);
+            packed[2 * q + 1] = pack_bf16x2(v2, v3);
+          }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_empty + 8 * hb);  // H[hb] may be overwritten by MMA1 of chunk g + hbufs
+        // 32 columns = four 16-byte pieces of K chunk (colgrp >> 1), pieces 4*(colgrp & 1) ..
+        const uint32_t dst_row = a2_base + (ab * 2 + (colgrp >> 1)) * kChunkBytes + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (p.debug & 4) break;
+          const int piece = 4 * (colgrp & 1) + i;
+          const uint32_t dst = dst_row + (static_cast<uint32_t>(piece ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * i]), "r"(packed[4 * i + 1]),
+                       "r"(packed[4 * i + 2]), "r"(packed[4 * i + 3])
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full + 8 * ab);
+        ++g;
+        if (j == 0 && pend) {
+          y_epilogue();
+          pend = false;
+        }
+      }
+      // this tile's hidden chunks are done: request its residual rows now, write its Y tile after the next GELU chunk
+      pend = true;
+      pgrow = grow;
+      pvalid = valid;
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int c0 = 16 * colgrp + 64 * u;
+          if (c0 < p.c) {
+            resq[u][0] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0));
+            resq[u][1] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0 + 8));
+          }
+        }
+      }
     }
+    if (pend) y_epilogue();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -330,8 +449,12 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   };
   CUtensorMap map_x, map_w1, map_w2;
   CUresult r1 = make2d(&map_x, x, c, static_cast<uint64_t>(m), c, 128);
-  CUresult r2 = make2d(&map_w1, w1, c_pad, hidden, c_pad, 128);
-  CUresult r3 = make2d(&map_w2, w2, hidden, c, hidden, c);
+  int cl = 1;  // CTAs per cluster sharing the weight stream by TMA multicast (MSPI_MLP_CLUSTER=1|2|4); measured: no
+               // gain on B200 (the kernel is bound by the MMA <-> epilogue hand-offs, not by L2), so off by default
+  if (const char* e = getenv("MSPI_MLP_CLUSTER")) cl = atoi(e);
+  if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+  CUresult r2 = make2d(&map_w1, w1, c_pad, hidden, c_pad, 128 / cl);
+  CUresult r3 = make2d(&map_w2, w2, hidden, c, hidden, c / cl);
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS)
     return set_error(MSPI_ERR_CUDA, "mspi_mlp_fused: cuTensorMapEncodeTiled failed (%d, %d, %d)", (int)r1, (int)r2, (int)r3);
 
@@ -359,9 +482,35 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   MSPI_CHECK_ARG(p.ring_stages >= 2, "mspi_mlp_fused: shared memory leaves %d ring stages", p.ring_stages);
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.ring_stages) * p.ring_stage_bytes;
   MSPI_CUDA(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  int grid = num_sms();
-  if (p.m_tiles < grid) grid = p.m_tiles;
-  fused_mlp_kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w1, map_w2, p);
+  p.cl = cl;
+  if (const char* e = getenv("MSPI_MLP_DEBUG")) p.debug = atoi(e);
+  p.hbufs = (3 * kHC + c <= 512) ? 3 : 2;
+  const int groups = (p.m_tiles + cl - 1) / cl;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent grid: as many clusters as can be resident at once (1 CTA per SM), never more than there are tile groups
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (max_clusters[cl] == 0) {
+    cfg.gridDim = dim3(num_sms() / cl * cl, 1, 1);
+    int n = 0;
+    MSPI_CUDA(cudaOccupancyMaxActiveClusters(&n, fused_mlp_kernel, &cfg));
+    max_clusters[cl] = n > 0 ? n : 1;
+  }
+  int nclusters = max_clusters[cl];
+  if (nclusters > num_sms() / cl) nclusters = num_sms() / cl;
+  if (nclusters > groups) nclusters = groups;
+  cfg.gridDim = dim3(nclusters * cl, 1, 1);
+  MSPI_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, map_x, map_w1, map_w2, p));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -1,6 +1,7 @@
 // tcgen05 / TMA / mbarrier PTX wrappers shared by the tensor-core kernels (conv_gemm.cu, fused_mlp.cu).  sm_100a only.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -19,23 +20,36 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.  The common case (phase already
+// complete) is one try_wait; the clock is only read once a wait has actually failed.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > (1ll << 32)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 32)) __trap();
   }
+}
+// One lane of a fully converged warp (warp-uniform control flow around tcgen05 / TMA issue, instead of `if (lane == 0)`
+// which makes ptxas wrap every uniform-datapath instruction in a per-lane loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {
@@ -103,10 +117,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// GELU for bf16 results: the tanh form 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715x^3))) with the hardware tanh (one MUFU
-// op, six FMA-pipe ops).  Against the exact erf form it differs by < 5e-4 absolute and < 2^-10 relative, below the half-ulp
-// (2^-9) of the bf16 value it is rounded to.  (Measured alternative: x / (1 + 2^(x (k0 + k1 x^2))) with ex2 + rcp — two
-// MUFU ops — is 23 % slower on the stage-0 fc1 layer: the epilogue is bound by MUFU + issue slots.)
+// GELU for bf16 results: the tanh form 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715x^3))).  Against the exact erf form it differs
+// by < 5e-4 absolute (worst near |x| = 2.7), i.e. below the bf16 half-ulp of any result of magnitude > 0.25 and far below
+// the bf16 noise of the fc2 sum the hidden activation feeds.
+// The GELU epilogues are MUFU bound: with one scalar tanh.approx.f32 per element every variant measured 3.9 elements/clk/SM
+// whatever the warp count (ex2 + rcp instead of tanh: 3.2).  gelu_pair therefore evaluates TWO elements per MUFU op with
+// tanh.approx.f16x2 (argument and result in fp16: 2^-11 on a value in [-1,1], again < 5e-4 absolute on the result);
+// everything else stays fp32.
 __device__ __forceinline__ float gelu_bf16(float x) {
   const float u = x * x;
   const float t = x * fmaf(u, 0.0356774081f, 0.7978845608f);
@@ -114,6 +131,18 @@ __device__ __forceinline__ float gelu_bf16(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
+}
+__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
+  const float t0 = x0 * fmaf(x0 * x0, 0.0356774081f, 0.7978845608f);
+  const float t1 = x1 * fmaf(x1 * x1, 0.0356774081f, 0.7978845608f);
+  uint32_t tp, th;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(tp) : "f"(t1), "f"(t0));  // {hi, lo} = {t1, t0}
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(tp));
+  const __half2 h = *reinterpret_cast<const __half2*>(&th);
+  const float2 f = __half22float2(h);
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  x0 = fmaf(h0, f.x, h0);
+  x1 = fmaf(h1, f.y, h1);
 }
 
 // Epilogue activation.
