@@ -115,31 +115,41 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   for (int j = 0; j < P; ++j) reinterpret_cast<float4*>(out_s + static_cast<size_t>(s * P + j) * C)[q] = acc[j];
   __syncthreads();
 
-  // ---- LayerNorm over C.  A warp normalises G pixels at a time (lane owns channel pairs lane, lane+32, ... of
-  // each): the G butterfly reductions are independent, so their shuffle latencies overlap.
+  // ---- LayerNorm over C.  LPP lanes share a pixel (16 for C = 96, else 32), each owning channel pairs lane, lane+LPP, ...;
+  // a warp handles G pixels per lane group at a time so the butterfly reductions of different pixels overlap, and the
+  // affine parameters live in registers for the whole tile.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kThreads / 32;
   constexpr int pairs = C / 2;
-  constexpr int MAXI = (pairs + 31) / 32;
-  constexpr int G = 4;
-  static_assert((S * P) % G == 0, "pixel groups");
-  for (int p0 = warp * G; p0 < S * P; p0 += nwarps * G) {
-    float2 v[G][MAXI];
+  constexpr int LPP = (pairs % 32 == 0) ? 32 : 16;   // lanes per pixel
+  static_assert(pairs % LPP == 0, "channel pairs must tile the lane group");
+  constexpr int NP = pairs / LPP;                     // pairs per lane
+  constexpr int GRP = 32 / LPP;                       // pixels handled side by side in one warp
+  constexpr int G = 4;                                // pixels per lane group per iteration
+  static_assert((S * P) % (G * GRP) == 0, "pixel groups");
+  const int sub = lane / LPP, sl = lane % LPP;
+  float2 gam[NP], bet[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    gam[i] = ln_w != nullptr ? __ldg(reinterpret_cast<const float2*>(ln_w) + sl + LPP * i) : make_float2(1.f, 1.f);
+    bet[i] = ln_w != nullptr ? __ldg(reinterpret_cast<const float2*>(ln_b) + sl + LPP * i) : make_float2(0.f, 0.f);
+  }
+  for (int p0 = (warp * GRP + sub) * G; p0 < S * P; p0 += nwarps * GRP * G) {
+    float2 v[G][NP];
     float sum[G], sq[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const float2* src = reinterpret_cast<const float2*>(out_s + static_cast<size_t>(p0 + g) * C);
       sum[g] = 0.f;
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
-        const int p = lane + 32 * i;
-        v[g][i] = p < pairs ? src[p] : make_float2(0.f, 0.f);
+      for (int i = 0; i < NP; ++i) {
+        v[g][i] = src[sl + LPP * i];
         sum[g] += v[g][i].x + v[g][i].y;
       }
     }
     if (ln_w != nullptr) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = LPP / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int g = 0; g < G; ++g) sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], o);
       }
@@ -148,20 +158,21 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
         sum[g] *= (1.f / C);  // mean
         sq[g] = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXI; ++i) {
-          if (lane + 32 * i < pairs) {
-            const float a = v[g][i].x - sum[g], b = v[g][i].y - sum[g];
-            sq[g] += a * a + b * b;
-          }
+        for (int i = 0; i < NP; ++i) {
+          const float a = v[g][i].x - sum[g], b = v[g][i].y - sum[g];
+          sq[g] += a * a + b * b;
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = LPP / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int g = 0; g < G; ++g) sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], o);
       }
 #pragma unroll
       for (int g = 0; g < G; ++g) sq[g] = rsqrtf(sq[g] * (1.f / C) + eps);  // rstd
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) { sum[g] = 0.f; sq[g] = 1.f; }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -170,21 +181,14 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
       if (py >= H || px >= W) continue;
       const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * C;
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
-        const int p = lane + 32 * i;
-        if (p < pairs) {
-          float a = v[g][i].x, b = v[g][i].y;
-          if (ln_w != nullptr) {
-            const float2 gm = __ldg(reinterpret_cast<const float2*>(ln_w) + p);
-            const float2 sh = __ldg(reinterpret_cast<const float2*>(ln_b) + p);
-            a = (a - sum[g]) * sq[g] * gm.x + sh.x;
-            b = (b - sum[g]) * sq[g] * gm.y + sh.y;
-          }
-          if (out_bf16)
-            reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
-          else
-            reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
-        }
+      for (int i = 0; i < NP; ++i) {
+        const int p = sl + LPP * i;
+        const float a = (v[g][i].x - sum[g]) * sq[g] * gam[i].x + bet[i].x;
+        const float b = (v[g][i].y - sum[g]) * sq[g] * gam[i].y + bet[i].y;
+        if (out_bf16)
+          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
+        else
+          reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
       }
     }
   }

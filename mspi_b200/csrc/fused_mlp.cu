@@ -156,44 +156,54 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (p.cl > 1) cluster_sync_all();  // barrier inits of every CTA are visible before anyone multicasts
 
   if (warp == 0) {
-    // ================================================================== TMA producer
-    if (lane == 0) {
+    // ================================================================== TMA producer (warp-uniform, one elected issuer)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int xs = 0;
       uint32_t xph = 0;
       auto load_x = [&](int tile) {
         mbar_wait(x_empty + 8 * xs, xph ^ 1u);
-        mbar_expect_tx(x_full + 8 * xs, static_cast<uint32_t>(x_buf_bytes));
-        for (int kc = 0; kc < p.kc1; ++kc)
-          tma_load_2d(x_base + xs * x_buf_bytes + kc * kChunkBytes, &map_x, x_full + 8 * xs, kc * 64, tile * 128);
+        if (issuer) {
+          mbar_expect_tx(x_full + 8 * xs, static_cast<uint32_t>(x_buf_bytes));
+          for (int kc = 0; kc < p.kc1; ++kc)
+            tma_load_2d(x_base + xs * x_buf_bytes + kc * kChunkBytes, &map_x, x_full + 8 * xs, kc * 64, tile * 128);
+        }
+        __syncwarp();
         if (++xs == p.x_bufs) { xs = 0; xph ^= 1u; }
       };
       auto load_w1 = [&](int j) {
         for (int kc = 0; kc < p.kc1; ++kc) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
-          mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
-          if (p.cl > 1) {
-            const int share = kHC / p.cl;  // rows of the piece this CTA fetches for the whole cluster
-            tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w1, ring_full + 8 * stage,
-                           kc * 64, j * kHC + rank * share, mc_mask);
-          } else {
-            tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w1, ring_full + 8 * stage, kc * 64, j * kHC);
+          if (issuer) {
+            mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
+            if (p.cl > 1) {
+              const int share = kHC / p.cl;  // rows of the piece this CTA fetches for the whole cluster
+              tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w1, ring_full + 8 * stage,
+                             kc * 64, j * kHC + rank * share, mc_mask);
+            } else {
+              tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w1, ring_full + 8 * stage, kc * 64, j * kHC);
+            }
           }
+          __syncwarp();
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
       };
       auto load_w2 = [&](int j) {
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
-          mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
-          if (p.cl > 1) {
-            const int share = p.c / p.cl;
-            tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w2, ring_full + 8 * stage,
-                           j * kHC + kc2 * 64, rank * share, mc_mask);
-          } else {
-            tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w2, ring_full + 8 * stage, j * kHC + kc2 * 64, 0);
+          if (issuer) {
+            mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
+            if (p.cl > 1) {
+              const int share = p.c / p.cl;
+              tma_load_2d_mc(ring_base + stage * p.ring_stage_bytes + rank * share * 128, &map_w2, ring_full + 8 * stage,
+                             j * kHC + kc2 * 64, rank * share, mc_mask);
+            } else {
+              tma_load_2d(ring_base + stage * p.ring_stage_bytes, &map_w2, ring_full + 8 * stage, j * kHC + kc2 * 64, 0);
+            }
           }
+          __syncwarp();
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
       };
