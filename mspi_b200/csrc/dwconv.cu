@@ -268,7 +268,8 @@ int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const
   if (!aligned) return 1;
   if (d->kt == 1 && d->kh == 7 && d->kw == 7) {
     using bf = __nv_bfloat16;
-    const bool wide = d->w % 16 == 0;  // strip of 16 where it tiles the row, else 8 (P+6 loads feed 7P FMA groups)
+    static const bool force8 = getenv("MSPI_DW_P8") != nullptr;  // tuning aid
+    const bool wide = d->w % 16 == 0 && !force8;  // strip of 16 where it tiles the row, else 8 (P+6 loads feed 7P FMA groups)
     if (d->in_dtype == MSPI_BF16) {
       if (d->c == 96) return wide ? launch_dw7x7<bf, 24, 8, 16>(d, x, wgt, bias, ln_w, ln_b, y, stream)
                                   : launch_dw7x7<bf, 24, 8, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
