@@ -19,6 +19,7 @@
 // convolution's zero padding.  See include/mspi_b200.h (MspiConvDesc) for the contract.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -55,11 +56,29 @@ struct GemmParams {
   int num_stages, a_bytes, b_bytes, a_tx_bytes, tmem_cols;
   int row_bytes;  // K chunk of one row: 128 (default), 64 or 32 bytes; selects the swizzle mode of the operand tiles
   int ss_floats;  // staged scale/shift length (n_tiles * bn)
+  int cl;         // CTAs per cluster that share every B (weight) tile by TMA multicast: 1 or 2
   int w_batched;  // 1: the B operand has its own matrix per (d3, d4) index of the M tile (batched GEMM, attention)
   int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
 };
 
 using namespace tc;
+
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------ kernel
 // ACT / RES are compile-time for the layer types the model uses (ACT: MSPI_ACT_*, RES: 0 none, 1 added before
@@ -93,7 +112,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_y) : "memory");
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, static_cast<uint32_t>(p.cl));  // one (multicast) commit per CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -117,8 +136,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.ntaps * p.kchunks;
+  // Work items: with a cluster of `cl` CTAs, item q = (group of cl consecutive M tiles, N tile); CTA `rank` takes M tile
+  // group*cl + rank.  All CTAs of a cluster walk the same items in lockstep because every B tile is fetched once per
+  // cluster (each CTA loads 1/cl of its rows and multicasts them); an M tile past the end is a dummy (loads zero-fill,
+  // nothing is stored).  cl == 1 degenerates to the plain persistent loop over tiles.
+  uint32_t rank = 0, cid = blockIdx.x, ncl = gridDim.x;
+  if (p.cl > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    cluster_sync_all();  // every CTA's barriers are initialised before anyone multicasts into them
+  }
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cl) - 1u);
+  const int total_items = ((p.m_tiles + p.cl - 1) / p.cl) * p.n_tiles;
+  constexpr int kFar = 0x3fffffff;  // a coordinate outside every tensor: dummy tiles read zeros and store nothing
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -129,15 +161,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
+      for (int item = cid; item < total_items; item += ncl) {
+        const int nt = item % p.n_tiles;
+        int mt = (item / p.n_tiles) * p.cl + rank;
+        const bool dummy = mt >= p.m_tiles;
         int org[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           org[j] = (mt % p.tiles_d[j]) * p.box[j];
           mt /= p.tiles_d[j];
         }
+        if (dummy) org[3] = kFar;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int c1 = org[0] + p.tap_off[tap][0], c2 = org[1] + p.tap_off[tap][1];
           const int c3 = org[2] + p.tap_off[tap][2], c4 = org[3] + p.tap_off[tap][3];
@@ -148,10 +182,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
               const uint32_t sa = tiles_base + stage * stage_bytes;
               tma_load_5d(sa, &tma_a, full, kc * p.bk_elems, c1, c2, c3, c4);
-              if (p.w_batched)
+              if (p.w_batched) {
                 tma_load_4d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn, org[2], org[3]);
-              else
+              } else if (p.cl > 1) {
+                const int share = p.bn / p.cl;  // rows of the B tile this CTA fetches for the whole cluster
+                tma_load_2d_mc(sa + p.a_bytes + rank * share * p.row_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems,
+                               nt * p.bn + rank * share, mc_mask);
+              } else {
                 tma_load_2d(sa + p.a_bytes, &tma_b, full, tap * p.cin_pad + kc * p.bk_elems, nt * p.bn);
+              }
             }
             __syncwarp();
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -168,7 +207,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int as = 0;
       uint32_t aphase = 0;
       const int mmas = p.row_bytes >> 5;  // one UMMA consumes 32 bytes of K per row
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = cid; item < total_items; item += ncl) {
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.bn);
@@ -185,7 +224,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             } else {
               for (int k = 0; k < mmas; ++k) tc_mma<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
             }
-            tc_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+            // frees the smem slot (in every CTA of the cluster: the next B tile is multicast into all of them)
+            if (p.cl > 1) tc_commit_mc(bar_empty + 8 * stage, mc_mask); else tc_commit(bar_empty + 8 * stage);
           }
           __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -213,11 +253,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool res_after = RES >= 0 ? RES == 2 : p.res_after_act != 0;
     const int nchunks = (p.bn + CH - 1) / CH;
     uint32_t store_seq = 0;  // bulk stores issued so far: chunk k of the kernel uses staging buffer k & 1
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
+    for (int item = cid; item < total_items; item += ncl) {
+      const int nt = item % p.n_tiles;
+      int mt = (item / p.n_tiles) * p.cl + rank;
+      const bool dummy = mt >= p.m_tiles;
       int r = row;
-      bool valid = true;
+      bool valid = !dummy;
       long long yoff = 0, roff = 0;
       int org[4];
 #pragma unroll
@@ -231,6 +272,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         roff += static_cast<long long>(c) * p.r_strides[j];
       }
       valid = valid && (r == 0);
+      if (dummy) org[3] = kFar;
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
@@ -395,6 +437,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -462,6 +505,17 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
                        d->box[1], d->box[2], d->box[3], d->box[4]);
   }
   const bool w_batched = d->w_batch_dims[0] > 0;
+  // Optional cluster of 2 CTAs sharing every B tile by TMA multicast (MSPI_GEMM_CLUSTER=1).  Measured on B200
+  // (tools/prof_gemm.py): no gain — the big-K layers are bound by what one SM can take in through TMA (~43 B/clk/SM:
+  // 40 KB per 128x192x64 k-step = 940 clk against 384 clk of MMA), not by L2 reads, and multicast does not reduce the
+  // bytes an SM receives.  Off by default; kept because the 2-CTA (cta_group::2) path will reuse its plumbing.
+  int cl = 1;
+  {
+    long long m_tiles_est = 1;
+    for (int j = 0; j < 4; ++j) m_tiles_est *= (d->o_dims[j] + d->box[j + 1] - 1) / d->box[j + 1];
+    static const int mode = [] { const char* e = getenv("MSPI_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
+    if (mode == 1 && !w_batched && d->bn % 16 == 0 && m_tiles_est >= 2) cl = 2;
+  }
   if (w_batched) {
     MSPI_CHECK_ARG(d->ntaps == 1 && d->w_batch_dims[0] == d->o_dims[2] && d->w_batch_dims[1] == d->o_dims[3] &&
                        d->box[3] == 1 && d->box[4] == 1,
@@ -473,7 +527,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     cuuint64_t gdim[4] = {w_batched ? static_cast<cuuint64_t>(d->a_dims[0]) : static_cast<cuuint64_t>(d->ntaps) * d->cin_pad,
                           static_cast<cuuint64_t>(d->w_rows), 1, 1};
     cuuint64_t gstr[3] = {gdim[0] * elsize, 0, 0};
-    cuuint32_t bdim[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->bn), 1, 1};
+    cuuint32_t bdim[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->bn / cl), 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (w_batched) {
       gdim[2] = static_cast<cuuint64_t>(d->w_batch_dims[0]);
@@ -523,6 +577,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
             (static_cast<uint32_t>(kTileM >> 4) << 24);
   p.row_bytes = row_bytes;
   p.w_batched = w_batched ? 1 : 0;
+  p.cl = cl;
   p.a_bytes = kTileM * row_bytes;
   p.b_bytes = d->bn * row_bytes;
   p.a_tx_bytes = static_cast<int>(rows) * row_bytes;
@@ -602,8 +657,28 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   MSPI_CHECK_ARG(total < (1ll << 31), "too many tiles");
   int grid = num_sms();
   if (grid <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  if (total < grid) grid = static_cast<int>(total);
-  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, p);
+  if (cl == 1) {
+    if (total < grid) grid = static_cast<int>(total);
+    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, p);
+  } else {
+    const long long items = static_cast<long long>((p.m_tiles + cl - 1) / cl) * p.n_tiles;
+    long long nclusters = grid / cl;
+    if (items < nclusters) nclusters = items;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(nclusters * cl), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, p));
+  }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
