@@ -88,6 +88,54 @@ def run_case(name, audio, b, h, w, init, wseed, iseed, encoder="s3d"):
     print(f"{name}: out range [{out.min():.4f}, {out.max():.4f}] loss {float(loss):.6f} taps {len(taps)}")
 
 
+# (name, forward fixture the ground truth is derived from, audio, B, H, W, init, weight seed, input seed)
+TRAIN_CASES = [
+    ("train_s3d_av_64x64_b2_cal", "s3d_av_64x64_b2_cal", True, 2, 64, 64, "calibrated", 0, 2023),
+    ("train_s3d_av_64x96_b2_def", None, True, 2, 64, 96, "default", 1, 2023),
+]
+
+
+def run_train_case(name, fwd_fixture, audio, b, h, w, init, wseed, iseed, encoder="s3d"):
+    """One optimisation step of the UNMODIFIED reference (engine_train.py:19-20,37-38,74-76; train.py:151-158):
+    model.train(); frozen_encoder(); SalLoss()(out, gt) + loss_va; backward; AdamW(lr 1e-4, wd 0).step().
+    Stored: the losses, a summary (norm + strided samples) of every gradient, of every updated parameter and of every
+    BatchNorm buffer after the step."""
+    import importlib
+    sd = orc.make_state_dict(wseed, init, audio=audio, encoder=encoder)
+    tokens = (16 if encoder == "x3dl" else 4) * (h // 32) * (w // 32)
+    model = ref_shim.build_reference_model(sd, encoder, num_vis_tokens=tokens, audio=audio)
+    lossmod = importlib.import_module("utils.loss")
+    clips, aud = orc.make_inputs(b, h, w, iseed)
+    if fwd_fixture:
+        log_map = torch.load(os.path.join(GOLDEN, fwd_fixture + ".pt"), weights_only=False)["out"]
+    else:
+        log_map = orc.forward(sd, clips, aud if audio else None, encoder=encoder)[0]
+    gt, _fix = orc.make_gt(log_map)
+    model.train()
+    model.frozen_encoder()
+    for n, p in model.named_parameters():
+        if n.startswith("audnet") or n.startswith("image_encoder"):
+            p.requires_grad_(False)
+    opt = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), 1e-4, weight_decay=0)
+    crit = lossmod.SalLoss()
+    out, loss_va = model(clips, aud) if audio else model(clips)
+    loss = crit(out, gt) + 1.0 * loss_va
+    opt.zero_grad()
+    loss.backward()
+    grads = {n: summarize(p.grad, 64) | {"norm": p.grad.norm().item()} for n, p in model.named_parameters() if p.requires_grad}
+    opt.step()
+    after = {n: summarize(p, 32) for n, p in model.named_parameters() if p.requires_grad}
+    bufs = {n: summarize(bf, 32) for n, bf in model.named_buffers()
+            if n.endswith(("running_mean", "running_var")) and not n.startswith(("audnet", "image_encoder"))}
+    fix = {"case": dict(name=name, fwd_fixture=fwd_fixture, audio=audio, b=b, h=h, w=w, init=init, wseed=wseed, iseed=iseed,
+                        encoder=encoder),
+           "loss": float(loss), "loss_va": float(loss_va), "kl": crit.log["kl"].val, "cc": crit.log["cc"].val,
+           "out": out.detach().clone(), "grads": grads, "params_after": after, "buffers_after": bufs}
+    torch.save(fix, os.path.join(GOLDEN, name + ".pt"))
+    print(f"{name}: loss {float(loss):.6f} (kl {crit.log['kl'].val:.6f} cc {crit.log['cc'].val:.6f} va {float(loss_va):.6f}) "
+          f"{len(grads)} grads, total norm {sum(g['norm'] ** 2 for g in grads.values()) ** 0.5:.4e}")
+
+
 def run_metrics():
     ref_shim.install()
     import importlib
@@ -148,6 +196,9 @@ def main():
     for c in CASES:
         if not only or any(o in c[0] for o in only):
             run_case(*c)
+    for c in TRAIN_CASES:
+        if not only or any(o in c[0] for o in only):
+            run_train_case(*c)
 
 
 if __name__ == "__main__":

@@ -47,8 +47,26 @@ DE = 192                                           # de_embed_dim, model_utils.p
 
 
 # ============================================================================ building blocks
+# Train mode (engine_train.py:19-20: model.train(); model.frozen_encoder()): every BatchNorm outside `audnet.` /
+# `image_encoder.` normalises with the statistics of the current batch (biased variance) and moves its running statistics
+# by `momentum` (unbiased variance), torch.nn.BatchNorm semantics.  _TRAIN["stats"] collects the updated buffers.
+_TRAIN = {"on": False, "stats": None}
+FROZEN_PREFIXES = ("audnet.", "image_encoder.")  # train.py:151-155, model_utils.py:516-518
+
+
 def _bn(sd: SD, p: str, x, eps):
     shape = [1, -1] + [1] * (x.dim() - 2)
+    if _TRAIN["on"] and not p.startswith(FROZEN_PREFIXES):
+        # momentum: the S3D-style blocks (eps 1e-3) use 0.001 (backbones/s3d.py:45,99,103), nn.BatchNorm3d defaults
+        # (eps 1e-5, readout: model_utils.py:493,496) use 0.1
+        mom = 0.001 if eps == 1e-3 else 0.1
+        rm, rv = sd[p + ".running_mean"].clone(), sd[p + ".running_var"].clone()
+        # y = (x - mean_batch) / sqrt(var_batch_biased + eps) * w + b; rm/rv <- (1-mom)*old + mom*(mean, unbiased var)
+        y = F.batch_norm(x, rm, rv, sd[p + ".weight"], sd[p + ".bias"], True, mom, eps)
+        if _TRAIN["stats"] is not None:
+            _TRAIN["stats"][p + ".running_mean"], _TRAIN["stats"][p + ".running_var"] = rm, rv
+            _TRAIN["stats"][p + ".num_batches_tracked"] = sd[p + ".num_batches_tracked"] + 1
+        return y
     scale = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + eps)
     return (x - sd[p + ".running_mean"].view(shape)) * scale.view(shape) + sd[p + ".bias"].view(shape)
 
@@ -334,7 +352,7 @@ def simsiam_loss(sd: SD, vis_fea, aud_fea):
     za = _head(sd, "aud_projector", aud_fea.mean(1), (0, 3, 6), True)
     pv = _head(sd, "mlp_vis", zv, (0, 3), False)
     pa = _head(sd, "mlp_aud", za, (0, 3), False)
-    d = lambda a, b: -F.cosine_similarity(a, b, dim=-1).mean()
+    d = lambda a, b: -F.cosine_similarity(a, b.detach(), dim=-1).mean()  # stop-gradient on z, model_utils.py:285-290
     return 0.5 * (d(pv, za) + d(pa, zv))
 
 
@@ -403,9 +421,14 @@ def motion_features(sd: SD, encoder: str, clips):
     raise Exception("Invalid Motion Encoder!")  # get_video_backbones.py:28-29
 
 
-@torch.no_grad()
 def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: Optional[dict] = None,
             encoder: str = "s3d"):
+    with torch.no_grad():
+        return _forward(sd, clips, audios, taps, encoder)
+
+
+def _forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: Optional[dict] = None,
+             encoder: str = "s3d"):
     """AudioVisualSaliencyModel.forward (audios given) / VisualSaliencyModel.forward (audios None) for the motion
     encoders s3d / x3dl / slowfast4x16.  model_utils.py:520-574, 685-702.  Returns (log_map [B,H,W], loss_av)."""
     enc = ENCODERS[encoder]
@@ -446,6 +469,47 @@ def forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: O
     rec("readout", out)
     out = out - torch.logsumexp(out, dim=(1, 2), keepdim=True)
     return out, loss
+
+
+# ============================================================================ training step
+def trainable_keys(sd: SD) -> List[str]:
+    """Parameters the optimiser sees (train.py:151-158): everything with a gradient outside audnet / image_encoder,
+    in state_dict order (= named_parameters() order, which is the AdamW parameter order)."""
+    return [k for k, v in sd.items() if v.is_floating_point() and not k.startswith(FROZEN_PREFIXES)
+            and not k.endswith((".running_mean", ".running_var"))]
+
+
+def train_grads(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], gt: torch.Tensor, encoder: str = "s3d",
+                gamma: float = 1.0):
+    """loss and gradients of one training step: model.train() + frozen_encoder(); output, loss_va = model(imgs, audio);
+    loss = SalLoss()(output, label) + gamma * loss_va; loss.backward().  engine_train.py:19-20,37-38,74-75, train.py:31.
+    Returns dict(loss, kl, cc, loss_va, out, grads{name: tensor}, stats{name: updated BN buffer})."""
+    keys = trainable_keys(sd)
+    work = dict(sd)
+    for k in keys:
+        work[k] = sd[k].detach().clone().requires_grad_(True)
+    _TRAIN["on"], _TRAIN["stats"] = True, {}
+    try:
+        out, loss_va = _forward(work, clips, audios, None, encoder)
+        parts = sal_loss(out, gt)
+        loss = parts["loss"] + gamma * loss_va
+        loss.backward()
+        stats = _TRAIN["stats"]
+    finally:
+        _TRAIN["on"], _TRAIN["stats"] = False, None
+    grads = {k: (work[k].grad if work[k].grad is not None else torch.zeros_like(work[k])) for k in keys}
+    return {"loss": loss.detach(), "kl": parts["kl"].detach(), "cc": parts["cc"].detach(), "loss_va": loss_va.detach(),
+            "out": out.detach(), "grads": grads, "stats": stats}
+
+
+def adamw_step(p, g, m, v, step: int, lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+               weight_decay: float = 0.0):
+    """torch.optim.AdamW(lr=cfg.SOLVER.LR, weight_decay=0) single-tensor update (train.py:157-158); returns (p, m, v)."""
+    p = p * (1 - lr * weight_decay)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    denom = (v.sqrt() / math.sqrt(1 - beta2 ** step)) + eps
+    return p - (lr / (1 - beta1 ** step)) * m / denom, m, v
 
 
 # ============================================================================ loss and metrics

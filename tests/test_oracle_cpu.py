@@ -133,3 +133,44 @@ def test_param_spec_counts():
     assert len(sp) == 993  # 993 state_dict keys for the S3D variant
     n = sum(int(torch.tensor(s).prod()) if s else 1 for _, s in sp.values())
     assert n == 87609972
+
+
+@pytest.mark.parametrize("name", ["train_s3d_av_64x64_b2_cal", "train_s3d_av_64x96_b2_def"])
+def test_train_step_matches_reference(name):
+    """Row a20: the oracle's train-mode forward (batch-statistics BatchNorm outside the frozen encoders), loss, autograd
+    gradients of all 411 trainable tensors, BatchNorm buffer updates and the AdamW update against one optimisation step
+    of the live reference (oracle/gen_golden.py: run_train_case)."""
+    fx = _load(name + ".pt")
+    c = fx["case"]
+    sd = orc.make_state_dict(c["wseed"], c["init"], audio=c["audio"], encoder=c["encoder"])
+    clips, aud = orc.make_inputs(c["b"], c["h"], c["w"], c["iseed"])
+    log_map = _load(c["fwd_fixture"] + ".pt")["out"] if c["fwd_fixture"] else orc.forward(sd, clips, aud)[0]
+    gt, _ = orc.make_gt(log_map)
+    r = orc.train_grads(sd, clips, aud, gt)
+    assert abs(float(r["loss"]) - fx["loss"]) < 2e-5 and abs(float(r["loss_va"]) - fx["loss_va"]) < 1e-5
+    assert abs(float(r["kl"]) - fx["kl"]) < 2e-5 and abs(float(r["cc"]) - fx["cc"]) < 2e-5
+    assert (r["out"] - fx["out"]).abs().max().item() < 2e-4 * fx["out"].abs().max().item()
+    keys = orc.trainable_keys(sd)
+    assert keys == list(fx["grads"].keys()) and len(keys) == 411
+    total = sum(g["norm"] ** 2 for g in fx["grads"].values()) ** 0.5
+    worst = 0.0
+    for k in keys:
+        g, summ = r["grads"][k], fx["grads"][k]
+        assert tuple(g.shape) == summ["shape"], k
+        # same fp32 arithmetic in a different summation order; tiny gradients are judged against the global scale
+        tol = 2e-3 * max(summ["absmax"], 1e-6 * total)
+        diff = (_tap_samples(g, summ) - summ["samples"]).abs().max().item()
+        worst = max(worst, diff / tol)
+        assert diff < tol, (k, diff, summ["absmax"])
+        assert abs(g.norm().item() - summ["norm"]) < 2e-3 * summ["norm"] + 1e-6 * total, k
+    for k, summ in fx["buffers_after"].items():
+        diff = (_tap_samples(r["stats"][k], summ) - summ["samples"]).abs().max().item()
+        assert diff < 1e-5 * max(1.0, summ["absmax"]), (k, diff)
+    # AdamW, first step (train.py:157): m = v = 0
+    for k in keys[::37]:
+        p1, _, _ = orc.adamw_step(sd[k], r["grads"][k], torch.zeros_like(sd[k]), torch.zeros_like(sd[k]), 1)
+        summ = fx["params_after"][k]
+        got, ref0 = _tap_samples(p1, summ), _tap_samples(sd[k], summ)
+        # the first AdamW step is lr*sign(g) wherever |g| >> eps: compare where the reference moved by the full lr
+        moved = (summ["samples"] - ref0).abs() > 0.99e-4
+        assert ((got - summ["samples"]).abs()[moved] < 2e-6).all(), k
