@@ -95,6 +95,18 @@ int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const fl
                    const float* shift, const void* residual, void* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Weight gradient of mspi_conv_gemm's convolution on tcgen05 tensor cores (training step, engine_train.py:74:
+ * loss.backward() through nn.Conv3d / nn.Linear):
+ *   dw[co*s_co + tap*s_tap + ci*s_ci] += sum over output positions p of dy[p][co] * x[p + tap_off[tap]][ci]
+ * `d` is the FORWARD descriptor of the layer (a_dims/a_strides/box/tap_off describe x, o_dims/o_strides describe dy,
+ * d->o_dtype == d->a_dtype: both operands bf16 or both fp32/tf32; box positions a multiple of 16 (bf16) / 8 (tf32)).
+ * The position axis is the GEMM's reduction axis (both operands "MN-major"), split across CTAs; partial sums are
+ * added into the fp32 gradient tensor with red.global.add.f32, so dw must be initialised (zero or the running sum).
+ * s_co / s_ci / s_tap: element strides of dw, e.g. (cin*taps, taps, 1) for PyTorch's [Cout][Cin][kt][kh][kw]. */
+int mspi_conv_wgrad(const MspiConvDesc* d, const void* x, const void* dy, float* dw, int64_t s_co, int64_t s_ci,
+                    int64_t s_tap, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused ConvNeXt MLP (timm convnext Mlp + layer scale + residual, model_utils.py:361), C = 96 or 192:
  *   y[m][:] = residual[m][:] + scale * ( W2 . gelu(W1 . x[m][:] + b1) ) + shift        (scale = gamma, shift = gamma*b2)
  * x bf16 [m][c] (row stride c), w1 bf16 [4c][c_pad] (K zero padded to c_pad = multiple of 64), w2 bf16 [c][4c],

@@ -127,6 +127,44 @@ def choose_box(dims: Tuple[int, int, int, int], max_rows: int = 128) -> Tuple[in
     return best
 
 
+@functools.lru_cache(maxsize=None)
+def choose_box_k(dims: Tuple[int, int, int, int], mult: int, max_rows: int = 128) -> Tuple[int, int, int, int]:
+    """Position box for the weight-gradient GEMM: the box is the MMA's K extent, so its volume must be a multiple of
+    `mult` (one MMA K step: 16 bf16 / 8 tf32 positions); it may overhang the tensor (TMA zero-fills dY there).
+    Fewest boxes first, then the least overhang."""
+    best, best_key = None, None
+
+    def cands(d):
+        out = set()
+        for b in range(1, min(max_rows, 2 * d) + 1):
+            if b <= d or (b & (b - 1)) == 0 or b % mult == 0:
+                out.add(b)
+        return sorted(out)
+
+    c = [cands(d) for d in dims]
+    for b1 in c[0]:
+        for b2 in c[1]:
+            if b1 * b2 > max_rows:
+                break
+            for b3 in c[2]:
+                if b1 * b2 * b3 > max_rows:
+                    break
+                for b4 in c[3]:
+                    v = b1 * b2 * b3 * b4
+                    if v > max_rows:
+                        break
+                    if v % mult:
+                        continue
+                    tiles = 1
+                    for d, b in zip(dims, (b1, b2, b3, b4)):
+                        tiles *= -(-d // b)
+                    key = (tiles, tiles * v, -b1)
+                    if best_key is None or key < best_key:
+                        best, best_key = (b1, b2, b3, b4), key
+    assert best is not None
+    return best
+
+
 def choose_bn(cout: int, chunk: int = 64) -> int:
     """N tile of the UMMA (multiple of 16, <= 256).  With several N tiles every tile must end on a 128-byte
     output chunk (`chunk` columns: 64 bf16 / 32 fp32) so the epilogue can bulk-store whole chunks."""
@@ -221,6 +259,77 @@ class Conv:
         p_lo, _, _ = pack_conv_weight(w5 - hi, self.dtype)
         return torch.cat([p_hi, p_lo], 1).contiguous(), 2 * taps, cin_pad
 
+    def _geom(self, mode: str, x: Act, ot: int, oh: int, ow: int):
+        """TMA view of the input (dims/strides, inner -> outer), output extents, per-tap box offsets and the output
+        row-stride function for the implicit-GEMM modes (shared by the forward plan and the weight-gradient plan)."""
+        (st, sh, sw), (pt, ph, pw) = self.stride, self.pad
+        if mode == "shift":
+            a_dims = (x.c, x.w, x.h, x.t, x.n)
+            a_str = (1, x.cs, x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
+            o_dims = (ow, oh, ot, x.n)
+            offs = [(kw - pw, kh - ph, kt - pt, 0) for kt in range(self.kt) for kh in range(self.kh) for kw in range(self.kw)]
+            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+        elif mode == "pick":
+            a_dims = (x.c, ow, oh, x.t, x.n)
+            a_str = (1, sw * x.cs, sh * x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
+            o_dims = (ow, oh, ot, x.n)
+            offs = [(0, 0, 0, 0)]
+            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+        elif mode == "tstride":
+            hw = x.h * x.w
+            a_dims = (x.c, hw, st, x.t // st, x.n)
+            a_str = (1, x.cs, hw * x.cs, st * hw * x.cs, x.t * hw * x.cs)
+            o_dims = (hw, 1, ot, x.n)
+            offs = []
+            for kt in range(self.kt):
+                dlt = kt - pt
+                q = dlt // st  # floor
+                offs.append((0, dlt - q * st, q, 0))
+            ostr = lambda a: (a.cs, 0, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+        else:
+            raise ValueError(mode)
+        return a_dims, a_str, o_dims, offs, ostr
+
+    def wgrad_plan(self, x: Act, dy: Act, dw: torch.Tensor) -> Callable[[], None]:
+        """dw (fp32, the layer's own [Cout, Cin, kt, kh, kw] / [Cout, Cin] gradient tensor, contiguous) +=
+        sum_p dy[p] (x) x[p + tap]  on the tensor cores (mspi_conv_wgrad).  x and dy share the layer dtype."""
+        lib = _lib.load()
+        ot, oh, ow = self.out_shape(x.t, x.h, x.w)
+        assert (dy.n, dy.t, dy.h, dy.w, dy.c) == (x.n, ot, oh, ow, self.cout) and x.c == self.cin
+        assert x.dtype == dy.dtype == self.dtype and dw.dtype == torch.float32 and dw.is_contiguous()
+        assert dw.numel() == self.cout * self.cin * self.kt * self.kh * self.kw
+        mode = self._mode(x)
+        assert mode in ("shift", "pick", "tstride"), f"{self.name}: wgrad needs an implicit-GEMM layer, got {mode}"
+        es = _ES[self.dtype]
+        assert (dy.cs * es) % 16 == 0 and (dy.c0 * es) % 16 == 0, f"{self.name}: dy slice not 16-byte aligned"
+        a_dims, a_str, o_dims, offs, ostr = self._geom(mode, x, ot, oh, ow)
+        d = ConvDesc()
+        d.a_dtype = d.o_dtype = _DT[self.dtype]
+        d.cout = self.cout
+        # tf32 chunks are 128 B per position like bf16 ones but hold half the channels: 64-position stages keep >= 3
+        # pipeline stages in shared memory at the widest tiles (128 x 128 channels)
+        box = choose_box_k(tuple(o_dims), 16, 128) if self.dtype == torch.bfloat16 else choose_box_k(tuple(o_dims), 8, 64)
+        for j in range(5):
+            d.a_dims[j], d.a_strides[j] = a_dims[j], a_str[j]
+        d.box[0] = 0
+        for j in range(4):
+            d.box[j + 1], d.o_dims[j], d.o_strides[j] = box[j], o_dims[j], ostr(dy)[j]
+        taps = len(offs)
+        d.ntaps = taps
+        for i, o in enumerate(offs):
+            for j in range(4):
+                d.tap_off[i][j] = o[j]
+        s_co, s_ci, s_tap = self.cin * taps, taps, 1
+        xp, dyp, dwp = x.ptr, dy.ptr, _ptr(dw)
+        name = self.name
+
+        def run(_keep=(x.buf, dy.buf, dw, d)):
+            _lib.check(lib.mspi_conv_wgrad(C.byref(d), xp, dyp, dwp, s_co, s_ci, s_tap, _stream()), f"conv_wgrad[{name}]")
+
+        run.desc = d
+        run.flops = self.flops(x)
+        return run
+
     def plan(self, x: Act, y: Act, residual: Optional[Act] = None) -> Callable[[], None]:
         """Build the descriptor(s) for this input/output pair; returns a closure that enqueues the kernels."""
         lib = _lib.load()
@@ -240,34 +349,9 @@ class Conv:
         es = _ES[self.dtype]
         pre = None
         (st, sh, sw), (pt, ph, pw) = self.stride, self.pad
-        if mode == "shift":
+        if mode in ("shift", "pick", "tstride"):
             packed, taps, cin_pad = self._pack(self.w_raw)
-            a_dims = (x.c, x.w, x.h, x.t, x.n)
-            a_str = (1, x.cs, x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
-            o_dims = (ow, oh, ot, x.n)
-            offs = [(kw - pw, kh - ph, kt - pt, 0) for kt in range(self.kt) for kh in range(self.kh) for kw in range(self.kw)]
-            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
-            x_ptr = x.ptr
-        elif mode == "pick":
-            packed, taps, cin_pad = self._pack(self.w_raw)
-            a_dims = (x.c, ow, oh, x.t, x.n)
-            a_str = (1, sw * x.cs, sh * x.w * x.cs, x.h * x.w * x.cs, x.t * x.h * x.w * x.cs)
-            o_dims = (ow, oh, ot, x.n)
-            offs = [(0, 0, 0, 0)]
-            ostr = lambda a: (a.cs, a.w * a.cs, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
-            x_ptr = x.ptr
-        elif mode == "tstride":
-            packed, taps, cin_pad = self._pack(self.w_raw)
-            hw = x.h * x.w
-            a_dims = (x.c, hw, st, x.t // st, x.n)
-            a_str = (1, x.cs, hw * x.cs, st * hw * x.cs, x.t * hw * x.cs)
-            o_dims = (hw, 1, ot, x.n)
-            offs = []
-            for kt in range(self.kt):
-                dlt = kt - pt
-                q = dlt // st  # floor
-                offs.append((0, dlt - q * st, q, 0))
-            ostr = lambda a: (a.cs, 0, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+            a_dims, a_str, o_dims, offs, ostr = self._geom(mode, x, ot, oh, ow)
             x_ptr = x.ptr
         else:  # explicit patch gather + flat GEMM
             k = self.kt * self.kh * self.kw * self.cin
