@@ -301,6 +301,112 @@ int mspi_postprocess_maps(const float* log_maps, uint8_t* out, float* work, int 
  * frames_out. */
 int mspi_logspec(const float* wave, float* out, int b, int n, int frames_out, void* stream);
 
+/* ==========================================================================================
+ * Training step (engine_train.py:27-76, train.py:151-166): model.train() + frozen_encoder(), SalLoss + gamma*loss_va,
+ * loss.backward(), AdamW.  Data and weight gradients of every Conv3d / Linear are mspi_conv_gemm (on the transposed /
+ * flipped weights) and mspi_conv_wgrad; the entry points below are everything else.  All tensors fp32, channels-last
+ * [pixels][C] views with an element stride between pixels ("cstride", so channel slices of concatenated buffers work in
+ * place).  Gradient outputs: `accumulate` 0 overwrites, 1 adds; scatter-type adjoints (max-pool, upsample) and parameter
+ * gradients always add, so their targets must hold zero or the running sum.
+ * ========================================================================================== */
+
+/* BatchNorm3d in training mode (torch.nn.BatchNorm semantics; backbones/s3d.py:45,99,103, model_utils.py:493,496):
+ * y = act((x - mean_batch) * invstd_batch * weight + bias), biased batch variance; running buffers move by `momentum`
+ * towards (mean, unbiased variance), *num_batches_tracked += 1 (both optional).  save_mean / save_invstd [c] are kept for
+ * the backward; scale_shift [2c] and work (double [2c], zero on entry, left zero) are scratch.  relu: 0 / 1. */
+int mspi_bn_train_fwd(const float* x, int64_t x_cstride, float* y, int64_t y_cstride, int64_t pixels, int c,
+                      const float* weight, const float* bias, float eps, float momentum, float* running_mean,
+                      float* running_var, int64_t* num_batches_tracked, float* save_mean, float* save_invstd,
+                      float* scale_shift, double* work, int relu, void* stream);
+/* Its backward: g = dy masked by the ReLU (y > 0) when relu; dweight += sum g*xhat; dbias += sum g;
+ * dx (+)= weight*invstd*(g - mean(g) - xhat*mean(g*xhat)).  coef: float [3c] scratch; work as above. */
+int mspi_bn_train_bwd(const float* x, int64_t x_cstride, const float* y, int64_t y_cstride, const float* dy,
+                      int64_t dy_cstride, float* dx, int64_t dx_cstride, int64_t pixels, int c, const float* weight,
+                      const float* save_mean, const float* save_invstd, float* dweight, float* dbias, float* coef,
+                      double* work, int relu, int accumulate, void* stream);
+
+/* y = act(x) elementwise (exact-erf GELU of nn.GELU, model_utils.py:45,325; kept separate from the GEMM epilogue in training
+ * because the backward needs the pre-activation). */
+int mspi_act_fwd(const float* x, float* y, int64_t n, int act, void* stream);
+/* g = dy * act'(ref): ref is the activation's OUTPUT for RELU, its INPUT for GELU, unused for NONE.  dz = g when dz != NULL
+ * (may alias dy); dbias[ch] += sum over pixels of g when dbias != NULL (the bias gradient of the conv / linear before it). */
+int mspi_act_bwd(const float* dy, int64_t dy_cstride, const float* ref, int64_t ref_cstride, float* dz, int64_t dz_cstride,
+                 int64_t pixels, int c, int act, float* dbias, void* stream);
+
+/* fp32 MaxPool3d (same descriptor as mspi_maxpool3d) and its adjoint: each output element adds its gradient to the first
+ * maximal input of its window in (t,h,w) scan order, the index torch's forward records. */
+int mspi_maxpool3d_f32(const MspiPoolDesc* d, const float* x, float* y, void* stream);
+int mspi_maxpool3d_bwd(const MspiPoolDesc* d, const float* x, const float* dy, int64_t dy_cstride, float* dx,
+                       int64_t dx_cstride, void* stream);
+
+/* Adjoint of mspi_upsample_bilinear (fp32; `d` is the forward descriptor): dx += up^T(g), g = dy masked by y > 0 when
+ * d->act == MSPI_ACT_RELU (y = the forward output, else unused).  d->accumulate is ignored: y = y_old + up(x) passes dy to
+ * y_old unchanged. */
+int mspi_upsample_bilinear_bwd(const MspiUpDesc* d, const float* dy, const float* y, float* dx, void* stream);
+
+/* LayerNorm backward over rows (nn.LayerNorm / LayerNorm3d, model_utils.py:138-144,231-233,293-303,406-434).  Row r of dy
+ * (and of y_relu, the forward output, when the LayerNorm was followed by a ReLU) lives at
+ * (r / rows_per_group)*dy_gstride + (r % rows_per_group)*dy_rstride.  dx (+)= ...; dw += sum g*xhat; db += sum g. */
+int mspi_layernorm_bwd(const float* x, int64_t x_rstride, const float* dy, int64_t dy_rstride, int64_t rows_per_group,
+                       int64_t dy_gstride, const float* y_relu, const float* w, float eps, float* dx, int64_t dx_rstride,
+                       int64_t rows, int c, int accumulate, float* dw, float* db, void* stream);
+
+/* Softmax backward in place: dp <- scale * p * (dp - sum_k dp*p) per row (attention, model_utils.py:104-106). */
+int mspi_softmax_bwd_rows(const float* p, float* dp, int64_t rows, int n, int64_t stride, float scale, void* stream);
+
+/* Small strided batched fp32 GEMM, C[b1][b0][i][j] (+)= alpha * sum_k A[..][i][k] B[..][k][j]; strides (elements) are
+ * {i, k, batch0, batch1} for A, {k, j, batch0, batch1} for B, {i, j, batch0, batch1} for C.  The attention backward
+ * (dV = P^T dO, dP = dO V^T, dQ = dS K, dK = dS^T Q over 372 tokens x 4 heads) reads four differently transposed views. */
+typedef struct {
+  int32_t m, n, k, batch0, batch1, accumulate;
+  float alpha;
+  int64_t a_strides[4], b_strides[4], c_strides[4];
+} MspiSgemmDesc;
+int mspi_sgemm_strided(const MspiSgemmDesc* d, const float* a, const float* b, float* c, void* stream);
+
+/* SA gating backward (model_utils.py:167-170), y = x*sigmoid(l) + x: dx (+)= dy*(1 + s); dlogits = s(1-s) sum_c dy*x. */
+int mspi_sa_gate_bwd(const float* x, int64_t x_cstride, const float* mask_logits, const float* dy, int64_t dy_cstride,
+                     float* dx, int64_t dx_cstride, float* dlogits, int64_t pixels, int c, int accumulate, void* stream);
+
+/* Backward of the 32 -> 1 channel (1,3,3) convolutions (SA.conv_mask.2, model_utils.py:163; readout.12, :503), whose
+ * one-channel gradient cannot feed a tensor-core tile: x [planes][h][w][32] (pixel stride x_cstride), dy [planes][h][w],
+ * w / dw in PyTorch layout [1][32][1][3][3].  dx (+)= conv^T(dy) (skipped when dx == NULL); dw += ...; db += sum dy. */
+int mspi_conv_c1_bwd(const float* x, int64_t x_cstride, const float* dy, const float* w, float* dx, int64_t dx_cstride,
+                     float* dw, float* db, int64_t planes, int h, int wd, int cin, int accumulate, void* stream);
+
+/* Depthwise-conv weight / bias gradient (ConvNextBlock.dwconv_t (7,1,1) / dwconv_s (1,7,7), model_utils.py:321-322):
+ * dw [c][kt*kh*kw] (PyTorch layout) += sum_p dy[p][ch] x[p+off][ch]; db += sum_p dy.  x, dy whole [n,t,h,w,c] buffers.
+ * (The data gradient is mspi_dwconv_ln on the flipped filter.) */
+int mspi_dwconv_wgrad(const MspiDwDesc* d, const float* x, const float* dy, float* dw, float* db, void* stream);
+
+/* Saliency loss + its gradient (utils/loss.py:26-49, engine_train.py:38): loss = mean_b[KLD - CC](exp(log_map), gt) +
+ * gamma*loss_va.  dlogits [b][pixels] = scale * dloss/d(readout logits) (through exp and the log-softmax);
+ * out = {loss, kld, cc, loss_va}; loss_va: device scalar or NULL; work: 2*b floats. */
+int mspi_salloss_bwd(const float* log_map, const float* gt, const float* loss_va, float gamma, float* dlogits, float* out,
+                     float* work, int b, int64_t pixels, float scale, void* stream);
+/* SimSiam loss backward (model_utils.py:285-290,551): dp_v, dp_a [b][c] = scale * dL/dp (z is detached). */
+int mspi_simsiam_bwd(const float* p_v, const float* z_a, const float* p_a, const float* z_v, float* dp_v, float* dp_a,
+                     int b, int c, float scale, void* stream);
+/* Adjoint of mspi_token_mean: dx[b][r][:] += dy[b][:] / (r1 - r0) for r in [r0, r1). */
+int mspi_token_mean_bwd(const float* dy, float* dx, int b, int rows, int r0, int r1, int c, void* stream);
+/* dst[g][r][0..c) (+)= src[g][r][0..c): residual / concat gradient routing (strides in elements, multiples of 4). */
+int mspi_add_rows(const float* src, int64_t src_rstride, int64_t src_gstride, float* dst, int64_t dst_rstride,
+                  int64_t dst_gstride, int groups, int rows, int c, int accumulate, void* stream);
+
+/* 4-D strided permute copy, fp32 -> fp32 / bf16: re-packs the updated fp32 master weights into the K-major GEMM matrices
+ * (forward, and transposed + tap-flipped for the data gradient) after every optimiser step. */
+typedef struct {
+  int32_t n[4];
+  int64_t src_strides[4], dst_strides[4];
+  int32_t dst_dtype, accumulate;
+} MspiPermDesc;
+int mspi_permute_copy(const MspiPermDesc* d, const float* src, void* dst, void* stream);
+
+/* torch.optim.AdamW single step over a flat fp32 buffer (train.py:157-158); g is multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce).  step_dev (device int32, optional) overrides `step` so a CUDA graph can replay. */
+int mspi_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, const int32_t* step_dev, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,23 @@ class LnDesc(C.Structure):
     ]
 
 
+class SgemmDesc(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("batch0", C.c_int32), ("batch1", C.c_int32),
+        ("accumulate", C.c_int32), ("alpha", C.c_float),
+        ("a_strides", C.c_int64 * 4), ("b_strides", C.c_int64 * 4), ("c_strides", C.c_int64 * 4),
+    ]
+
+
+class PermDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32 * 4), ("src_strides", C.c_int64 * 4), ("dst_strides", C.c_int64 * 4),
+        ("dst_dtype", C.c_int32), ("accumulate", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
+_I, _L, _F = C.c_int, C.c_int64, C.c_float
 _SIGNATURES = {
     "mspi_last_error": (C.c_char_p, []),
     "mspi_version": (C.c_int, []),
@@ -141,6 +157,26 @@ _SIGNATURES = {
     "mspi_saliency_metrics": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int64, _P]),
     "mspi_postprocess_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_logspec": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    # training step
+    "mspi_bn_train_fwd": (C.c_int, [_P, _L, _P, _L, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "mspi_bn_train_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mspi_act_fwd": (C.c_int, [_P, _P, _L, _I, _P]),
+    "mspi_act_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
+    "mspi_maxpool3d_f32": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P]),
+    "mspi_maxpool3d_bwd": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _L, _P, _L, _P]),
+    "mspi_upsample_bilinear_bwd": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P, _P]),
+    "mspi_layernorm_bwd": (C.c_int, [_P, _L, _P, _L, _L, _L, _P, _P, _F, _P, _L, _L, _I, _I, _P, _P, _P]),
+    "mspi_softmax_bwd_rows": (C.c_int, [_P, _P, _L, _I, _L, _F, _P]),
+    "mspi_sgemm_strided": (C.c_int, [C.POINTER(SgemmDesc), _P, _P, _P, _P]),
+    "mspi_sa_gate_bwd": (C.c_int, [_P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _P]),
+    "mspi_conv_c1_bwd": (C.c_int, [_P, _L, _P, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "mspi_dwconv_wgrad": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P]),
+    "mspi_salloss_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _I, _L, _F, _P]),
+    "mspi_simsiam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "mspi_token_mean_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mspi_add_rows": (C.c_int, [_P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P]),
+    "mspi_permute_copy": (C.c_int, [C.POINTER(PermDesc), _P, _P, _P]),
+    "mspi_adamw_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

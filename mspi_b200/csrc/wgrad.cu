@@ -320,7 +320,11 @@ extern "C" int mspi_conv_wgrad(const MspiConvDesc* d, const void* x, const void*
   p.b_chunks = (bn + ch - 1) / ch;
   p.chunk_bytes = p.rows * 128;
   p.stage_bytes = (p.a_slots + p.b_chunks) * p.chunk_bytes;
-  p.num_stages = (kSmemBudget - kBarrierBytes - 1024) / p.stage_bytes;
+  // The MMA always reads M = 128 rows of A, i.e. 128/ch chunk slots LBO apart, whatever a_slots is: with Cout < 128 the
+  // extra slots alias the B chunks / the next stage (their accumulator rows are never stored), and behind the LAST stage
+  // they must still be inside the allocation.
+  const int slack = (128 / ch - p.a_slots) * p.chunk_bytes;
+  p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - slack) / p.stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   MSPI_CHECK_ARG(p.num_stages >= 2, "shared memory budget leaves %d pipeline stages", p.num_stages);
   int cols = 32;
@@ -345,7 +349,7 @@ extern "C" int mspi_conv_wgrad(const MspiConvDesc* d, const void* x, const void*
   p.splits = (p.pos_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   const long long total = base_items * p.splits;
   MSPI_CHECK_ARG(total < (1ll << 31), "too many work items");
-  const size_t smem = 1024 + kBarrierBytes + static_cast<size_t>(p.num_stages) * p.stage_bytes;
+  const size_t smem = 1024 + kBarrierBytes + static_cast<size_t>(p.num_stages) * p.stage_bytes + slack;
   auto kern = bf16 ? wgrad_kernel<MSPI_BF16> : wgrad_kernel<MSPI_F32>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = static_cast<int>(total < sms ? total : sms);

@@ -545,6 +545,7 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
 
     run.mode = "stem"
     run.desc = d
+    run.packed, run.geom = packed, (k, kt, run_px, x_lead, rows16)   # the training plan re-packs the weights in place
     run.flops = 2.0 * launches * nf * oh * ow * cout * 3 * kt * k * k
     return run
 

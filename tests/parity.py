@@ -81,3 +81,95 @@ def run_forward_parity(height=64, width=64, batch=1, init="calibrated", seed=0, 
     res["ok"] = bool(worst < tap_tol and res["map_maxabs_minmax"] < map_tol and res["loss_abs"] < 1e-2)
     res["ref_out"], res["out"] = ref_out, out_c
     return res
+
+
+def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, input_seed=2023, verbose=False,
+                     grad_tol=3e-2, optimizer=True):
+    """One training step (row a20) on the CUDA path vs the oracle's autograd step on identical weights / inputs / GT.
+
+    Gradients are compared per parameter tensor by relative L2 error, tiny tensors against the global gradient norm
+    (the CUDA path multiplies in tf32: 2^-11 relative per product, fp32 accumulation)."""
+    from mspi_b200.train_engine import TrainPlan
+    sd = orc.make_state_dict(seed, init, audio=True, encoder="s3d")
+    clips, aud = orc.make_inputs(batch, height, width, input_seed)
+    log_map = orc.forward(sd, clips, aud)[0]
+    gt, _ = orc.make_gt(log_map)
+    t0 = time.time()
+    ref = orc.train_grads(sd, clips, aud, gt)
+    t_cpu = time.time() - t0
+    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=verbose)
+    loss_out = plan.forward_backward(clips.cuda(), aud.cuda(), gt.cuda())
+    torch.cuda.synchronize()
+    if verbose:   # train-mode forward taps against the oracle's train-mode forward
+        taps_ref = {}
+        orc._TRAIN["on"], orc._TRAIN["stats"] = True, {}
+        mixed_orig = orc.mixed_block
+
+        def mixed_rec(sd_, p_, x_):
+            y_ = mixed_orig(sd_, p_, x_)
+            taps_ref["mixed:" + p_] = y_
+            return y_
+
+        orc.mixed_block = mixed_rec
+        try:
+            with torch.no_grad():
+                orc._forward(dict(sd), clips, aud, taps_ref, "s3d")
+        finally:
+            orc._TRAIN["on"], orc._TRAIN["stats"] = False, None
+            orc.mixed_block = mixed_orig
+        for name, act in plan.taps.items():
+            if name in taps_ref:
+                got, ref_t = act.to_ncdhw().cpu(), taps_ref[name]
+                if ref_t.dim() == 4:
+                    got = got.permute(0, 2, 1, 3, 4).reshape(ref_t.shape)
+                extra = ""
+                if name.startswith("mixed:"):
+                    q = name[6:]
+                    cs_ = [sd[q + k_].shape[0] for k_ in (".branch0.0.conv.weight", ".branch1.1.conv_t.weight",
+                                                          ".branch2.1.conv_t.weight", ".branch3.1.conv.weight")]
+                    o_ = 0
+                    for c_ in cs_:
+                        extra += f" {rel_l2(got[:, o_:o_ + c_], ref_t[:, o_:o_ + c_]):.2e}"
+                        o_ += c_
+                print(f"  tap {name:24s} rel-L2 {rel_l2(got, ref_t):.3e}{extra}")
+        print(f"  tap aud_vis_sync_block      rel-L2 {rel_l2(plan.taps_stream.cpu(), taps_ref['aud_vis_sync_block']):.3e}")
+    lo = loss_out.cpu().tolist()
+    res = {"cpu_seconds": t_cpu, "launches": plan.num_launches,
+           "loss": lo[0], "kl": lo[1], "cc": lo[2], "loss_va": lo[3],
+           "ref_loss": float(ref["loss"]), "ref_kl": float(ref["kl"]), "ref_cc": float(ref["cc"]),
+           "ref_loss_va": float(ref["loss_va"])}
+    res["out_maxabs"] = (plan.out.cpu() - ref["out"]).abs().max().item()
+    grads = plan.grads()
+    total = sum(float(g.norm()) ** 2 for g in ref["grads"].values()) ** 0.5
+    errs = {}
+    for k in plan.param_keys:
+        g, r = grads[k].cpu(), ref["grads"][k]
+        errs[k] = float((g - r).norm()) / max(float(r.norm()), 1e-4 * total)
+    res["grad_errs"] = errs
+    res["worst_grad"] = max(errs.values())
+    res["worst_key"] = max(errs, key=errs.get)
+    got_total = sum(float(g.norm()) ** 2 for g in grads.values()) ** 0.5
+    res["grad_norm"], res["ref_grad_norm"] = got_total, total
+    # BatchNorm running buffers after the step
+    berr = 0.0
+    for k, v in ref["stats"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(plan.sd[k]) == int(v), k
+            continue
+        berr = max(berr, float((plan.sd[k].cpu() - v).abs().max()) / max(1.0, float(v.abs().max())))
+    res["bn_buffer_err"] = berr
+    if verbose:
+        for k in reversed(plan.param_keys):
+            print(f"  {errs[k]:9.3e}  |g| {float(ref['grads'][k].norm()):9.3e}  {k}")
+    if optimizer:
+        plan.optimizer_step()
+        torch.cuda.synchronize()
+        perr = 0.0
+        for k in plan.param_keys[::17]:
+            p1, _, _ = orc.adamw_step(sd[k], grads[k].cpu(), torch.zeros_like(sd[k]), torch.zeros_like(sd[k]), 1)
+            perr = max(perr, float((plan.sd[k].cpu() - p1).abs().max()))
+        res["adamw_err"] = perr
+    tol_l = 2e-3
+    res["ok"] = bool(res["worst_grad"] < grad_tol and abs(res["loss"] - res["ref_loss"]) < tol_l * max(1.0, abs(res["ref_loss"]))
+                     and berr < 1e-3 and res.get("adamw_err", 0.0) < 1e-6)
+    return res
