@@ -154,6 +154,189 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def train_cpu_baseline(batch: int):
+    """The oracle's training step (train-mode forward, loss, autograd backward of the 411 trainable tensors) on the host."""
+    import torch
+    from oracle import mspi_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.make_state_dict(1, "default")
+    clips, aud = orc.make_inputs(batch, H, W, 2023)
+    gt = torch.rand(batch, H, W)
+    t0 = time.perf_counter()
+    orc.train_grads(sd, clips, aud, gt)
+    dt = time.perf_counter() - t0
+    return {"value": batch / dt, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"one step, B={batch} clips 16x{H}x{W} + audio + GT maps, fp32 oracle port of the reference training step "
+                      f"(forward + autograd backward, optimiser excluded), {dt:.2f} s, {torch.get_num_threads()} threads"}
+
+
+def run_train(args, rank, world, local):
+    """--train: BASELINE config 5 — MSPI-S3D training step (KLD - CC + SimSiam loss, backward, NCCL gradient all-reduce,
+    AdamW) with `--batch` clips per GPU (cfg.TRAIN.BATCH_SIZE = 2, config.py:18)."""
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W_, K, B = max(3, args.warmup), args.steps, args.batch
+    from mspi_b200 import _lib
+    from mspi_b200.config import cfg as base_cfg, select_motion_encoder
+    from mspi_b200.model.model_utils import AudioVisualSaliencyModel
+    from mspi_b200.train_engine import TrainPlan
+    torch.manual_seed(2023)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = AudioVisualSaliencyModel(select_motion_encoder("s3d", copy.deepcopy(base_cfg)), load_pretrained=False)
+    plan = TrainPlan(model.state_dict(), B, T, H, W, device=dev, world_size=world)
+    g = torch.Generator(device=dev).manual_seed(2023 + rank)
+    n_sets = 4
+    clips = [torch.randn(B, 3, T, H, W, device=dev, generator=g) for _ in range(n_sets)]
+    audio = [torch.randn(B, 1, 257, 111, device=dev, generator=g) for _ in range(n_sets)]
+    gts = [torch.rand(B, H, W, device=dev, generator=g) for _ in range(n_sets)]
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    plan.train_step(clips[0], audio[0], gts[0], allreduce)   # builds the lazy weight-gradient plans
+    torch.cuda.synchronize()
+    l0 = lib.mspi_launch_count()
+    plan.train_step(clips[1], audio[1], gts[1], allreduce)
+    torch.cuda.synchronize()
+    launches = int(lib.mspi_launch_count() - l0)
+    if not args.no_graph:
+        plan.capture_step()
+    for i in range(W_):
+        plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(K):
+            out = plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
+        ev1.record()
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * K / (ms / 1e3)
+    loss_last = out.cpu().tolist()
+    # ---- e2e: pinned host clips / audio / GT copied in every step, the 4 loss scalars copied back every step
+    pin = [(torch.randn(B, 3, T, H, W).pin_memory(), torch.randn(B, 1, 257, 111).pin_memory(), torch.rand(B, H, W).pin_memory())
+           for _ in range(2)]
+    dbuf = [(torch.empty(B, 3, T, H, W, device=dev), torch.empty(B, 1, 257, 111, device=dev), torch.empty(B, H, W, device=dev))
+            for _ in range(2)]
+    host_loss = torch.empty(4).pin_memory()
+
+    def e2e_run(n):
+        for i in range(n):
+            s = i % 2
+            for d_, p_ in zip(dbuf[s], pin[s]):
+                d_.copy_(p_, non_blocking=True)
+            o = plan.train_step(*dbuf[s], allreduce)
+            host_loss.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_run(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(K)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (t2.item() / 1e3)
+    # ---- per-kernel breakdown of one step (CUDA events, eager replay), rank 0
+    roofline, kinds = None, None
+    if rank == 0:
+        peaks = read_peaks()
+        plan.bind(clips[0], audio[0])
+        acc = {}
+        phases = (("pack", plan.pack_steps), ("fwd", plan.steps), ("bwd", plan.bwd_steps))
+        for rep in range(3):
+            plan.flat_g.zero_()
+            evs = [torch.cuda.Event(enable_timing=True)]
+            evs[0].record()
+            names = []
+            for ph, steps in phases:
+                for name, fn in steps:
+                    fn()
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    evs.append(e)
+                    names.append((ph, name, fn))
+            torch.cuda.synchronize()
+            if rep:
+                for j in range(len(names)):
+                    acc.setdefault(j, []).append(evs[j].elapsed_time(evs[j + 1]))
+        rows = []
+        for j, (ph, name, fn) in enumerate(names):
+            kind = "other"
+            if name.startswith("conv_dgrad"):
+                kind = "conv_gemm_tf32(dgrad)"
+            elif name.endswith(".wgrad") and "dwconv" not in name:
+                kind = "conv_wgrad"
+            elif getattr(fn, "desc", None) is not None:
+                kind = "conv_gemm_bf16" if fn.desc.a_dtype == 0 else "conv_gemm_tf32(fwd)"
+            elif ph == "pack":
+                kind = "pack"
+            rows.append({"phase": ph, "step": name, "kind": kind, "ms": sum(acc[j]) / len(acc[j])})
+        tot = sum(r["ms"] for r in rows)
+        kinds = {}
+        for r in rows:
+            k = kinds.setdefault(r["kind"], {"launches": 0, "ms": 0.0})
+            k["launches"] += 1
+            k["ms"] += r["ms"]
+        for k in kinds.values():
+            k["share_of_step"] = k["ms"] / tot
+        # algorithmic FLOPs: forward 416.05 GFLOP/clip; backward = 2x the trainable part (416.05 - 253.89 - 2.17), SURVEY 8(a) a20
+        train_gflop_per_clip = ALGO_GFLOP_PER_CLIP + 2.0 * (ALGO_GFLOP_PER_CLIP - 253.89 - 2.17)
+        tc_ms = sum(v["ms"] for k, v in kinds.items() if k.startswith("conv_"))
+        tc_gflop = B * train_gflop_per_clip
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<tf32|bf16> + wgrad_kernel<tf32> (tcgen05 implicit GEMMs: forward, "
+                                                 "data gradient, weight gradient)",
+                    "achieved": tc_gflop / tc_ms, "peak": peaks["bf16_sustained"] / 2, "unit": "TFLOP/s",
+                    "frac": tc_gflop / tc_ms / (peaks["bf16_sustained"] / 2), "traffic": None,
+                    "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)",
+                    "algorithmic_gflop_per_step": tc_gflop, "tensor_core_ms": tc_ms, "share_of_step": tc_ms / tot,
+                    "note": "B=2 clips per GPU (the reference's batch size): the step is launch- and latency-bound, not tensor-bound"}
+        if args.breakdown:
+            with open(args.breakdown, "w") as f:
+                json.dump({"rows": rows, "total_ms": tot, "kinds": kinds}, f, indent=1)
+    if rank == 0:
+        line = {"metric": "clips/sec MSPI-S3D training step", "value": value, "unit": "clips/s", "n_gpus": world, "steps": K,
+                "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32 (trainable part: fp32 storage, tf32 tensor cores) + bf16 (frozen encoders)", "data": "synthetic",
+                "config": {"workload": f"MSPI-S3D training step (BASELINE config 5): train-mode forward, KLD - CC + SimSiam loss, backward "
+                                       f"of the 411 trainable tensors (46.0 M parameters), "
+                                       f"{'NCCL all-reduce of the flat fp32 gradient buffer, ' if world > 1 else ''}AdamW; "
+                                       f"{B} clips/GPU/step of 16x{H}x{W} + spectrograms + GT maps, random init",
+                           "batch_per_gpu": B, "parallelism": f"dp{world}", "cuda_graph": plan.graph is not None,
+                           "l2": f"{n_sets} rotating input sets; activations + gradients of one step ({plan.bytes_alloc / 2**30:.1f} GiB) "
+                                 "exceed L2"},
+                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * (3 * T * H * W + 257 * 111 + H * W) * 4,
+                        "d2h_bytes_per_step": 16},
+                "gpu_launches": launches * K, "launches_per_step": launches, "loss_last_step": loss_last,
+                "trainable_parameters": plan.n_params, "grad_allreduce_bytes": plan.n_flat * 4 if world > 1 else 0,
+                "clocks": clocks.summary(), "roofline": roofline, "kernel_kinds": kinds,
+                "activation_bytes_allocated": plan.bytes_alloc}
+        line["cpu_baseline"] = train_cpu_baseline(B) if (world == 1 and not args.no_cpu_baseline) else None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="mspi_b200", choices=["mspi_b200", "reference"])
     ap.add_argument("--encoder", default="s3d", choices=["s3d", "x3dl", "slowfast4x16"],
                     help="motion encoder (BASELINE configs: s3d = headline, x3dl = config 3, slowfast4x16 = config 4)")
+    ap.add_argument("--train", action="store_true", help="BASELINE config 5: the training step (use --batch 2)")
     ap.add_argument("--no-graph", action="store_true", help="replay the kernel list eagerly instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this file")
@@ -173,6 +357,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.train:
+        return run_train(args, rank, world, local)
 
     import torch
     import torch.distributed as dist

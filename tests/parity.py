@@ -84,7 +84,7 @@ def run_forward_parity(height=64, width=64, batch=1, init="calibrated", seed=0, 
 
 
 def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, input_seed=2023, verbose=False,
-                     grad_tol=3e-2, optimizer=True):
+                     grad_tol=3e-2, optimizer=True, emulate=True):
     """One training step (row a20) on the CUDA path vs the oracle's autograd step on identical weights / inputs / GT.
 
     Gradients are compared per parameter tensor by relative L2 error, tiny tensors against the global gradient norm
@@ -97,9 +97,17 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
     t0 = time.time()
     ref = orc.train_grads(sd, clips, aud, gt)
     t_cpu = time.time() - t0
-    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=verbose)
+    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=True)
     loss_out = plan.forward_backward(clips.cuda(), aud.cuda(), gt.cuda())
     torch.cuda.synchronize()
+    ref_fp32 = ref
+    if emulate:
+        # the same oracle step with the CUDA path's operand rounding and its frozen-encoder features (oracle/precision.py)
+        from oracle import precision as prec
+        o1 = plan.taps["image_encoder.o1"].to_ncdhw().cpu().squeeze(2)
+        o0 = plan.taps["image_encoder.o0"].to_ncdhw().cpu().squeeze(2)
+        af = plan.taps["audnet"].to_ncdhw().cpu().squeeze(2)
+        ref = prec.train_grads_product_numerics(sd, clips, aud, gt, (o1, o0), af)
     if verbose:   # train-mode forward taps against the oracle's train-mode forward
         taps_ref = {}
         orc._TRAIN["on"], orc._TRAIN["stats"] = True, {}
@@ -111,8 +119,10 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
             return y_
 
         orc.mixed_block = mixed_rec
+        import contextlib as _cl
+        ctx = prec.product_numerics(False, (o1, o0), af) if emulate else _cl.nullcontext()
         try:
-            with torch.no_grad():
+            with torch.no_grad(), ctx:
                 orc._forward(dict(sd), clips, aud, taps_ref, "s3d")
         finally:
             orc._TRAIN["on"], orc._TRAIN["stats"] = False, None
@@ -146,6 +156,12 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
         g, r = grads[k].cpu(), ref["grads"][k]
         errs[k] = float((g - r).norm()) / max(float(r.norm()), 1e-4 * total)
     res["grad_errs"] = errs
+    if emulate:
+        tot32 = sum(float(g.norm()) ** 2 for g in ref_fp32["grads"].values()) ** 0.5
+        e32 = sorted(float((grads[k].cpu() - ref_fp32["grads"][k]).norm()) / max(float(ref_fp32["grads"][k].norm()), 1e-4 * tot32)
+                     for k in plan.param_keys)
+        res["vs_fp32_oracle"] = {"median_grad_err": e32[len(e32) // 2], "max_grad_err": e32[-1],
+                                 "loss": float(ref_fp32["loss"]), "out_maxabs": (plan.out.cpu() - ref_fp32["out"]).abs().max().item()}
     res["worst_grad"] = max(errs.values())
     res["worst_key"] = max(errs, key=errs.get)
     got_total = sum(float(g.norm()) ** 2 for g in grads.values()) ** 0.5
@@ -172,4 +188,139 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
     tol_l = 2e-3
     res["ok"] = bool(res["worst_grad"] < grad_tol and abs(res["loss"] - res["ref_loss"]) < tol_l * max(1.0, abs(res["ref_loss"]))
                      and berr < 1e-3 and res.get("adamw_err", 0.0) < 1e-6)
+    return res
+
+
+def run_train_segment_parity(height=64, width=64, batch=2, init="calibrated", seed=3, input_seed=2023, verbose=False):
+    """Training-step parity under teacher forcing (row a20).
+
+    Train-mode BatchNorm at random init makes the S3D forward chaotic (oracle/precision.py: a 1e-4 input perturbation of the
+    fp32 oracle itself is 3e-2 after base4.1, and tf32 operand rounding alone moves the oracle's gradients by ~95%), so a
+    whole-model gradient comparison cannot be tight for ANY tf32 implementation.  This harness therefore checks the step
+    segment by segment: every segment of the oracle (stem..base1, each Mixed block, the Adapter's Inception, and the whole
+    SyncBlock + heads + laterals + SA + fusion + readout + loss "decoder") is evaluated by mspi_oracle's own functions with
+    the CUDA path's operand rounding (oracle/precision.py) on the CUDA run's INPUT of that segment, back-propagated from the
+    CUDA run's gradient at the segment OUTPUT, and its output and parameter gradients are compared with the CUDA run's.
+    Together the segments cover all 411 trainable tensors."""
+    from mspi_b200.train_engine import TrainPlan
+    from oracle import precision as prec
+    sd = orc.make_state_dict(seed, init, audio=True, encoder="s3d")
+    clips, aud = orc.make_inputs(batch, height, width, input_seed)
+    gt, _ = orc.make_gt(orc.forward(sd, clips, aud)[0])
+    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=True)
+    loss_out = plan.forward_backward(clips.cuda(), aud.cuda(), gt.cuda())
+    torch.cuda.synchronize()
+    grads = {k: v.cpu() for k, v in plan.grads().items()}
+    total = sum(float(g.norm()) ** 2 for g in grads.values()) ** 0.5
+    T = lambda a: a.to_ncdhw().cpu()
+    G = lambda a: plan.act_grad(a).to_ncdhw().cpu()
+    taps = plan.taps
+    res = {"segments": {}, "covered": set()}
+
+    def params_under(prefixes):
+        return [k for k in plan.param_keys if k.startswith(tuple(prefixes))]
+
+    def run_segment(name, prefixes, fn, y_gpu, dy_gpu):
+        """fn(work_sd) -> y (oracle, rounded numerics, train mode).  Compares y and d(params under prefixes)."""
+        keys = params_under(prefixes)
+        work = dict(sd)
+        for k in keys:
+            work[k] = sd[k].detach().clone().requires_grad_(True)
+        orc._TRAIN["on"], orc._TRAIN["stats"] = True, {}
+        try:
+            with prec.product_numerics(False):
+                y = fn(work)
+                y.backward(dy_gpu)
+            stats = orc._TRAIN["stats"]
+        finally:
+            orc._TRAIN["on"], orc._TRAIN["stats"] = False, None
+        out_err = rel_l2(y_gpu, y.detach())
+        for bk, bv in stats.items():    # BatchNorm running buffers after the step (torch.nn.BatchNorm semantics)
+            if bk.endswith("num_batches_tracked"):
+                assert int(plan.sd[bk]) == int(bv), bk
+            else:
+                res["bn_buffer_err"] = max(res.get("bn_buffer_err", 0.0),
+                                           float((plan.sd[bk].cpu() - bv).abs().max()) / max(1.0, float(bv.abs().max())))
+        worst, wkey = 0.0, None
+        for k in keys:
+            g_ref = work[k].grad if work[k].grad is not None else torch.zeros_like(sd[k])
+            scale = max(float(g_ref.norm()), 1e-5 * total)
+            # a bias feeding a batch-statistics BatchNorm has an exactly zero gradient: compare against the floor only
+            e = float((grads[k] - g_ref).norm()) / scale
+            if e > worst:
+                worst, wkey = e, k
+            res["covered"].add(k)
+        res["segments"][name] = {"out_err": out_err, "worst_grad": worst, "worst_key": wkey, "n": len(keys)}
+        if verbose:
+            print(f"  segment {name:22s} out {out_err:.2e}  worst grad {worst:.2e}  ({wkey})")
+
+    # ---- S3D: stem..base1, then every Mixed block on its own input --------------------------------------------------
+    def seg_base1(w):
+        x = orc.sep_conv3d(w, "visnet.base1.0", clips, 7, 2, 3)
+        x = torch.nn.functional.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        x = orc.basic_conv3d(w, "visnet.base1.2", x)
+        return orc.sep_conv3d(w, "visnet.base1.3", x, 3, 1, 1)
+
+    v1 = taps["visnet.base1"]
+    run_segment("visnet.base1", ["visnet.base1."], seg_base1, T(v1), G(v1))
+    for name in [k[6:] for k in taps if k.startswith("mixed:")]:
+        x_in = T(taps["mixed_in:" + name])
+        out = taps["mixed:" + name]
+        run_segment(name, [name + "."], lambda w, n=name, x=x_in: orc.mixed_block(w, n, x), T(out), G(out))
+
+    # ---- everything after the encoders: SyncBlock, SimSiam heads, laterals, SA, fusion, readout, loss ----------------
+    vs = [T(taps[f"visnet.base{i}"]) for i in range(1, 5)]
+    masks = T(taps["adapter"])
+    af = T(taps["audnet"]).squeeze(2)
+    dec_prefixes = ["aud_vis_sync_block.", "vis_projector.", "mlp_vis.", "aud_projector.", "mlp_aud.", "latlayer_", "sa_", "readout."]
+    keys = params_under(dec_prefixes)
+    work = dict(sd)
+    for k in keys:
+        work[k] = sd[k].detach().clone().requires_grad_(True)
+    saved = (orc.motion_features, orc.adapter)
+    orc.motion_features = lambda sd_, enc, c: vs
+    orc.adapter = lambda sd_, p, o3, o2, nf: masks
+    dummy = (torch.zeros(1), torch.zeros(1))
+    orc._TRAIN["on"], orc._TRAIN["stats"] = True, {}
+    try:
+        with prec.product_numerics(False, dummy, af):
+            out, loss_va = orc._forward(work, clips, aud, None, "s3d")
+            parts = orc.sal_loss(out, gt)
+            loss = parts["loss"] + loss_va
+            loss.backward()
+    finally:
+        orc._TRAIN["on"], orc._TRAIN["stats"] = False, None
+        orc.motion_features, orc.adapter = saved
+    lo = loss_out.cpu().tolist()
+    res["loss"], res["ref_loss"] = lo[0], float(loss)
+    res["kl"], res["ref_kl"], res["cc"], res["ref_cc"] = lo[1], float(parts["kl"]), lo[2], float(parts["cc"])
+    res["loss_va"], res["ref_loss_va"] = lo[3], float(loss_va)
+    res["out_maxabs"] = (plan.out.cpu() - out.detach()).abs().max().item()
+    worst, wkey, errs = 0.0, None, {}
+    for k in keys:
+        g_ref = work[k].grad if work[k].grad is not None else torch.zeros_like(sd[k])
+        e = float((grads[k] - g_ref).norm()) / max(float(g_ref.norm()), 1e-5 * total)
+        errs[k] = e
+        if e > worst:
+            worst, wkey = e, k
+        res["covered"].add(k)
+    res["segments"]["decoder"] = {"out_err": res["out_maxabs"], "worst_grad": worst, "worst_key": wkey, "n": len(keys),
+                                  "median_grad": sorted(errs.values())[len(errs) // 2]}
+    res["decoder_errs"] = errs
+    # AdamW on the flat buffers (train.py:157-158), first step, given the CUDA path's own gradients
+    plan.optimizer_step()
+    torch.cuda.synchronize()
+    perr = 0.0
+    for k in plan.param_keys[::13]:
+        p1, _, _ = orc.adamw_step(sd[k], grads[k], torch.zeros_like(sd[k]), torch.zeros_like(sd[k]), 1)
+        perr = max(perr, float((plan.sd[k].cpu() - p1).abs().max()))
+    res["adamw_err"] = perr
+    if verbose:
+        for k in keys:
+            print(f"  {errs[k]:9.3e}  |g| {float(work[k].grad.norm()) if work[k].grad is not None else 0.0:9.3e}  {k}")
+        print(f"  segment decoder                out(maxabs) {res['out_maxabs']:.2e}  worst grad {worst:.2e}  ({wkey})")
+    res["n_covered"], res["n_params"] = len(res["covered"]), len(plan.param_keys)
+    res["worst_grad"] = max(s["worst_grad"] for s in res["segments"].values())
+    res["worst_out"] = max(s["out_err"] for n, s in res["segments"].items() if n != "decoder")
+    del res["covered"]
     return res
