@@ -262,9 +262,10 @@ def run_train(args, rank, world, local):
         peaks = read_peaks()
         plan.bind(clips[0], audio[0])
         acc = {}
-        phases = (("pack", plan.pack_steps), ("fwd", plan.steps), ("bwd", plan.bwd_steps))
+        phases = (("pack", [("pack(batched)", plan.pack)]), ("fwd", plan.steps), ("bwd", plan.bwd_steps))
         for rep in range(3):
             plan.flat_g.zero_()
+            plan._bn_arena.zero_()
             evs = [torch.cuda.Event(enable_timing=True)]
             evs[0].record()
             names = []

@@ -313,17 +313,18 @@ int mspi_logspec(const float* wave, float* out, int b, int n, int frames_out, vo
 /* BatchNorm3d in training mode (torch.nn.BatchNorm semantics; backbones/s3d.py:45,99,103, model_utils.py:493,496):
  * y = act((x - mean_batch) * invstd_batch * weight + bias), biased batch variance; running buffers move by `momentum`
  * towards (mean, unbiased variance), *num_batches_tracked += 1 (both optional).  save_mean / save_invstd [c] are kept for
- * the backward; scale_shift [2c] and work (double [2c], zero on entry, left zero) are scratch.  relu: 0 / 1. */
+ * the backward.  work: double [2c] that MUST BE ZERO on entry (the batch sums are accumulated into it and left there; the
+ * training plan clears all of its BatchNorm scratch with one memset per step).  Two launches: sums, normalise.  relu: 0 / 1. */
 int mspi_bn_train_fwd(const float* x, int64_t x_cstride, float* y, int64_t y_cstride, int64_t pixels, int c,
                       const float* weight, const float* bias, float eps, float momentum, float* running_mean,
-                      float* running_var, int64_t* num_batches_tracked, float* save_mean, float* save_invstd,
-                      float* scale_shift, double* work, int relu, void* stream);
+                      float* running_var, int64_t* num_batches_tracked, float* save_mean, float* save_invstd, double* work,
+                      int relu, void* stream);
 /* Its backward: g = dy masked by the ReLU (y > 0) when relu; dweight += sum g*xhat; dbias += sum g;
- * dx (+)= weight*invstd*(g - mean(g) - xhat*mean(g*xhat)).  coef: float [3c] scratch; work as above. */
+ * dx (+)= weight*invstd*(g - mean(g) - xhat*mean(g*xhat)).  work: double [2c], zero on entry (not the forward's). */
 int mspi_bn_train_bwd(const float* x, int64_t x_cstride, const float* y, int64_t y_cstride, const float* dy,
                       int64_t dy_cstride, float* dx, int64_t dx_cstride, int64_t pixels, int c, const float* weight,
-                      const float* save_mean, const float* save_invstd, float* dweight, float* dbias, float* coef,
-                      double* work, int relu, int accumulate, void* stream);
+                      const float* save_mean, const float* save_invstd, float* dweight, float* dbias, double* work, int relu,
+                      int accumulate, void* stream);
 
 /* y = act(x) elementwise (exact-erf GELU of nn.GELU, model_utils.py:45,325; kept separate from the GEMM epilogue in training
  * because the backward needs the pre-activation). */
@@ -401,6 +402,13 @@ typedef struct {
   int32_t dst_dtype, accumulate;
 } MspiPermDesc;
 int mspi_permute_copy(const MspiPermDesc* d, const float* src, void* dst, void* stream);
+/* The same for a whole list of jobs in ONE launch (the ~280 weight re-packs of a training step).  table: DEVICE array of
+ * 16 x int64 per job {src pointer, dst pointer, n[4], src_strides[4], dst_strides[4], dst_is_bf16, total elements};
+ * block_job / block_chunk: DEVICE arrays mapping each of the nblocks thread blocks to its job and to its 2048-element
+ * chunk of that job. */
+#define MSPI_PACK_CHUNK 2048
+int mspi_permute_copy_batched(const int64_t* table, const int32_t* block_job, const int32_t* block_chunk, int nblocks,
+                              void* stream);
 
 /* torch.optim.AdamW single step over a flat fp32 buffer (train.py:157-158); g is multiplied by grad_scale first
  * (1/world_size after a sum all-reduce).  step_dev (device int32, optional) overrides `step` so a CUDA graph can replay. */

@@ -158,8 +158,8 @@ _SIGNATURES = {
     "mspi_postprocess_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_logspec": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     # training step
-    "mspi_bn_train_fwd": (C.c_int, [_P, _L, _P, _L, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
-    "mspi_bn_train_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mspi_bn_train_fwd": (C.c_int, [_P, _L, _P, _L, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "mspi_bn_train_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mspi_act_fwd": (C.c_int, [_P, _P, _L, _I, _P]),
     "mspi_act_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "mspi_maxpool3d_f32": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P]),
@@ -176,6 +176,7 @@ _SIGNATURES = {
     "mspi_token_mean_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mspi_add_rows": (C.c_int, [_P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P]),
     "mspi_permute_copy": (C.c_int, [C.POINTER(PermDesc), _P, _P, _P]),
+    "mspi_permute_copy_batched": (C.c_int, [_P, _P, _P, _I, _P]),
     "mspi_adamw_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
 }
 

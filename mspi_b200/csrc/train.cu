@@ -76,42 +76,44 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, long long cs, long 
   }
 }
 
-// mean / biased variance -> saved statistics, the affine (scale, shift) the apply kernel uses, running buffers
-// (torch.nn.BatchNorm: running_var takes the unbiased variance); clears `work` for the next use.
-__global__ void bn_finalize_kernel(double* __restrict__ work, int c, double count, const float* __restrict__ w,
-                                   const float* __restrict__ b, float eps, float momentum, float* __restrict__ rmean,
-                                   float* __restrict__ rvar, long long* __restrict__ tracked, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd, float* __restrict__ scale, float* __restrict__ shift) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch == 0 && tracked) *tracked += 1;
-  if (ch >= c) return;
-  const double mean = work[ch] / count;
-  double var = work[c + ch] / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  work[ch] = 0.0;
-  work[c + ch] = 0.0;
-  const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
-  save_mean[ch] = static_cast<float>(mean);
-  save_invstd[ch] = static_cast<float>(invstd);
-  const double sc = static_cast<double>(w[ch]) * invstd;
-  scale[ch] = static_cast<float>(sc);
-  shift[ch] = static_cast<float>(static_cast<double>(b[ch]) - mean * sc);
-  if (rmean) {
-    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-    rmean[ch] = static_cast<float>((1.0 - momentum) * rmean[ch] + momentum * mean);
-    rvar[ch] = static_cast<float>((1.0 - momentum) * rvar[ch] + momentum * unb);
+// Normalise + affine + ReLU.  Every block first derives (scale, shift) of all channels from the batch sums in `work`
+// (mean, biased variance) into shared memory; block 0 also stores the saved statistics for the backward pass and moves
+// the running buffers (torch.nn.BatchNorm: running_var takes the unbiased variance).  `work` is only read here: the
+// caller clears it before the next step.
+__global__ void bn_apply_kernel(const float* __restrict__ x, long long xcs, float* __restrict__ y, long long ycs,
+                                long long total, int c4, int c, const double* __restrict__ work, double count,
+                                const float* __restrict__ w, const float* __restrict__ b, float eps, float momentum,
+                                float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ tracked,
+                                float* __restrict__ save_mean, float* __restrict__ save_invstd, int relu) {
+  extern __shared__ float sm[];  // scale[c], shift[c]
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const double mean = work[ch] / count;
+    double var = work[c + ch] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double sc = static_cast<double>(w[ch]) * invstd;
+    sm[ch] = static_cast<float>(sc);
+    sm[c + ch] = static_cast<float>(static_cast<double>(b[ch]) - mean * sc);
+    if (blockIdx.x == 0) {
+      save_mean[ch] = static_cast<float>(mean);
+      save_invstd[ch] = static_cast<float>(invstd);
+      if (rmean) {
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        rmean[ch] = static_cast<float>((1.0 - momentum) * rmean[ch] + momentum * mean);
+        rvar[ch] = static_cast<float>((1.0 - momentum) * rvar[ch] + momentum * unb);
+      }
+    }
   }
-}
-
-__global__ void affine_act_kernel(const float* __restrict__ x, long long xcs, float* __restrict__ y, long long ycs,
-                                  long long total, int c4, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  int relu) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) *tracked += 1;
+  __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / c4;
     const int cc = static_cast<int>(i - pix * c4) * 4;
     float4 v = ldf4(x + pix * xcs + cc);
-    const float4 a = ldf4(scale + cc), b = ldf4(shift + cc);
-    v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+    v.x = fmaf(v.x, sm[cc], sm[c + cc]);
+    v.y = fmaf(v.y, sm[cc + 1], sm[c + cc + 1]);
+    v.z = fmaf(v.z, sm[cc + 2], sm[c + cc + 2]);
+    v.w = fmaf(v.w, sm[cc + 3], sm[c + cc + 3]);
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     stf4(y + pix * ycs + cc, v);
   }
@@ -151,27 +153,28 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, long long xcs,
   }
 }
 
-// dweight += sum g*xhat, dbias += sum g; coef = {w*invstd, mean(g), mean(g*xhat)} for the apply kernel; clears work
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ work, int c, double count, const float* __restrict__ w,
-                                       const float* __restrict__ invstd, float* __restrict__ dweight,
-                                       float* __restrict__ dbias, float* __restrict__ coef) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  const double S = work[ch], Q = work[c + ch];
-  work[ch] = 0.0;
-  work[c + ch] = 0.0;
-  dweight[ch] += static_cast<float>(Q);
-  dbias[ch] += static_cast<float>(S);
-  coef[ch] = w[ch] * invstd[ch];
-  coef[c + ch] = static_cast<float>(S / count);
-  coef[2 * c + ch] = static_cast<float>(Q / count);
-}
-
-// dx (+)= w*invstd * (g - mean(g) - xhat * mean(g*xhat))
+// dx (+)= w*invstd * (g - mean(g) - xhat * mean(g*xhat)).  Every block derives the three per-channel coefficients from the
+// sums in `work` into shared memory; block 0 adds the parameter gradients (dweight += sum g*xhat, dbias += sum g).
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, long long xcs, const float* __restrict__ y, long long ycs,
                                     const float* __restrict__ dy, long long dcs, float* __restrict__ dx, long long dxcs,
                                     long long total, int c4, int c, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ coef, int relu, int acc) {
+                                    const float* __restrict__ invstd, const float* __restrict__ w,
+                                    const double* __restrict__ work, double count, float* __restrict__ dweight,
+                                    float* __restrict__ dbias, int relu, int acc) {
+  extern __shared__ float sm[];  // k[c], a[c], b[c], mean[c], invstd[c]
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const double S = work[ch], Q = work[c + ch];
+    sm[ch] = w[ch] * invstd[ch];
+    sm[c + ch] = static_cast<float>(S / count);
+    sm[2 * c + ch] = static_cast<float>(Q / count);
+    sm[3 * c + ch] = mean[ch];
+    sm[4 * c + ch] = invstd[ch];
+    if (blockIdx.x == 0) {
+      dweight[ch] += static_cast<float>(Q);
+      dbias[ch] += static_cast<float>(S);
+    }
+  }
+  __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / c4;
     const int cc = static_cast<int>(i - pix * c4) * 4;
@@ -184,13 +187,14 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, long long xcs, 
       if (!(yv.z > 0.f)) g.z = 0.f;
       if (!(yv.w > 0.f)) g.w = 0.f;
     }
-    const float4 m = ldf4(mean + cc), is = ldf4(invstd + cc);
-    const float4 k = ldf4(coef + cc), a = ldf4(coef + c + cc), b = ldf4(coef + 2 * c + cc);
-    float4 o;
-    o.x = k.x * (g.x - a.x - (xv.x - m.x) * is.x * b.x);
-    o.y = k.y * (g.y - a.y - (xv.y - m.y) * is.y * b.y);
-    o.z = k.z * (g.z - a.z - (xv.z - m.z) * is.z * b.z);
-    o.w = k.w * (g.w - a.w - (xv.w - m.w) * is.w * b.w);
+    const float xe[4] = {xv.x, xv.y, xv.z, xv.w}, ge[4] = {g.x, g.y, g.z, g.w};
+    float oe[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = cc + j;
+      oe[j] = sm[ch] * (ge[j] - sm[c + ch] - (xe[j] - sm[3 * c + ch]) * sm[4 * c + ch] * sm[2 * c + ch]);
+    }
+    float4 o = make_float4(oe[0], oe[1], oe[2], oe[3]);
     float* dp = dx + pix * dxcs + cc;
     if (acc) {
       const float4 old = ldf4(dp);
@@ -805,6 +809,36 @@ __global__ void permute_copy_kernel(PermArgs a, const float* __restrict__ src, v
   }
 }
 
+// All weight re-packs of one step in ONE launch: a device table of jobs (16 x int64 each: src, dst, n[4], src_strides[4],
+// dst_strides[4], dst_is_bf16, total) and a block -> (job, chunk) map built once by the host.
+constexpr int kPackChunk = 2048;   // elements per block
+__global__ void __launch_bounds__(256) permute_copy_batched_kernel(const long long* __restrict__ table,
+                                                                   const int* __restrict__ block_job,
+                                                                   const int* __restrict__ block_chunk) {
+  const long long* j = table + static_cast<long long>(block_job[blockIdx.x]) * 16;
+  const float* src = reinterpret_cast<const float*>(j[0]);
+  void* dst = reinterpret_cast<void*>(j[1]);
+  const int n1 = static_cast<int>(j[3]), n2 = static_cast<int>(j[4]), n3 = static_cast<int>(j[5]);
+  const long long s0 = j[6], s1 = j[7], s2 = j[8], s3 = j[9], d0 = j[10], d1 = j[11], d2 = j[12], d3 = j[13];
+  const bool bf = j[14] != 0;
+  const long long total = j[15];
+  const long long base = static_cast<long long>(block_chunk[blockIdx.x]) * kPackChunk;
+#pragma unroll
+  for (int e = 0; e < kPackChunk / 256; ++e) {
+    const long long i = base + e * 256 + threadIdx.x;
+    if (i >= total) break;
+    long long r = i;
+    const int i3 = static_cast<int>(r % n3); r /= n3;
+    const int i2 = static_cast<int>(r % n2); r /= n2;
+    const int i1 = static_cast<int>(r % n1); r /= n1;
+    const long long i0 = r;
+    const float v = src[i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3];
+    const long long o = i0 * d0 + i1 * d1 + i2 * d2 + i3 * d3;
+    if (bf) static_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
+    else static_cast<float*>(dst)[o] = v;
+  }
+}
+
 // ------------------------------------------------------------------------- AdamW over the flat parameter buffer
 // torch.optim.AdamW (train.py:157-158): p *= 1 - lr*wd; m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -848,40 +882,37 @@ using namespace mspi;
 extern "C" int mspi_bn_train_fwd(const float* x, int64_t x_cstride, float* y, int64_t y_cstride, int64_t pixels, int c,
                                  const float* weight, const float* bias, float eps, float momentum, float* running_mean,
                                  float* running_var, int64_t* num_batches_tracked, float* save_mean, float* save_invstd,
-                                 float* scale_shift, double* work, int relu, void* stream_) {
+                                 double* work, int relu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MSPI_CHECK_ARG(x && y && weight && bias && save_mean && save_invstd && scale_shift && work, "mspi_bn_train_fwd: null argument");
-  MSPI_CHECK_ARG(c % 4 == 0 && x_cstride % 4 == 0 && y_cstride % 4 == 0 && pixels > 0, "channels / strides must be multiples of 4");
-  MSPI_CHECK_ARG(MSPI_ALIGNED16(x) && MSPI_ALIGNED16(y) && MSPI_ALIGNED16(scale_shift), "16-byte alignment");
+  MSPI_CHECK_ARG(x && y && weight && bias && save_mean && save_invstd && work, "mspi_bn_train_fwd: null argument");
+  MSPI_CHECK_ARG(c % 4 == 0 && c <= 4096 && x_cstride % 4 == 0 && y_cstride % 4 == 0 && pixels > 0,
+                 "channels / strides must be multiples of 4 (c <= 4096)");
+  MSPI_CHECK_ARG(MSPI_ALIGNED16(x) && MSPI_ALIGNED16(y), "16-byte alignment");
   MSPI_NEED_GPU();
   const int cblocks = (c + 31) / 32;
   const int ppb = pixels_per_block(pixels, cblocks);
   dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), cblocks), block(32, 8);
   bn_stats_kernel<<<grid, block, 0, stream>>>(x, x_cstride, pixels, c, ppb, work);
   MSPI_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(work, c, static_cast<double>(pixels), weight, bias, eps, momentum,
-                                                         running_mean, running_var,
-                                                         reinterpret_cast<long long*>(num_batches_tracked), save_mean,
-                                                         save_invstd, scale_shift, scale_shift + c);
-  MSPI_LAUNCH_CHECK();
   const long long total = pixels * (c / 4);
-  affine_act_kernel<<<grid_for(total), kBlock, 0, stream>>>(x, x_cstride, y, y_cstride, total, c / 4, scale_shift,
-                                                            scale_shift + c, relu);
+  bn_apply_kernel<<<grid_for(total), kBlock, 2 * c * sizeof(float), stream>>>(
+      x, x_cstride, y, y_cstride, total, c / 4, c, work, static_cast<double>(pixels), weight, bias, eps, momentum, running_mean,
+      running_var, reinterpret_cast<long long*>(num_batches_tracked), save_mean, save_invstd, relu);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
 
 extern "C" int mspi_bn_train_bwd(const float* x, int64_t x_cstride, const float* y, int64_t y_cstride, const float* dy,
                                  int64_t dy_cstride, float* dx, int64_t dx_cstride, int64_t pixels, int c, const float* weight,
-                                 const float* save_mean, const float* save_invstd, float* dweight, float* dbias, float* coef,
-                                 double* work, int relu, int accumulate, void* stream_) {
+                                 const float* save_mean, const float* save_invstd, float* dweight, float* dbias, double* work,
+                                 int relu, int accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MSPI_CHECK_ARG(x && dy && dx && weight && save_mean && save_invstd && dweight && dbias && coef && work && (y || !relu),
+  MSPI_CHECK_ARG(x && dy && dx && weight && save_mean && save_invstd && dweight && dbias && work && (y || !relu),
                  "mspi_bn_train_bwd: null argument");
-  MSPI_CHECK_ARG(c % 4 == 0 && x_cstride % 4 == 0 && dy_cstride % 4 == 0 && dx_cstride % 4 == 0 && (!relu || y_cstride % 4 == 0),
-                 "channels / strides must be multiples of 4");
-  MSPI_CHECK_ARG(MSPI_ALIGNED16(x) && MSPI_ALIGNED16(dy) && MSPI_ALIGNED16(dx) && MSPI_ALIGNED16(coef) && (!relu || MSPI_ALIGNED16(y)),
-                 "16-byte alignment");
+  MSPI_CHECK_ARG(c % 4 == 0 && c <= 2048 && x_cstride % 4 == 0 && dy_cstride % 4 == 0 && dx_cstride % 4 == 0 &&
+                     (!relu || y_cstride % 4 == 0),
+                 "channels / strides must be multiples of 4 (c <= 2048)");
+  MSPI_CHECK_ARG(MSPI_ALIGNED16(x) && MSPI_ALIGNED16(dy) && MSPI_ALIGNED16(dx) && (!relu || MSPI_ALIGNED16(y)), "16-byte alignment");
   MSPI_NEED_GPU();
   const int cblocks = (c + 31) / 32;
   const int ppb = pixels_per_block(pixels, cblocks);
@@ -889,12 +920,10 @@ extern "C" int mspi_bn_train_bwd(const float* x, int64_t x_cstride, const float*
   bn_bwd_reduce_kernel<<<grid, block, 0, stream>>>(x, x_cstride, y, y_cstride, dy, dy_cstride, pixels, c, ppb, save_mean,
                                                    save_invstd, relu, work);
   MSPI_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(work, c, static_cast<double>(pixels), weight, save_invstd,
-                                                             dweight, dbias, coef);
-  MSPI_LAUNCH_CHECK();
   const long long total = pixels * (c / 4);
-  bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, stream>>>(x, x_cstride, y, y_cstride, dy, dy_cstride, dx, dx_cstride, total,
-                                                              c / 4, c, save_mean, save_invstd, coef, relu, accumulate);
+  bn_bwd_apply_kernel<<<grid_for(total), kBlock, 5 * c * sizeof(float), stream>>>(
+      x, x_cstride, y, y_cstride, dy, dy_cstride, dx, dx_cstride, total, c / 4, c, save_mean, save_invstd, weight, work,
+      static_cast<double>(pixels), dweight, dbias, relu, accumulate);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -1124,6 +1153,16 @@ extern "C" int mspi_permute_copy(const MspiPermDesc* d, const float* src, void* 
   a.dst_bf16 = d->dst_dtype == MSPI_BF16;
   a.acc = d->accumulate;
   permute_copy_kernel<<<grid_for(total), kBlock, 0, stream>>>(a, src, dst, total);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_permute_copy_batched(const int64_t* table, const int32_t* block_job, const int32_t* block_chunk,
+                                         int nblocks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(table && block_job && block_chunk && nblocks > 0, "mspi_permute_copy_batched: bad argument");
+  MSPI_NEED_GPU();
+  permute_copy_batched_kernel<<<nblocks, 256, 0, stream>>>(reinterpret_cast<const long long*>(table), block_job, block_chunk);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
