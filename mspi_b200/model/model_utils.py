@@ -203,12 +203,58 @@ class _SaliencyBase(nn.Module):
             self._plans[key] = plan
         return plan
 
+    # -- training step (engine_train.py:27-76) ------------------------------------------------------
+    def training_plan(self, clips: torch.Tensor, lr: float = 1e-4, gamma: float = 1.0, world_size: int = 1):
+        """The TrainPlan (mspi_b200/train_engine.py) for this batch shape; it owns the fp32 master copy of the trainable
+        parameters (flat buffer, AdamW moments) from the moment it is created — `sync_from_training()` copies them back."""
+        from ..train_engine import TrainPlan
+        if not self.has_audio or self.cfg.MODEL.MOTION_ENCODER != "s3d":
+            raise NotImplementedError("the training step is implemented for the S3D audio-visual model (BASELINE config 5)")
+        b, c, t, h, w = clips.shape
+        key = ("train", b, t, h, w, clips.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            m = self.cfg.MODEL
+            with torch.cuda.device(clips.device):
+                plan = TrainPlan(self.state_dict(), b, t, h, w, lr=lr, gamma=gamma, device=clips.device,
+                                 lateral_bool=tuple(m.LATERAL_BOOL), lateral_stride=tuple(m.LATERAL_STRIDE),
+                                 world_size=world_size)
+            self._plans[key] = plan
+        plan.lr, plan.gamma = lr, gamma
+        return plan
+
+    def train_step(self, clips, audios, labels, lr: float = 1e-4, gamma: float = 1.0, allreduce=None, world_size: int = 1):
+        """One optimisation step of engine_train.py:27-76 — `model.train(); model.frozen_encoder()` forward,
+        `SalLoss()(output, label) + gamma*loss_va`, backward, (gradient all-reduce,) AdamW(lr, weight_decay=0).
+        Returns a device tensor [loss, kld, cc, loss_va]."""
+        if not clips.is_cuda:
+            raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        with torch.cuda.device(clips.device):
+            plan = self.training_plan(clips, lr, gamma, world_size)
+            return plan.train_step(clips.contiguous().float(), audios.contiguous().float(), labels.contiguous().float(),
+                                   allreduce).clone()
+
+    def sync_from_training(self):
+        """Copy the trained parameters and BatchNorm buffers of the training plan back into this module."""
+        plans = [p for k, p in self._plans.items() if k[0] == "train"]
+        if not plans:
+            return
+        sd = plans[-1].state_dict()
+        with torch.no_grad():
+            own = super().state_dict()
+            for k, v in sd.items():
+                if k in own:
+                    own[k].copy_(v)
+        for k in [k for k in self._plans if k[0] != "train"]:
+            del self._plans[k]
+
     def _forward(self, clips, audios):
         if not clips.is_cuda:
             raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only: move the model inputs to the GPU; "
                                "there is no CPU fallback")
         if self.training:
-            raise RuntimeError("mspi_b200 implements the inference forward (eval-mode BatchNorm); call model.eval()")
+            raise RuntimeError("forward() is the inference path (eval-mode BatchNorm): call model.eval(); a training step "
+                               "(train-mode forward + loss + backward + AdamW) is model.train_step(clips, audios, labels)")
         clips = clips.contiguous().float()
         if audios is not None:
             audios = audios.contiguous().float()

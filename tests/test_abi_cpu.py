@@ -40,7 +40,8 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_the_c_layout():
     from mspi_b200 import _lib
     structs = {"MspiConvDesc": _lib.ConvDesc, "MspiPatchDesc": _lib.PatchDesc, "MspiPoolDesc": _lib.PoolDesc,
-               "MspiUpDesc": _lib.UpDesc, "MspiDwDesc": _lib.DwDesc, "MspiDw3dDesc": _lib.Dw3dDesc, "MspiLnDesc": _lib.LnDesc}
+               "MspiUpDesc": _lib.UpDesc, "MspiDwDesc": _lib.DwDesc, "MspiDw3dDesc": _lib.Dw3dDesc, "MspiLnDesc": _lib.LnDesc,
+               "MspiSgemmDesc": _lib.SgemmDesc, "MspiPermDesc": _lib.PermDesc}
     prog = '#include <stdio.h>\n#include "mspi_b200.h"\nint main(void){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in structs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

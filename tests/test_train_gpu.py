@@ -50,3 +50,40 @@ def test_train_step_whole_model_loss_and_determinism():
     assert abs(r["loss"] - r["ref_loss"]) <= 1e-2 * max(1.0, abs(r["ref_loss"])), r["loss"]
     assert abs(r["grad_norm"] - r["ref_grad_norm"]) <= 0.1 * r["ref_grad_norm"]
     assert torch.isfinite(torch.tensor(r["grad_norm"]))
+
+
+def test_module_train_step_and_engine_train_api():
+    """The reference-facing surface: engine_train.train_one_epoch(model, criterion, loader, optimizer, ...) drives
+    model.train_step; the parameters move by at most lr per AdamW step, frozen encoders stay put, BatchNorm buffers move,
+    and the trained weights flow back into the module for the inference forward."""
+    import copy
+    import torch
+    from oracle import mspi_oracle as orc
+    from tests.parity import build_product_model
+    from mspi_b200.engine_train import train_one_epoch
+    from mspi_b200.utils.loss import SalLoss
+    sd = orc.make_state_dict(5, "calibrated")
+    model = build_product_model(sd)
+    clips, aud = orc.make_inputs(2, 64, 64, 2023)
+    gt, _ = orc.make_gt(orc.forward(sd, clips, aud)[0])
+    cfg = copy.deepcopy(model.cfg)
+    cfg.DATA.USE_SOUND = True
+    opt = type("Opt", (), {"param_groups": [{"lr": 1e-4, "weight_decay": 0}]})()
+    crit = SalLoss()
+    stats = train_one_epoch(model, crit, [(clips, aud, gt)] * 3, opt, torch.device("cuda"), 0, cfg, start_steps=0, gamma=1.0)
+    assert all(map(lambda v: v == v, stats.values())) and stats["lr"] == 1e-4
+    after = model.state_dict()
+    moved = 0
+    for k, v in sd.items():
+        d = (after[k].cpu().float() - v.float()).abs().max().item()
+        if k.startswith(("audnet.", "image_encoder.")):
+            assert d == 0.0, k                                  # frozen (train.py:151-155)
+        elif k.endswith("num_batches_tracked"):
+            assert int(after[k]) == int(v) + 3, k
+        elif v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            assert d <= 3 * 1e-4 * 1.001 + 1e-7, (k, d)         # |AdamW update| <= lr per step
+            moved += d > 0
+    assert moved > 400
+    model.eval()
+    out, loss = model(clips.cuda(), aud.cuda())
+    assert torch.isfinite(out).all() and abs(float(out.exp().sum()) - 2.0) < 1e-3
