@@ -258,6 +258,14 @@ int mspi_transpose_v(const float* qkv, float* vt, int b, int n, int heads, int h
 int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, void* y, int64_t y_cstride,
                  int64_t pixels, int c, int dtype, void* stream);
 
+/* The same gate fused with the top-down sums of model_utils.py:566-568 (fp32):
+ *   y = x * sigmoid_mask + x + sum_i up_{k_i}(src_i),   up = bilinear (1,k,k) upsample, align_corners=False
+ * x, y: [nt][h][w][c]; src_i: [nt][h/k_i][w/k_i][c] (pixel stride src_cstrides[i]); srcs / src_cstrides / src_scales are
+ * HOST arrays of nsrc <= 3 entries.  y is written once instead of once per term. */
+int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float* mask_logits, float* y, int64_t y_cstride, int nt,
+                       int h, int w, int c, int nsrc, const float* const* srcs, const int64_t* src_cstrides,
+                       const int32_t* src_scales, void* stream);
+
 /* Elementwise y = a + b over bf16 (used for ViT residuals when not fused) */
 int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
 
@@ -372,6 +380,11 @@ int mspi_sa_gate_bwd(const float* x, int64_t x_cstride, const float* mask_logits
 /* Backward of the 32 -> 1 channel (1,3,3) convolutions (SA.conv_mask.2, model_utils.py:163; readout.12, :503), whose
  * one-channel gradient cannot feed a tensor-core tile: x [planes][h][w][32] (pixel stride x_cstride), dy [planes][h][w],
  * w / dw in PyTorch layout [1][32][1][3][3].  dx (+)= conv^T(dy) (skipped when dx == NULL); dw += ...; db += sum dy. */
+/* Forward of those layers (also used by the inference plan): y [planes][h][w] fp32 = bias + conv(x, w); x bf16 or fp32
+ * [planes][h][w][32] with pixel stride x_cstride, w fp32 [1][32][1][3][3].  One output channel would waste a tensor-core
+ * tile and make the implicit GEMM re-fetch the input per tap; this reads every input line once and reduces with shuffles. */
+int mspi_conv_c1_fwd(const void* x, int x_dtype, int64_t x_cstride, const float* w, const float* bias, float* y,
+                     int64_t planes, int h, int wd, int cin, void* stream);
 int mspi_conv_c1_bwd(const float* x, int64_t x_cstride, const float* dy, const float* w, float* dx, int64_t dx_cstride,
                      float* dw, float* db, int64_t planes, int h, int wd, int cin, int accumulate, void* stream);
 

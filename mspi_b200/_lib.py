@@ -149,6 +149,7 @@ _SIGNATURES = {
     "mspi_softmax_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P]),
     "mspi_transpose_v": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_sa_gate": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
+    "mspi_sa_gate_fused": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "mspi_add_bf16": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "mspi_token_mean": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_cast_rows": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
@@ -169,6 +170,7 @@ _SIGNATURES = {
     "mspi_softmax_bwd_rows": (C.c_int, [_P, _P, _L, _I, _L, _F, _P]),
     "mspi_sgemm_strided": (C.c_int, [C.POINTER(SgemmDesc), _P, _P, _P, _P]),
     "mspi_sa_gate_bwd": (C.c_int, [_P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _P]),
+    "mspi_conv_c1_fwd": (C.c_int, [_P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P]),
     "mspi_conv_c1_bwd": (C.c_int, [_P, _L, _P, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _P]),
     "mspi_dwconv_wgrad": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P]),
     "mspi_salloss_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _I, _L, _F, _P]),

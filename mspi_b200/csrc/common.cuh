@@ -85,6 +85,21 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
+// r -> (r / d, r % d).  Index decompositions run once per thread-element, and a 64-bit division costs ~100 instructions
+// on the GPU (it made the pooling / upsampling / LayerNorm kernels issue bound): use the 32-bit unit whenever r fits.
+__device__ __forceinline__ int divmod(long long& r, int d) {
+  int rem;
+  if (static_cast<unsigned long long>(r) <= 0xffffffffull) {
+    const unsigned r32 = static_cast<unsigned>(r), q = r32 / static_cast<unsigned>(d);
+    rem = static_cast<int>(r32 - q * static_cast<unsigned>(d));
+    r = q;
+  } else {
+    rem = static_cast<int>(r % d);
+    r /= d;
+  }
+  return rem;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case MSPI_ACT_RELU: return fmaxf(v, 0.f);

@@ -47,12 +47,18 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 }
 
 // CQ = C/4 threads per strip, S strips (rows) per block, P output pixels per strip.
+#ifndef MSPI_DW_MINB
+#define MSPI_DW_MINB 1
+#endif
 template <typename TI, int CQ, int S, int P>
-__global__ void __launch_bounds__(CQ * S)
+__global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_MINB : 1)
 dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, void* __restrict__ y, int out_bf16,
-                int H, int W, int tiles_x, int tiles_y, float eps) {
+                int H, int W, int tiles_x, int tiles_y, float eps, int cs) {
+  // cs: channels of the tensor (pixel stride).  cs == C: the block owns whole pixels and can normalise them.  cs > C: the
+  // blocks of grid.y each own a group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
   constexpr int C = 4 * CQ;
+  const int c0 = blockIdx.y * C;
   constexpr int TW = P + 6, TH = S + 6;
   constexpr int kThreads = CQ * S;
   constexpr int kVec = 16 / sizeof(TI);            // elements per 16-byte copy
@@ -66,14 +72,14 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   const int ty = tile % tiles_y; tile /= tiles_y;
   const int n = tile;
   const int x0 = tx * P, y0 = ty * S;
-  const TI* xin = x + static_cast<long long>(n) * H * W * C;
+  const TI* xin = x + static_cast<long long>(n) * H * W * cs + c0;
 
   for (int i = threadIdx.x; i < TH * TW * kRowVecs; i += kThreads) {
     const int cv = i % kRowVecs, pix = i / kRowVecs;
     const int tc = pix % TW, tr = pix / TW;
     const int gy = y0 + tr - 3, gx = x0 + tc - 3;
     const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const TI* src = xin + (static_cast<long long>(in ? gy : 0) * W + (in ? gx : 0)) * C + cv * kVec;
+    const TI* src = xin + (static_cast<long long>(in ? gy : 0) * W + (in ? gx : 0)) * cs + cv * kVec;
     cp_async16_zfill(tile_s + static_cast<size_t>(pix) * C + cv * kVec, src, in);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -82,7 +88,7 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   const int s = threadIdx.x / CQ;
   float4 acc[P];
   {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
 #pragma unroll
     for (int j = 0; j < P; ++j) acc[j] = b;
   }
@@ -93,7 +99,7 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   for (int kh = 0; kh < 7; ++kh) {
     float4 w[7];
 #pragma unroll
-    for (int kw = 0; kw < 7; ++kw) w[kw] = __ldg(reinterpret_cast<const float4*>(wgt + (kh * 7 + kw) * C) + q);
+    for (int kw = 0; kw < 7; ++kw) w[kw] = __ldg(reinterpret_cast<const float4*>(wgt + (kh * 7 + kw) * cs + c0) + q);
     const TI* trow = tile_s + static_cast<size_t>(s + kh) * TW * C + 4 * q;
 #pragma unroll
     for (int ix = 0; ix < TW; ++ix) {
@@ -179,7 +185,7 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
       const int pix = p0 + g;
       const int py = y0 + pix / P, px = x0 + pix % P;
       if (py >= H || px >= W) continue;
-      const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * C;
+      const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * cs + c0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int p = sl + LPP * i;
@@ -241,7 +247,7 @@ __global__ void dwt_kernel(const TI* __restrict__ x, const float* __restrict__ w
 
 template <typename TI, int CQ, int S, int P>
 int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
-                 const float* ln_b, void* y, cudaStream_t stream) {
+                 const float* ln_b, void* y, cudaStream_t stream, int groups = 1) {
   constexpr int C = 4 * CQ;
   constexpr size_t tile_bytes = static_cast<size_t>(S + 6) * (P + 6) * C * sizeof(TI);
   constexpr size_t out_bytes = static_cast<size_t>(S) * P * C * sizeof(float);
@@ -252,11 +258,33 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv 7x7: grid out of range");
   auto kern = dw7x7_ln_kernel<TI, CQ, S, P>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<static_cast<int>(blocks), CQ * S, smem, stream>>>(static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y,
-                                                            d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
-                                                            d->ln_eps);
+  kern<<<dim3(static_cast<unsigned>(blocks), groups), CQ * S, smem, stream>>>(
+      static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
+      d->ln_eps, C * groups);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
+}
+
+// Wide, small maps (ConvNeXt stages 2 and 3: 384 ch at 14x24, 768 ch at 7x12 for the default clip).  A block that owned
+// whole pixels could only hold a 2x8-pixel tile (7x halo redundancy, latency bound: 0.38 ms for a 132 MB tensor), so here
+// blocks own 192-channel groups of 7x12-pixel tiles (2.8x redundancy, 2352 FMA per thread per tile load) and write the
+// raw convolution; LayerNorm over the full channel vector follows as its own (in-place, HBM-bound) kernel.
+template <typename TI>
+int launch_dw7x7_grouped(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
+                         const float* ln_b, void* y, cudaStream_t stream) {
+  const int rc = launch_dw7x7<TI, 48, 7, 12>(d, x, wgt, bias, nullptr, nullptr, y, stream, d->c / 192);
+  if (rc != MSPI_OK || ln_w == nullptr) return rc;
+  MspiLnDesc ln;
+  ln.rows = static_cast<int64_t>(d->n) * d->t * d->h * d->w;
+  ln.c = d->c;
+  ln.in_rstride = ln.out_rstride = d->c;
+  ln.in_dtype = ln.out_dtype = d->out_dtype;
+  ln.eps = d->ln_eps;
+  ln.relu = 0;
+  ln.pos_rows = 0;
+  ln.rows_per_group = ln.rows;
+  ln.out_gstride = 0;
+  return mspi_layernorm(&ln, y, ln_w, ln_b, nullptr, y, stream);
 }
 
 }  // namespace
@@ -275,7 +303,12 @@ int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const
                                   : launch_dw7x7<bf, 24, 8, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
       if (d->c == 192) return wide ? launch_dw7x7<bf, 48, 4, 16>(d, x, wgt, bias, ln_w, ln_b, y, stream)
                                    : launch_dw7x7<bf, 48, 4, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
-      if (d->c == 384) return launch_dw7x7<bf, 96, 2, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+      // C = 384: the fused 2x8-tile kernel (0.38 ms at 14x24) still beats grouped stencil + LayerNorm kernel (0.45 ms);
+      // C = 768 has no whole-pixel tile that fits: grouped (0.50 -> 0.21 ms at 7x12)
+      static const bool grp384 = getenv("MSPI_DW_GROUP384") != nullptr;  // tuning aid
+      if (d->c == 384 && !grp384) return launch_dw7x7<bf, 96, 2, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
+      if ((d->c == 384 || d->c == 768) && d->out_dtype == MSPI_BF16)
+        return launch_dw7x7_grouped<bf>(d, x, wgt, bias, ln_w, ln_b, y, stream);
     } else {
       if (d->c == 192) return launch_dw7x7<float, 48, 4, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
     }

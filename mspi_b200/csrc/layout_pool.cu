@@ -186,12 +186,12 @@ __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict
                                  long long total, int c8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % c8);
-    long long r = i / c8;
+    long long r = i;
+    const int cc = divmod(r, c8);
     const long long opix = r;
-    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
-    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
-    const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+    const int ow = divmod(r, d.ow);
+    const int oh = divmod(r, d.oh);
+    const int ot = divmod(r, d.ot);
     const int n = static_cast<int>(r);
     const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
     __nv_bfloat162 m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
@@ -221,6 +221,55 @@ __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict
   }
 }
 
+// (3,3,3) / stride 1 / padding 1 (the Inception pooling branch, s3d.py:134): a thread owns 8 channels of one (n,t,h) row and
+// walks along w keeping the maxima of the last three columns (each over its 3x3 (t,h) neighbourhood): 9 loads per output
+// instead of 27.
+__global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                  long long total, int c8) {
+  const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int cc = divmod(r, c8);
+    const long long row = r;                       // (n*T + t)*H + h
+    const int hh = divmod(r, d.h);
+    const int tt = divmod(r, d.t);
+    const int t_lo = max(tt - 1, 0), t_hi = min(tt + 1, d.t - 1), h_lo = max(hh - 1, 0), h_hi = min(hh + 1, d.h - 1);
+    const long long plane0 = (r * d.t) * d.h;      // first row of sample n
+    __nv_bfloat162 cm[3][4];                       // column maxima at w-1, w, w+1 (4 x bf16x2 = 8 channels)
+    auto column = [&](int ww, __nv_bfloat162 (&m)[4]) {
+      m[0] = m[1] = m[2] = m[3] = ninf;
+      if (ww < 0 || ww >= d.w) return;
+      for (int t2 = t_lo; t2 <= t_hi; ++t2)
+        for (int h2 = h_lo; h2 <= h_hi; ++h2) {
+          const long long pix = (plane0 + static_cast<long long>(t2) * d.h + h2) * d.w + ww;
+          const uint4 v = ldg16(x + pix * d.in_cstride + cc * 8);
+          m[0] = __hmax2(m[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x));
+          m[1] = __hmax2(m[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y));
+          m[2] = __hmax2(m[2], *reinterpret_cast<const __nv_bfloat162*>(&v.z));
+          m[3] = __hmax2(m[3], *reinterpret_cast<const __nv_bfloat162*>(&v.w));
+        }
+    };
+    column(-1, cm[0]);
+    column(0, cm[1]);
+    for (int ww = 0; ww < d.w; ++ww) {
+      column(ww + 1, cm[2]);
+      uint4 o;
+      __nv_bfloat162 m;
+      m = __hmax2(__hmax2(cm[0][0], cm[1][0]), cm[2][0]); o.x = *reinterpret_cast<uint32_t*>(&m);
+      m = __hmax2(__hmax2(cm[0][1], cm[1][1]), cm[2][1]); o.y = *reinterpret_cast<uint32_t*>(&m);
+      m = __hmax2(__hmax2(cm[0][2], cm[1][2]), cm[2][2]); o.z = *reinterpret_cast<uint32_t*>(&m);
+      m = __hmax2(__hmax2(cm[0][3], cm[1][3]), cm[2][3]); o.w = *reinterpret_cast<uint32_t*>(&m);
+      *reinterpret_cast<uint4*>(y + (row * d.w + ww) * d.out_cstride + cc * 8) = o;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cm[0][q] = cm[1][q];
+        cm[1][q] = cm[2][q];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- bilinear upsample
 // align_corners=False, integer scale k: src = (dst + 0.5)/k - 0.5 clamped at 0 (PyTorch's
 // area_pixel_compute_source_index), second index clamped at size-1.
@@ -230,11 +279,11 @@ __global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __re
   const float inv = 1.f / static_cast<float>(d.k);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % cv);
-    long long r = i / cv;
+    long long r = i;
+    const int cc = divmod(r, cv);
     const long long opix = r;
-    const int ox = static_cast<int>(r % ow_); r /= ow_;
-    const int oy = static_cast<int>(r % oh_); r /= oh_;
+    const int ox = divmod(r, ow_);
+    const int oy = divmod(r, oh_);
     const long long plane = r;
     float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
     const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
@@ -270,14 +319,61 @@ __global__ void sa_gate_kernel(const T* __restrict__ x, long long xcs, const flo
                                long long ycs, long long total, int c8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / c8;
-    const int cc = static_cast<int>(i - pix * c8);
+    long long pix = i;
+    const int cc = divmod(pix, c8);
     const float g = 1.f + 1.f / (1.f + expf(-__ldg(m + pix)));  // x*mask + x
     float f[8];
     load_vec<T, 8>(x + pix * xcs + cc * 8, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] *= g;
     store_vec<T, 8>(y + pix * ycs + cc * 8, f);
+  }
+}
+
+// SA gate + the top-down sums in one pass (model_utils.py:167-170,566-568):
+//   y = x * (1 + sigmoid(l)) + sum_i up_{k_i}(src_i),  fp32, up = bilinear (1,k,k), align_corners=False.
+// The unfused form writes y once and then reads + rewrites it for every upsampled term (4.2 GB for s0 at B=32); here y is
+// written once and the (4x .. 64x smaller) sources are gathered from L2.
+struct GateSrc {
+  const float* p[3];
+  long long cs[3];
+  int k[3];
+  int n;
+};
+__global__ void sa_gate_fused_kernel(const float* __restrict__ x, long long xcs, const float* __restrict__ m,
+                                     float* __restrict__ y, long long ycs, long long total, int c8, int h, int w, GateSrc s) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i;
+    const int cc = divmod(pix, c8) * 8;
+    long long r = pix;
+    const int ox = divmod(r, w);
+    const int oy = divmod(r, h);
+    const long long plane = r;
+    const float g = 1.f + 1.f / (1.f + expf(-__ldg(m + pix)));
+    float f[8];
+    load_vec<float, 8>(x + pix * xcs + cc, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= g;
+    for (int j = 0; j < s.n; ++j) {
+      const int k = s.k[j], sh = h / k, sw = w / k;
+      const float inv = 1.f / static_cast<float>(k);
+      const float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+      const int y1 = min(y0 + 1, sh - 1), x1 = min(x0 + 1, sw - 1);
+      const float ly = sy - y0, lx = sx - x0;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      const long long base = plane * sh * sw;
+      const float* sp = s.p[j] + cc;
+      float a[8], b[8], c[8], e2[8];
+      load_vec<float, 8>(sp + (base + static_cast<long long>(y0) * sw + x0) * s.cs[j], a);
+      load_vec<float, 8>(sp + (base + static_cast<long long>(y0) * sw + x1) * s.cs[j], b);
+      load_vec<float, 8>(sp + (base + static_cast<long long>(y1) * sw + x0) * s.cs[j], c);
+      load_vec<float, 8>(sp + (base + static_cast<long long>(y1) * sw + x1) * s.cs[j], e2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += w00 * a[e] + w01 * b[e] + w10 * c[e] + w11 * e2[e];
+    }
+    store_vec<float, 8>(y + pix * ycs + cc, f);
   }
 }
 
@@ -413,6 +509,14 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const int c8 = d->c / 8;
   const long long total = static_cast<long long>(d->n) * d->ot * d->oh * d->ow * c8;
+  if (d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 1 && d->ph == 1 &&
+      d->pw == 1 && d->ot == d->t && d->oh == d->h && d->ow == d->w) {
+    const long long rows = static_cast<long long>(d->n) * d->t * d->h * c8;
+    maxpool333_kernel<<<grid_for(rows), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
+                                                             static_cast<__nv_bfloat16*>(y), rows, c8);
+    MSPI_LAUNCH_CHECK();
+    return MSPI_OK;
+  }
   maxpool3d_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
                                                            static_cast<__nv_bfloat16*>(y), total, c8);
   MSPI_LAUNCH_CHECK();
@@ -456,6 +560,28 @@ extern "C" int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_
   else
     sa_gate_kernel<float><<<grid_for(total), kBlock, 0, stream>>>(static_cast<const float*>(x), x_cstride, mask_logits,
                                                                   static_cast<float*>(y), y_cstride, total, c / 8);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float* mask_logits, float* y, int64_t y_cstride,
+                                  int nt, int h, int w, int c, int nsrc, const float* const* srcs, const int64_t* src_cstrides,
+                                  const int32_t* src_scales, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0 && nsrc >= 0 && nsrc <= 3,
+                 "mspi_sa_gate_fused: bad argument");
+  GateSrc s;
+  s.n = nsrc;
+  for (int j = 0; j < nsrc; ++j) {
+    MSPI_CHECK_ARG(srcs[j] && src_scales[j] >= 1 && h % src_scales[j] == 0 && w % src_scales[j] == 0 && src_cstrides[j] % 8 == 0,
+                   "source %d: scale %d must divide %dx%d", j, src_scales[j], h, w);
+    s.p[j] = srcs[j];
+    s.cs[j] = src_cstrides[j];
+    s.k[j] = src_scales[j];
+  }
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const long long total = static_cast<long long>(nt) * h * w * (c / 8);
+  sa_gate_fused_kernel<<<grid_for(total), kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

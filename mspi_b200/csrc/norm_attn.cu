@@ -155,54 +155,84 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-template <typename TI, typename TO, int NI>
+// G rows per warp iteration: all of their loads are issued before the first reduction, so a warp keeps G x C elements
+// in flight (one row per warp left the kernel latency bound at ~1.8 TB/s for C = 96).
+template <typename TI, typename TO, int NI, int G>
 __global__ void layernorm_vec_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ b, const float* __restrict__ pos, TO* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const int c4 = d.c >> 2;
   const float inv_c = 1.f / d.c;
-  for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < d.rows;
-       row += static_cast<long long>(gridDim.x) * warps) {
-    const TI* xr = x + row * d.in_rstride;
-    float4 v[NI];
-    float s = 0.f;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5)) * G; row0 < d.rows;
+       row0 += static_cast<long long>(gridDim.x) * warps * G) {
+    float4 v[G][NI];
+    float s[G], sq[G];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int q = lane + 32 * i;
-      v[i] = q < c4 ? ld4<TI>(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(s) * inv_c;
-    float sq = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const long long row = row0 + g;
+      const TI* xr = x + row * d.in_rstride;
+      s[g] = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      if (lane + 32 * i < c4) {
-        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-        sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      for (int i = 0; i < NI; ++i) {
+        const int q = lane + 32 * i;
+        v[g][i] = (q < c4 && row < d.rows) ? ld4<TI>(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s[g] += (v[g][i].x + v[g][i].y) + (v[g][i].z + v[g][i].w);
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_c + d.eps);
-    const long long g = row / d.rows_per_group, within = row - g * d.rows_per_group;
-    TO* yr = y + g * d.out_gstride + within * d.out_rstride;
-    const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c : nullptr;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int q = lane + 32 * i;
-      if (q < c4) {
-        const float4 gw = __ldg(reinterpret_cast<const float4*>(w) + q);
-        const float4 gb = __ldg(reinterpret_cast<const float4*>(b) + q);
-        float4 o;
-        o.x = (v[i].x - mean) * rstd * gw.x + gb.x;
-        o.y = (v[i].y - mean) * rstd * gw.y + gb.y;
-        o.z = (v[i].z - mean) * rstd * gw.z + gb.z;
-        o.w = (v[i].w - mean) * rstd * gw.w + gb.w;
-        if (d.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (pr) {
-          const float4 pp = __ldg(reinterpret_cast<const float4*>(pr) + q);
-          o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      s[g] *= inv_c;  // mean
+      sq[g] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (lane + 32 * i < c4) {
+          const float a0 = v[g][i].x - s[g], a1 = v[g][i].y - s[g], a2 = v[g][i].z - s[g], a3 = v[g][i].w - s[g];
+          sq[g] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
         }
-        st4(yr + 4 * q, o);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], o);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long row = row0 + g;
+      if (row >= d.rows) break;
+      const float mean = s[g];
+      const float rstd = rsqrtf(sq[g] * inv_c + d.eps);
+      long long grp = 0, within = row;   // (the 64-bit divisions below cost more than the rest of a C = 96 row)
+      if (d.rows_per_group < d.rows) {
+        grp = row;
+        within = divmod(grp, static_cast<int>(d.rows_per_group));
+      }
+      TO* yr = y + grp * d.out_gstride + within * d.out_rstride;
+      const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c : nullptr;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int q = lane + 32 * i;
+        if (q < c4) {
+          const float4 gw = __ldg(reinterpret_cast<const float4*>(w) + q);
+          const float4 gb = __ldg(reinterpret_cast<const float4*>(b) + q);
+          float4 o;
+          o.x = (v[g][i].x - mean) * rstd * gw.x + gb.x;
+          o.y = (v[g][i].y - mean) * rstd * gw.y + gb.y;
+          o.z = (v[g][i].z - mean) * rstd * gw.z + gb.z;
+          o.w = (v[g][i].w - mean) * rstd * gw.w + gb.w;
+          if (d.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (pr) {
+            const float4 pp = __ldg(reinterpret_cast<const float4*>(pr) + q);
+            o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+          }
+          st4(yr + 4 * q, o);
+        }
       }
     }
   }
@@ -438,6 +468,13 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
   if (blocks < 1) blocks = 1;
   using bf = __nv_bfloat16;
   const int g = static_cast<int>(blocks);
+  // vector kernel: G rows per warp iteration (8 / 4 / 2 / 1 for C <= 128 / 256 / 512 / 1024)
+  const int rows_per_iter = d->c <= 128 ? 8 : (d->c <= 256 ? 4 : (d->c <= 512 ? 2 : 1));
+  long long vblocks = (d->rows + static_cast<long long>(warps) * rows_per_iter - 1) / (static_cast<long long>(warps) * rows_per_iter);
+  const long long vcap = static_cast<long long>(num_sms()) * 16;
+  if (vblocks > vcap) vblocks = vcap;
+  if (vblocks < 1) vblocks = 1;
+  const int gv = static_cast<int>(vblocks);
   const int ies = d->in_dtype == MSPI_BF16 ? 2 : 4, oes = d->out_dtype == MSPI_BF16 ? 2 : 4;
   const bool vec_ok = d->c % 4 == 0 && d->c <= 1024 && (d->in_rstride * ies) % (4 * ies) == 0 &&
                       (d->out_rstride * oes) % (4 * oes) == 0 && (d->out_gstride * oes) % (4 * oes) == 0 &&
@@ -447,12 +484,14 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
   if (vec_ok) {
 #define MSPI_LN_VEC(TI, TO)                                                                                              \
   do {                                                                                                                   \
-    if (d->c <= 256)                                                                                                     \
-      layernorm_vec_kernel<TI, TO, 2><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+    if (d->c <= 128)                                                                                                     \
+      layernorm_vec_kernel<TI, TO, 1, 8><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+    else if (d->c <= 256)                                                                                                \
+      layernorm_vec_kernel<TI, TO, 2, 4><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
     else if (d->c <= 512)                                                                                                \
-      layernorm_vec_kernel<TI, TO, 4><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      layernorm_vec_kernel<TI, TO, 4, 2><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
     else                                                                                                                 \
-      layernorm_vec_kernel<TI, TO, 8><<<g, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      layernorm_vec_kernel<TI, TO, 8, 1><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
   } while (0)
     if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16) MSPI_LN_VEC(bf, bf);
     else if (d->in_dtype == MSPI_BF16) MSPI_LN_VEC(bf, float);

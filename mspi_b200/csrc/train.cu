@@ -107,8 +107,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, long long xcs, floa
   if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) *tracked += 1;
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / c4;
-    const int cc = static_cast<int>(i - pix * c4) * 4;
+    long long pix = i;
+    const int cc = divmod(pix, c4) * 4;
     float4 v = ldf4(x + pix * xcs + cc);
     v.x = fmaf(v.x, sm[cc], sm[c + cc]);
     v.y = fmaf(v.y, sm[cc + 1], sm[c + cc + 1]);
@@ -176,8 +176,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, long long xcs, 
   }
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / c4;
-    const int cc = static_cast<int>(i - pix * c4) * 4;
+    long long pix = i;
+    const int cc = divmod(pix, c4) * 4;
     const float4 xv = ldf4(x + pix * xcs + cc);
     float4 g = ldf4(dy + pix * dcs + cc);
     if (relu) {
@@ -252,12 +252,12 @@ __global__ void act_bwd_kernel(const float* dy, long long dcs, const float* __re
 __global__ void maxpool3d_f32_kernel(MspiPoolDesc d, const float* __restrict__ x, float* __restrict__ y, long long total,
                                      int c4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % c4) * 4;
-    long long r = i / c4;
+    long long r = i;
+    const int cc = divmod(r, c4) * 4;
     const long long opix = r;
-    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
-    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
-    const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+    const int ow = divmod(r, d.ow);
+    const int oh = divmod(r, d.oh);
+    const int ot = divmod(r, d.ot);
     const int n = static_cast<int>(r);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     const int t0 = ot * d.st - d.pt, h0 = oh * d.sh - d.ph, w0 = ow * d.sw - d.pw;
@@ -285,12 +285,12 @@ __global__ void maxpool3d_f32_kernel(MspiPoolDesc d, const float* __restrict__ x
 __global__ void maxpool3d_bwd_kernel(MspiPoolDesc d, const float* __restrict__ x, const float* __restrict__ dy,
                                      long long dcs, float* __restrict__ dx, long long dxcs, long long total, int c4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % c4) * 4;
-    long long r = i / c4;
+    long long r = i;
+    const int cc = divmod(r, c4) * 4;
     const long long opix = r;
-    const int ow = static_cast<int>(r % d.ow); r /= d.ow;
-    const int oh = static_cast<int>(r % d.oh); r /= d.oh;
-    const int ot = static_cast<int>(r % d.ot); r /= d.ot;
+    const int ow = divmod(r, d.ow);
+    const int oh = divmod(r, d.oh);
+    const int ot = divmod(r, d.ot);
     const int n = static_cast<int>(r);
     float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     long long arg[4] = {-1, -1, -1, -1};
@@ -327,11 +327,11 @@ __global__ void upsample_bwd_kernel(MspiUpDesc d, const float* __restrict__ dy, 
   const int oh_ = d.h * d.k, ow_ = d.w * d.k;
   const float inv = 1.f / static_cast<float>(d.k);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % c4) * 4;
-    long long r = i / c4;
+    long long r = i;
+    const int cc = divmod(r, c4) * 4;
     const long long opix = r;
-    const int ox = static_cast<int>(r % ow_); r /= ow_;
-    const int oy = static_cast<int>(r % oh_); r /= oh_;
+    const int ox = divmod(r, ow_);
+    const int oy = divmod(r, oh_);
     const long long plane = r;
     float4 g = ldf4(dy + opix * d.out_cstride + cc);
     if (d.act == MSPI_ACT_RELU) {
@@ -539,8 +539,9 @@ __global__ void conv_c1_bwd_kernel(const float* __restrict__ x, long long xcs, c
   const long long p0 = static_cast<long long>(blockIdx.x) * ppb;
   const long long p1 = min(p0 + ppb, pixels);
   for (long long q = p0 + threadIdx.y; q < p1; q += 8) {
-    const int qx = static_cast<int>(q % wd);
-    const int qy = static_cast<int>((q / wd) % h);
+    long long qq = q;
+    const int qx = divmod(qq, wd);
+    const int qy = divmod(qq, h);
     const float xv = x[q * xcs + ci];
     float o = 0.f;
 #pragma unroll
@@ -583,6 +584,68 @@ __global__ void conv_c1_bwd_kernel(const float* __restrict__ x, long long xcs, c
   }
 }
 
+// Forward of the same layer: y[q] = bias + sum_tap sum_ci x[q + off(tap)][ci] W[ci][tap].  One output channel cannot use a
+// tensor-core tile (N = 1 of 16) and the implicit GEMM re-fetches the input once per tap; here each input row (32 channels =
+// one 128-byte / 64-byte line per pixel) is read once per output row-neighbourhood from L1/L2 and reduced with shuffles.
+// A warp produces 4 consecutive pixels of a row: lane = input channel.
+template <typename TI>
+__global__ void conv_c1_fwd_kernel(const TI* __restrict__ x, long long xcs, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ y, long long planes, int h, int wd,
+                                   int strip) {
+  // one warp = a 4-pixel wide, `strip`-row tall column of one plane, walked top to bottom with the three input rows under
+  // the current output row in registers (lane = channel): every input pixel is loaded 1.5 times instead of 9
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  float wr[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wr[t] = w[lane * 9 + t];
+  const float b0 = bias ? bias[0] : 0.f;
+  const int gpr = (wd + 3) / 4;                      // pixel groups per image row
+  const int spp = (h + strip - 1) / strip;           // strips per plane
+  const long long items = planes * spp * gpr;
+  for (long long it = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); it < items;
+       it += static_cast<long long>(gridDim.x) * warps) {
+    long long r = it;
+    const int x0 = divmod(r, gpr) * 4;
+    const int y0 = divmod(r, spp) * strip;
+    const long long plane = r;
+    const int y1 = min(y0 + strip, h);
+    const TI* xp = x + plane * h * wd * xcs + lane;
+    float row[3][6];
+    auto load_row = [&](int yy, float (&dst)[6]) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int sx = x0 + c - 1;
+        dst[c] = (yy >= 0 && yy < h && sx >= 0 && sx < wd)
+                     ? static_cast<float>(xp[(static_cast<long long>(yy) * wd + sx) * xcs]) : 0.f;
+      }
+    };
+    load_row(y0 - 1, row[0]);
+    load_row(y0, row[1]);
+    for (int yy = y0; yy < y1; ++yy) {
+      load_row(yy + 1, row[2]);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc[j] = fmaf(row[kh][j + kw], wr[kh * 3 + kw], acc[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
+      if (lane < 4 && x0 + lane < wd) y[(plane * h + yy) * wd + x0 + lane] = acc[lane] + b0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        row[0][c] = row[1][c];
+        row[1][c] = row[2][c];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- depthwise conv weight / bias gradient
 // dw[ch][tap] += sum_p dy[p][ch] x[p + off(tap)][ch];  db[ch] += sum_p dy[p][ch].   block (32 channels, 8 pixel lanes)
 template <int KT, int KH, int KW>
@@ -599,9 +662,10 @@ __global__ void dw_wgrad_kernel(const float* __restrict__ x, const float* __rest
   float ab = 0.f;
   if (ch < c)
     for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
-      const int pw = static_cast<int>(p % w);
-      const int ph = static_cast<int>((p / w) % h);
-      const int pt = static_cast<int>((p / (static_cast<long long>(w) * h)) % t);
+      long long pp = p;
+      const int pw = divmod(pp, w);
+      const int ph = divmod(pp, h);
+      const int pt = divmod(pp, t);
       const float g = dy[p * c + ch];
       ab += g;
 #pragma unroll
@@ -774,9 +838,9 @@ __global__ void token_mean_bwd_kernel(const float* __restrict__ dy, float* __res
 __global__ void add_rows_kernel(const float* __restrict__ src, long long srs, long long sgs, float* __restrict__ dst,
                                 long long drs, long long dgs, int rows, int c4, long long total, int acc) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(i % c4) * 4;
-    const long long r = i / c4;
-    const long long g = r / rows, within = r - g * rows;
+    long long g = i;
+    const int cc = divmod(g, c4) * 4;
+    const long long within = divmod(g, rows);
     float4 v = ldf4(src + g * sgs + within * srs + cc);
     float* dp = dst + g * dgs + within * drs + cc;
     if (acc) {
@@ -1068,6 +1132,30 @@ extern "C" int mspi_conv_c1_bwd(const float* x, int64_t x_cstride, const float* 
   dim3 block(32, 8);
   conv_c1_bwd_kernel<<<static_cast<unsigned>((pixels + ppb - 1) / ppb), block, 0, stream>>>(x, x_cstride, dy, w, dx, dx_cstride,
                                                                                            dw, db, pixels, h, wd, ppb, accumulate);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_conv_c1_fwd(const void* x, int x_dtype, int64_t x_cstride, const float* w, const float* bias, float* y,
+                                int64_t planes, int h, int wd, int cin, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(x && w && y && planes > 0 && h > 0 && wd > 0, "mspi_conv_c1_fwd: bad argument");
+  MSPI_CHECK_ARG(cin == 32, "mspi_conv_c1_fwd serves the 32 -> 1 (1,3,3) convs (cin = %d)", cin);
+  MSPI_NEED_GPU();
+  const int warps = 8;
+  // strips tall enough to amortise the two halo rows, short enough to give every SM several warps
+  int strip = 16;
+  while (strip > 4 && planes * ((h + strip - 1) / strip) * ((wd + 3) / 4) < static_cast<long long>(num_sms()) * 64) strip /= 2;
+  const long long items = planes * ((h + strip - 1) / strip) * ((wd + 3) / 4);
+  long long blocks = (items + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (x_dtype == MSPI_BF16)
+    conv_c1_fwd_kernel<__nv_bfloat16><<<static_cast<int>(blocks), warps * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, w, bias, y, planes, h, wd, strip);
+  else
+    conv_c1_fwd_kernel<float><<<static_cast<int>(blocks), warps * 32, 0, stream>>>(static_cast<const float*>(x), x_cstride, w,
+                                                                                  bias, y, planes, h, wd, strip);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

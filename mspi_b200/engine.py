@@ -617,17 +617,24 @@ class ForwardPlan:
         return self.conv("sa_*.conv_mask.0", masks, torch.cat(ws, 0), torch.cat(scs), torch.cat(shs), pad=(1, 1, 1),
                          act=ACT_RELU)
 
-    def sa_gate(self, k: int, x: Act, m96: Act, scale: int, out: Optional[Act] = None) -> Act:
-        """SA.forward, model_utils.py:167-170"""
+    def sa_gate(self, k: int, x: Act, m96: Act, scale: int, out: Optional[Act] = None, sources=()) -> Act:
+        """SA.forward (model_utils.py:167-170); `sources` = [(Act, k)] adds the top-down terms up_k(src) in the same pass
+        (model_utils.py:566-568)."""
         p = f"sa_{k}"
         m = m96.slice(32 * k, 32)
         if scale != 1:
             m = self.up(p + ".up", m, scale)
-        logit = self.conv(p + ".conv_mask.2", m, self.P(p + ".conv_mask.2.weight"), None, self.P(p + ".conv_mask.2.bias"),
-                          pad=(0, 1, 1), out_dtype=torch.float32)
+        logit = self.new(m.n, m.t, m.h, m.w, 1, torch.float32)
+        self.add(p + ".conv_mask.2", ops.conv_c1(m, self.P(p + ".conv_mask.2.weight"), self.P(p + ".conv_mask.2.bias"), logit))
+        self.flops += 2.0 * m.pixels * 32 * 9
         if out is None:
             out = self.new(x.n, x.t, x.h, x.w, x.c, x.dtype)
+        if sources and x.dtype == torch.float32:
+            self.add(p + ".gate+fuse", ops.sa_gate_fused(x, logit.buf.view(-1), out, list(sources)))
+            return out
         self.add(p + ".gate", ops.sa_gate(x, logit.buf.view(-1), out))
+        for src, kk in sources:
+            self.up(f"{p}.fuse+=up{kk}", src, kk, out, accumulate=True)
         return out
 
     def readout(self, g0: Act, g1: Act, g2: Act, s3: Act) -> torch.Tensor:
@@ -656,8 +663,10 @@ class ForwardPlan:
         x = self.up(p + ".7", x, 4, act=ACT_RELU)
         x = self.conv(p + ".10", x, self.P(p + ".10.weight"), None, self.P(p + ".10.bias"), pad=(0, 1, 1), act=ACT_RELU,
                       out_dtype=f32, dtype=f32)
-        x = self.conv(p + ".12", x, self.P(p + ".12.weight"), None, self.P(p + ".12.bias"), pad=(0, 1, 1),
-                      out_dtype=f32, dtype=f32)
+        x12 = self.new(x.n, x.t, x.h, x.w, 1, f32)
+        self.add(p + ".12", ops.conv_c1(x, self.P(p + ".12.weight"), self.P(p + ".12.bias"), x12))
+        self.flops += 2.0 * x.pixels * 32 * 9
+        x = x12
         assert x.t == 1 and x.c == 1
         self.logits = x.buf.view(self.B, self.H * self.W)
         self.out = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device)
@@ -690,15 +699,9 @@ class ForwardPlan:
         assert s0.t == s1.t == s2.t == s3.t == masks.t, "laterals must land on the adapter's 4 frames (model_utils.py:169)"
         m96 = self.sa_masks(masks)
         # top-down fusion, model_utils.py:566-568 (fp32)
-        g2 = self.sa_gate(2, s2, m96, 1)
-        self.up("fuse.s2+=up2(s3)", s3, 2, g2, accumulate=True)
-        g1 = self.sa_gate(1, s1, m96, 2)
-        self.up("fuse.s1+=up2(s2)", g2, 2, g1, accumulate=True)
-        self.up("fuse.s1+=up4(s3)", s3, 4, g1, accumulate=True)
-        g0 = self.sa_gate(0, s0, m96, 4)
-        self.up("fuse.s0+=up2(s1)", g1, 2, g0, accumulate=True)
-        self.up("fuse.s0+=up4(s2)", g2, 4, g0, accumulate=True)
-        self.up("fuse.s0+=up8(s3)", s3, 8, g0, accumulate=True)
+        g2 = self.sa_gate(2, s2, m96, 1, sources=[(s3, 2)])
+        g1 = self.sa_gate(1, s1, m96, 2, sources=[(g2, 2), (s3, 4)])
+        g0 = self.sa_gate(0, s0, m96, 4, sources=[(g1, 2), (g2, 4), (s3, 8)])
         self.tap("fuse.s2", g2), self.tap("fuse.s1", g1), self.tap("fuse.s0", g0)
         self.readout(g0, g1, g2, s3)
 

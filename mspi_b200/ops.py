@@ -248,6 +248,10 @@ class Conv:
             return "tstride"
         if (self.kt, self.kh, self.kw) == (1, 1, 1) and st == 1 and self.pad == (0, 0, 0):
             return "pick"  # 1x1x1 conv with spatial stride (ResBlock.branch1, resnet_helper.py:556-566): a strided view
+        if (self.kt, self.kh, self.kw) == (1, 2, 2) and (st, sh, sw) == (1, 2, 2) and self.pad == (0, 0, 0) \
+                and x.h % 2 == 0 and x.w % 2 == 0:
+            return "patch2"  # non-overlapping 2x2/s2 patches (ConvNeXt downsample, timm convnext): the row / column parity
+            #                   of the input is its own tensor axis, each of the 4 taps a box at parity (kh, kw)
         return "gather"
 
     def _pack(self, w5: torch.Tensor):
@@ -286,6 +290,13 @@ class Conv:
                 q = dlt // st  # floor
                 offs.append((0, dlt - q * st, q, 0))
             ostr = lambda a: (a.cs, 0, a.h * a.w * a.cs, a.t * a.h * a.w * a.cs)
+        elif mode == "patch2":
+            rows = x.n * x.t * (x.h // 2)     # (n, t, h/2) merge: stride(t) = H*W*cs = (H/2) * stride(h/2)
+            a_dims = (x.c, 2, x.w // 2, 2, rows)
+            a_str = (1, x.cs, 2 * x.cs, x.w * x.cs, 2 * x.w * x.cs)
+            o_dims = (1, ow, 1, rows)
+            offs = [(kw, 0, kh, 0) for kh in range(2) for kw in range(2)]
+            ostr = lambda a: (0, a.cs, 0, a.w * a.cs)
         else:
             raise ValueError(mode)
         return a_dims, a_str, o_dims, offs, ostr
@@ -349,7 +360,7 @@ class Conv:
         es = _ES[self.dtype]
         pre = None
         (st, sh, sw), (pt, ph, pw) = self.stride, self.pad
-        if mode in ("shift", "pick", "tstride"):
+        if mode in ("shift", "pick", "tstride", "patch2"):
             packed, taps, cin_pad = self._pack(self.w_raw)
             a_dims, a_str, o_dims, offs, ostr = self._geom(mode, x, ot, oh, ow)
             x_ptr = x.ptr
@@ -830,6 +841,25 @@ def attention_gemm(qkv: torch.Tensor, out: torch.Tensor, b: int, n: int, heads: 
     return [("scores", k_scores), ("softmax", k_softmax), ("transpose_v", k_vt), ("out", k_out)]
 
 
+def conv_c1(x: Act, weight: torch.Tensor, bias: Optional[torch.Tensor], y: Act) -> Callable[[], None]:
+    """Conv3d(32, 1, (1,3,3), padding (0,1,1)) + bias -> fp32 [N,T,H,W,1] (SA.conv_mask.2, model_utils.py:163; readout.12,
+    model_utils.py:503) on the direct kernel (mspi_conv_c1_fwd).  weight / bias are used in place (live fp32 tensors)."""
+    lib = _lib.load()
+    assert x.c == 32 and tuple(weight.shape[-3:]) == (1, 3, 3) and weight.shape[0] == 1 and weight.shape[1] == 32
+    assert y.dtype == torch.float32 and y.c == 1 and y.cs == 1 and y.pixels == x.pixels
+    w = weight.detach()
+    w = w if (w.dtype == torch.float32 and w.is_contiguous() and w.device == x.buf.device) else w.float().contiguous().to(x.buf.device)
+    b = None if bias is None else (bias.detach() if (bias.dtype == torch.float32 and bias.device == x.buf.device)
+                                   else bias.detach().float().to(x.buf.device))
+    planes, h, wd = x.n * x.t, x.h, x.w
+    xp, yp, dt, xcs = x.ptr, y.ptr, _DT[x.dtype], x.cs
+
+    def run(_keep=(x.buf, y.buf, w, b)):
+        _lib.check(lib.mspi_conv_c1_fwd(xp, dt, xcs, _ptr(w), _ptr(b), yp, planes, h, wd, 32, _stream()), "conv_c1_fwd")
+
+    return run
+
+
 def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
     lib = _lib.load()
     assert mask_logits.dtype == torch.float32 and x.c == y.c and x.dtype == y.dtype
@@ -840,6 +870,28 @@ def sa_gate(x: Act, mask_logits: torch.Tensor, y: Act) -> Callable[[], None]:
 
     def run(_keep=(x.buf, y.buf, mask_logits)):
         _lib.check(lib.mspi_sa_gate(xp, xcs, _ptr(mask_logits), yp, ycs, pixels, c, dt, _stream()), "sa_gate")
+
+    return run
+
+
+def sa_gate_fused(x: Act, mask_logits: torch.Tensor, y: Act, sources) -> Callable[[], None]:
+    """y = x * sigmoid(mask) + x + sum up_k(src) for (src Act, k) in sources (fp32): SA gate + top-down fusion in one pass
+    (model_utils.py:167-170,566-568)."""
+    lib = _lib.load()
+    assert x.dtype == y.dtype == torch.float32 and mask_logits.dtype == torch.float32 and len(sources) <= 3
+    assert mask_logits.numel() == x.pixels and (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h, x.w, x.c)
+    n = len(sources)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ptr for a, _k in sources])
+    css = (C.c_int64 * max(n, 1))(*[a.cs for a, _k in sources])
+    ks = (C.c_int32 * max(n, 1))(*[k for _a, k in sources])
+    for a, k in sources:
+        assert a.dtype == torch.float32 and (a.n, a.t, a.h * k, a.w * k, a.c) == (x.n, x.t, x.h, x.w, x.c)
+    xp, yp, xcs, ycs = x.ptr, y.ptr, x.cs, y.cs
+    nt, h, w, c = x.n * x.t, x.h, x.w, x.c
+
+    def run(_keep=(x.buf, y.buf, mask_logits, [a.buf for a, _k in sources], ptrs, css, ks)):
+        _lib.check(lib.mspi_sa_gate_fused(xp, xcs, _ptr(mask_logits), yp, ycs, nt, h, w, c, n, ptrs, css, ks, _stream()),
+                   "sa_gate_fused")
 
     return run
 

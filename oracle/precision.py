@@ -12,7 +12,7 @@ tight tolerance, this module evaluates THE SAME restated algorithm (mspi_oracle.
   * every trainable Conv3d / Linear computed on tf32-rounded operands, forward, data gradient and weight gradient
     (custom autograd functions: products of rounded operands are exact in fp32, accumulation stays fp32);
   * the Cin=3 S3D stem on bf16-rounded clip and weights (forward and weight gradient);
-  * the 32->1 mask / readout convolutions rounded in the forward only (their backward runs in fp32 on the CUDA path);
+  * the 32->1 mask / readout convolutions left in fp32 (direct CUDA-core kernels on the CUDA path);
   * the outputs of the frozen encoders (image encoder features, audio features) injected from the CUDA run, since those
     run the bf16 inference pipeline and need no gradient.
 
@@ -117,8 +117,8 @@ class _FProxy:
         stride, padding = _tup(stride), _tup(padding)
         if w.shape[1] == 3:       # S3D stem on the clip: bf16 operands, bf16 weight gradient
             return _ConvR.apply(x, w, bias, stride, padding, round_bf16, round_bf16)
-        if w.shape[0] == 1:       # 32 -> 1 convs: tf32 forward, fp32 backward
-            return _ConvR.apply(x, w, bias, stride, padding, self._tf32, None)
+        if w.shape[0] == 1:       # 32 -> 1 convs: fp32 CUDA-core kernels, forward and backward
+            return F_real.conv3d(x, w, bias, stride, padding)
         return _ConvR.apply(x, w, bias, stride, padding, self._tf32, self._tf32)
 
     def linear(self, x, w, bias=None):

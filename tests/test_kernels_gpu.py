@@ -204,6 +204,13 @@ def test_conv_1x1_spatial_stride_pick_mode():
     assert mode == "pick" and _rel(got, ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("cin,cout,shape", [(96, 192, (5, 1, 8, 12)), (384, 768, (3, 1, 14, 24)), (64, 96, (2, 3, 6, 10))])
+def test_conv_patch2_mode(cin, cout, shape):
+    """2x2 / stride-2 patch convolution (ConvNeXt downsample) as an implicit GEMM: row / column parity as tensor axes."""
+    got, ref, mode = _run_conv(cin, cout, (1, 2, 2), (1, 2, 2), (0, 0, 0), shape, seed=cin)
+    assert mode == "patch2" and _rel(got, ref) < BF16_TOL
+
+
 def test_clip_frame_map_and_time_padding():
     """SlowFast inputs: slow pathway = frames [0,4,12,T-1] (model_utils.py:523); fast pathway time-padded by 2."""
     from mspi_b200 import ops
@@ -339,7 +346,8 @@ def test_dwconv_ln(c, kern):
 
 
 @pytest.mark.parametrize("c,h,w,dt", [(96, 16, 32, torch.bfloat16), (384, 6, 24, torch.bfloat16), (192, 7, 12, torch.float32),
-                                      (40, 5, 16, torch.float32)])
+                                      (40, 5, 16, torch.float32), (768, 7, 12, torch.bfloat16), (384, 14, 24, torch.bfloat16),
+                                      (768, 2, 2, torch.bfloat16)])
 def test_dwconv7x7_ln_strip_kernel(c, h, w, dt):
     """Register-tiled 7x7 depthwise + LayerNorm (dwconv.cu): strip lengths 16/12/8, bf16 and fp32 inputs, bf16 output."""
     from mspi_b200 import ops
@@ -360,7 +368,9 @@ def test_dwconv7x7_ln_strip_kernel(c, h, w, dt):
     y16 = Act.empty(3, 1, h, w, c, dtype=torch.bfloat16)
     ops.dwconv_ln(xa, y16, wgt, b, lw, lb, eps=1e-6)()
     torch.cuda.synchronize()
-    assert (y16.to_ncdhw().cpu() - ref).abs().max() < 4e-2  # one bf16 rounding of values up to ~5
+    # one bf16 rounding of values up to ~5; the channel-grouped path (C = 384 / 768) also rounds the convolution to bf16
+    # before the LayerNorm kernel
+    assert (y16.to_ncdhw().cpu() - ref).abs().max() < 4e-2
 
 
 def test_layernorm_pos_groups():
@@ -533,3 +543,24 @@ def test_postprocess_maps_against_cv2():
         d = abs(got[i].astype(int) - ref.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 0.02, (d.max(), (d > 0).mean())
         assert got[i].max() == 255 and got[i].min() == 0
+
+
+def test_sa_gate_fused_with_topdown_sums():
+    """y = x*sigmoid(l) + x + up2(a) + up4(b) + up8(c) in one kernel (model_utils.py:167-170,566-568) vs PyTorch."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(8)
+    n, t, h, w, c = 2, 2, 16, 24, 16
+    x = torch.randn(n, c, t, h, w, generator=g)
+    l = torch.randn(n, 1, t, h, w, generator=g)
+    srcs = [(torch.randn(n, c, t, h // k, w // k, generator=g), k) for k in (2, 4, 8)]
+    ref = x * torch.sigmoid(l) + x
+    for a, k in srcs:
+        ref = ref + F.interpolate(a, scale_factor=(1, k, k), mode="trilinear", align_corners=False)
+    xa = _act_from_ncdhw(x, 24, 8, dtype=torch.float32)
+    ya = Act(torch.zeros(n, t, h, w, c, device="cuda"))
+    sa = [(_act_from_ncdhw(a, dtype=torch.float32), k) for a, k in srcs]
+    lg = l.permute(0, 2, 3, 4, 1).contiguous().cuda().view(-1)
+    ops.sa_gate_fused(xa, lg, ya, sa)()
+    torch.cuda.synchronize()
+    assert (ya.to_ncdhw().cpu() - ref).abs().max() < 1e-5

@@ -238,6 +238,19 @@ def test_conv_c1_bwd():
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy)
     xb = _cl(x.detach())
+    # forward (fp32 and bf16 inputs, the latter as a channel slice of a wider buffer like the SA masks)
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    yb = Act(torch.zeros(n, t, h, w, 1, device="cuda"))
+    ops.conv_c1(Act(xb), wt.detach().cuda(), b.detach().cuda(), yb)()
+    wide = torch.randn(n, t, h, w, 96, device="cuda").to(torch.bfloat16)
+    wide[..., 64:] = xb.to(torch.bfloat16)
+    yb16 = Act(torch.zeros(n, t, h, w, 1, device="cuda"))
+    ops.conv_c1(Act(wide, 64, 32), wt.detach().cuda(), b.detach().cuda(), yb16)()
+    torch.cuda.synchronize()
+    assert _rel_l2(yb.buf.cpu().reshape(y.shape), y.detach()) < 1e-5
+    y16_ref = F.conv3d(_bf(x.detach()), wt.detach(), b.detach(), padding=(0, 1, 1))
+    assert _rel_l2(yb16.buf.cpu().reshape(y.shape), y16_ref) < 1e-5
     dxb = torch.zeros_like(xb)
     dw, db = torch.zeros(288, device="cuda"), torch.zeros(1, device="cuda")
     _ck(lib.mspi_conv_c1_bwd(_ptr(xb), 32, _ptr(_dev(dy.reshape(-1))), _ptr(_dev(wt.detach().reshape(-1))), _ptr(dxb), 32, _ptr(dw),
