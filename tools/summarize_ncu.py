@@ -78,5 +78,21 @@ def full(src, dst):
     print(open(dst).read()[:3000])
 
 
+def traffic(src, dst):
+    """profiles/*_launches.csv -> the roofline traffic json bench.py reads (dram bytes per launch of the tensor-core kernels)."""
+    import json
+    rows = list(csv.DictReader(open(src)))
+    out = {"source": f"{src} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum, one eager B=32 forward)"}
+    for key, pred in (("conv_gemm_bf16", lambda k: k.startswith("conv_gemm_kernel<0") or k.startswith("conv_gemm_kernel<bf16")),
+                      ("conv_gemm_tf32", lambda k: k.startswith("conv_gemm_kernel<1")),
+                      ("fused_mlp", lambda k: k.startswith("fused_mlp"))):
+        sel = [r for r in rows if pred(r["kernel"])]
+        b = sum((float(r["dram_read_MB"]) + float(r["dram_write_MB"])) * 1e6 for r in sel)
+        out[key] = {"launches_per_step": len(sel), "dram_bytes_per_step": b, "dram_bytes_per_launch": b / max(len(sel), 1),
+                    "ms_per_step_ncu": sum(float(r["duration_us"]) for r in sel) / 1e3}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
