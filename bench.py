@@ -69,7 +69,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: samples taken before it (the sampler starts ahead of the warm-up so that nvidia-smi is
+        already streaming when the short timed region begins) are only used if the region itself yields none."""
+        self.t0 = time.time()
 
     def __exit__(self, *a):
         if self.proc:
@@ -81,7 +86,10 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        timed = [r[1:] for r in self.rows if r[0] >= t0]
+        rows = timed if timed else [r[1:] for r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -92,7 +100,7 @@ class ClockSampler:
                 pass
         busy = [c for c in sm if c > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "during": "timed region" if timed else "warm-up + timed region"}
 
 
 def read_traffic():
@@ -212,12 +220,12 @@ def run_train(args, rank, world, local):
     launches = int(lib.mspi_launch_count() - l0)
     if not args.no_graph:
         plan.capture_step()
-    for i in range(W_):
-        plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for i in range(W_):
+            plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
         barrier()
+        clocks.mark()
         ev0.record()
         for i in range(K):
             out = plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
@@ -411,14 +419,13 @@ def main():
     plan.run_eager()
     torch.cuda.synchronize()
     launches_per_fwd = int(lib.mspi_launch_count() - l0)
-    for i in range(W_):
-        step(i)
-    barrier()
-
     # ------------------------------------------------------------------ timed region: device-resident inputs
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for i in range(W_):
+            step(i)
         barrier()
+        clocks.mark()
         ev0.record()
         for i in range(K):
             step(i)
