@@ -20,17 +20,19 @@ def train_one_epoch(model, criterion, data_loader: Iterable, optimizer, device, 
                     update_freq=1, gamma=1.0):
     model.train()
     model.frozen_encoder()
-    if not cfg.DATA.USE_SOUND:
-        raise NotImplementedError("the CUDA training plan covers the audio-visual model (cfg.DATA.USE_SOUND)")
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
     allreduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else None
     sums, n = {"loss": 0.0, "kld": 0.0, "cc": 0.0, "loss_va": 0.0}, 0
     lr = cfg.SOLVER.LR
-    for n_iter, (imgs, audio, label) in enumerate(data_loader):
+    for n_iter, batch_data in enumerate(data_loader):
         if optimizer is not None:
             lr = max(g["lr"] for g in optimizer.param_groups)
+        if cfg.DATA.USE_SOUND:                       # engine_train.py:30-38
+            imgs, audio, label = batch_data
+            audio = audio.to(device, non_blocking=True)
+        else:                                        # engine_train.py:39-47 (VisualSaliencyModel)
+            (imgs, label), audio = batch_data, None
         imgs = imgs.to(device, non_blocking=True)
-        audio = audio.to(device, non_blocking=True)
         label = label.to(device, non_blocking=True)
         res = model.train_step(imgs, audio, label, lr=lr, gamma=gamma, allreduce=allreduce, world_size=world)
         loss_value, kld, cc, loss_va = res.tolist()          # the step's only device->host copy (4 floats)

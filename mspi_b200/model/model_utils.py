@@ -208,15 +208,15 @@ class _SaliencyBase(nn.Module):
         """The TrainPlan (mspi_b200/train_engine.py) for this batch shape; it owns the fp32 master copy of the trainable
         parameters (flat buffer, AdamW moments) from the moment it is created — `sync_from_training()` copies them back."""
         from ..train_engine import TrainPlan
-        if not self.has_audio or self.cfg.MODEL.MOTION_ENCODER != "s3d":
-            raise NotImplementedError("the training step is implemented for the S3D audio-visual model (BASELINE config 5)")
+        if self.cfg.MODEL.MOTION_ENCODER != "s3d":
+            raise NotImplementedError("the training step is implemented for the S3D motion encoder (BASELINE config 5)")
         b, c, t, h, w = clips.shape
         key = ("train", b, t, h, w, clips.device.index)
         plan = self._plans.get(key)
         if plan is None:
             m = self.cfg.MODEL
             with torch.cuda.device(clips.device):
-                plan = TrainPlan(self.state_dict(), b, t, h, w, lr=lr, gamma=gamma, device=clips.device,
+                plan = TrainPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lr=lr, gamma=gamma, device=clips.device,
                                  lateral_bool=tuple(m.LATERAL_BOOL), lateral_stride=tuple(m.LATERAL_STRIDE),
                                  world_size=world_size)
             self._plans[key] = plan
@@ -231,8 +231,8 @@ class _SaliencyBase(nn.Module):
             raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         with torch.cuda.device(clips.device):
             plan = self.training_plan(clips, lr, gamma, world_size)
-            return plan.train_step(clips.contiguous().float(), audios.contiguous().float(), labels.contiguous().float(),
-                                   allreduce).clone()
+            audios = audios.contiguous().float() if (self.has_audio and audios is not None) else None
+            return plan.train_step(clips.contiguous().float(), audios, labels.contiguous().float(), allreduce).clone()
 
     def sync_from_training(self):
         """Copy the trained parameters and BatchNorm buffers of the training plan back into this module."""

@@ -84,21 +84,23 @@ def run_forward_parity(height=64, width=64, batch=1, init="calibrated", seed=0, 
 
 
 def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, input_seed=2023, verbose=False,
-                     grad_tol=3e-2, optimizer=True, emulate=True):
+                     grad_tol=3e-2, optimizer=True, emulate=True, audio=True):
     """One training step (row a20) on the CUDA path vs the oracle's autograd step on identical weights / inputs / GT.
 
     Gradients are compared per parameter tensor by relative L2 error, tiny tensors against the global gradient norm
     (the CUDA path multiplies in tf32: 2^-11 relative per product, fp32 accumulation)."""
     from mspi_b200.train_engine import TrainPlan
-    sd = orc.make_state_dict(seed, init, audio=True, encoder="s3d")
+    sd = orc.make_state_dict(seed, init, audio=audio, encoder="s3d")
     clips, aud = orc.make_inputs(batch, height, width, input_seed)
+    if not audio:
+        aud = None
     log_map = orc.forward(sd, clips, aud)[0]
     gt, _ = orc.make_gt(log_map)
     t0 = time.time()
     ref = orc.train_grads(sd, clips, aud, gt)
     t_cpu = time.time() - t0
-    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=True)
-    loss_out = plan.forward_backward(clips.cuda(), aud.cuda(), gt.cuda())
+    plan = TrainPlan(sd, batch, clips.shape[2], height, width, keep_taps=True, audio=audio)
+    loss_out = plan.forward_backward(clips.cuda(), aud.cuda() if audio else None, gt.cuda())
     torch.cuda.synchronize()
     ref_fp32 = ref
     if emulate:
@@ -106,7 +108,7 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
         from oracle import precision as prec
         o1 = plan.taps["image_encoder.o1"].to_ncdhw().cpu().squeeze(2)
         o0 = plan.taps["image_encoder.o0"].to_ncdhw().cpu().squeeze(2)
-        af = plan.taps["audnet"].to_ncdhw().cpu().squeeze(2)
+        af = plan.taps["audnet"].to_ncdhw().cpu().squeeze(2) if audio else None
         ref = prec.train_grads_product_numerics(sd, clips, aud, gt, (o1, o0), af)
     if verbose:   # train-mode forward taps against the oracle's train-mode forward
         taps_ref = {}
@@ -142,7 +144,8 @@ def run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=0, in
                         extra += f" {rel_l2(got[:, o_:o_ + c_], ref_t[:, o_:o_ + c_]):.2e}"
                         o_ += c_
                 print(f"  tap {name:24s} rel-L2 {rel_l2(got, ref_t):.3e}{extra}")
-        print(f"  tap aud_vis_sync_block      rel-L2 {rel_l2(plan.taps_stream.cpu(), taps_ref['aud_vis_sync_block']):.3e}")
+        if audio:
+            print(f"  tap aud_vis_sync_block      rel-L2 {rel_l2(plan.taps_stream.cpu(), taps_ref['aud_vis_sync_block']):.3e}")
     lo = loss_out.cpu().tolist()
     res = {"cpu_seconds": t_cpu, "launches": plan.num_launches,
            "loss": lo[0], "kl": lo[1], "cc": lo[2], "loss_va": lo[3],
@@ -292,7 +295,7 @@ def run_train_segment_parity(height=64, width=64, batch=2, init="calibrated", se
         orc._TRAIN["on"], orc._TRAIN["stats"] = False, None
         orc.motion_features, orc.adapter = saved
     lo = loss_out.cpu().tolist()
-    res["loss"], res["ref_loss"] = lo[0], float(loss)
+    res["loss"], res["ref_loss"] = lo[0], float(loss.detach())
     res["kl"], res["ref_kl"], res["cc"], res["ref_cc"] = lo[1], float(parts["kl"]), lo[2], float(parts["cc"])
     res["loss_va"], res["ref_loss_va"] = lo[3], float(loss_va)
     res["out_maxabs"] = (plan.out.cpu() - out.detach()).abs().max().item()

@@ -87,3 +87,14 @@ def test_module_train_step_and_engine_train_api():
     model.eval()
     out, loss = model(clips.cuda(), aud.cuda())
     assert torch.isfinite(out).all() and abs(float(out.exp().sum()) - 2.0) < 1e-3
+
+
+def test_train_step_visual_only_model():
+    """VisualSaliencyModel (engine_train.py:39-47: no audio branch, loss = SalLoss only): the plan runs, the loss matches the
+    rounded-numerics oracle and the 255 trainable tensors of that model all receive a finite gradient."""
+    import math
+    from tests.parity import run_train_parity
+    r = run_train_parity(height=64, width=64, batch=2, init="calibrated", seed=4, optimizer=True, audio=False)
+    assert abs(r["loss"] - r["ref_loss"]) <= 1e-2 * max(1.0, abs(r["ref_loss"])), (r["loss"], r["ref_loss"])
+    assert r["loss_va"] == 0.0 and math.isfinite(r["grad_norm"]) and r["adamw_err"] < 1e-6
+    assert abs(r["grad_norm"] - r["ref_grad_norm"]) <= 0.2 * r["ref_grad_norm"]
