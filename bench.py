@@ -527,8 +527,8 @@ def main():
                 roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<bf16> (tcgen05 implicit GEMM)",
                             "achieved": info["tflops"], "peak": peak, "unit": "TFLOP/s",
                             "frac": (info["tflops"] / peak) if info["tflops"] else None, "traffic": traffic,
-                            "traffic_note": "dram read+write bytes per launch, mean over the 164 bf16 launches of one step "
-                                            "(ncu, profiles/r01_launches.csv)" if tr else None,
+                            "traffic_note": f"dram read+write bytes per launch, mean over the {tr['conv_gemm_bf16']['launches_per_step']} "
+                                            "bf16 launches of one step (ncu, profiles/r01_launches.csv)" if tr else None,
                             "hbm_gbs_from_traffic": (tr["conv_gemm_bf16"]["dram_bytes_per_step"] / ms_k / 1e6) if tr else None,
                             "hbm_peak_gbs": peaks["hbm"],
                             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",

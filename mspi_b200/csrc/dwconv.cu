@@ -131,7 +131,10 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   static_assert(pairs % LPP == 0, "channel pairs must tile the lane group");
   constexpr int NP = pairs / LPP;                     // pairs per lane
   constexpr int GRP = 32 / LPP;                       // pixels handled side by side in one warp
-  constexpr int G = 4;                                // pixels per lane group per iteration
+#ifndef MSPI_DW_LN_G
+#define MSPI_DW_LN_G 4
+#endif
+  constexpr int G = ((S * P) % (MSPI_DW_LN_G * GRP) == 0) ? MSPI_DW_LN_G : 4;  // pixels per lane group per iteration
   static_assert((S * P) % (G * GRP) == 0, "pixel groups");
   const int sub = lane / LPP, sl = lane % LPP;
   float2 gam[NP], bet[NP];
