@@ -204,7 +204,8 @@ def run_train(args, rank, world, local):
     clips = [torch.randn(B, 3, T, H, W, device=dev, generator=g) for _ in range(n_sets)]
     audio = [torch.randn(B, 1, 257, 111, device=dev, generator=g) for _ in range(n_sets)]
     gts = [torch.rand(B, H, W, device=dev, generator=g) for _ in range(n_sets)]
-    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    from mspi_b200.distributed import allreduce_gradients
+    allreduce = allreduce_gradients if world > 1 else None      # one NCCL SUM all-reduce of the flat gradient buffer
     lib = _lib.load()
 
     def barrier():

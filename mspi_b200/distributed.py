@@ -71,3 +71,28 @@ def forward_sharded(forward: Callable, clips: torch.Tensor, audios: Optional[tor
     full = gather_maps(maps, n, group)
     dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     return full, loss[0] / n
+
+
+# ------------------------------------------------------------------------------------------ training (BASELINE config 5)
+def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> float:
+    """The training step's only collective: SUM all-reduce of the flat fp32 gradient buffer (411 tensors, 184 MB for
+    MSPI-S3D) in one call — NCCL on GPUs, gloo in the CPU tests.  Returns the scale (1 / world_size) the optimiser kernel
+    applies (`mspi_adamw_step(..., grad_scale)`), which together reproduce DistributedDataParallel's gradient averaging
+    of per-rank batch-mean losses.  BatchNorm statistics stay per rank (the reference has no SyncBN)."""
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def flat_layout(shapes, align: int = 4):
+    """Offsets of tensors packed into one flat buffer with every tensor starting on an `align`-element boundary (16 bytes for
+    fp32): (offsets, total).  The layout the training plan uses for parameters, gradients and both AdamW moments."""
+    offs, n = [], 0
+    for s in shapes:
+        numel = 1
+        for d in s:
+            numel *= d
+        offs.append(n)
+        n += -(-numel // align) * align
+    return offs, n

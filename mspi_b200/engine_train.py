@@ -21,7 +21,8 @@ def train_one_epoch(model, criterion, data_loader: Iterable, optimizer, device, 
     model.train()
     model.frozen_encoder()
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
-    allreduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else None
+    from .distributed import allreduce_gradients
+    allreduce = allreduce_gradients if world > 1 else None
     sums, n = {"loss": 0.0, "kld": 0.0, "cc": 0.0, "loss_va": 0.0}, 0
     lr = cfg.SOLVER.LR
     for n_iter, batch_data in enumerate(data_loader):

@@ -74,3 +74,51 @@ def test_forward_sharded_gloo(world, n):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (n, 8, 12) for _, _, shape in res)
+
+
+# ------------------------------------------------------------------------------------------ training collective
+def _train_worker(rank, world, port, q):
+    """Each rank back-propagates the batch-mean loss of ITS clips through a small trainable stack (a slice of the oracle:
+    the SimSiam projector head); the summed flat gradients times 1/world must equal the gradient of the mean over ranks of
+    the per-rank losses, which is what the reference's DistributedDataParallel computes."""
+    from mspi_b200.distributed import allreduce_gradients, flat_layout
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        w1, w2 = torch.randn(16, 8, generator=g), torch.randn(4, 16, generator=g)
+        x = torch.randn(world, 3, 8, generator=g)            # 3 samples per rank
+
+        def local_loss(a, b, xs):
+            return torch.tanh(xs @ a.t()).matmul(b.t()).pow(2).mean()
+
+        a, b = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+        local_loss(a, b, x[rank]).backward()
+        offs, n = flat_layout([a.shape, b.shape])
+        flat = torch.zeros(n)
+        flat[offs[0]:offs[0] + a.numel()] = a.grad.flatten()
+        flat[offs[1]:offs[1] + b.numel()] = b.grad.flatten()
+        scale = allreduce_gradients(flat)
+        flat *= scale
+        a2, b2 = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+        sum(local_loss(a2, b2, x[r]) for r in range(world)).div(world).backward()
+        ok = torch.allclose(flat[offs[0]:offs[0] + a.numel()].view_as(a2), a2.grad, atol=1e-6) and \
+            torch.allclose(flat[offs[1]:offs[1] + b.numel()].view_as(b2), b2.grad, atol=1e-6) and offs[1] % 4 == 0
+        q.put((rank, bool(ok), scale))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_matches_ddp_averaging_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok and scale == 0.5 for _, ok, scale in res), res
