@@ -28,7 +28,11 @@
 namespace mspi {
 namespace {
 
-constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: they split the column chunks
+#ifndef MSPI_EPI_SETS
+#define MSPI_EPI_SETS 2
+#endif
+constexpr int kEpiSets = MSPI_EPI_SETS;       // independent groups of 8 epilogue warps working on alternate column chunks
+constexpr int kEpiWarps = 8 * kEpiSets;       // per set: two warps per TMEM lane quarter, they split the chunk's columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // producer warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
 constexpr int kRowBytes = 128;               // one K chunk of one row: 64 bf16 or 32 tf32
@@ -237,12 +241,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================================================================== epilogue warps
-    // All eight warps work on the same 128-byte column chunk of the tile (64 bf16 / 32 fp32 columns): warp w reads
-    // TMEM lanes 32*(w%4).. (its rows) and the half of the chunk given by its group, HC columns.
+    // The eight warps of a SET work on the same 128-byte column chunk of the tile (64 bf16 / 32 fp32 columns): warp w reads
+    // TMEM lanes 32*(w%4).. (its rows) and the half of the chunk given by its group, HC columns.  A chunk is one serial
+    // chain (tcgen05.ld -> math -> st.shared -> proxy fence -> barrier -> bulk store, ~2000 cycles: 4 elements/clk/SM, the
+    // bound of every small-K layer), so kEpiSets sets run the chain on alternate chunks side by side, each with its own
+    // staging buffer and named barrier.
     const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;
+    const int set = (warp - 2) >> 3;
+    const int group = ((warp - 2) >> 2) & 1;
     const int row = quarter * 32 + lane;
-    const bool leader = warp == 2 && lane == 0;
+    const bool leader = warp == 2 + 8 * set && lane == 0;
     int as = 0;
     uint32_t aphase = 0;
     constexpr bool out_bf16 = OUT == MSPI_BF16;
@@ -252,7 +260,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool has_res = RES >= 0 ? RES != 0 : p.has_res != 0;
     const bool res_after = RES >= 0 ? RES == 2 : p.res_after_act != 0;
     const int nchunks = (p.bn + CH - 1) / CH;
-    uint32_t store_seq = 0;  // bulk stores issued so far: chunk k of the kernel uses staging buffer k & 1
+    // staging buffers: kEpiSets == 1 alternates two buffers (store_seq & 1); with two sets each owns one buffer — the other
+    // set's chunk lies between two uses, so the previous bulk store has long finished reading it
+    uint32_t store_seq = 0;
+    const uint32_t my_stage = kEpiSets > 1 ? static_cast<uint32_t>(set) * kABytes : 0u;
+    const int bar_id = 1 + set;
     for (int item = cid; item < total_items; item += ncl) {
       const int nt = item % p.n_tiles;
       int mt = (item / p.n_tiles) * p.cl + rank;
@@ -279,8 +291,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * p.bn);
       const int n_base = nt * p.bn;
+      if (set >= nchunks) {  // this set has no chunk in the tile: release the accumulator buffer right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      }
 #pragma unroll 1
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = set; ch < nchunks; ch += kEpiSets) {
         const int c0 = ch * CH + group * HC;
         const int width = min(HC, p.bn - c0);  // HC, 16 (bf16, odd multiple of 16), or <= 0 past the tile
         const int n0 = n_base + c0;
@@ -398,8 +415,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
-        if (ch == nchunks - 1) {
-          // every TMEM read of this tile is done: hand the accumulator buffer back to the MMA warp now,
+        if (ch + kEpiSets >= nchunks) {
+          // every TMEM read of this warp for this tile is done: hand the accumulator buffer back to the MMA warp now,
           // before the last chunk is staged and stored
           tc_fence_before();
           __syncwarp();
@@ -407,9 +424,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         if (p.tma_store) {
           // staging buffer (store_seq & 1) is free once the bulk store issued two chunks ago has finished READING it
-          const uint32_t stage_row = stage_base + (store_seq & 1u) * kABytes + row * kRowBytes;
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const uint32_t stage_buf = stage_base + (kEpiSets > 1 ? my_stage : (store_seq & 1u) * kABytes);
+          const uint32_t stage_row = stage_buf + row * kRowBytes;
+          if (leader) {
+            if (kEpiSets > 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
 #pragma unroll
           for (int j = 0; j < 4; ++j) {  // this thread's four 16-byte pieces, 128B-swizzled like the tensor map expects
             const uint32_t dst = stage_row + (static_cast<uint32_t>((4 * group + j) ^ (row & 7)) << 4);
@@ -418,11 +439,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                          : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
           if (leader) {
             asm volatile(
                 "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tma_y),
-                "r"(stage_base + (store_seq & 1u) * kABytes), "r"(n_base + ch * CH), "r"(org[0]), "r"(org[1]), "r"(org[2]),
+                "r"(stage_buf), "r"(n_base + ch * CH), "r"(org[0]), "r"(org[1]), "r"(org[2]),
                 "r"(org[3])
                 : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -32,6 +32,10 @@ def main():
         ("s0.fc2.res", (nf, 1, 56, 96), 384, 96, (1, 1, 1), (0, 0, 0), ACT_NONE, True, bf, bf),
         ("s0.fc2.nores", (nf, 1, 56, 96), 384, 96, (1, 1, 1), (0, 0, 0), ACT_NONE, False, bf, bf),
         ("s2.fc1.gelu", (nf, 1, 14, 24), 384, 1536, (1, 1, 1), (0, 0, 0), ACT_GELU, False, bf, bf),
+        ("s2.fc1.none", (nf, 1, 14, 24), 384, 1536, (1, 1, 1), (0, 0, 0), ACT_NONE, False, bf, bf),
+        ("s2.fc1.relu", (nf, 1, 14, 24), 384, 1536, (1, 1, 1), (0, 0, 0), ACT_RELU, False, bf, bf),
+        ("s3.fc1.gelu", (nf, 1, 7, 12), 768, 3072, (1, 1, 1), (0, 0, 0), ACT_GELU, False, bf, bf),
+        ("s3.fc1.none", (nf, 1, 7, 12), 768, 3072, (1, 1, 1), (0, 0, 0), ACT_NONE, False, bf, bf),
         ("s2.fc2.res", (nf, 1, 14, 24), 1536, 384, (1, 1, 1), (0, 0, 0), ACT_NONE, True, bf, bf),
         ("base1.3.conv_s", (nf // 16, 8, 56, 96), 64, 192, (1, 3, 3), (0, 1, 1), ACT_RELU, False, bf, bf),
         ("readout.1.tf32", (nf // 16, 4, 56, 96), 192, 192, (3, 3, 3), (1, 1, 1), ACT_RELU, False, f32, f32),
