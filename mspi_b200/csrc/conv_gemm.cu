@@ -63,6 +63,8 @@ struct GemmParams {
   int cl;         // CTAs per cluster that share every B (weight) tile by TMA multicast: 1 or 2
   int w_batched;  // 1: the B operand has its own matrix per (d3, d4) index of the M tile (batched GEMM, attention)
   int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
+  int pair;       // 1: CTA pair (cl == 2, tcgen05 cta_group::2): b_bytes is this CTA's HALF of the B tile
+  uint32_t idesc2;
 };
 
 using namespace tc;
@@ -80,6 +82,53 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- CTA pair (tcgen05 cta_group::2): the two CTAs of a cluster compute one 256-row tile; each holds its own 128 rows of A
+// and HALF of the B tile in shared memory, the leader (rank 0) issues the MMAs for both, accumulators land in each CTA's own
+// TMEM.  Every operand load of either CTA signals the LEADER's full barrier.
+__device__ __forceinline__ uint32_t leader_smem(uint32_t local) {   // same offset in CTA rank 0 of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local));
+  return r;
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == MSPI_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -87,11 +136,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 // ------------------------------------------------------------------------------------ kernel
 // ACT / RES are compile-time for the layer types the model uses (ACT: MSPI_ACT_*, RES: 0 none, 1 added before
 // the activation, 2 added after it); -1 selects the run-time value from the parameters (generic instance).
-template <int KIND, int OUT, int ACT, int RES>
+// PAIR: the CTA-pair (cta_group::2) variant.  It is a separate instantiation because a kernel that contains cta_group::2
+// instructions can only be launched with an even cluster width (a plain launch fails with "cluster misconfiguration").
+template <int KIND, int OUT, int ACT, int RES, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr bool pair = PAIR;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barrier block: full[8] empty[8] tmem_full[2] tmem_empty[2] tmem_ptr
   const uint32_t bar_full = smem_base;
@@ -116,19 +168,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_y) : "memory");
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, static_cast<uint32_t>(p.cl));  // one (multicast) commit per CTA of the cluster
+      // one (multicast) commit per CTA of the cluster; in pair mode only the leader's MMA warp commits
+      mbar_init(bar_empty + 8 * s, pair ? 1u : static_cast<uint32_t>(p.cl));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, kEpiWarps);
+      mbar_init(bar_tempty + 8 * s, pair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues release the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"(static_cast<uint32_t>(p.tmem_cols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (pair) {  // the same warp of both CTAs allocates the same columns in both TMEMs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"(static_cast<uint32_t>(p.tmem_cols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"(static_cast<uint32_t>(p.tmem_cols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < p.ss_floats; i += kThreads) {
     s_scale[i] = (p.scale != nullptr && i < p.cout) ? __ldg(p.scale + i) : 1.f;
@@ -181,7 +241,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int c3 = org[2] + p.tap_off[tap][2], c4 = org[3] + p.tap_off[tap][3];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            if (issuer) {
+            if constexpr (pair) {
+              // both CTAs load their A tile and their half of the B tile; everything lands on the leader's full barrier
+              if (issuer) {
+                const uint32_t full = bar_full + 8 * stage;
+                if (rank == 0) mbar_expect_tx(full, 2u * static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
+                const uint32_t full_l = leader_smem(full);
+                const uint32_t sa = tiles_base + stage * stage_bytes;
+                tma_load_5d_2sm(sa, &tma_a, full_l, kc * p.bk_elems, c1, c2, c3, c4);
+                tma_load_2d_2sm(sa + p.a_bytes, &tma_b, full_l, tap * p.cin_pad + kc * p.bk_elems,
+                                nt * p.bn + static_cast<int>(rank) * (p.bn / 2));
+              }
+            } else if (issuer) {
               const uint32_t full = bar_full + 8 * stage;
               mbar_expect_tx(full, static_cast<uint32_t>(p.a_tx_bytes + p.b_bytes));
               const uint32_t sa = tiles_base + stage * stage_bytes;
@@ -211,6 +282,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int as = 0;
       uint32_t aphase = 0;
       const int mmas = p.row_bytes >> 5;  // one UMMA consumes 32 bytes of K per row
+      if constexpr (pair) {
+        // CTA pair: the leader alone issues (M = 256: its own 128 rows + the peer's), commits go to both CTAs
+        if (rank == 0) {
+          for (int item = cid; item < total_items; item += ncl) {
+            mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.bn);
+            for (int it = 0; it < k_iters; ++it) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              if (issuer) {
+                const uint32_t sa = tiles_base + stage * stage_bytes;
+                const uint64_t adesc = make_smem_desc(sa, p.row_bytes);
+                const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.row_bytes);
+                for (int k = 0; k < mmas; ++k)
+                  tc_mma2<KIND>(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (it | k) != 0 ? 1u : 0u);
+                tc_commit2_mc(bar_empty + 8 * stage, 3);
+              }
+              __syncwarp();
+              if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            }
+            if (issuer) tc_commit2_mc(bar_tfull + 8 * as, 3);
+            __syncwarp();
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+          }
+        }
+      } else
       for (int item = cid; item < total_items; item += ncl) {
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
         tc_fence_after();
@@ -294,7 +392,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (set >= nchunks) {  // this set has no chunk in the tile: release the accumulator buffer right away
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        if (lane == 0) {
+          if constexpr (pair) mbar_arrive_cluster(leader_smem(bar_tempty + 8 * as)); else mbar_arrive(bar_tempty + 8 * as);
+        }
       }
 #pragma unroll 1
       for (int ch = set; ch < nchunks; ch += kEpiSets) {
@@ -420,7 +520,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           // before the last chunk is staged and stored
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          if (lane == 0) {
+            if constexpr (pair) mbar_arrive_cluster(leader_smem(bar_tempty + 8 * as)); else mbar_arrive(bar_tempty + 8 * as);
+          }
         }
         if (p.tma_store) {
           // staging buffer (store_seq & 1) is free once the bulk store issued two chunks ago has finished READING it
@@ -461,9 +563,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (p.cl > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(p.tmem_cols))
-                 : "memory");
+    if constexpr (pair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(p.tmem_cols))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(p.tmem_cols))
+                   : "memory");
   }
 }
 
@@ -526,16 +633,20 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
                        d->box[1], d->box[2], d->box[3], d->box[4]);
   }
   const bool w_batched = d->w_batch_dims[0] > 0;
-  // Optional cluster of 2 CTAs sharing every B tile by TMA multicast (MSPI_GEMM_CLUSTER=1).  Measured on B200
-  // (tools/prof_gemm.py): no gain — the big-K layers are bound by what one SM can take in through TMA (~43 B/clk/SM:
-  // 40 KB per 128x192x64 k-step = 940 clk against 384 clk of MMA), not by L2 reads, and multicast does not reduce the
-  // bytes an SM receives.  Off by default; kept because the 2-CTA (cta_group::2) path will reuse its plumbing.
-  int cl = 1;
+  // The layers are bound by what one SM can take in through TMA (~40 B/clk/SM, 11 TB/s over the chip: 40 KB per
+  // 128x192x64 k-step = 940 clk against 384 clk of MMA).  A 2-CTA cluster that shares every B tile by TMA multicast
+  // (MSPI_GEMM_CLUSTER=1) does not reduce the bytes an SM receives and measured no gain; the CTA pair (tcgen05
+  // cta_group::2, mode 2, the default) does: the two SMs compute one 256-row tile and each ingests HALF of the B tile
+  // (measured: readout.1 1.93 -> 1.67 ms, ConvNeXt stage-3 MLP GEMMs 0.18 -> 0.15 ms = 1.33 PF/s, step 39.9 -> 38.7 ms).
+  int cl = 1, pair = 0;
   {
     long long m_tiles_est = 1;
     for (int j = 0; j < 4; ++j) m_tiles_est *= (d->o_dims[j] + d->box[j + 1] - 1) / d->box[j + 1];
-    static const int mode = [] { const char* e = getenv("MSPI_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
+    // MSPI_GEMM_CLUSTER: 0 = one CTA per tile, 1 = 2-CTA cluster with TMA-multicast B tiles, 2 (default) = CTA pair
+    static const int mode = [] { const char* e = getenv("MSPI_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
     if (mode == 1 && !w_batched && d->bn % 16 == 0 && m_tiles_est >= 2) cl = 2;
+    // mode 2: CTA pair (tcgen05 cta_group::2): each SM ingests HALF of every B tile
+    if (mode == 2 && !w_batched && d->bn % 16 == 0 && row_bytes == 128 && m_tiles_est >= 2) { cl = 2; pair = 1; }
   }
   if (w_batched) {
     MSPI_CHECK_ARG(d->ntaps == 1 && d->w_batch_dims[0] == d->o_dims[2] && d->w_batch_dims[1] == d->o_dims[3] &&
@@ -599,8 +710,11 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.row_bytes = row_bytes;
   p.w_batched = w_batched ? 1 : 0;
   p.cl = cl;
+  p.pair = pair;
+  p.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(d->bn >> 3) << 17) |
+             (static_cast<uint32_t>((2 * kTileM) >> 4) << 24);
   p.a_bytes = kTileM * row_bytes;
-  p.b_bytes = d->bn * row_bytes;
+  p.b_bytes = (pair ? d->bn / 2 : d->bn) * row_bytes;
   p.a_tx_bytes = static_cast<int>(rows) * row_bytes;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   p.ss_floats = p.n_tiles * d->bn + 64;  // padded: the last staged chunk may run past the tile
@@ -650,8 +764,9 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
   const int res_mode = d->has_residual ? (d->res_after_act ? 2 : 1) : 0;
   Kern kern = nullptr;
-#define MSPI_PICK(K, O, A, R) \
-  if (d->a_dtype == K && d->o_dtype == O && d->act == A && res_mode == R) kern = conv_gemm_kernel<K, O, A, R>;
+#define MSPI_PICK(K, O, A, R)                                                      \
+  if (d->a_dtype == K && d->o_dtype == O && d->act == A && res_mode == R)          \
+    kern = pair ? conv_gemm_kernel<K, O, A, R, true> : conv_gemm_kernel<K, O, A, R, false>;
   MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_RELU, 0)
   MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_NONE, 0)
   MSPI_PICK(MSPI_BF16, MSPI_BF16, MSPI_ACT_GELU, 0)
@@ -668,7 +783,12 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   MSPI_PICK(MSPI_BF16, MSPI_F32, MSPI_ACT_RELU, 1)
 #undef MSPI_PICK
   if (kern == nullptr) {
-    if (d->a_dtype == MSPI_BF16) kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, -1, -1>
+    if (pair) {
+      if (d->a_dtype == MSPI_BF16) kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, -1, -1, true>
+                                                                  : conv_gemm_kernel<MSPI_BF16, MSPI_F32, -1, -1, true>;
+      else kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_F32, MSPI_BF16, -1, -1, true>
+                                          : conv_gemm_kernel<MSPI_F32, MSPI_F32, -1, -1, true>;
+    } else if (d->a_dtype == MSPI_BF16) kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, -1, -1>
                                                                 : conv_gemm_kernel<MSPI_BF16, MSPI_F32, -1, -1>;
     else kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_F32, MSPI_BF16, -1, -1>
                                         : conv_gemm_kernel<MSPI_F32, MSPI_F32, -1, -1>;
