@@ -65,6 +65,36 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- CTA pair (tcgen05 cta_group::2), see conv_gemm.cu: both CTAs load their own x tile and HALF of every weight piece, all
+// loads complete on the leader's barriers, the leader issues the M = 256 MMAs, commits are multicast to both CTAs and the
+// peer's epilogue warps arrive on the leader's barriers.
+__device__ __forceinline__ uint32_t leader_smem(uint32_t local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -84,6 +114,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// PAIR: CTA-pair instance (cluster of 2 required); a kernel that contains cta_group::2 instructions cannot be launched plainly.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ MlpParams p) {
@@ -111,25 +143,30 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     for (int s = 0; s < p.ring_stages; ++s) {
       mbar_init(ring_full + 8 * s, 1);
-      mbar_init(ring_empty + 8 * s, static_cast<uint32_t>(p.cl));  // one multicast commit from every CTA of the cluster
+      mbar_init(ring_empty + 8 * s, PAIR ? 1u : static_cast<uint32_t>(p.cl));  // one multicast commit per issuing CTA
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(x_full + 8 * s, 1);
       mbar_init(x_empty + 8 * s, 1);
-      mbar_init(a2_full + 8 * s, kEpiWarps);
+      mbar_init(a2_full + 8 * s, PAIR ? 2 * kEpiWarps : kEpiWarps);  // pair: the leader waits for both CTAs' epilogues
       mbar_init(a2_empty + 8 * s, 1);
     }
     for (int s = 0; s < kMaxHBuf; ++s) {
       mbar_init(h_full + 8 * s, 1);
-      mbar_init(h_empty + 8 * s, kEpiWarps);
+      mbar_init(h_empty + 8 * s, PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     mbar_init(y_full, 1);
-    mbar_init(y_empty, kEpiWarps);
+    mbar_init(y_empty, PAIR ? 2 * kEpiWarps : kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < 4 * p.c; i += kThreads) s_b1[i] = __ldg(p.b1 + i);
   for (int i = threadIdx.x; i < p.c; i += kThreads) {
@@ -165,7 +202,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       uint32_t xph = 0;
       auto load_x = [&](int tile) {
         mbar_wait(x_empty + 8 * xs, xph ^ 1u);
-        if (issuer) {
+        if constexpr (PAIR) {
+          if (issuer) {
+            if (rank == 0) mbar_expect_tx(x_full + 8 * xs, 2u * static_cast<uint32_t>(x_buf_bytes));
+            const uint32_t full_l = leader_smem(x_full + 8 * xs);
+            for (int kc = 0; kc < p.kc1; ++kc)
+              tma_load_2d_2sm(x_base + xs * x_buf_bytes + kc * kChunkBytes, &map_x, full_l, kc * 64, tile * 128);
+          }
+        } else if (issuer) {
           mbar_expect_tx(x_full + 8 * xs, static_cast<uint32_t>(x_buf_bytes));
           for (int kc = 0; kc < p.kc1; ++kc)
             tma_load_2d(x_base + xs * x_buf_bytes + kc * kChunkBytes, &map_x, x_full + 8 * xs, kc * 64, tile * 128);
@@ -176,7 +220,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       auto load_w1 = [&](int j) {
         for (int kc = 0; kc < p.kc1; ++kc) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
-          if (issuer) {
+          if constexpr (PAIR) {
+            if (issuer) {   // this CTA's 64 of the piece's 128 hidden rows, into its own ring slot
+              if (rank == 0) mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
+              tma_load_2d_2sm(ring_base + stage * p.ring_stage_bytes, &map_w1, leader_smem(ring_full + 8 * stage), kc * 64,
+                              j * kHC + static_cast<int>(rank) * (kHC / 2));
+            }
+          } else if (issuer) {
             mbar_expect_tx(ring_full + 8 * stage, kChunkBytes);
             if (p.cl > 1) {
               const int share = kHC / p.cl;  // rows of the piece this CTA fetches for the whole cluster
@@ -193,7 +243,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       auto load_w2 = [&](int j) {
         for (int kc2 = 0; kc2 < 2; ++kc2) {
           mbar_wait(ring_empty + 8 * stage, phase ^ 1u);
-          if (issuer) {
+          if constexpr (PAIR) {
+            if (issuer) {   // this CTA's C/2 of the piece's C output rows
+              if (rank == 0) mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
+              tma_load_2d_2sm(ring_base + stage * p.ring_stage_bytes, &map_w2, leader_smem(ring_full + 8 * stage),
+                              j * kHC + kc2 * 64, static_cast<int>(rank) * (p.c / 2));
+            }
+          } else if (issuer) {
             mbar_expect_tx(ring_full + 8 * stage, static_cast<uint32_t>(w2_bytes));
             if (p.cl > 1) {
               const int share = p.c / p.cl;
@@ -233,6 +289,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       uint32_t g = 0, ytile = 0;
       int prev_j = -1;
       uint32_t prev_g = 0;
+      // pair mode: the leader issues for both CTAs and every commit is multicast to both; the peer's MMA warp idles
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if constexpr (PAIR) tc_mma2_bf16(d, ad, bd, idesc, acc); else tc_mma<MSPI_BF16>(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if constexpr (PAIR) tc_commit2_mc(bar); else tc_commit(bar);
+      };
+      auto commit_ring = [&](uint32_t bar) {
+        if constexpr (PAIR) tc_commit2_mc(bar);
+        else if (p.cl > 1) tc_commit_mc(bar, mc_mask);
+        else tc_commit(bar);
+      };
+      const bool mma_active = !PAIR || rank == 0;
       auto mma2 = [&](int pj, uint32_t pg) {
         const uint32_t pb = pg & 1u;
         mbar_wait(a2_full + 8 * pb, (pg >> 1) & 1u);
@@ -246,20 +315,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma<MSPI_BF16>(tmem_y, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (pj | kc2 | k) != 0 ? 1u : 0u);
-            if (p.cl > 1) tc_commit_mc(ring_empty + 8 * stage, mc_mask); else tc_commit(ring_empty + 8 * stage);
+              mma(tmem_y, adesc + 2u * k, bdesc + 2u * k, p.idesc2, (pj | kc2 | k) != 0 ? 1u : 0u);
+            commit_ring(ring_empty + 8 * stage);
           }
           __syncwarp();
           if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
         }
         if (issuer) {
-          tc_commit(a2_empty + 8 * pb);
-          if (pj == p.nh - 1) tc_commit(y_full);
+          commit(a2_empty + 8 * pb);
+          if (pj == p.nh - 1) commit(y_full);
         }
         __syncwarp();
         if (pj == p.nh - 1) ++ytile;
       };
-      for (int grp = cid; grp < groups; grp += ncl) {
+      for (int grp = cid; mma_active && grp < groups; grp += ncl) {
         mbar_wait(x_full + 8 * xs, xph);
         tc_fence_after();
         for (int j = 0; j < p.nh; ++j) {
@@ -274,15 +343,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int ksteps = min(4, (p.c - kc * 64 + 15) >> 4);  // skip the zero-padded K tail
             if (issuer) {
               for (int k = 0; k < ksteps; ++k)
-                tc_mma<MSPI_BF16>(tmem_base + b * kHC, adesc + 2u * k, bdesc + 2u * k, p.idesc1, (kc | k) != 0 ? 1u : 0u);
-              if (p.cl > 1) tc_commit_mc(ring_empty + 8 * stage, mc_mask); else tc_commit(ring_empty + 8 * stage);
+                mma(tmem_base + b * kHC, adesc + 2u * k, bdesc + 2u * k, p.idesc1, (kc | k) != 0 ? 1u : 0u);
+              commit_ring(ring_empty + 8 * stage);
             }
             __syncwarp();
             if (++stage == p.ring_stages) { stage = 0; phase ^= 1u; }
           }
           if (issuer) {
-            tc_commit(h_full + 8 * b);
-            if (j == p.nh - 1) tc_commit(x_empty + 8 * xs);  // x tile free once these MMAs have read it
+            commit(h_full + 8 * b);
+            if (j == p.nh - 1) commit(x_empty + 8 * xs);  // x tile free once these MMAs have read it
           }
           __syncwarp();
           if (prev_j >= 0) mma2(prev_j, prev_g);
@@ -292,10 +361,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         if (++xs == p.x_bufs) { xs = 0; xph ^= 1u; }
       }
-      if (prev_j >= 0) mma2(prev_j, prev_g);
+      if (mma_active && prev_j >= 0) mma2(prev_j, prev_g);
     }
   } else {
     // ================================================================== epilogue warps
+    // pair mode: the barriers the MMA warp waits on live in the leader CTA
+    auto arrive = [&](uint32_t bar) {
+      if constexpr (PAIR) mbar_arrive_cluster(leader_smem(bar)); else mbar_arrive(bar);
+    };
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 = this warp's rows
     const int colgrp = (warp - 2) >> 2;      // which 32 of a chunk's 128 hidden columns
     const int row = quarter * 32 + lane;
@@ -340,7 +413,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(y_empty);
+      if (lane == 0) arrive(y_empty);
       ++ytile;
     };
     for (int grp = cid; grp < groups; grp += ncl) {
@@ -382,7 +455,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_empty + 8 * hb);  // H[hb] may be overwritten by MMA1 of chunk g + hbufs
+        if (lane == 0) arrive(h_empty + 8 * hb);  // H[hb] may be overwritten by MMA1 of chunk g + hbufs
         // 32 columns = four 16-byte pieces of K chunk (colgrp >> 1), pieces 4*(colgrp & 1) ..
         const uint32_t dst_row = a2_base + (ab * 2 + (colgrp >> 1)) * kChunkBytes + row * 128;
 #pragma unroll
@@ -396,7 +469,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(a2_full + 8 * ab);
+        if (lane == 0) arrive(a2_full + 8 * ab);
         ++g;
         if (j == 0 && pend) {
           y_epilogue();
@@ -426,7 +499,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (p.cl > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -459,9 +535,12 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   };
   CUtensorMap map_x, map_w1, map_w2;
   CUresult r1 = make2d(&map_x, x, c, static_cast<uint64_t>(m), c, 128);
-  int cl = 1;  // CTAs per cluster sharing the weight stream by TMA multicast (MSPI_MLP_CLUSTER=1|2|4); measured: no
-               // gain on B200 (the kernel is bound by the MMA <-> epilogue hand-offs, not by L2), so off by default
+  // MSPI_MLP_CLUSTER: 1 = one CTA per tile; 2 | 4 = cluster sharing the weight stream by TMA multicast (measured: no gain, an
+  // SM still ingests every piece); -2 (default) = CTA pair (tcgen05 cta_group::2): each SM ingests HALF of every weight piece
+  int cl = -2;
   if (const char* e = getenv("MSPI_MLP_CLUSTER")) cl = atoi(e);
+  const bool pair = cl == -2 && m > 128;
+  if (cl == -2) cl = pair ? 2 : 1;
   if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   CUresult r2 = make2d(&map_w1, w1, c_pad, hidden, c_pad, 128 / cl);
   CUresult r3 = make2d(&map_w2, w2, hidden, c, hidden, c / cl);
@@ -475,7 +554,7 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   p.kc1 = c_pad / 64;
   p.nh = hidden / kHC;
   p.m_tiles = static_cast<int>((m + 127) / 128);
-  p.ring_stage_bytes = (c > 128 ? c : 128) * 128;
+  p.ring_stage_bytes = (c > 128 ? c : 128) * 128 / (pair ? 2 : 1);   // pair: a slot holds this CTA's half of a piece
   p.b1 = b1;
   p.scale = scale;
   p.shift = shift;
@@ -483,15 +562,17 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   p.y = static_cast<__nv_bfloat16*>(y);
   p.res_stride = res_stride;
   p.y_stride = y_stride;
-  p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kHC >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(c >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  const uint32_t mdim = pair ? 256u : 128u;   // pair: one MMA covers the 128 rows of both CTAs
+  p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kHC >> 3) << 17) | ((mdim >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(c >> 3) << 17) | ((mdim >> 4) << 24);
   p.x_bufs = c <= 96 ? 2 : 1;  // C = 192: the weight ring needs the room (30 pieces per tile, each one L2 round trip)
   const int fixed = 1024 + 1024 + 8192 + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes;
   p.ring_stages = (225 * 1024 - fixed) / p.ring_stage_bytes;
   if (p.ring_stages > kMaxRing) p.ring_stages = kMaxRing;
   MSPI_CHECK_ARG(p.ring_stages >= 2, "mspi_mlp_fused: shared memory leaves %d ring stages", p.ring_stages);
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.ring_stages) * p.ring_stage_bytes;
-  MSPI_CUDA(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  auto kern = pair ? fused_mlp_kernel<true> : fused_mlp_kernel<false>;
+  MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   p.cl = cl;
   if (const char* e = getenv("MSPI_MLP_DEBUG")) p.debug = atoi(e);
   p.hbufs = (3 * kHC + c <= 512) ? 3 : 2;
@@ -509,18 +590,18 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent grid: as many clusters as can be resident at once (1 CTA per SM), never more than there are tile groups
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
-  if (max_clusters[cl] == 0) {
+  static int max_clusters[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  if (max_clusters[pair][cl] == 0) {
     cfg.gridDim = dim3(num_sms() / cl * cl, 1, 1);
     int n = 0;
-    MSPI_CUDA(cudaOccupancyMaxActiveClusters(&n, fused_mlp_kernel, &cfg));
-    max_clusters[cl] = n > 0 ? n : 1;
+    MSPI_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters[pair][cl] = n > 0 ? n : 1;
   }
-  int nclusters = max_clusters[cl];
+  int nclusters = max_clusters[pair][cl];
   if (nclusters > num_sms() / cl) nclusters = num_sms() / cl;
   if (nclusters > groups) nclusters = groups;
   cfg.gridDim = dim3(nclusters * cl, 1, 1);
-  MSPI_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, map_x, map_w1, map_w2, p));
+  MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_x, map_w1, map_w2, p));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
