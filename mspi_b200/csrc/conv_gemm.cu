@@ -363,7 +363,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t store_seq = 0;
     const uint32_t my_stage = kEpiSets > 1 ? static_cast<uint32_t>(set) * kABytes : 0u;
     const int bar_id = 1 + set;
-    for (int item = cid; item < total_items; item += ncl) {
+    uint32_t chunk_seq = 0;  // column chunks processed by this CTA so far: chunk g of the kernel belongs to set g % kEpiSets
+    for (int item = cid; item < total_items; item += ncl, chunk_seq += nchunks) {
       const int nt = item % p.n_tiles;
       int mt = (item / p.n_tiles) * p.cl + rank;
       const bool dummy = mt >= p.m_tiles;
@@ -389,7 +390,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * p.bn);
       const int n_base = nt * p.bn;
-      if (set >= nchunks) {  // this set has no chunk in the tile: release the accumulator buffer right away
+      // the sets alternate over the GLOBAL chunk sequence, so tiles with a single chunk (N <= 64 bf16 / 32 fp32: the stems,
+      // most Inception branches) alternate between the sets as well and two tiles' chains overlap
+      const int first = kEpiSets > 1 ? static_cast<int>((static_cast<uint32_t>(set) + kEpiSets - chunk_seq % kEpiSets) % kEpiSets) : 0;
+      if (first >= nchunks) {  // this set has no chunk in the tile: release the accumulator buffer (after the tfull wait above,
+                               // so a set can never get ahead of the MMA warp and arrive twice in one phase)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -397,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
 #pragma unroll 1
-      for (int ch = set; ch < nchunks; ch += kEpiSets) {
+      for (int ch = first; ch < nchunks; ch += kEpiSets) {
         const int c0 = ch * CH + group * HC;
         const int width = min(HC, p.bn - c0);  // HC, 16 (bf16, odd multiple of 16), or <= 0 past the tile
         const int n0 = n_base + c0;

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import functools
 import math
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -467,7 +468,7 @@ def clip_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int,
 
 
 def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale, shift, k: int, stride: int, pad: int,
-              act: int, y: "Act", name: str = "stem", clips: int = 0) -> Callable[[], None]:
+              act: int, y: "Act", name: str = "stem", clips: int = 0, allow_wide: bool = True) -> Callable[[], None]:
     """(1,k,k)/stride conv with Cin=3 straight off the padded 4-channel frames (no im2col buffer).
 
     One row of the filter (k taps x 4 channels, at most 8 pixels) is a contiguous 16-byte aligned run of the frame;
@@ -491,11 +492,18 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
         fpc = nf // clips
         nf = fpc - (kt - 1)  # frames produced per launch
     oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    # outputs per GEMM row: the S3D stem computes 4 neighbouring output pixels from one 16-pixel (128-byte) window, see below
+    wide_ok = allow_wide and kt == 1 and y.c0 == 0 and y.cs == cout and os.environ.get("MSPI_STEM_WIDE", "1") != "0"
+    wide = 1
+    if wide_ok and (k, stride, pad) == (7, 2, 3) and ow % 4 == 0 and cout * 4 <= 256:
+        wide = 4      # S3D conv_s: 16-pixel window (128 B), 4 outputs, N = 256
+    elif wide_ok and (k, stride, pad) == (4, 4, 0) and ow % 2 == 0 and cout * 2 <= 256:
+        wide = 2      # ConvNeXt stem: 8-pixel window (64 B instead of 32 B rows), 2 outputs, N = 192
     if (k, stride, pad) == (7, 2, 3):
-        run_px, x_lead = 8, 1     # window starts one pixel before tap 0 (alignment)
+        run_px, x_lead = (16, 1) if wide == 4 else (8, 1)     # window starts one pixel before tap 0 (alignment)
         row0, col0 = PAD_T - pad, PAD_L - pad - x_lead
     elif (k, stride, pad) == (4, 4, 0):
-        run_px, x_lead = 4, 0
+        run_px, x_lead = 4 * wide, 0
         row0, col0 = PAD_T, PAD_L
     elif (k, stride, pad) == (3, 2, 1):   # X3D stem conv_xy (stem_helper.py:262-270): 4-px window from 2*ow-2
         run_px, x_lead = 4, 1
@@ -505,24 +513,30 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     run_el = run_px * 4
     assert (col0 * 4 * 2) % 16 == 0 and (stride * 4 * 2) % 16 == 0 and row0 >= 0 and col0 >= 0
     # weight matrix [cout16][k taps][run_px][4]
-    rows16 = -(-cout // 16) * 16
+    gemm_n = cout * wide
+    rows16 = -(-gemm_n // 16) * 16
     wm = torch.zeros((rows16, kt, k, run_px, 4), dtype=torch.float32, device=frames.device)
-    wm[:cout, :, :, x_lead:x_lead + k, :3] = w5.permute(0, 2, 3, 4, 1)
+    for j in range(wide):
+        # wide == 4 (S3D stem): GEMM column (j, co) is output pixel 4g + j of the row's group g; its 7 taps sit at pixels
+        # 2j + kw + x_lead of the 16-pixel window, the rest of its K entries are zero.  The TMA engine issues one request
+        # per (row, tap) whatever the row length, and those requests — not bytes, not MMA time — bound the 8-pixel form
+        # (896 per 128 outputs); four outputs per row need a quarter of them at twice the (cheap) MMA work.
+        wm[j * cout:(j + 1) * cout, :, :, stride * j + x_lead:stride * j + x_lead + k, :3] = w5.permute(0, 2, 3, 4, 1)
     packed = wm.reshape(rows16, kt * k * run_el).to(torch.bfloat16).contiguous()
     # frame row of (oh, kh) = row0 + stride*oh + kh = row0 + stride*(oh + kh // stride) + kh % stride
     n_r, n_j = min(stride, k), (k - 1) // stride + 1
-    assert row0 + stride * (oh - 1) + k - 1 < hp and col0 + stride * (ow - 1) + run_px - 1 < wp
+    assert row0 + stride * (oh - 1) + k - 1 < hp and col0 + wide * stride * (ow // wide - 1) + run_px - 1 < wp
     d = ConvDesc()
     d.a_dtype = MSPI_BF16
     d.k_row_bytes = run_el * 2
-    a_dims = (run_el, n_r, ow, oh + n_j - 1, nf + kt - 1)
-    a_str = (1, wp * 4, stride * 4, stride * wp * 4, hp * wp * 4)
+    a_dims = (run_el, n_r, ow // wide, oh + n_j - 1, nf + kt - 1)
+    a_str = (1, wp * 4, wide * stride * 4, stride * wp * 4, hp * wp * 4)
     for j in range(5):
         d.a_dims[j] = a_dims[j]
         d.a_strides[j] = a_str[j]
-    o_dims = (1, ow, oh, nf)
-    box = (1,) + choose_box((ow, oh, nf, 1))[:3]
-    ostr = (0, y.cs, y.w * y.cs, y.h * y.w * y.cs)  # frames (n, t) are contiguous in y
+    o_dims = (1, ow // wide, oh, nf)
+    box = (1,) + choose_box((ow // wide, oh, nf, 1))[:3]
+    ostr = (0, wide * y.cs, y.w * y.cs, y.h * y.w * y.cs)  # frames (n, t) are contiguous in y; a wide row = `wide` pixels
     d.box[0] = 0
     for j in range(4):
         d.box[j + 1] = box[j]
@@ -536,12 +550,12 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
             i = it * k + kh
             d.tap_off[i][0], d.tap_off[i][1], d.tap_off[i][2], d.tap_off[i][3] = kh % stride, 0, kh // stride, it
     d.cin_pad = run_el
-    d.cout, d.w_rows = cout, rows16
-    d.bn = choose_bn(cout, 64 if y.dtype == torch.bfloat16 else 32)
+    d.cout, d.w_rows = gemm_n, rows16
+    d.bn = choose_bn(gemm_n, 64 if y.dtype == torch.bfloat16 else 32)
     d.o_dtype = _DT[y.dtype]
     d.act = act
-    sc = None if scale is None else scale.detach().float().contiguous().to(frames.device)
-    sh = None if shift is None else shift.detach().float().contiguous().to(frames.device)
+    sc = None if scale is None else scale.detach().float().repeat(wide).contiguous().to(frames.device)
+    sh = None if shift is None else shift.detach().float().repeat(wide).contiguous().to(frames.device)
     launches = 1 if kt == 1 else clips
     x_ptrs = [_ptr(frames, ((b * (nf + kt - 1) * hp + row0) * wp + col0) * 4 * 2) for b in range(launches)]
     es_y = _ES[y.dtype]
