@@ -261,7 +261,8 @@ int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_logits, voi
 /* The same gate fused with the top-down sums of model_utils.py:566-568 (fp32):
  *   y = x * sigmoid_mask + x + sum_i up_{k_i}(src_i),   up = bilinear (1,k,k) upsample, align_corners=False
  * x, y: [nt][h][w][c]; src_i: [nt][h/k_i][w/k_i][c] (pixel stride src_cstrides[i]); srcs / src_cstrides / src_scales are
- * HOST arrays of nsrc <= 3 entries.  y is written once instead of once per term. */
+ * HOST arrays of nsrc <= 3 entries.  y is written once instead of once per term.  mask_logits == NULL drops the gate
+ * (y = x + sum up(src); x == y allowed): the readout.0 partial products are accumulated that way (model_utils.py:570). */
 int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float* mask_logits, float* y, int64_t y_cstride, int nt,
                        int h, int w, int c, int nsrc, const float* const* srcs, const int64_t* src_cstrides,
                        const int32_t* src_scales, void* stream);

@@ -340,8 +340,8 @@ struct GateSrc {
   int k[3];
   int n;
 };
-__global__ void sa_gate_fused_kernel(const float* __restrict__ x, long long xcs, const float* __restrict__ m,
-                                     float* __restrict__ y, long long ycs, long long total, int c8, int h, int w, GateSrc s) {
+__global__ void sa_gate_fused_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs,
+                                     long long total, int c8, int h, int w, GateSrc s) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long pix = i;
@@ -350,9 +350,13 @@ __global__ void sa_gate_fused_kernel(const float* __restrict__ x, long long xcs,
     const int ox = divmod(r, w);
     const int oy = divmod(r, h);
     const long long plane = r;
-    const float g = 1.f + 1.f / (1.f + expf(-__ldg(m + pix)));
+    const float g = m != nullptr ? 1.f + 1.f / (1.f + expf(-__ldg(m + pix))) : 1.f;   // no mask: plain y = x + sum up(src)
     float f[8];
-    load_vec<float, 8>(x + pix * xcs + cc, f);
+    {
+      const float4* xp = reinterpret_cast<const float4*>(x + pix * xcs + cc);   // x may alias y (in place): no __ldg
+      const float4 a0 = xp[0], a1 = xp[1];
+      f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] *= g;
     for (int j = 0; j < s.n; ++j) {
@@ -568,7 +572,7 @@ extern "C" int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float
                                   int nt, int h, int w, int c, int nsrc, const float* const* srcs, const int64_t* src_cstrides,
                                   const int32_t* src_scales, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MSPI_CHECK_ARG(x && mask_logits && y && c % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0 && nsrc >= 0 && nsrc <= 3,
+  MSPI_CHECK_ARG(x && y && c % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0 && nsrc >= 0 && nsrc <= 3,
                  "mspi_sa_gate_fused: bad argument");
   GateSrc s;
   s.n = nsrc;

@@ -383,29 +383,25 @@ __global__ void token_mean_kernel(const T* __restrict__ x, float* __restrict__ y
 }
 
 // ------------------------------------------------------------------------- SimSiam loss
+// grid (B, 2): one block per (sample, pair); out must be zero on entry (the host wrapper clears it)
 __global__ void simsiam_kernel(const float* __restrict__ pv, const float* __restrict__ za, const float* __restrict__ pa,
                                const float* __restrict__ zv, float* __restrict__ out, int bsz, int c) {
   __shared__ float red[32];
-  float total = 0.f;
-  for (int b = 0; b < bsz; ++b) {
-    for (int pair = 0; pair < 2; ++pair) {
-      const float* p = (pair == 0 ? pv : pa) + static_cast<long long>(b) * c;
-      const float* z = (pair == 0 ? za : zv) + static_cast<long long>(b) * c;
-      float dot = 0.f, pp = 0.f, zz = 0.f;
-      for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        const float a = p[i], q = z[i];
-        dot = fmaf(a, q, dot);
-        pp = fmaf(a, a, pp);
-        zz = fmaf(q, q, zz);
-      }
-      dot = block_sum(dot, red);
-      pp = block_sum(pp, red);
-      zz = block_sum(zz, red);
-      // F.cosine_similarity: x.y / sqrt(max(|x|^2 |y|^2, eps^2)), eps = 1e-8
-      total += dot * rsqrtf(fmaxf(pp * zz, 1e-16f));
-    }
+  const int b = blockIdx.x, pair = blockIdx.y;
+  const float* p = (pair == 0 ? pv : pa) + static_cast<long long>(b) * c;
+  const float* z = (pair == 0 ? za : zv) + static_cast<long long>(b) * c;
+  float dot = 0.f, pp = 0.f, zz = 0.f;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const float a = p[i], q = z[i];
+    dot = fmaf(a, q, dot);
+    pp = fmaf(a, a, pp);
+    zz = fmaf(q, q, zz);
   }
-  if (threadIdx.x == 0) out[0] = -0.5f * total / static_cast<float>(bsz);
+  dot = block_sum(dot, red);
+  pp = block_sum(pp, red);
+  zz = block_sum(zz, red);
+  // F.cosine_similarity: x.y / sqrt(max(|x|^2 |y|^2, eps^2)), eps = 1e-8
+  if (threadIdx.x == 0) atomicAdd(out, -0.5f * dot * rsqrtf(fmaxf(pp * zz, 1e-16f)) / static_cast<float>(bsz));
 }
 
 }  // namespace
@@ -581,7 +577,8 @@ extern "C" int mspi_simsiam_loss(const float* p_v, const float* z_a, const float
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(p_v && z_a && p_a && z_v && out && b > 0 && c > 0, "mspi_simsiam_loss: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  simsiam_kernel<<<1, 256, 0, stream>>>(p_v, z_a, p_a, z_v, out, b, c);
+  MSPI_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  simsiam_kernel<<<dim3(b, 2), 256, 0, stream>>>(p_v, z_a, p_a, z_v, out, b, c);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

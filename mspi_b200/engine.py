@@ -649,9 +649,11 @@ class ForwardPlan:
         w0 = self.P(p + ".0.weight")
         c = g0.c
         x = self.conv(p + ".0[s0]", g0, w0[:, 0:c], None, self.P(p + ".0.bias"), out_dtype=f32, dtype=f32)
+        parts = []
         for i, (g, k) in enumerate(((g1, 2), (g2, 4), (s3, 8)), 1):
-            part = self.conv(f"{p}.0[s{i}]", g, w0[:, i * c:(i + 1) * c], out_dtype=f32, dtype=f32)
-            self.up(f"{p}.0+=up{k}", part, k, x, accumulate=True)
+            parts.append((self.conv(f"{p}.0[s{i}]", g, w0[:, i * c:(i + 1) * c], out_dtype=f32, dtype=f32), k))
+        # x += up2(part1) + up4(part2) + up8(part3) in ONE pass over x (in place; the gate kernel without a mask)
+        self.add(f"{p}.0+=up2,4,8", ops.sa_gate_fused(x, None, x, parts))
         sc, sh = self.bn(p + ".2", 1e-5, self.P(p + ".1.bias"))
         x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
         sc, sh = self.bn(p + ".5", 1e-5, self.P(p + ".4.bias"))

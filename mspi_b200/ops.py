@@ -892,8 +892,9 @@ def sa_gate_fused(x: Act, mask_logits: torch.Tensor, y: Act, sources) -> Callabl
     """y = x * sigmoid(mask) + x + sum up_k(src) for (src Act, k) in sources (fp32): SA gate + top-down fusion in one pass
     (model_utils.py:167-170,566-568)."""
     lib = _lib.load()
-    assert x.dtype == y.dtype == torch.float32 and mask_logits.dtype == torch.float32 and len(sources) <= 3
-    assert mask_logits.numel() == x.pixels and (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h, x.w, x.c)
+    assert x.dtype == y.dtype == torch.float32 and len(sources) <= 3
+    assert mask_logits is None or (mask_logits.dtype == torch.float32 and mask_logits.numel() == x.pixels)
+    assert (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h, x.w, x.c)
     n = len(sources)
     ptrs = (C.c_void_p * max(n, 1))(*[a.ptr for a, _k in sources])
     css = (C.c_int64 * max(n, 1))(*[a.cs for a, _k in sources])
