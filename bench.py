@@ -398,11 +398,23 @@ def main():
     audio_sets = [torch.randn(B, 1, 257, 111, device=dev, generator=g) for _ in range(n_sets)]
     from mspi_b200.distributed import gather_maps
 
+    pending = [None]
+
     def step(i):
         out, loss = model(clips_sets[i % n_sets], audio_sets[i % n_sets])
         if world > 1:
-            out = gather_maps(out, world * B)  # NCCL all-gather of the [B,H,W] maps, global clip order
+            # NCCL all-gather of the [B,H,W] maps (global clip order) on the communicator's stream: it overlaps the next
+            # step's kernels; the previous step's gather is waited for here, the last one by drain()
+            h = gather_maps(out, world * B, async_op=True)
+            if pending[0] is not None:
+                pending[0].wait()
+            pending[0] = h
         return out, loss
+
+    def drain():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
 
     def barrier():
         if world > 1:
@@ -430,6 +442,7 @@ def main():
         ev0.record()
         for i in range(K):
             step(i)
+        drain()
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)

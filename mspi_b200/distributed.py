@@ -27,11 +27,25 @@ def max_shard(global_batch: int, world: int) -> int:
     return -(-global_batch // world)
 
 
-def gather_maps(local_maps: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+class PendingGather:
+    """Handle of an asynchronous gather_maps: .wait() makes the current stream wait for the collective and returns the maps."""
+
+    def __init__(self, work, finish):
+        self._work, self._finish = work, finish
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self._finish()
+
+
+def gather_maps(local_maps: torch.Tensor, global_batch: int, group=None, async_op: bool = False):
     """All-gather the per-rank [b_local, H, W] maps into [global_batch, H, W] in global clip order.
 
     Ragged shards are padded to the largest shard for the collective (all_gather_into_tensor needs equal sizes)
-    and the padding rows are dropped afterwards."""
+    and the padding rows are dropped afterwards.  async_op=True returns a PendingGather: the collective runs on the
+    communicator's own stream, so the next batch's kernels overlap it (wait() before the maps are read)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = shard_bounds(global_batch, rank, world)
@@ -44,14 +58,19 @@ def gather_maps(local_maps: torch.Tensor, global_batch: int, group=None) -> torc
         send = torch.zeros((m, h, w), dtype=local_maps.dtype, device=local_maps.device)
         send[: hi - lo] = local_maps
     recv = torch.empty((world * m, h, w), dtype=local_maps.dtype, device=local_maps.device)
-    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-    if global_batch == world * m:
-        return recv
-    parts = []
-    for r in range(world):
-        a, b = shard_bounds(global_batch, r, world)
-        parts.append(recv[r * m: r * m + (b - a)])
-    return torch.cat(parts, 0)
+    send = send.contiguous()
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=async_op)
+
+    def finish(_keep=(send,)):
+        if global_batch == world * m:
+            return recv
+        parts = []
+        for r in range(world):
+            a, b = shard_bounds(global_batch, r, world)
+            parts.append(recv[r * m: r * m + (b - a)])
+        return torch.cat(parts, 0)
+
+    return PendingGather(work, finish) if async_op else finish()
 
 
 def forward_sharded(forward: Callable, clips: torch.Tensor, audios: Optional[torch.Tensor], group=None):

@@ -48,6 +48,11 @@ def _worker(rank, world, port, n, q):
         ref_maps, _ = _fake_forward(clips, aud)
         ref_loss = ref_maps.mean((1, 2)).mean() if n else torch.tensor(0.0)
         ok = torch.allclose(full, ref_maps, atol=1e-6) and abs(float(loss) - float(ref_loss)) < 1e-6
+        # the asynchronous form returns the same maps after wait()
+        lo_, hi_ = shard_bounds(n, rank, world)
+        if hi_ > lo_ or True:
+            local = ref_maps[lo_:hi_].contiguous()
+            ok = ok and torch.allclose(gather_maps(local, n, async_op=True).wait(), ref_maps, atol=1e-6)
         # gather_maps rejects a shard of the wrong size
         lo, hi = shard_bounds(n, rank, world)
         try:
