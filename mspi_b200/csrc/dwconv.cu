@@ -15,8 +15,10 @@
 //      warps normalise one pixel at a time (two-pass mean / variance in registers), writing whole
 //      channel rows.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mspi {
 namespace {
@@ -52,9 +54,9 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 #endif
 template <typename TI, int CQ, int S, int P>
 __global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_MINB : 1)
-dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-                const float* __restrict__ ln_w, const float* __restrict__ ln_b, void* __restrict__ y, int out_bf16,
-                int H, int W, int tiles_x, int tiles_y, float eps, int cs) {
+dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict__ x, const float* __restrict__ wgt,
+                const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int tiles_y, float eps, int cs, int use_tma) {
   // cs: channels of the tensor (pixel stride).  cs == C: the block owns whole pixels and can normalise them.  cs > C: the
   // blocks of grid.y each own a group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
   constexpr int C = 4 * CQ;
@@ -63,7 +65,10 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   constexpr int kThreads = CQ * S;
   constexpr int kVec = 16 / sizeof(TI);            // elements per 16-byte copy
   constexpr int kRowVecs = C / kVec;               // 16-byte copies per pixel
-  extern __shared__ __align__(16) uint8_t dw_smem[];
+  constexpr int kBoxC = C > 256 ? C / 2 : C;       // channels per TMA box (box dimensions are limited to 256 elements)
+  constexpr int kBoxes = C / kBoxC;                // the tile is stored [box][TH][TW][kBoxC]
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  __shared__ __align__(8) unsigned long long tma_bar;
   TI* tile_s = reinterpret_cast<TI*>(dw_smem);        // [TH][TW][C] input tile, zero halo
   float* out_s = reinterpret_cast<float*>(dw_smem);   // [S*P][C] results; re-uses the tile buffer after the stencil
 
@@ -74,15 +79,31 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
   const int x0 = tx * P, y0 = ty * S;
   const TI* xin = x + static_cast<long long>(n) * H * W * cs + c0;
 
+  if (use_tma) {
+    // the whole (S+6) x (P+6) x C tile, zero halo included, is one bulk tensor load per <=256-channel box: TMA fills coordinates
+    // outside the image with zeros, which is exactly the convolution's padding (no per-thread address math, no predicates)
+    const uint32_t bar = tc::smem_u32(&tma_bar);
+    if (threadIdx.x == 0) {
+      tc::mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      tc::mbar_expect_tx(bar, static_cast<uint32_t>(TH * TW * C * sizeof(TI)));
+#pragma unroll
+      for (int b = 0; b < kBoxes; ++b)
+        tc::tma_load_4d(tc::smem_u32(tile_s + static_cast<size_t>(b) * TH * TW * kBoxC), &map_x, bar, c0 + b * kBoxC, x0 - 3,
+                        y0 - 3, n);
+    }
+  } else {
   for (int i = threadIdx.x; i < TH * TW * kRowVecs; i += kThreads) {
     const int cv = i % kRowVecs, pix = i / kRowVecs;
     const int tc = pix % TW, tr = pix / TW;
     const int gy = y0 + tr - 3, gx = x0 + tc - 3;
     const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
     const TI* src = xin + (static_cast<long long>(in ? gy : 0) * W + (in ? gx : 0)) * cs + cv * kVec;
-    cp_async16_zfill(tile_s + static_cast<size_t>(pix) * C + cv * kVec, src, in);
+    const int ch = cv * kVec, box = ch / kBoxC;
+    cp_async16_zfill(tile_s + (static_cast<size_t>(box) * TH * TW + pix) * kBoxC + (ch - box * kBoxC), src, in);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   const int q = threadIdx.x % CQ;
   const int s = threadIdx.x / CQ;
@@ -92,18 +113,23 @@ dw7x7_ln_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const f
 #pragma unroll
     for (int j = 0; j < P; ++j) acc[j] = b;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  if (use_tma) {
+    __syncthreads();   // the barrier init is visible to every waiter
+    tc::mbar_wait(tc::smem_u32(&tma_bar), 0);
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
 
 #pragma unroll 1
   for (int kh = 0; kh < 7; ++kh) {
     float4 w[7];
 #pragma unroll
     for (int kw = 0; kw < 7; ++kw) w[kw] = __ldg(reinterpret_cast<const float4*>(wgt + (kh * 7 + kw) * cs + c0) + q);
-    const TI* trow = tile_s + static_cast<size_t>(s + kh) * TW * C + 4 * q;
+    const TI* trow = tile_s + (static_cast<size_t>((4 * q) / kBoxC) * TH + s + kh) * TW * kBoxC + (4 * q) % kBoxC;
 #pragma unroll
     for (int ix = 0; ix < TW; ++ix) {
-      const float4 v = Ld4<TI>::lds(trow + ix * C);
+      const float4 v = Ld4<TI>::lds(trow + ix * kBoxC);
 #pragma unroll
       for (int kw = 0; kw < 7; ++kw) {
         const int j = ix - kw;  // output pixel fed by this input through tap kw
@@ -261,9 +287,35 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv 7x7: grid out of range");
   auto kern = dw7x7_ln_kernel<TI, CQ, S, P>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // tile load by TMA (one 4-D box [C, P+6, S+6, 1] per block, out-of-image coordinates zero-filled) where the channel
+  // group fits a box; MSPI_DW_TMA=0 keeps the per-thread cp.async path
+  static const bool tma_on = [] { const char* e = getenv("MSPI_DW_TMA"); return !e || atoi(e) != 0; }();
+  const int ctot = C * groups;
+  constexpr int kBoxC = C > 256 ? C / 2 : C;
+  int use_tma = tma_on && kBoxC <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ctot * sizeof(TI)) % 16 == 0;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (use_tma) {
+    tc::EncodeTiledFn encode = tc::get_encode_fn();
+    if (!encode) {
+      use_tma = 0;
+    } else {
+      const cuuint64_t es = sizeof(TI);
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(ctot), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
+                            static_cast<cuuint64_t>(d->n) * d->t};
+      cuuint64_t gstr[3] = {ctot * es, static_cast<cuuint64_t>(d->w) * ctot * es,
+                            static_cast<cuuint64_t>(d->h) * d->w * ctot * es};
+      cuuint32_t bdim[4] = {static_cast<cuuint32_t>(kBoxC), static_cast<cuuint32_t>(P + 6), static_cast<cuuint32_t>(S + 6), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&map, sizeof(TI) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                          const_cast<void*>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) use_tma = 0;
+    }
+  }
   kern<<<dim3(static_cast<unsigned>(blocks), groups), CQ * S, smem, stream>>>(
-      static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
-      d->ln_eps, C * groups);
+      map, static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
+      d->ln_eps, C * groups, use_tma);
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
