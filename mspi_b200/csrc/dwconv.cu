@@ -28,9 +28,13 @@ struct Ld4;
 template <>
 struct Ld4<__nv_bfloat16> {
   static __device__ __forceinline__ float4 cvt(uint2 u) {
+    // bf16 -> fp32 is a 16-bit left shift: one shift for the low half, one mask for the high half (4 ALU ops per 4 values;
+    // the ALU pipe is the co-bottleneck of the stencil next to the FMA pipe)
     float4 f;
-    unpack_bf16x2(u.x, f.x, f.y);
-    unpack_bf16x2(u.y, f.z, f.w);
+    f.x = __uint_as_float(u.x << 16);
+    f.y = __uint_as_float(u.x & 0xffff0000u);
+    f.z = __uint_as_float(u.y << 16);
+    f.w = __uint_as_float(u.y & 0xffff0000u);
     return f;
   }
   static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) { return cvt(__ldg(reinterpret_cast<const uint2*>(p))); }
@@ -42,6 +46,20 @@ struct Ld4<float> {
   static __device__ __forceinline__ float4 lds(const float* p) { return *reinterpret_cast<const float4*>(p); }
 };
 
+// packed fp32 pair in a 64-bit register (sm_100 f32x2 arithmetic)
+typedef unsigned long long F2;
+__device__ __forceinline__ F2 pack2(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(F2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
   const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   const int bytes = pred ? 16 : 0;  // src-size 0: the 16 destination bytes are zero filled
@@ -52,14 +70,19 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 #ifndef MSPI_DW_MINB
 #define MSPI_DW_MINB 1
 #endif
-template <typename TI, int CQ, int S, int P>
-__global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_MINB : 1)
+#ifndef MSPI_DW_MINB8
+#define MSPI_DW_MINB8 4
+#endif
+template <typename TI, int CQ, int S, int P, bool GROUPED>
+__global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_MINB : (CQ * S <= 192 && P == 8 && CQ <= 48 && sizeof(TI) == 2) ? MSPI_DW_MINB8 : 1)
 dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict__ x, const float* __restrict__ wgt,
                 const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int tiles_y, float eps, int cs, int use_tma) {
-  // cs: channels of the tensor (pixel stride).  cs == C: the block owns whole pixels and can normalise them.  cs > C: the
-  // blocks of grid.y each own a group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
+                void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int tiles_y, float eps, int cs_arg, int use_tma) {
+  // cs: channels of the tensor (pixel stride).  cs == C (GROUPED false, a compile-time stride: the weight and output addresses
+  // become immediates): the block owns whole pixels and can normalise them.  cs > C (GROUPED): the blocks of grid.y each own a
+  // group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
   constexpr int C = 4 * CQ;
+  const int cs = GROUPED ? cs_arg : C;
   const int c0 = blockIdx.y * C;
   constexpr int TW = P + 6, TH = S + 6;
   constexpr int kThreads = CQ * S;
@@ -107,11 +130,13 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
 
   const int q = threadIdx.x % CQ;
   const int s = threadIdx.x / CQ;
-  float4 acc[P];
+  // Accumulators, taps and inputs are kept as packed fp32 pairs: sm_100's fma.rn.f32x2 retires two FMAs per lane per
+  // issue slot (each half rounds exactly like fmaf), which is what bounds this kernel (49 FMAs per output element).
+  F2 acc[P][2];
   {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
 #pragma unroll
-    for (int j = 0; j < P; ++j) acc[j] = b;
+    for (int j = 0; j < P; ++j) { acc[j][0] = pack2(b.x, b.y); acc[j][1] = pack2(b.z, b.w); }
   }
   if (use_tma) {
     __syncthreads();   // the barrier init is visible to every waiter
@@ -121,30 +146,39 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
     __syncthreads();
   }
 
+  const float4* wq = reinterpret_cast<const float4*>(wgt + c0) + q;
 #pragma unroll 1
   for (int kh = 0; kh < 7; ++kh) {
-    float4 w[7];
+    F2 w[7][2];
 #pragma unroll
-    for (int kw = 0; kw < 7; ++kw) w[kw] = __ldg(reinterpret_cast<const float4*>(wgt + (kh * 7 + kw) * cs + c0) + q);
+    for (int kw = 0; kw < 7; ++kw) {
+      const float4 t = __ldg(wq + (kh * 7 + kw) * (cs / 4));
+      w[kw][0] = pack2(t.x, t.y);
+      w[kw][1] = pack2(t.z, t.w);
+    }
     const TI* trow = tile_s + (static_cast<size_t>((4 * q) / kBoxC) * TH + s + kh) * TW * kBoxC + (4 * q) % kBoxC;
 #pragma unroll
     for (int ix = 0; ix < TW; ++ix) {
       const float4 v = Ld4<TI>::lds(trow + ix * kBoxC);
+      const F2 v0 = pack2(v.x, v.y), v1 = pack2(v.z, v.w);
 #pragma unroll
       for (int kw = 0; kw < 7; ++kw) {
         const int j = ix - kw;  // output pixel fed by this input through tap kw
         if (j >= 0 && j < P) {
-          acc[j].x = fmaf(v.x, w[kw].x, acc[j].x);
-          acc[j].y = fmaf(v.y, w[kw].y, acc[j].y);
-          acc[j].z = fmaf(v.z, w[kw].z, acc[j].z);
-          acc[j].w = fmaf(v.w, w[kw].w, acc[j].w);
+          acc[j][0] = fma2(v0, w[kw][0], acc[j][0]);
+          acc[j][1] = fma2(v1, w[kw][1], acc[j][1]);
         }
       }
     }
   }
   __syncthreads();  // everyone is done reading the tile: its memory becomes the result buffer
 #pragma unroll
-  for (int j = 0; j < P; ++j) reinterpret_cast<float4*>(out_s + static_cast<size_t>(s * P + j) * C)[q] = acc[j];
+  for (int j = 0; j < P; ++j) {
+    float4 o;
+    unpack2(acc[j][0], o.x, o.y);
+    unpack2(acc[j][1], o.z, o.w);
+    reinterpret_cast<float4*>(out_s + static_cast<size_t>(s * P + j) * C)[q] = o;
+  }
   __syncthreads();
 
   // ---- LayerNorm over C.  LPP lanes share a pixel (16 for C = 96, else 32), each owning channel pairs lane, lane+LPP, ...;
@@ -169,6 +203,7 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
     gam[i] = ln_w != nullptr ? __ldg(reinterpret_cast<const float2*>(ln_w) + sl + LPP * i) : make_float2(1.f, 1.f);
     bet[i] = ln_w != nullptr ? __ldg(reinterpret_cast<const float2*>(ln_b) + sl + LPP * i) : make_float2(0.f, 0.f);
   }
+  const long long tile_base = ((static_cast<long long>(n) * H + y0) * W + x0) * cs + c0;
   for (int p0 = (warp * GRP + sub) * G; p0 < S * P; p0 += nwarps * GRP * G) {
     float2 v[G][NP];
     float sum[G], sq[G];
@@ -212,18 +247,20 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int pix = p0 + g;
-      const int py = y0 + pix / P, px = x0 + pix % P;
-      if (py >= H || px >= W) continue;
-      const long long obase = ((static_cast<long long>(n) * H + py) * W + px) * cs + c0;
+      const int ly = pix / P, lx = pix % P;   // P is a compile-time constant
+      if (y0 + ly >= H || x0 + lx >= W) continue;
+      const unsigned off = static_cast<unsigned>(ly * W + lx) * static_cast<unsigned>(cs);   // within the tile: 32-bit
+      const float rs = sq[g], ms = -sum[g] * sq[g];
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int p = sl + LPP * i;
-        const float a = (v[g][i].x - sum[g]) * sq[g] * gam[i].x + bet[i].x;
-        const float b = (v[g][i].y - sum[g]) * sq[g] * gam[i].y + bet[i].y;
+        // (v - mean) * rstd * gamma + beta as two FMAs
+        const float a = fmaf(fmaf(v[g][i].x, rs, ms), gam[i].x, bet[i].x);
+        const float b = fmaf(fmaf(v[g][i].y, rs, ms), gam[i].y, bet[i].y);
         if (out_bf16)
-          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + obase)[p] = __floats2bfloat162_rn(a, b);
+          reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(y) + tile_base + off)[p] = __floats2bfloat162_rn(a, b);
         else
-          reinterpret_cast<float2*>(static_cast<float*>(y) + obase)[p] = make_float2(a, b);
+          reinterpret_cast<float2*>(static_cast<float*>(y) + tile_base + off)[p] = make_float2(a, b);
       }
     }
   }
@@ -274,7 +311,7 @@ __global__ void dwt_kernel(const TI* __restrict__ x, const float* __restrict__ w
   }
 }
 
-template <typename TI, int CQ, int S, int P>
+template <typename TI, int CQ, int S, int P, bool GROUPED = false>
 int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
                  const float* ln_b, void* y, cudaStream_t stream, int groups = 1) {
   constexpr int C = 4 * CQ;
@@ -285,7 +322,7 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   const int tiles_x = (d->w + P - 1) / P, tiles_y = (d->h + S - 1) / S;
   const long long blocks = static_cast<long long>(d->n) * d->t * tiles_x * tiles_y;
   MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv 7x7: grid out of range");
-  auto kern = dw7x7_ln_kernel<TI, CQ, S, P>;
+  auto kern = dw7x7_ln_kernel<TI, CQ, S, P, GROUPED>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   // tile load by TMA (one 4-D box [C, P+6, S+6, 1] per block, out-of-image coordinates zero-filled) where the channel
   // group fits a box; MSPI_DW_TMA=0 keeps the per-thread cp.async path
@@ -327,7 +364,7 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
 template <typename TI>
 int launch_dw7x7_grouped(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
                          const float* ln_b, void* y, cudaStream_t stream) {
-  const int rc = launch_dw7x7<TI, 48, 7, 12>(d, x, wgt, bias, nullptr, nullptr, y, stream, d->c / 192);
+  const int rc = launch_dw7x7<TI, 48, 7, 12, true>(d, x, wgt, bias, nullptr, nullptr, y, stream, d->c / 192);
   if (rc != MSPI_OK || ln_w == nullptr) return rc;
   MspiLnDesc ln;
   ln.rows = static_cast<int64_t>(d->n) * d->t * d->h * d->w;
@@ -351,8 +388,12 @@ int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const
   if (!aligned) return 1;
   if (d->kt == 1 && d->kh == 7 && d->kw == 7) {
     using bf = __nv_bfloat16;
-    static const bool force8 = getenv("MSPI_DW_P8") != nullptr;  // tuning aid
-    const bool wide = d->w % 16 == 0 && !force8;  // strip of 16 where it tiles the row, else 8 (P+6 loads feed 7P FMA groups)
+    // strips of 8 pixels: 78 registers -> 4 blocks (24 warps) per SM.  Strips of 16 feed more FMAs per shared-memory load
+    // (P+6 loads for 7P FMA groups) but need 118 registers (2 blocks per SM), and since the stencil runs on packed FFMA2 the
+    // kernel is bound by how well the load / stencil / LayerNorm phases of different blocks overlap, not by instruction count
+    // (stage 0: 0.95 ms with 16, 0.85 ms with 8).  MSPI_DW_P16=1 restores the wide strips (tuning aid).
+    static const bool allow16 = getenv("MSPI_DW_P16") != nullptr;
+    const bool wide = d->w % 16 == 0 && allow16;
     if (d->in_dtype == MSPI_BF16) {
       if (d->c == 96) return wide ? launch_dw7x7<bf, 24, 8, 16>(d, x, wgt, bias, ln_w, ln_b, y, stream)
                                   : launch_dw7x7<bf, 24, 8, 8>(d, x, wgt, bias, ln_w, ln_b, y, stream);
