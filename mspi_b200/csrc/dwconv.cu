@@ -67,6 +67,26 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 }
 
 // CQ = C/4 threads per strip, S strips (rows) per block, P output pixels per strip.
+// Warp geometry.  fp32 tiles: a warp's lanes are QW channel quads x SW strips, so the SW strips' lanes load the SAME
+// weight vector (one L1 wavefront instead of SW; the weights are per channel) and each strip's lanes read whole 128-byte
+// rows of the tile (0.60 -> 0.59 ms on the 192-channel lateral).  bf16 tiles keep one strip per CQ consecutive threads: the
+// 4-strip mapping needs an odd stored row width (64-byte strip segments must alternate bank halves), which costs the
+// 192-channel stage its 4th resident block and gains nothing at 96 channels (measured: L1 wavefronts are not the limiter,
+// the FMA pipe is ~75% busy while a block is in its stencil phase; the rest is load / LayerNorm phases of other blocks).
+template <typename TI, int CQ, int S, int P>
+struct DwGeom {
+  static constexpr int C = 4 * CQ;
+  static constexpr int SW = sizeof(TI) != 4 ? 1 : (S % 4 == 0 && CQ % 8 == 0) ? 4 : (S % 2 == 0 && CQ % 16 == 0) ? 2 : 1;   // strips per warp
+  static constexpr int QW = 32 / SW;                                                                  // channel quads per warp
+  static constexpr bool kPad = SW == 4 && sizeof(TI) == 2 && C % 96 == 0;
+  static constexpr int TW = P + 6, TH = S + 6;
+  static constexpr int TWP = kPad ? (TW | 1) : TW;                       // stored row width (pixels)
+  static constexpr int kBoxC = kPad ? 96 : (C > 256 ? C / 2 : C);        // channels per TMA box (box dimensions are <= 256)
+  static constexpr int kBoxes = C / kBoxC;                               // the tile is stored [box][TH][TWP][kBoxC]
+  static constexpr size_t tile_bytes = static_cast<size_t>(TH) * TWP * C * sizeof(TI);
+  static_assert(!kPad || (TWP * kBoxC * sizeof(TI)) % 128 == 64, "row stride must alternate 64-byte bank halves");
+  static_assert(SW == 1 || kBoxC % (4 * QW) == 0, "a warp's channel group must lie inside one box");
+};
 #ifndef MSPI_DW_MINB
 #define MSPI_DW_MINB 1
 #endif
@@ -84,15 +104,14 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
   constexpr int C = 4 * CQ;
   const int cs = GROUPED ? cs_arg : C;
   const int c0 = blockIdx.y * C;
-  constexpr int TW = P + 6, TH = S + 6;
+  using Geo = DwGeom<TI, CQ, S, P>;
+  constexpr int TW = Geo::TW, TH = Geo::TH, TWP = Geo::TWP, kBoxC = Geo::kBoxC, kBoxes = Geo::kBoxes;
   constexpr int kThreads = CQ * S;
   constexpr int kVec = 16 / sizeof(TI);            // elements per 16-byte copy
   constexpr int kRowVecs = C / kVec;               // 16-byte copies per pixel
-  constexpr int kBoxC = C > 256 ? C / 2 : C;       // channels per TMA box (box dimensions are limited to 256 elements)
-  constexpr int kBoxes = C / kBoxC;                // the tile is stored [box][TH][TW][kBoxC]
   extern __shared__ __align__(128) uint8_t dw_smem[];
   __shared__ __align__(8) unsigned long long tma_bar;
-  TI* tile_s = reinterpret_cast<TI*>(dw_smem);        // [TH][TW][C] input tile, zero halo
+  TI* tile_s = reinterpret_cast<TI*>(dw_smem);        // [box][TH][TWP][kBoxC] input tile, zero halo
   float* out_s = reinterpret_cast<float*>(dw_smem);   // [S*P][C] results; re-uses the tile buffer after the stencil
 
   int tile = blockIdx.x;
@@ -109,10 +128,10 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
     if (threadIdx.x == 0) {
       tc::mbar_init(bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      tc::mbar_expect_tx(bar, static_cast<uint32_t>(TH * TW * C * sizeof(TI)));
+      tc::mbar_expect_tx(bar, static_cast<uint32_t>(Geo::tile_bytes));
 #pragma unroll
       for (int b = 0; b < kBoxes; ++b)
-        tc::tma_load_4d(tc::smem_u32(tile_s + static_cast<size_t>(b) * TH * TW * kBoxC), &map_x, bar, c0 + b * kBoxC, x0 - 3,
+        tc::tma_load_4d(tc::smem_u32(tile_s + static_cast<size_t>(b) * TH * TWP * kBoxC), &map_x, bar, c0 + b * kBoxC, x0 - 3,
                         y0 - 3, n);
     }
   } else {
@@ -123,13 +142,21 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
     const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
     const TI* src = xin + (static_cast<long long>(in ? gy : 0) * W + (in ? gx : 0)) * cs + cv * kVec;
     const int ch = cv * kVec, box = ch / kBoxC;
-    cp_async16_zfill(tile_s + (static_cast<size_t>(box) * TH * TW + pix) * kBoxC + (ch - box * kBoxC), src, in);
+    cp_async16_zfill(tile_s + (static_cast<size_t>(box) * TH * TWP + tr * TWP + tc) * kBoxC + (ch - box * kBoxC), src, in);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  const int q = threadIdx.x % CQ;
-  const int s = threadIdx.x / CQ;
+  int q, s;
+  if (Geo::SW == 1) {
+    q = threadIdx.x % CQ;
+    s = threadIdx.x / CQ;
+  } else {
+    constexpr int NQG = CQ / Geo::QW;   // channel groups
+    const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    q = (wp % NQG) * Geo::QW + ln % Geo::QW;
+    s = (wp / NQG) * Geo::SW + ln / Geo::QW;
+  }
   // Accumulators, taps and inputs are kept as packed fp32 pairs: sm_100's fma.rn.f32x2 retires two FMAs per lane per
   // issue slot (each half rounds exactly like fmaf), which is what bounds this kernel (49 FMAs per output element).
   F2 acc[P][2];
@@ -156,7 +183,7 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
       w[kw][0] = pack2(t.x, t.y);
       w[kw][1] = pack2(t.z, t.w);
     }
-    const TI* trow = tile_s + (static_cast<size_t>((4 * q) / kBoxC) * TH + s + kh) * TW * kBoxC + (4 * q) % kBoxC;
+    const TI* trow = tile_s + (static_cast<size_t>((4 * q) / kBoxC) * TH + s + kh) * TWP * kBoxC + (4 * q) % kBoxC;
 #pragma unroll
     for (int ix = 0; ix < TW; ++ix) {
       const float4 v = Ld4<TI>::lds(trow + ix * kBoxC);
@@ -192,7 +219,7 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
   constexpr int NP = pairs / LPP;                     // pairs per lane
   constexpr int GRP = 32 / LPP;                       // pixels handled side by side in one warp
 #ifndef MSPI_DW_LN_G
-#define MSPI_DW_LN_G 4
+#define MSPI_DW_LN_G 2
 #endif
   constexpr int G = ((S * P) % (MSPI_DW_LN_G * GRP) == 0) ? MSPI_DW_LN_G : 4;  // pixels per lane group per iteration
   static_assert((S * P) % (G * GRP) == 0, "pixel groups");
@@ -315,7 +342,8 @@ template <typename TI, int CQ, int S, int P, bool GROUPED = false>
 int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const float* bias, const float* ln_w,
                  const float* ln_b, void* y, cudaStream_t stream, int groups = 1) {
   constexpr int C = 4 * CQ;
-  constexpr size_t tile_bytes = static_cast<size_t>(S + 6) * (P + 6) * C * sizeof(TI);
+  using Geo = DwGeom<TI, CQ, S, P>;
+  constexpr size_t tile_bytes = Geo::tile_bytes;
   constexpr size_t out_bytes = static_cast<size_t>(S) * P * C * sizeof(float);
   constexpr size_t smem = tile_bytes > out_bytes ? tile_bytes : out_bytes;
   static_assert(smem <= 113 * 1024, "two blocks per SM must fit");
@@ -328,7 +356,7 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   // group fits a box; MSPI_DW_TMA=0 keeps the per-thread cp.async path
   static const bool tma_on = [] { const char* e = getenv("MSPI_DW_TMA"); return !e || atoi(e) != 0; }();
   const int ctot = C * groups;
-  constexpr int kBoxC = C > 256 ? C / 2 : C;
+  constexpr int kBoxC = Geo::kBoxC;
   int use_tma = tma_on && kBoxC <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ctot * sizeof(TI)) % 16 == 0;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -342,7 +370,7 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
                             static_cast<cuuint64_t>(d->n) * d->t};
       cuuint64_t gstr[3] = {ctot * es, static_cast<cuuint64_t>(d->w) * ctot * es,
                             static_cast<cuuint64_t>(d->h) * d->w * ctot * es};
-      cuuint32_t bdim[4] = {static_cast<cuuint32_t>(kBoxC), static_cast<cuuint32_t>(P + 6), static_cast<cuuint32_t>(S + 6), 1};
+      cuuint32_t bdim[4] = {static_cast<cuuint32_t>(kBoxC), static_cast<cuuint32_t>(Geo::TWP), static_cast<cuuint32_t>(S + 6), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = encode(&map, sizeof(TI) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                           const_cast<void*>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
