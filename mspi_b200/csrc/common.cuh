@@ -100,6 +100,31 @@ __device__ __forceinline__ int divmod(long long& r, int d) {
   return rem;
 }
 
+// Packed fp32 pair in a 64-bit register: sm_100's {fma,add,mul}.f32x2 retire two fp32 operations per lane per issue slot,
+// each half rounded exactly like the scalar instruction.
+typedef unsigned long long F2;
+__device__ __forceinline__ F2 pack2(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(F2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  F2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  F2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case MSPI_ACT_RELU: return fmaxf(v, 0.f);

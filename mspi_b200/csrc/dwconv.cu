@@ -46,20 +46,6 @@ struct Ld4<float> {
   static __device__ __forceinline__ float4 lds(const float* p) { return *reinterpret_cast<const float4*>(p); }
 };
 
-// packed fp32 pair in a 64-bit register (sm_100 f32x2 arithmetic)
-typedef unsigned long long F2;
-__device__ __forceinline__ F2 pack2(float lo, float hi) {
-  F2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(F2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
-  F2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
   const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   const int bytes = pred ? 16 : 0;  // src-size 0: the 16 destination bytes are zero filled
@@ -97,13 +83,15 @@ template <typename TI, int CQ, int S, int P, bool GROUPED>
 __global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_MINB : (CQ * S <= 192 && P == 8 && CQ <= 48 && sizeof(TI) == 2) ? MSPI_DW_MINB8 : 1)
 dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict__ x, const float* __restrict__ wgt,
                 const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int tiles_y, float eps, int cs_arg, int use_tma) {
+                void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int n0, float eps, int cs_arg, int use_tma) {
   // cs: channels of the tensor (pixel stride).  cs == C (GROUPED false, a compile-time stride: the weight and output addresses
   // become immediates): the block owns whole pixels and can normalise them.  cs > C (GROUPED): the blocks of grid.y each own a
   // group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
   constexpr int C = 4 * CQ;
   const int cs = GROUPED ? cs_arg : C;
-  const int c0 = blockIdx.y * C;
+  // grid = (tiles_x * groups, tiles_y, frames): no per-block integer divisions for the whole-pixel kernels
+  const int grp = GROUPED ? blockIdx.x / tiles_x : 0;
+  const int c0 = grp * C;
   using Geo = DwGeom<TI, CQ, S, P>;
   constexpr int TW = Geo::TW, TH = Geo::TH, TWP = Geo::TWP, kBoxC = Geo::kBoxC, kBoxes = Geo::kBoxes;
   constexpr int kThreads = CQ * S;
@@ -114,10 +102,9 @@ dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict_
   TI* tile_s = reinterpret_cast<TI*>(dw_smem);        // [box][TH][TWP][kBoxC] input tile, zero halo
   float* out_s = reinterpret_cast<float*>(dw_smem);   // [S*P][C] results; re-uses the tile buffer after the stencil
 
-  int tile = blockIdx.x;
-  const int tx = tile % tiles_x; tile /= tiles_x;
-  const int ty = tile % tiles_y; tile /= tiles_y;
-  const int n = tile;
+  const int tx = GROUPED ? blockIdx.x - grp * tiles_x : blockIdx.x;
+  const int ty = blockIdx.y;
+  const int n = n0 + blockIdx.z;   // frame
   const int x0 = tx * P, y0 = ty * S;
   const TI* xin = x + static_cast<long long>(n) * H * W * cs + c0;
 
@@ -348,8 +335,8 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   constexpr size_t smem = tile_bytes > out_bytes ? tile_bytes : out_bytes;
   static_assert(smem <= 113 * 1024, "two blocks per SM must fit");
   const int tiles_x = (d->w + P - 1) / P, tiles_y = (d->h + S - 1) / S;
-  const long long blocks = static_cast<long long>(d->n) * d->t * tiles_x * tiles_y;
-  MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv 7x7: grid out of range");
+  const long long frames = static_cast<long long>(d->n) * d->t;
+  MSPI_CHECK_ARG(frames < (1ll << 31) && tiles_y <= 65535, "dwconv 7x7: grid out of range (%lld frames)", frames);
   auto kern = dw7x7_ln_kernel<TI, CQ, S, P, GROUPED>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   // tile load by TMA (one 4-D box [C, P+6, S+6, 1] per block, out-of-image coordinates zero-filled) where the channel
@@ -378,10 +365,13 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
       if (r != CUDA_SUCCESS) use_tma = 0;
     }
   }
-  kern<<<dim3(static_cast<unsigned>(blocks), groups), CQ * S, smem, stream>>>(
-      map, static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x, tiles_y,
-      d->ln_eps, C * groups, use_tma);
-  MSPI_LAUNCH_CHECK();
+  for (long long n0 = 0; n0 < frames; n0 += 65535) {   // grid.z limit
+    const unsigned nz = static_cast<unsigned>(frames - n0 < 65535 ? frames - n0 : 65535);
+    kern<<<dim3(tiles_x * groups, tiles_y, nz), CQ * S, smem, stream>>>(
+        map, static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x,
+        static_cast<int>(n0), d->ln_eps, C * groups, use_tma);
+    MSPI_LAUNCH_CHECK();
+  }
   return MSPI_OK;
 }
 

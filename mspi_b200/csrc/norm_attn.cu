@@ -238,6 +238,159 @@ __global__ void layernorm_vec_kernel(MspiLnDesc d, const TI* __restrict__ x, con
   }
 }
 
+// Row LayerNorm for channel counts that are multiples of 8, the ConvNeXt stem / downsample / stage-3 shapes.  The 4-element
+// kernel above needs ~70 issue slots per 4 x 24 lanes of a 96-channel row, which caps it near 2 TB/s (the SMs run out of
+// issue slots before HBM runs out of bandwidth).  Here a lane owns 8 consecutive channels (one 16-byte bf16 load), a row is
+// spread over LPR = 8 / 16 / 32 lanes so that 32 / LPR rows sit side by side in a warp and share every shuffle, the
+// arithmetic is packed f32x2, and the affine parameters stay in registers across rows.
+template <typename T>
+struct V8;
+template <>
+struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, F2 (&v)[4]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = pack2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    v[1] = pack2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    v[2] = pack2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+    v[3] = pack2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const F2 (&v)[4]) {
+    uint4 o;
+    float a, b;
+    unpack2(v[0], a, b); o.x = pack_bf16x2(a, b);
+    unpack2(v[1], a, b); o.y = pack_bf16x2(a, b);
+    unpack2(v[2], a, b); o.z = pack_bf16x2(a, b);
+    unpack2(v[3], a, b); o.w = pack_bf16x2(a, b);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+};
+template <>
+struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, F2 (&v)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = pack2(a.x, a.y); v[1] = pack2(a.z, a.w); v[2] = pack2(b.x, b.y); v[3] = pack2(b.z, b.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const F2 (&v)[4]) {
+    float4 a, b;
+    unpack2(v[0], a.x, a.y); unpack2(v[1], a.z, a.w); unpack2(v[2], b.x, b.y); unpack2(v[3], b.z, b.w);
+    reinterpret_cast<float4*>(p)[0] = a;
+    reinterpret_cast<float4*>(p)[1] = b;
+  }
+};
+
+template <typename TI, typename TO, int LPR, int NV, int G>
+__global__ void __launch_bounds__(256)
+layernorm_rows8_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                       const float* __restrict__ pos, TO* __restrict__ y) {
+  constexpr int RPW = 32 / LPR;   // rows side by side in a warp
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
+  const int warps = blockDim.x >> 5;
+  const float inv_c = 1.f / d.c;
+  F2 gw[NV][4], gb[NV][4];
+  bool act[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = 8 * (sl + LPR * i);
+    act[i] = e < d.c;
+    if (act[i]) {
+      V8<float>::load(w + e, gw[i]);
+      V8<float>::load(b + e, gb[i]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gw[i][k] = gb[i][k] = 0ull;
+    }
+  }
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5)) * (RPW * G); row0 < d.rows;
+       row0 += static_cast<long long>(gridDim.x) * warps * (RPW * G)) {
+    F2 v[G][NV][4];
+    float s[G], sq[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long row = row0 + g * RPW + sub;
+      const TI* xr = x + row * d.in_rstride + 8 * sl;
+      F2 acc = 0ull;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (act[i] && row < d.rows) {
+          V8<TI>::load(xr + 8 * LPR * i, v[g][i]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[g][i][k] = 0ull;
+        }
+        acc = add2(acc, add2(add2(v[g][i][0], v[g][i][1]), add2(v[g][i][2], v[g][i][3])));
+      }
+      float lo, hi;
+      unpack2(acc, lo, hi);
+      s[g] = lo + hi;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float nm = -s[g] * inv_c;
+      const F2 nm2 = pack2(nm, nm);
+      F2 acc = 0ull;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (act[i]) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            v[g][i][k] = add2(v[g][i][k], nm2);   // centred
+            acc = fma2(v[g][i][k], v[g][i][k], acc);
+          }
+        }
+      }
+      float lo, hi;
+      unpack2(acc, lo, hi);
+      sq[g] = lo + hi;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) sq[g] += __shfl_xor_sync(0xffffffffu, sq[g], o);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long row = row0 + g * RPW + sub;
+      if (row >= d.rows) continue;
+      const float rstd = rsqrtf(sq[g] * inv_c + d.eps);
+      const F2 rs2 = pack2(rstd, rstd);
+      long long grp = 0, within = row;
+      if (d.rows_per_group < d.rows) {
+        grp = row;
+        within = divmod(grp, static_cast<int>(d.rows_per_group));
+      }
+      TO* yr = y + grp * d.out_gstride + within * d.out_rstride + 8 * sl;
+      const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c + 8 * sl : nullptr;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (!act[i]) continue;
+        F2 o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = fma2(mul2(v[g][i][k], rs2), gw[i][k], gb[i][k]);
+        if (d.relu) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float lo, hi;
+            unpack2(o[k], lo, hi);
+            o[k] = pack2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+          }
+        }
+        if (pr) {
+          F2 pp[4];
+          V8<float>::load(pr + 8 * LPR * i, pp);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = add2(o[k], pp[k]);
+        }
+        V8<TO>::store(yr + 8 * LPR * i, o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- attention
 // qkv: [B][N][3][H][HD] bf16.  Block = (b*H + h, query tile of QT rows).  Scores for the whole
 // key range live in shared memory (N <= 1024), softmax in fp32, then P·V.
@@ -477,6 +630,39 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
                       (reinterpret_cast<uintptr_t>(x) % (4 * ies)) == 0 && (reinterpret_cast<uintptr_t>(y) % (4 * oes)) == 0 &&
                       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
                       (pos == nullptr || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
+  const bool rows8_ok = d->c % 8 == 0 && d->c <= 1024 && d->in_rstride % 8 == 0 && d->out_rstride % 8 == 0 && d->out_gstride % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (pos == nullptr || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
+  static const bool rows8_on = [] { const char* e = getenv("MSPI_LN_ROWS8"); return !e || atoi(e) != 0; }();
+  if (rows8_ok && rows8_on) {
+#define MSPI_LN_R8(TI, TO, LPR, NV, G)                                                                                   \
+  do {                                                                                                                   \
+    const long long per = static_cast<long long>(warps) * (32 / LPR) * G;                                                \
+    long long nb = (d->rows + per - 1) / per;                                                                            \
+    if (nb > vcap) nb = vcap;                                                                                            \
+    if (nb < 1) nb = 1;                                                                                                  \
+    layernorm_rows8_kernel<TI, TO, LPR, NV, G><<<static_cast<int>(nb), threads, 0, stream>>>(                            \
+        *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y));                                                  \
+  } while (0)
+#define MSPI_LN_R8_C(TI, TO)                                                                                             \
+  do {                                                                                                                   \
+    if (d->c <= 64) MSPI_LN_R8(TI, TO, 8, 1, 4);                                                                         \
+    else if (d->c <= 128) MSPI_LN_R8(TI, TO, 16, 1, 4);                                                                  \
+    else if (d->c <= 256) MSPI_LN_R8(TI, TO, 32, 1, 4);                                                                  \
+    else if (d->c <= 512) MSPI_LN_R8(TI, TO, 32, 2, 2);                                                                  \
+    else if (d->c <= 768) MSPI_LN_R8(TI, TO, 32, 3, 2);                                                                  \
+    else MSPI_LN_R8(TI, TO, 32, 4, 1);                                                                                   \
+  } while (0)
+    if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16) MSPI_LN_R8_C(bf, bf);
+    else if (d->in_dtype == MSPI_BF16) MSPI_LN_R8_C(bf, float);
+    else if (d->out_dtype == MSPI_BF16) MSPI_LN_R8_C(float, bf);
+    else MSPI_LN_R8_C(float, float);
+#undef MSPI_LN_R8_C
+#undef MSPI_LN_R8
+    MSPI_LAUNCH_CHECK();
+    return MSPI_OK;
+  }
   if (vec_ok) {
 #define MSPI_LN_VEC(TI, TO)                                                                                              \
   do {                                                                                                                   \

@@ -373,6 +373,30 @@ def test_dwconv7x7_ln_strip_kernel(c, h, w, dt):
     assert (y16.to_ncdhw().cpu() - ref).abs().max() < 4e-2
 
 
+@pytest.mark.parametrize("c", [64, 96, 192, 384, 768, 1024, 100])
+@pytest.mark.parametrize("idt,odt", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
+                                      (torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_layernorm_rows(c, idt, odt):
+    """Row LayerNorm over the channel vector (convnext.py LayerNorm channels_last / timm LayerNorm2d): the 8-channels-per-lane
+    kernel (C % 8 == 0) and the 4-channel fallback (C = 100), ragged row count, also in place."""
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(50 + c)
+    rows = 1037
+    x = (torch.randn(rows, c, generator=g) * 2 + 0.7).to(idt)
+    w, bb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    xd = x.cuda()
+    y = torch.empty(rows, c, dtype=odt, device="cuda")
+    ops.layernorm(xd, y, rows, c, w, bb, 1e-6)()
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (c,), w, bb, 1e-6)
+    tol = 3e-2 if odt == torch.bfloat16 else 2e-5
+    assert (y.float().cpu() - ref).abs().max() < tol
+    if idt == odt:
+        ops.layernorm(xd, xd, rows, c, w, bb, 1e-6)()
+        torch.cuda.synchronize()
+        assert torch.equal(xd, y)
+
+
 def test_layernorm_pos_groups():
     from mspi_b200 import ops
     g = torch.Generator().manual_seed(5)
