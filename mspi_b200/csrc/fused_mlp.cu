@@ -50,7 +50,22 @@ struct MlpParams {
   __nv_bfloat16* y;
   long long res_stride, y_stride;
   uint32_t idesc1, idesc2;
+  int wide_io;          // residual / y rows are 32-byte aligned: 256-bit global loads and stores in the Y epilogue
+  int y_staged;         // Y epilogue through shared memory: the residual tile arrives by TMA, is updated in place and leaves by
+                        // TMA (a warp's direct row accesses cost 32 L1 tag cycles per instruction: 6144 per 128 x 96 tile)
+  int ystage_bytes;
 };
+
+__device__ __forceinline__ void ldg256(const __nv_bfloat16* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(__nv_bfloat16* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                uint16_t mask) {
@@ -118,7 +133,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ MlpParams p) {
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -129,12 +145,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t a2_full = h_empty + 8 * kMaxHBuf, a2_empty = a2_full + 16;
   const uint32_t y_full = a2_empty + 16, y_empty = y_full + 8;
   const uint32_t tmem_slot = y_empty + 8;
+  const uint32_t res_full = y_empty + 16;
   float* s_b1 = reinterpret_cast<float*>(base_ptr + 1024);       // [4C]
   float* s_scale = s_b1 + 4 * p.c;                               // [C]
   float* s_shift = s_scale + p.c;                                // [C]
   const uint32_t x_base = base + 1024 + 8192;                    // 2 x kc1 chunks
   const uint32_t a2_base = x_base + static_cast<uint32_t>(p.x_bufs) * p.kc1 * kChunkBytes;  // 2 buffers x 2 chunks
-  const uint32_t ring_base = a2_base + 4u * kChunkBytes;
+  const uint32_t ystage_base = a2_base + 4u * kChunkBytes;       // [c/32 boxes][128 rows][64 B], 64B-swizzled (y_staged)
+  const uint32_t ring_base = ystage_base + static_cast<uint32_t>(p.ystage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -157,6 +175,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     mbar_init(y_full, 1);
     mbar_init(y_empty, PAIR ? 2 * kEpiWarps : kEpiWarps);
+    mbar_init(res_full, 1);
+    if (p.y_staged) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -381,9 +404,56 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     long long pgrow = 0;
     bool pvalid = false;
     uint4 resq[3][2];
+    int prow0 = 0;                       // first row of the pending tile
+    const bool io_thread = warp == 2 && lane == 0;
     auto y_epilogue = [&]() {
       mbar_wait(y_full, ytile & 1u);
       tc_fence_after();
+      if (p.y_staged) {
+        mbar_wait(res_full, ytile & 1u);   // the residual tile has landed in the staging buffer
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int c0 = 16 * colgrp + 64 * u;
+          if (c0 >= p.c) break;
+          uint32_t acc[16];
+          __syncwarp();
+          tmem_ld16(lane_y + c0, acc);
+          tmem_ld_wait();
+          const uint32_t rowb = ystage_base + static_cast<uint32_t>(c0 >> 5) * (128u * 64u) + static_cast<uint32_t>(row) * 64u;
+          const uint32_t k0 = static_cast<uint32_t>(c0 & 31) >> 3, swz = (static_cast<uint32_t>(row) >> 1) & 3u;
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int col = c0 + 8 * h8;
+            const uint32_t addr = rowb + (((k0 + h8) ^ swz) << 4);
+            uint4 rr;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(addr) : "memory");
+            float res[8];
+            unpack_bf16x2(rr.x, res[0], res[1]); unpack_bf16x2(rr.y, res[2], res[3]);
+            unpack_bf16x2(rr.z, res[4], res[5]); unpack_bf16x2(rr.w, res[6], res[7]);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = fmaf(__uint_as_float(acc[8 * h8 + e]), s_scale[col + e], s_shift[col + e]) + res[e];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])),
+                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                         : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(y_empty);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every epilogue thread has written its pieces
+        if (io_thread) {
+          for (int b = 0; b < p.c / 32; ++b)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_y),
+                         "r"(ystage_base + static_cast<uint32_t>(b) * (128u * 64u)), "r"(b * 32), "r"(prow0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++ytile;
+        return;
+      }
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         const int c0 = 16 * colgrp + 64 * u;
@@ -392,7 +462,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         tmem_ld16(lane_y + c0, acc);
         tmem_ld_wait();
-        if (pvalid) {
+        if (pvalid && !(p.debug & 8)) {
+          uint4 o2[2];
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             const int col = c0 + 8 * h8;
@@ -407,7 +478,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.y + pgrow * p.y_stride + col) = o;
+            o2[h8] = o;
+          }
+          __nv_bfloat16* yp = p.y + pgrow * p.y_stride + c0;
+          if (p.wide_io) {
+            stg256(yp, o2[0], o2[1]);
+          } else {
+            *reinterpret_cast<uint4*>(yp) = o2[0];
+            *reinterpret_cast<uint4*>(yp + 8) = o2[1];
           }
         }
       }
@@ -480,18 +558,33 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       pend = true;
       pgrow = grow;
       pvalid = valid;
-      if (valid) {
+      prow0 = static_cast<int>((static_cast<long long>(grp) * p.cl + rank) * 128);
+      if (p.y_staged) {
+        if (io_thread) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's store has read the buffer
+          mbar_expect_tx(res_full, static_cast<uint32_t>(p.ystage_bytes));
+          for (int b = 0; b < p.c / 32; ++b)
+            tma_load_2d(ystage_base + static_cast<uint32_t>(b) * (128u * 64u), &map_r, res_full, b * 32, prow0);
+        }
+      } else if (valid && !(p.debug & 8)) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int c0 = 16 * colgrp + 64 * u;
           if (c0 < p.c) {
-            resq[u][0] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0));
-            resq[u][1] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0 + 8));
+            // one 256-bit load per 16 columns: the 32 lanes of a warp read 32 different rows, so every load instruction
+            // costs 32 L1 tag cycles whatever its width
+            if (p.wide_io) {
+              ldg256(p.residual + grow * p.res_stride + c0, resq[u][0], resq[u][1]);
+            } else {
+              resq[u][0] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0));
+              resq[u][1] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + c0 + 8));
+            }
           }
         }
       }
     }
     if (pend) y_epilogue();
+    if (p.y_staged && io_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -533,7 +626,9 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUtensorMap map_x, map_w1, map_w2;
+  CUtensorMap map_x, map_w1, map_w2, map_r, map_y;
+  memset(&map_r, 0, sizeof(map_r));
+  memset(&map_y, 0, sizeof(map_y));
   CUresult r1 = make2d(&map_x, x, c, static_cast<uint64_t>(m), c, 128);
   // MSPI_MLP_CLUSTER: 1 = one CTA per tile; 2 | 4 = cluster sharing the weight stream by TMA multicast (measured: no gain, an
   // SM still ingests every piece); -2 (default) = CTA pair (tcgen05 cta_group::2): each SM ingests HALF of every weight piece
@@ -562,11 +657,32 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   p.y = static_cast<__nv_bfloat16*>(y);
   p.res_stride = res_stride;
   p.y_stride = y_stride;
+  static const bool wide_on = [] { const char* e = getenv("MSPI_MLP_WIDE_IO"); return !e || atoi(e) != 0; }();
+  p.wide_io = wide_on && (reinterpret_cast<uintptr_t>(residual) & 31) == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 &&
+              (res_stride * 2) % 32 == 0 && (y_stride * 2) % 32 == 0;
+  // Y epilogue through a [128 x C] staging tile (C = 96: 24 KB taken from the weight ring, which is not the limiter)
+  static const bool stage_on = [] { const char* e = getenv("MSPI_MLP_STAGE_Y"); return !e || atoi(e) != 0; }();
+  if (stage_on && c <= 128 && c % 32 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (res_stride * 2) % 16 == 0 && (y_stride * 2) % 16 == 0) {
+    auto make_io = [&](CUtensorMap* map, const void* ptr, int64_t stride) {
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(m)};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(stride) * 2};
+      cuuint32_t bdim[2] = {32, 128};
+      cuuint32_t estr[2] = {1, 1};
+      return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    if (make_io(&map_r, residual, res_stride) == CUDA_SUCCESS && make_io(&map_y, y, y_stride) == CUDA_SUCCESS) {
+      p.y_staged = 1;
+      p.ystage_bytes = 128 * c * 2;
+    }
+  }
   const uint32_t mdim = pair ? 256u : 128u;   // pair: one MMA covers the 128 rows of both CTAs
   p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kHC >> 3) << 17) | ((mdim >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(c >> 3) << 17) | ((mdim >> 4) << 24);
   p.x_bufs = c <= 96 ? 2 : 1;  // C = 192: the weight ring needs the room (30 pieces per tile, each one L2 round trip)
-  const int fixed = 1024 + 1024 + 8192 + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes;
+  const int fixed = 1024 + 1024 + 8192 + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes + p.ystage_bytes;
   p.ring_stages = (225 * 1024 - fixed) / p.ring_stage_bytes;
   if (p.ring_stages > kMaxRing) p.ring_stages = kMaxRing;
   MSPI_CHECK_ARG(p.ring_stages >= 2, "mspi_mlp_fused: shared memory leaves %d ring stages", p.ring_stages);
@@ -601,7 +717,7 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   if (nclusters > num_sms() / cl) nclusters = num_sms() / cl;
   if (nclusters > groups) nclusters = groups;
   cfg.gridDim = dim3(nclusters * cl, 1, 1);
-  MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_x, map_w1, map_w2, p));
+  MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_x, map_w1, map_w2, map_r, map_y, p));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
