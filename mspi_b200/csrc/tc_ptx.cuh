@@ -157,17 +157,23 @@ __device__ __forceinline__ float gelu_bf16(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
 }
-__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
-  const float t0 = x0 * fmaf(x0 * x0, 0.0356774081f, 0.7978845608f);
-  const float t1 = x1 * fmaf(x1 * x1, 0.0356774081f, 0.7978845608f);
+// Two elements at a time on packed fp32 pairs (common.cuh F2): 3 packed ops for the tanh argument, one f16x2 convert, one
+// MUFU for both tanh values, 2 packed ops for 0.5 x (1 + tanh).
+__device__ __forceinline__ F2 gelu_pair_f2(F2 x) {
+  const F2 u = mul2(x, x);
+  const F2 t = mul2(x, fma2(u, pack2(0.0356774081f, 0.0356774081f), pack2(0.7978845608f, 0.7978845608f)));
+  float t0, t1;
+  unpack2(t, t0, t1);
   uint32_t tp, th;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(tp) : "f"(t1), "f"(t0));  // {hi, lo} = {t1, t0}
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(tp));
-  const __half2 h = *reinterpret_cast<const __half2*>(&th);
-  const float2 f = __half22float2(h);
-  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
-  x0 = fmaf(h0, f.x, h0);
-  x1 = fmaf(h1, f.y, h1);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&th));
+  const F2 hx = mul2(x, pack2(0.5f, 0.5f));
+  return fma2(hx, pack2(f.x, f.y), hx);
+}
+__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
+  const F2 o = gelu_pair_f2(pack2(x0, x1));
+  unpack2(o, x0, x1);
 }
 #endif
 
