@@ -300,28 +300,34 @@ layernorm_rows8_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __re
       for (int k = 0; k < 4; ++k) gw[i][k] = gb[i][k] = 0ull;
     }
   }
-  for (long long row0 = (static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5)) * (RPW * G); row0 < d.rows;
-       row0 += static_cast<long long>(gridDim.x) * warps * (RPW * G)) {
+  // 32-bit row indices and strides (the host takes this kernel only when they fit): the 64-bit index arithmetic of the
+  // generic kernel was a third of the instructions of a 96-channel row
+  const int rows = static_cast<int>(d.rows), istride = static_cast<int>(d.in_rstride), ostride = static_cast<int>(d.out_rstride);
+  const bool grouped = d.rows_per_group < d.rows;
+  const int step = gridDim.x * warps * (RPW * G);
+  for (int row0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * (RPW * G); row0 < rows; row0 += step) {
     F2 v[G][NV][4];
     float s[G], sq[G];
+    // Loads are unconditional so that all G x NV of them are issued before the first use: rows past the end re-read the
+    // last row (their results are dropped below) and lanes past the channel count re-read the row start (their partial
+    // sums are discarded by a select).
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const long long row = row0 + g * RPW + sub;
-      const TI* xr = x + row * d.in_rstride + 8 * sl;
-      F2 acc = 0ull;
+      const int row = min(row0 + g * RPW + sub, rows - 1);
+      const TI* xr = x + static_cast<size_t>(static_cast<unsigned>(row)) * static_cast<unsigned>(istride);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) V8<TI>::load(xr + (act[i] ? 8 * (sl + LPR * i) : 0), v[g][i]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      s[g] = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        if (act[i] && row < d.rows) {
-          V8<TI>::load(xr + 8 * LPR * i, v[g][i]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[g][i][k] = 0ull;
-        }
-        acc = add2(acc, add2(add2(v[g][i][0], v[g][i][1]), add2(v[g][i][2], v[g][i][3])));
+        const F2 part = add2(add2(v[g][i][0], v[g][i][1]), add2(v[g][i][2], v[g][i][3]));
+        float lo, hi;
+        unpack2(part, lo, hi);
+        s[g] += act[i] ? lo + hi : 0.f;
       }
-      float lo, hi;
-      unpack2(acc, lo, hi);
-      s[g] = lo + hi;
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) {
@@ -332,20 +338,19 @@ layernorm_rows8_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __re
     for (int g = 0; g < G; ++g) {
       const float nm = -s[g] * inv_c;
       const F2 nm2 = pack2(nm, nm);
-      F2 acc = 0ull;
+      sq[g] = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        if (act[i]) {
+        F2 acc = 0ull;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            v[g][i][k] = add2(v[g][i][k], nm2);   // centred
-            acc = fma2(v[g][i][k], v[g][i][k], acc);
-          }
+        for (int k = 0; k < 4; ++k) {
+          v[g][i][k] = add2(v[g][i][k], nm2);   // centred
+          acc = fma2(v[g][i][k], v[g][i][k], acc);
         }
+        float lo, hi;
+        unpack2(acc, lo, hi);
+        sq[g] += act[i] ? lo + hi : 0.f;
       }
-      float lo, hi;
-      unpack2(acc, lo, hi);
-      sq[g] = lo + hi;
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) {
@@ -354,17 +359,17 @@ layernorm_rows8_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __re
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const long long row = row0 + g * RPW + sub;
-      if (row >= d.rows) continue;
+      const int row = row0 + g * RPW + sub;
+      if (row >= rows) continue;
       const float rstd = rsqrtf(sq[g] * inv_c + d.eps);
       const F2 rs2 = pack2(rstd, rstd);
-      long long grp = 0, within = row;
-      if (d.rows_per_group < d.rows) {
-        grp = row;
-        within = divmod(grp, static_cast<int>(d.rows_per_group));
+      unsigned grp = 0, within = static_cast<unsigned>(row);
+      if (grouped) {
+        grp = within / static_cast<unsigned>(d.rows_per_group);
+        within -= grp * static_cast<unsigned>(d.rows_per_group);
       }
-      TO* yr = y + grp * d.out_gstride + within * d.out_rstride + 8 * sl;
-      const float* pr = d.pos_rows > 0 ? pos + (within % d.pos_rows) * d.c + 8 * sl : nullptr;
+      TO* yr = y + grp * d.out_gstride + static_cast<size_t>(within) * static_cast<unsigned>(ostride) + 8 * sl;
+      const float* pr = d.pos_rows > 0 ? pos + static_cast<size_t>(within % static_cast<unsigned>(d.pos_rows)) * d.c + 8 * sl : nullptr;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (!act[i]) continue;
@@ -630,7 +635,8 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
                       (reinterpret_cast<uintptr_t>(x) % (4 * ies)) == 0 && (reinterpret_cast<uintptr_t>(y) % (4 * oes)) == 0 &&
                       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
                       (pos == nullptr || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
-  const bool rows8_ok = d->c % 8 == 0 && d->c <= 1024 && d->in_rstride % 8 == 0 && d->out_rstride % 8 == 0 && d->out_gstride % 8 == 0 &&
+  const bool rows8_ok = d->c % 8 == 0 && d->c <= 1024 && d->rows < (1ll << 30) && d->in_rstride < (1ll << 31) && d->out_rstride < (1ll << 31) &&
+                        d->rows * d->in_rstride < (1ll << 62) && d->in_rstride % 8 == 0 && d->out_rstride % 8 == 0 && d->out_gstride % 8 == 0 &&
                         (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (pos == nullptr || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
