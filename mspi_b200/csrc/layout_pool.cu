@@ -340,6 +340,7 @@ struct GateSrc {
   int k[3];
   int n;
 };
+template <int NS>   // number of top-down sources (compile time: the loads of all sources are issued before the first blend)
 __global__ void sa_gate_fused_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs,
                                      long long total, int c8, int h, int w, GateSrc s) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -359,7 +360,8 @@ __global__ void sa_gate_fused_kernel(const float* x, long long xcs, const float*
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] *= g;
-    for (int j = 0; j < s.n; ++j) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
       const int k = s.k[j], sh = h / k, sw = w / k;
       const float inv = 1.f / static_cast<float>(k);
       const float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
@@ -585,7 +587,13 @@ extern "C" int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float
   }
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const long long total = static_cast<long long>(nt) * h * w * (c / 8);
-  sa_gate_fused_kernel<<<grid_for(total), kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s);
+  const int grid = grid_for(total);
+  switch (nsrc) {
+    case 0: sa_gate_fused_kernel<0><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
+    case 1: sa_gate_fused_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
+    case 2: sa_gate_fused_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
+    default: sa_gate_fused_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
+  }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
