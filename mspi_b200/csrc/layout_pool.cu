@@ -226,7 +226,6 @@ __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict
 // instead of 27.
 __global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                   long long total, int c8) {
-  const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -234,21 +233,35 @@ __global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restric
     const long long row = r;                       // (n*T + t)*H + h
     const int hh = divmod(r, d.h);
     const int tt = divmod(r, d.t);
-    const int t_lo = max(tt - 1, 0), t_hi = min(tt + 1, d.t - 1), h_lo = max(hh - 1, 0), h_hi = min(hh + 1, d.h - 1);
+    // Border handling by clamping: a duplicated row / column does not change a maximum, so every column is always 9
+    // unrolled loads from 9 row pointers computed once per thread, all in flight together (the loops with run-time
+    // bounds this replaces issued one load at a time).
     const long long plane0 = (r * d.t) * d.h;      // first row of sample n
+    const __nv_bfloat16* rp[9];
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int t2 = min(max(tt + dt - 1, 0), d.t - 1), h2 = min(max(hh + dh - 1, 0), d.h - 1);
+        rp[dt * 3 + dh] = x + ((plane0 + static_cast<long long>(t2) * d.h + h2) * d.w) * d.in_cstride + cc * 8;
+      }
     __nv_bfloat162 cm[3][4];                       // column maxima at w-1, w, w+1 (4 x bf16x2 = 8 channels)
     auto column = [&](int ww, __nv_bfloat162 (&m)[4]) {
-      m[0] = m[1] = m[2] = m[3] = ninf;
-      if (ww < 0 || ww >= d.w) return;
-      for (int t2 = t_lo; t2 <= t_hi; ++t2)
-        for (int h2 = h_lo; h2 <= h_hi; ++h2) {
-          const long long pix = (plane0 + static_cast<long long>(t2) * d.h + h2) * d.w + ww;
-          const uint4 v = ldg16(x + pix * d.in_cstride + cc * 8);
-          m[0] = __hmax2(m[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x));
-          m[1] = __hmax2(m[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y));
-          m[2] = __hmax2(m[2], *reinterpret_cast<const __nv_bfloat162*>(&v.z));
-          m[3] = __hmax2(m[3], *reinterpret_cast<const __nv_bfloat162*>(&v.w));
-        }
+      const long long off = static_cast<long long>(min(max(ww, 0), d.w - 1)) * d.in_cstride;
+      uint4 v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = ldg16(rp[k] + off);
+      m[0] = *reinterpret_cast<const __nv_bfloat162*>(&v[0].x);
+      m[1] = *reinterpret_cast<const __nv_bfloat162*>(&v[0].y);
+      m[2] = *reinterpret_cast<const __nv_bfloat162*>(&v[0].z);
+      m[3] = *reinterpret_cast<const __nv_bfloat162*>(&v[0].w);
+#pragma unroll
+      for (int k = 1; k < 9; ++k) {
+        m[0] = __hmax2(m[0], *reinterpret_cast<const __nv_bfloat162*>(&v[k].x));
+        m[1] = __hmax2(m[1], *reinterpret_cast<const __nv_bfloat162*>(&v[k].y));
+        m[2] = __hmax2(m[2], *reinterpret_cast<const __nv_bfloat162*>(&v[k].z));
+        m[3] = __hmax2(m[3], *reinterpret_cast<const __nv_bfloat162*>(&v[k].w));
+      }
     };
     column(-1, cm[0]);
     column(0, cm[1]);
