@@ -221,6 +221,54 @@ __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict
   }
 }
 
+// Fixed window sizes (the S3D / ResNet pools: (1,3,3), (3,3,3), (2,2,2), (1,2,2)): the window is unrolled and out-of-range taps
+// are clamped into the window's valid part (a duplicate does not change a maximum), so all KT*KH*KW loads are independent
+// and in flight together; the generic kernel's run-time loops with `continue` issue them one at a time.
+template <int KT, int KH, int KW>
+__global__ void maxpool3d_fixed_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                       long long total, int c8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int cc = divmod(r, c8);
+    const long long opix = r;
+    const int ow = divmod(r, d.ow);
+    const int oh = divmod(r, d.oh);
+    const int ot = divmod(r, d.ot);
+    const int n = static_cast<int>(r);
+    const int t0 = ot * d.st - d.pt, h0 = oh * d.sh - d.ph, w0 = ow * d.sw - d.pw;
+    const __nv_bfloat16* xb = x + cc * 8;
+    uint4 v[KT * KH * KW];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const int it = min(max(t0 + kt, 0), d.t - 1);
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh) {
+        const int ih = min(max(h0 + kh, 0), d.h - 1);
+        const long long rowp = ((static_cast<long long>(n) * d.t + it) * d.h + ih) * d.w;
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          const int iw = min(max(w0 + kw, 0), d.w - 1);
+          v[(kt * KH + kh) * KW + kw] = ldg16(xb + (rowp + iw) * d.in_cstride);
+        }
+      }
+    }
+    __nv_bfloat162 m0 = *reinterpret_cast<const __nv_bfloat162*>(&v[0].x), m1 = *reinterpret_cast<const __nv_bfloat162*>(&v[0].y);
+    __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&v[0].z), m3 = *reinterpret_cast<const __nv_bfloat162*>(&v[0].w);
+#pragma unroll
+    for (int k = 1; k < KT * KH * KW; ++k) {
+      m0 = __hmax2(m0, *reinterpret_cast<const __nv_bfloat162*>(&v[k].x));
+      m1 = __hmax2(m1, *reinterpret_cast<const __nv_bfloat162*>(&v[k].y));
+      m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&v[k].z));
+      m3 = __hmax2(m3, *reinterpret_cast<const __nv_bfloat162*>(&v[k].w));
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+    o.z = *reinterpret_cast<uint32_t*>(&m2); o.w = *reinterpret_cast<uint32_t*>(&m3);
+    *reinterpret_cast<uint4*>(y + opix * d.out_cstride + cc * 8) = o;
+  }
+}
+
 // (3,3,3) / stride 1 / padding 1 (the Inception pooling branch, s3d.py:134): a thread owns 8 channels of one (n,t,h) row and
 // walks along w keeping the maxima of the last three columns (each over its 3x3 (t,h) neighbourhood): 9 loads per output
 // instead of 27.
@@ -536,6 +584,21 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
     MSPI_LAUNCH_CHECK();
     return MSPI_OK;
   }
+  // clamping is only valid if every window starts inside the tensor (true for pad < kernel and the usual output sizes)
+  const bool starts_in = (d->ot - 1) * d->st - d->pt < d->t && (d->oh - 1) * d->sh - d->ph < d->h && (d->ow - 1) * d->sw - d->pw < d->w &&
+                         d->pt < d->kt && d->ph < d->kh && d->pw < d->kw;
+#define MSPI_POOL_FIXED(KT, KH, KW)                                                                                       \
+  if (starts_in && d->kt == KT && d->kh == KH && d->kw == KW) {                                                             \
+    maxpool3d_fixed_kernel<KT, KH, KW><<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),   \
+                                                                                static_cast<__nv_bfloat16*>(y), total, c8); \
+    MSPI_LAUNCH_CHECK();                                                                                                  \
+    return MSPI_OK;                                                                                                       \
+  }
+  MSPI_POOL_FIXED(1, 3, 3)
+  MSPI_POOL_FIXED(3, 3, 3)
+  MSPI_POOL_FIXED(2, 2, 2)
+  MSPI_POOL_FIXED(1, 2, 2)
+#undef MSPI_POOL_FIXED
   maxpool3d_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
                                                            static_cast<__nv_bfloat16*>(y), total, c8);
   MSPI_LAUNCH_CHECK();
