@@ -248,6 +248,13 @@ def run_train(args, rank, world, local):
             out = plan.train_step(clips[i % n_sets], audio[i % n_sets], gts[i % n_sets], allreduce)
         ev1.record()
         barrier()
+        clocks.mark_end()
+        if rank == 0:   # forward+backward replays (no collective, no parameter update) until nvidia-smi has reported under load
+            def _load():
+                plan.forward_backward(clips[0], audio[0], gts[0])
+                torch.cuda.synchronize()
+            clocks.wait_for_sample(_load)
+        barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
