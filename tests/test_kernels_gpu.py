@@ -467,6 +467,11 @@ def test_mlp_fused(c, m):
     ref = _bf(r) + gamma * (h @ _bf(w2).t() + b2)
     got = ya.buf.view(m, c).float().cpu()
     assert _rel(got, ref) < BF16_TOL
+    # in place (y aliases the residual, as the ConvNeXt block's `x = input + drop_path(x)` allows): every tile reads its
+    # residual rows before it writes them
+    ops.mlp_fused(xa, ra, ra, w1, b1, w2, b2, gamma)()
+    torch.cuda.synchronize()
+    assert torch.equal(ra.buf.view(m, c), ya.buf.view(m, c))
 
 
 def test_sa_gate_token_mean_simsiam():
