@@ -149,6 +149,115 @@ def cpu_baseline(seconds_budget: float = 20.0):
                       f"({best:.3f} s/clip, torch {torch.__version__} CPU, {torch.get_num_threads()} threads)"}
 
 
+def parity_at_bench_config(model, clips, audio, out, encoder, picks=None):
+    """The checker for the configuration that is actually timed: clips `picks` (first and last by default) of the
+    B-clip graph-replayed forward against the fp32 oracle on the same weights and inputs (outside every timed region).
+    north_star gate: exp(out) min-max normalised within 1e-2 max-abs."""
+    import torch
+    from oracle import mspi_oracle as orc
+    b = clips.shape[0]
+    picks = sorted(set(picks if picks is not None else (0, b - 1)))
+    sd = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    c = clips[picks].float().cpu()
+    a = audio[picks].float().cpu() if audio is not None else None
+    t0 = time.time()
+    ref, _ = orc.forward(sd, c, a, encoder=encoder)
+    got = out[picks].float().cpu()
+
+    def mm(x):
+        f = x.exp().reshape(x.shape[0], -1)
+        mn, mx = f.min(1, keepdim=True)[0], f.max(1, keepdim=True)[0]
+        return (f - mn) / (mx - mn)
+
+    err = (mm(got) - mm(ref)).abs().max(1)[0]
+    return {"batch": b, "clips_checked": picks, "map_maxabs_minmax": [float(e) for e in err], "tolerance": 1e-2,
+            "logit_maxabs": float((got - ref).abs().max()), "sum_exp": [float(v) for v in got.exp().sum((1, 2))],
+            "ok": bool((err < 1e-2).all()), "oracle_seconds": time.time() - t0,
+            "how": "graph-replayed forward of the timed batch vs oracle.forward (fp32, CPU) on the same weights and inputs"}
+
+
+def gpu_eager_baseline(dev, batch, steps=5, warmup=3, modes=("tf32", "bf16_autocast_channels_last"), encoder="s3d"):
+    """Same-silicon baseline: the reference forward as PyTorch eager ops (cuDNN / cuBLAS) on this GPU.
+    /root/reference cannot travel to the GPU box, so the op sequence is the oracle's — a functional restatement of the
+    reference's nn.Modules (same torch.nn.functional calls, pinned to the live reference by tests/golden) — executed on
+    CUDA tensors: (i) fp32 storage with TF32 tensor cores allowed, (ii) bf16 autocast with channels-last weights and inputs;
+    cudnn.benchmark on in both, as inference.py:189 sets it."""
+    import torch
+    from oracle import mspi_oracle as orc
+    res = {}
+    sd0 = orc.make_state_dict(1, "default", encoder=encoder)
+    g = torch.Generator(device=dev).manual_seed(7)
+    sets = [(torch.randn(batch, 3, T, H, W, device=dev, generator=g), torch.randn(batch, 1, 257, 111, device=dev, generator=g))
+            for _ in range(2)]
+    old = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for mode in modes:
+            sd = {}
+            for k, v in sd0.items():
+                v = v.to(dev)
+                if mode.startswith("bf16") and v.dim() == 5:
+                    v = v.contiguous(memory_format=torch.channels_last_3d)
+                elif mode.startswith("bf16") and v.dim() == 4:
+                    v = v.contiguous(memory_format=torch.channels_last)
+                sd[k] = v
+            ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if mode.startswith("bf16") else contextlib.nullcontext
+
+            def fwd(i):
+                c, a = sets[i % 2]
+                if mode.startswith("bf16"):
+                    c = c.contiguous(memory_format=torch.channels_last_3d)
+                with ctx():
+                    return orc.forward(sd, c, a, encoder=encoder)
+
+            try:
+                for i in range(warmup):
+                    fwd(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    out, _ = fwd(i)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[mode] = {"value": batch / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+                             "warmup": warmup, "finite": bool(torch.isfinite(out.float()).all())}
+            except Exception as e:  # e.g. out of memory at this batch: report, do not fail the product's line
+                res[mode] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            del sd
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    res["what"] = ("the reference forward as PyTorch-eager cuDNN/cuBLAS ops on this GPU (oracle.forward on CUDA tensors, "
+                   f"torch {torch.__version__}, cudnn.benchmark): tf32 = fp32 storage + TF32 tensor cores; "
+                   "bf16_autocast_channels_last = torch.autocast(bf16) + channels_last(_3d) weights and clips")
+    return res
+
+
+def run_eager(args, rank, world, local):
+    """--impl eager: the same-silicon baseline alone (one JSON line, rank 0)."""
+    if rank != 0:
+        return
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    with ClockSampler(local) as clocks:
+        clocks.mark()
+        res = gpu_eager_baseline(dev, args.batch, steps=max(1, args.steps), warmup=max(3, args.warmup), encoder=args.encoder)
+    best = max((m["value"] for m in res.values() if isinstance(m, dict) and "value" in m), default=None)
+    line = {"impl": "eager", "metric": f"clips/sec {ENC_NAME[args.encoder]} inference", "value": best, "unit": "clips/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "higher_is_better": True, "dtype": "tf32 / bf16 autocast",
+            "data": "synthetic", "config": {"workload": f"{ENC_NAME[args.encoder]} forward, {args.batch} clips/step of 16x{H}x{W}, "
+                                                        "PyTorch eager (cuDNN/cuBLAS) on the same GPU"},
+            "gpu_eager_baseline": res, "clocks": clocks.summary()}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and cannot
     travel to the GPU box, so its CPU port (oracle/, pinned to the live reference by tests/golden) is timed."""
@@ -376,12 +485,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
-    ap.add_argument("--impl", default="mspi_b200", choices=["mspi_b200", "reference"])
+    ap.add_argument("--impl", default="mspi_b200", choices=["mspi_b200", "reference", "eager"])
     ap.add_argument("--encoder", default="s3d", choices=["s3d", "x3dl", "slowfast4x16"],
                     help="motion encoder (BASELINE configs: s3d = headline, x3dl = config 3, slowfast4x16 = config 4)")
     ap.add_argument("--train", action="store_true", help="BASELINE config 5: the training step (use --batch 2)")
     ap.add_argument("--no-graph", action="store_true", help="replay the kernel list eagerly instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN/cuBLAS) run on the same GPU")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this file")
     args = ap.parse_args()
 
@@ -390,6 +501,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.impl == "eager":
+        return run_eager(args, rank, world, local)
     if args.train:
         return run_train(args, rank, world, local)
 
@@ -481,6 +594,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     value = world * B * K / (ms / 1e3)
+
+    # ------------------------------------------------------------------ parity of the timed configuration (untimed)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        out_chk, _ = model(clips_sets[0], audio_sets[0])      # the same graph replay the timed region ran
+        torch.cuda.synchronize()
+        parity = parity_at_bench_config(model, clips_sets[0], audio_sets[0], out_chk, args.encoder)
 
     # ------------------------------------------------------------------ e2e: host inputs through the public API
     pin = [torch.randn(B, 3, T, H, W).pin_memory() for _ in range(2)]
@@ -607,7 +727,16 @@ def main():
             "roofline": roofline,
             "tf32_kernel": tf32_info,
             "activation_bytes_allocated": plan.bytes_alloc,
+            "parity_at_bench_config": parity,
         }
+        if world == 1 and not args.no_eager_baseline:
+            with ClockSampler(local) as eclocks:
+                eclocks.mark()
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev, B, encoder=args.encoder)
+            line["gpu_eager_baseline"]["clocks"] = eclocks.summary()
+            best = max((m["value"] for m in line["gpu_eager_baseline"].values() if isinstance(m, dict) and "value" in m),
+                       default=None)
+            line["vs_gpu_eager"] = (value / best) if best else None
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         else:

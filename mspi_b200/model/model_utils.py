@@ -51,6 +51,41 @@ class StaticSaliencyModelConvNext(ParamNode):
         conv_bn(self, "smooth_1.0", "smooth_1.1", 96, 384, (3, 3), bias=True)
 
 
+def load_image_encoder_checkpoint(module: nn.Module, ckpt: Dict[str, torch.Tensor], verbose: bool = True):
+    """`image_encoder.load_state_dict(ckpt, strict=False)` of model_utils.py:514, made loud: strict=False silently leaves
+    every unmatched tensor at its random init, so a checkpoint written under other key names (another timm release, a
+    bare timm ConvNeXt instead of the FeatureListNet wrapper) would load as noise.  Keys of the plain timm ConvNeXt
+    layout (`stem.0`, `stages.k.`) are mapped onto the FeatureListNet names (`stem_0`, `stages_k.`) the module declares;
+    the matched / missing / unexpected counts are reported and a checkpoint that matches nothing raises."""
+    import re
+    own = module.state_dict()
+    fixed = {}
+    for k, v in ckpt.items():
+        k2 = k[7:] if k.startswith("module.") else k
+        k2 = re.sub(r"^(encoder\.)?stem\.(\d)\.", r"encoder.stem_\2.", k2) if re.match(r"^(encoder\.)?stem\.\d\.", k2) else k2
+        k2 = re.sub(r"^(encoder\.)?stages\.(\d)\.", r"encoder.stages_\2.", k2) if re.match(r"^(encoder\.)?stages\.\d\.", k2) else k2
+        fixed[k2] = v
+    usable = {k: v for k, v in fixed.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+    shape_mismatch = sorted(k for k, v in fixed.items() if k in own and tuple(own[k].shape) != tuple(v.shape))
+    res = module.load_state_dict(usable, strict=False)
+    matched = len(usable)
+    unexpected = sorted(k for k in fixed if k not in own)
+    report = {"matched": matched, "of": len(own), "missing": list(res.missing_keys), "unexpected": unexpected,
+              "shape_mismatch": shape_mismatch}
+    if verbose:
+        print(f"image_encoder checkpoint: matched {matched}/{len(own)} tensors, missing {len(res.missing_keys)}, "
+              f"unexpected {len(unexpected)}, shape mismatch {len(shape_mismatch)}")
+        for name, keys in (("missing", res.missing_keys), ("unexpected", unexpected), ("shape mismatch", shape_mismatch)):
+            if keys:
+                print(f"  {name}: {', '.join(list(keys)[:6])}{' ...' if len(keys) > 6 else ''}")
+    if len(ckpt) and matched == 0:
+        raise RuntimeError("image saliency encoder checkpoint matched none of the module's tensors (strict=False would have "
+                           f"left the encoder at random init); first checkpoint keys: {list(ckpt)[:4]}, expected e.g. "
+                           f"{list(own)[:2]}")
+    module.load_report = report
+    return report
+
+
 class SyncBlock(ParamNode):
     """model_utils.py:223-282 (the sinusoid tables are not parameters and not in the state_dict)."""
 
@@ -161,6 +196,7 @@ class _SaliencyBase(nn.Module):
         self.sa_1 = _sa(512)
         self.sa_2 = _sa(512)
         self._plans: Dict[Tuple, ForwardPlan] = {}
+        self._wcache: Dict = {}      # packed, uploaded weights per device: shared by the plans of every batch shape
         self.use_cuda_graph = False
         self.keep_taps = False
         if load_pretrained:
@@ -168,8 +204,8 @@ class _SaliencyBase(nn.Module):
             self.visnet.load_weight(cfg.MODEL.MOTION_ENCODER_WEIGHT)
             if self.has_audio:
                 self.audnet.load_state_dict(torch.load(cfg.MODEL.AUDIO_ENCODER_WEIGHT, map_location="cpu"))
-            self.image_encoder.load_state_dict(torch.load(cfg.MODEL.IMAGE_SALIENCY_ENCODER_WEIGHT, map_location="cpu"),
-                                               strict=False)
+            load_image_encoder_checkpoint(self.image_encoder,
+                                          torch.load(cfg.MODEL.IMAGE_SALIENCY_ENCODER_WEIGHT, map_location="cpu"))
 
     def frozen_encoder(self):
         if self.has_audio:
@@ -179,11 +215,13 @@ class _SaliencyBase(nn.Module):
     # -- plan cache ---------------------------------------------------------------------------
     def load_state_dict(self, *a, **k):
         self._plans.clear()  # packed weights are derived from the parameters
+        self._wcache.clear()
         return super().load_state_dict(*a, **k)
 
     def invalidate_plans(self):
         """Call after mutating parameters in place (the packed bf16 weights are cached per input shape)."""
         self._plans.clear()
+        self._wcache.clear()
 
     def plan_for(self, clips: torch.Tensor) -> ForwardPlan:
         b, c, t, h, w = clips.shape
@@ -197,7 +235,8 @@ class _SaliencyBase(nn.Module):
             m = self.cfg.MODEL
             plan = ForwardPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL),
                                lateral_stride=tuple(m.LATERAL_STRIDE), pool_stride=m.S3D.POOL_STRIDE,
-                               device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER)
+                               device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER,
+                               weight_cache=self._wcache.setdefault(clips.device.index, {}))
             if self.use_cuda_graph:
                 plan.capture()
             self._plans[key] = plan

@@ -211,8 +211,9 @@ class Conv:
     def __init__(self, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
                  shift: Optional[torch.Tensor] = None, stride=(1, 1, 1), pad=(0, 0, 0), act: int = ACT_NONE,
                  dtype: torch.dtype = torch.bfloat16, res_after_act: bool = False, device="cuda", name: str = "",
-                 split_weights: bool = False):
+                 split_weights: bool = False, cache: Optional[dict] = None):
         w = weight.detach().float()
+        self.cache = cache
         if w.dim() == 2:
             w = w[:, :, None, None, None]
         elif w.dim() == 4:
@@ -256,13 +257,22 @@ class Conv:
         return "gather"
 
     def _pack(self, w5: torch.Tensor):
-        w5 = w5.to(self.device)
+        """Packing runs where the weights live (host tensors for an inference plan: no kernel launches, only the packed
+        matrix is uploaded; device tensors for the training plan) and is cached per (layer, layout) in `self.cache`."""
+        key = (self.name, str(self.dtype), self.split, tuple(w5.shape))
+        if self.cache is not None and key in self.cache:
+            return self.cache[key]
         if not self.split:
-            return pack_conv_weight(w5, self.dtype)
-        hi = w5.to(torch.bfloat16).float()
-        p_hi, taps, cin_pad = pack_conv_weight(hi, self.dtype)
-        p_lo, _, _ = pack_conv_weight(w5 - hi, self.dtype)
-        return torch.cat([p_hi, p_lo], 1).contiguous(), 2 * taps, cin_pad
+            packed, taps, cin_pad = pack_conv_weight(w5, self.dtype)
+        else:
+            hi = w5.to(torch.bfloat16).float()
+            p_hi, taps, cin_pad = pack_conv_weight(hi, self.dtype)
+            p_lo, _, _ = pack_conv_weight(w5 - hi, self.dtype)
+            packed, taps = torch.cat([p_hi, p_lo], 1).contiguous(), 2 * taps
+        res = (packed.to(self.device), taps, cin_pad)
+        if self.cache is not None:
+            self.cache[key] = res
+        return res
 
     def _geom(self, mode: str, x: Act, ot: int, oh: int, ow: int):
         """TMA view of the input (dims/strides, inner -> outer), output extents, per-tap box offsets and the output
@@ -481,7 +491,7 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     lib = _lib.load()
     nf, hp, wp, _ = frames.shape
     cout = weight.shape[0]
-    w5 = weight.detach().float().to(frames.device)
+    w5 = weight.detach().float()      # packed where the weights live, uploaded once
     if w5.dim() == 4:
         w5 = w5[:, :, None]
     kt = w5.shape[2]
@@ -515,14 +525,14 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     # weight matrix [cout16][k taps][run_px][4]
     gemm_n = cout * wide
     rows16 = -(-gemm_n // 16) * 16
-    wm = torch.zeros((rows16, kt, k, run_px, 4), dtype=torch.float32, device=frames.device)
+    wm = torch.zeros((rows16, kt, k, run_px, 4), dtype=torch.float32, device=w5.device)
     for j in range(wide):
         # wide == 4 (S3D stem): GEMM column (j, co) is output pixel 4g + j of the row's group g; its 7 taps sit at pixels
         # 2j + kw + x_lead of the 16-pixel window, the rest of its K entries are zero.  The TMA engine issues one request
         # per (row, tap) whatever the row length, and those requests — not bytes, not MMA time — bound the 8-pixel form
         # (896 per 128 outputs); four outputs per row need a quarter of them at twice the (cheap) MMA work.
         wm[j * cout:(j + 1) * cout, :, :, stride * j + x_lead:stride * j + x_lead + k, :3] = w5.permute(0, 2, 3, 4, 1)
-    packed = wm.reshape(rows16, kt * k * run_el).to(torch.bfloat16).contiguous()
+    packed = wm.reshape(rows16, kt * k * run_el).to(torch.bfloat16).contiguous().to(frames.device)
     # frame row of (oh, kh) = row0 + stride*oh + kh = row0 + stride*(oh + kh // stride) + kh % stride
     n_r, n_j = min(stride, k), (k - 1) // stride + 1
     assert row0 + stride * (oh - 1) + k - 1 < hp and col0 + wide * stride * (ow // wide - 1) + run_px - 1 < wp
@@ -584,13 +594,13 @@ def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma) 
     assert c in (96, 192) and x.c0 == 0 and x.cs == c and x.dtype == y.dtype == residual.dtype == torch.bfloat16
     assert y.c == c and residual.c == c and y.pixels == x.pixels == residual.pixels
     c_pad = -(-c // 64) * 64
-    w1 = torch.zeros((4 * c, c_pad), dtype=torch.float32, device=dev)
-    w1[:, :c] = fc1_w.detach().float().to(dev)
-    w1 = w1.to(torch.bfloat16).contiguous()
-    w2 = fc2_w.detach().float().to(dev).to(torch.bfloat16).contiguous()      # [c, 4c], K contiguous
+    w1 = torch.zeros((4 * c, c_pad), dtype=torch.float32, device=fc1_w.device)
+    w1[:, :c] = fc1_w.detach().float()
+    w1 = w1.to(torch.bfloat16).contiguous().to(dev)
+    w2 = fc2_w.detach().float().to(torch.bfloat16).contiguous().to(dev)      # [c, 4c], K contiguous
     b1 = fc1_b.detach().float().contiguous().to(dev)
     g = gamma.detach().float().contiguous().to(dev)
-    sh = (g * fc2_b.detach().float().to(dev)).contiguous()
+    sh = (gamma.detach().float() * fc2_b.detach().float()).contiguous().to(dev)
     m = x.pixels
     xp, yp, rp = x.ptr, y.ptr, residual.ptr
     rs, ys = residual.cs, y.cs
@@ -615,12 +625,14 @@ def dwconv3d_bn(x: Act, y: Act, weight: torch.Tensor, scale: Optional[torch.Tens
     cp = x.c
     assert cp >= c and cp % 8 == 0 and y.c == cp and x.dtype == y.dtype == torch.bfloat16
     dev = x.buf.device
-    wt = torch.zeros((kt * kh * kw, cp), dtype=torch.float32, device=dev)
-    sc = torch.ones(c, device=dev) if scale is None else scale.detach().float().to(dev)
-    wt[:, :c] = (w.reshape(c, -1).to(dev) * sc[:, None]).t()
-    sh = torch.zeros(cp, dtype=torch.float32, device=dev)
+    wt = torch.zeros((kt * kh * kw, cp), dtype=torch.float32, device=w.device)
+    sc = torch.ones(c, device=w.device) if scale is None else scale.detach().float().to(w.device)
+    wt[:, :c] = (w.reshape(c, -1) * sc[:, None]).t()
+    wt = wt.to(dev)
+    sh = torch.zeros(cp, dtype=torch.float32, device=w.device)
     if shift is not None:
-        sh[:c] = shift.detach().float().to(dev)
+        sh[:c] = shift.detach().float().to(w.device)
+    sh = sh.to(dev)
     d = Dw3dDesc()
     d.n, d.t, d.h, d.w, d.c = x.n, x.t, x.h, x.w, cp
     d.in_cstride, d.out_cstride = x.cs, y.cs
@@ -643,15 +655,18 @@ def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH) -> List[C
     dev = x.buf.device
     cp, n = x.c, x.n
     assert x.c0 == 0 and x.cs == cp and x.dtype == torch.bfloat16
-    w1 = fc1_w.detach().float().reshape(fc1_w.shape[0], -1).to(dev)
+    w1 = fc1_w.detach().float().reshape(fc1_w.shape[0], -1)
     cfc, c = w1.shape
-    w1p = torch.zeros((cfc, cp), dtype=torch.float32, device=dev)
+    w1p = torch.zeros((cfc, cp), dtype=torch.float32, device=w1.device)
     w1p[:, :c] = w1
-    w2p = torch.zeros((cp, cfc), dtype=torch.float32, device=dev)
-    w2p[:c] = fc2_w.detach().float().reshape(c, cfc).to(dev)
+    w1p = w1p.to(dev)
+    w2p = torch.zeros((cp, cfc), dtype=torch.float32, device=w1.device)
+    w2p[:c] = fc2_w.detach().float().reshape(c, cfc)
+    w2p = w2p.to(dev)
     b1 = fc1_b.detach().float().contiguous().to(dev)
-    b2 = torch.zeros(cp, dtype=torch.float32, device=dev)
-    b2[:c] = fc2_b.detach().float().to(dev)
+    b2 = torch.zeros(cp, dtype=torch.float32, device=w1.device)
+    b2[:c] = fc2_b.detach().float()
+    b2 = b2.to(dev)
     mean = torch.empty((n, cp), dtype=torch.float32, device=dev)
     gate = torch.empty((n, cp), dtype=torch.float32, device=dev)
     rows = x.t * x.h * x.w

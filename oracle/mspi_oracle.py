@@ -325,8 +325,8 @@ def sync_block(sd: SD, p: str, v4, aud):
     vis = F.linear(vis, sd[p + "vis_proj.weight"], sd[p + "vis_proj.bias"])
     vis = F.layer_norm(vis, (512,), sd[p + "vis_norm.weight"], sd[p + "vis_norm.bias"], 1e-5)
     au = F.layer_norm(au, (512,), sd[p + "aud_norm.weight"], sd[p + "aud_norm.bias"], 1e-5)
-    vis = vis + sinusoid_table(vis.shape[1], 512)
-    au = au + sinusoid_table(au.shape[1], 512)
+    vis = vis + sinusoid_table(vis.shape[1], 512).to(vis.device)   # (.to: the same functions time PyTorch eager on a GPU,
+    au = au + sinusoid_table(au.shape[1], 512).to(au.device)        #  bench.py --impl eager; a no-op on the CPU oracle)
     x = torch.cat([vis, au], 1)
     for i in range(3):
         x = vit_block(sd, f"{p}blocks.{i}.", x)
@@ -443,7 +443,7 @@ def _forward(sd: SD, clips: torch.Tensor, audios: Optional[torch.Tensor], taps: 
     v1, v2, v3, v4 = motion_features(sd, encoder, clips)
     for i, v in enumerate((v1, v2, v3, v4)):
         rec(f"visnet.base{i + 1}", v)
-    loss = torch.zeros(())
+    loss = torch.zeros((), device=clips.device)
     if audios is not None:
         aud = resnet18_audio(sd, "audnet.", audios)
         rec("audnet", aud)

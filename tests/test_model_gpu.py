@@ -79,6 +79,54 @@ def test_forward_parity_other_motion_encoders(encoder, init, seed):
         assert res["logit_maxabs"] / rng < 5e-2
 
 
+@pytest.mark.parametrize("encoder,seed", [("x3dl", 4), ("slowfast4x16", 6)])
+def test_forward_default_shape_other_motion_encoders(encoder, seed):
+    """BASELINE configs 3 / 4 at the reference's default 16x224x384 shape (X3D-L: 16*7*12 = 1344 visual tokens + 36 audio
+    tokens through the batched-GEMM attention; SlowFast: 336 + 36), B = 1, default init: the literal map contract and
+    every tap."""
+    from tests.parity import run_forward_parity
+    res = run_forward_parity(224, 384, 1, init="default", seed=seed, encoder=encoder, verbose=True)
+    print({k: v for k, v in res.items() if k not in ("ref_out", "out", "taps")})
+    assert res["map_maxabs_minmax"] < 1e-2
+    assert res["worst_tap"] < 3e-2, res["taps"]
+    assert res["loss_abs"] < 1e-3
+    assert all(abs(s - 1.0) < 1e-3 for s in res["sum_exp"])
+
+
+def test_forward_parity_at_the_benchmarked_configuration():
+    """The configuration bench.py times (B = 32 clips of 16x224x384 per GPU, one captured CUDA graph, CTA-pair GEMM
+    instances, 2368-block grids, 30 GB of buffers): first and last clip of the graph-replayed batch against the fp32
+    oracle on the same weights and inputs, min-max-normalised map within 1e-2."""
+    import contextlib, copy, io
+    import bench
+    from mspi_b200.config import cfg as base_cfg, select_motion_encoder
+    from mspi_b200.model.model_utils import AudioVisualSaliencyModel
+    torch.manual_seed(2023)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = AudioVisualSaliencyModel(select_motion_encoder("s3d", copy.deepcopy(base_cfg)), load_pretrained=False)
+    model = model.cuda().eval()
+    model.use_cuda_graph = True
+    g = torch.Generator(device="cuda").manual_seed(2023)
+    B = 32
+    clips = torch.randn(B, 3, 16, 224, 384, device="cuda", generator=g)
+    audio = torch.randn(B, 1, 257, 111, device="cuda", generator=g)
+    model(clips, audio)                      # builds the plan, captures the graph
+    out, _ = model(clips, audio)             # a replay, like the timed steps
+    torch.cuda.synchronize()
+    res = bench.parity_at_bench_config(model, clips, audio, out, "s3d")
+    print(res)
+    assert res["ok"], res
+    assert all(abs(s - 1.0) < 1e-3 for s in res["sum_exp"])
+    # every clip of the batch went through the same kernels: all 32 maps are finite, normalised log-probabilities
+    assert torch.isfinite(out).all()
+    assert (out.exp().sum((1, 2)) - 1.0).abs().max() < 1e-3
+    # clips are independent in eval mode: the same clip at another batch position gives the same map (to rounding of the
+    # batch-position-dependent tile schedule: identical kernels, identical per-row arithmetic)
+    perm = torch.arange(B - 1, -1, -1, device="cuda")
+    out2, _ = model(clips[perm].contiguous(), audio[perm].contiguous())
+    assert (out2[perm] - out).abs().max() < 1e-4
+
+
 def test_inference_entry_point_on_synthetic_dataset(tmp_path):
     """inference.py (the reference's entry point, same CLI / dataset layout / output naming) end to end on a tiny
     synthetic AVAD-style dataset: 33 frames -> 18 forward windows + 15 time-flipped ones = one image per frame."""
