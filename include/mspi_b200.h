@@ -44,6 +44,11 @@ int mspi_version(void);
 const char* mspi_arch(void);
 /* Number of kernels launched by this library since load (process-wide counter). */
 int64_t mspi_launch_count(void);
+/* Profiling aid for the depthwise 7x7 + LayerNorm kernel (MSPI_DW_DEBUG=1 selects its instrumented instance): cycles the
+ * warps spent [0] waiting for their tile, [1] in the stencil, [2] in the LayerNorm phase, [3] the number of warp samples,
+ * [4] in the barrier after the stencil, [5] storing the result tile, summed since the last reset.  out8 has 8 entries.
+ * Synchronises the device.  No counterpart in the reference. */
+int mspi_debug_dw_phase_cycles(uint64_t* out8, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

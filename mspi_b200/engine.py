@@ -45,6 +45,7 @@ class ForwardPlan:
             raise Exception("Invalid Motion Encoder!")  # get_video_backbones.py:28-29
         self.encoder = encoder
         self.fuse_mlp = os.environ.get("MSPI_FUSE_MLP", "1") != "0"
+        self.fuse_mixed = os.environ.get("MSPI_FUSE_MIXED", "1") != "0"
         self.steps: List[Tuple[str, Callable[[], None]]] = []
         self.flops = 0.0
         self.bytes_alloc = 0
@@ -206,17 +207,44 @@ class ForwardPlan:
 
     def mixed(self, p: str, x: Act, out: Optional[Act] = None) -> Act:
         """Mixed_* / Inception block: four branches written straight into their slices of the
-        concatenated output.  s3d.py:118-376, model_utils.py:173-199"""
+        concatenated output.  s3d.py:118-376, model_utils.py:173-199
+
+        The three branch-entry 1x1x1 convs (branch0.0, branch1.0, branch2.0: same input, BN + ReLU each) run as ONE GEMM
+        with their weights stacked along N.  Its output columns [t1 | t2 | b0] must be contiguous channels, so the block's
+        buffer is laid out [t1 | t2 | b0 | b1 | b2 | b3] and the block output is the channel slice behind the two
+        temporaries (every consumer addresses activations as channel slices anyway).  When the caller dictates the output
+        buffer (the fp32 v4 slice of the decoder input), t1 and t2 share one GEMM and branch0 keeps its own."""
         c0 = self.P(p + ".branch0.0.conv.weight").shape[0]
         c1 = self.P(p + ".branch1.1.conv_t.weight").shape[0]
         c2 = self.P(p + ".branch2.1.conv_t.weight").shape[0]
         c3 = self.P(p + ".branch3.1.conv.weight").shape[0]
-        if out is None:
-            out = self.new(x.n, x.t, x.h, x.w, c0 + c1 + c2 + c3)
-        self.basic(p + ".branch0.0", x, out.slice(0, c0))
-        t1 = self.basic(p + ".branch1.0", x)
+        c1a = self.P(p + ".branch1.0.conv.weight").shape[0]
+        c2a = self.P(p + ".branch2.0.conv.weight").shape[0]
+        fuse = self.fuse_mixed and c1a % 8 == 0 and c2a % 8 == 0 and c0 % 8 == 0
+
+        def entry(branches, dst: Act, name: str):
+            ws = [self.P(f"{p}.{b}.conv.weight") for b in branches]
+            folded = [self.bn(f"{p}.{b}.bn", 1e-3) for b in branches]
+            self.conv(name, x, torch.cat(ws, 0), torch.cat([f[0] for f in folded]), torch.cat([f[1] for f in folded]),
+                      act=ACT_RELU, out=dst)
+
+        if not fuse:
+            if out is None:
+                out = self.new(x.n, x.t, x.h, x.w, c0 + c1 + c2 + c3)
+            self.basic(p + ".branch0.0", x, out.slice(0, c0))
+            t1 = self.basic(p + ".branch1.0", x)
+            t2 = self.basic(p + ".branch2.0", x)
+        elif out is None:
+            wide = self.new(x.n, x.t, x.h, x.w, c1a + c2a + c0 + c1 + c2 + c3)
+            out = wide.slice(c1a + c2a, c0 + c1 + c2 + c3)
+            entry(("branch1.0", "branch2.0", "branch0.0"), wide.slice(0, c1a + c2a + c0), p + ".branch{1.0,2.0,0.0}")
+            t1, t2 = wide.slice(0, c1a), wide.slice(c1a, c2a)
+        else:
+            self.basic(p + ".branch0.0", x, out.slice(0, c0))
+            t12 = self.new(x.n, x.t, x.h, x.w, c1a + c2a)
+            entry(("branch1.0", "branch2.0"), t12, p + ".branch{1.0,2.0}")
+            t1, t2 = t12.slice(0, c1a), t12.slice(c1a, c2a)
         self.sep(p + ".branch1.1", t1, 3, 1, 1, out.slice(c0, c1))
-        t2 = self.basic(p + ".branch2.0", x)
         self.sep(p + ".branch2.1", t2, 3, 1, 1, out.slice(c0 + c1, c2))
         pooled = self.pool(p + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         self.basic(p + ".branch3.1", pooled, out.slice(c0 + c1 + c2, c3))

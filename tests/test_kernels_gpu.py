@@ -347,7 +347,8 @@ def test_dwconv_ln(c, kern):
 
 @pytest.mark.parametrize("c,h,w,dt", [(96, 16, 32, torch.bfloat16), (384, 6, 24, torch.bfloat16), (192, 7, 12, torch.float32),
                                       (40, 5, 16, torch.float32), (768, 7, 12, torch.bfloat16), (384, 14, 24, torch.bfloat16),
-                                      (768, 2, 2, torch.bfloat16)])
+                                      (768, 2, 2, torch.bfloat16), (192, 10, 20, torch.bfloat16), (96, 13, 21, torch.bfloat16),
+                                      (192, 28, 48, torch.bfloat16)])
 def test_dwconv7x7_ln_strip_kernel(c, h, w, dt):
     """Register-tiled 7x7 depthwise + LayerNorm (dwconv.cu): strip lengths 16/12/8, bf16 and fp32 inputs, bf16 output."""
     from mspi_b200 import ops
