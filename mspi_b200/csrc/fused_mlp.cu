@@ -54,6 +54,7 @@ struct MlpParams {
   int y_staged;         // Y epilogue through shared memory: the residual tile arrives by TMA, is updated in place and leaves by
                         // TMA (a warp's direct row accesses cost 32 L1 tag cycles per instruction: 6144 per 128 x 96 tile)
   int ystage_bytes;
+  int packed_gelu;      // GELU on packed fp32 pairs (fma.rn.f32x2 / mul / add) with one fp32 tanh per element
 };
 
 __device__ __forceinline__ void ldg256(const __nv_bfloat16* p, uint4& a, uint4& b) {
@@ -518,22 +519,27 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (p.debug & 1) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) packed[q] = pack_bf16x2(__uint_as_float(acc[2 * q]), __uint_as_float(acc[2 * q + 1]));
+          } else if (p.packed_gelu) {
+            // packed fp32 pairs end to end: TMEM registers are consecutive, so (acc[2k], acc[2k+1]) already is a register pair
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * q);
+              const F2 g01 = gelu_pair_f32(add2(pack2(__uint_as_float(acc[4 * q + 0]), __uint_as_float(acc[4 * q + 1])), pack2(bb.x, bb.y)));
+              const F2 g23 = gelu_pair_f32(add2(pack2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), pack2(bb.z, bb.w)));
+              float v0, v1, v2, v3;
+              unpack2(g01, v0, v1);
+              unpack2(g23, v2, v3);
+              packed[2 * q] = pack_bf16x2(v0, v1);
+              packed[2 * q + 1] = pack_bf16x2(v2, v3);
+            }
           } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * q);
-#ifndef MSPI_MLP_PACKED_GELU   // packed pairs measured no faster here (0.82 vs 0.80 ms at C = 96): the pair moves eat the gain
             const float v0 = gelu_bf16(__uint_as_float(acc[4 * q + 0]) + bb.x);
             const float v1 = gelu_bf16(__uint_as_float(acc[4 * q + 1]) + bb.y);
             const float v2 = gelu_bf16(__uint_as_float(acc[4 * q + 2]) + bb.z);
             const float v3 = gelu_bf16(__uint_as_float(acc[4 * q + 3]) + bb.w);
-#else
-            const F2 g01 = gelu_pair_f2(add2(pack2(__uint_as_float(acc[4 * q + 0]), __uint_as_float(acc[4 * q + 1])), pack2(bb.x, bb.y)));
-            const F2 g23 = gelu_pair_f2(add2(pack2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), pack2(bb.z, bb.w)));
-            float v0, v1, v2, v3;
-            unpack2(g01, v0, v1);
-            unpack2(g23, v2, v3);
-#endif
             packed[2 * q] = pack_bf16x2(v0, v1);
             packed[2 * q + 1] = pack_bf16x2(v2, v3);
           }
@@ -699,6 +705,8 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   p.cl = cl;
   if (const char* e = getenv("MSPI_MLP_DEBUG")) p.debug = atoi(e);
+  static const int packed_on = [] { const char* e = getenv("MSPI_MLP_PACKED_GELU"); return e ? atoi(e) : 1; }();
+  p.packed_gelu = packed_on;
   p.hbufs = (3 * kHC + c <= 512) ? 3 : 2;
   const int groups = (p.m_tiles + cl - 1) / cl;
   cudaLaunchConfig_t cfg;

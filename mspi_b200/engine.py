@@ -47,6 +47,13 @@ class ForwardPlan:
         self.fuse_mlp = os.environ.get("MSPI_FUSE_MLP", "1") != "0"
         self.fuse_mixed = os.environ.get("MSPI_FUSE_MIXED", "1") != "0"
         self.steps: List[Tuple[str, Callable[[], None]]] = []
+        # Branch schedule (see _build / run_branched): `sched` interleaves ("step", index) entries with ("edge", src, dst)
+        # entries meaning "branch dst waits for everything branch src has enqueued so far".  The list order of `steps` stays a
+        # valid serial order, which is what run_eager(), the per-kernel breakdown and the training plan use.
+        self.sched: List[Tuple] = []
+        self.step_branch: List[int] = []
+        self._branch = 0
+        self.branches = os.environ.get("MSPI_GRAPH_BRANCHES", "1") != "0"
         self.flops = 0.0
         self.bytes_alloc = 0
         self.taps: Dict[str, Act] = {}
@@ -66,7 +73,18 @@ class ForwardPlan:
         return a
 
     def add(self, name: str, fn: Callable[[], None]):
+        self.sched.append(("step", len(self.steps)))
+        self.step_branch.append(self._branch)
         self.steps.append((name, fn))
+
+    def on_branch(self, b: int):
+        """Steps added from now on belong to branch b (0 = the main stream)."""
+        self._branch = b
+
+    def edge(self, src: int, dst: int):
+        """Branch dst waits for the work branch src has been given so far."""
+        if src != dst:
+            self.sched.append(("edge", src, dst))
 
     def tap(self, name: str, a: Act):
         if self.keep_taps:
@@ -711,17 +729,31 @@ class ForwardPlan:
 
     # ------------------------------------------------------------------ whole forward
     def _build(self):
+        """The forward as three branches that only meet where the reference's data flow does (model_utils.py:556-570):
+             branch 0  clip conversion -> image encoder (ConvNeXt-T) -> adapter -> SA mask conv ........ -> gates, readout
+             branch 1  motion encoder (S3D / X3D-L / SlowFast) -> [wait 2] SyncBlock + heads -> laterals -^
+             branch 2  audio encoder (ResNet18)
+        Captured into one CUDA graph, the branches become parallel paths: the small-grid kernels (audio net, SyncBlock,
+        SimSiam heads, the deep S3D stages) fill SMs that the tails of the big encoder kernels leave idle."""
         B = self.B
+        if self.encoder != "slowfast4x16":
+            self.padded_frames()       # shared by the image-encoder stem and the motion-encoder stem
+        self.edge(0, 1), self.edge(0, 2)
         o1, o0 = self.convnext()
         masks = self.adapter(o1, o0)
+        m96 = self.sa_masks(masks)
         h32, w32 = self.H // 32, self.W // 32
         visnet = {"s3d": self.s3d, "x3dl": self.x3d, "slowfast4x16": self.slowfast}[self.encoder]
         c4 = {"s3d": 1024, "x3dl": 192, "slowfast4x16": 2048}[self.encoder]
         t4 = self.T if self.encoder == "x3dl" else self.T // 4   # X3D keeps all 16 frames (X3D.py), the others end on 4
+        self.on_branch(1)
         if self.audio:
             v4cat = self.new(B, t4, h32, w32, c4 + 512, torch.float32)  # cat([v4, vis_sync]) feeds the decoder
             v1, v2, v3, v4 = visnet(v4cat.slice(0, c4))
+            self.on_branch(2)
             aud = self.resnet18()
+            self.on_branch(1)
+            self.edge(2, 1)
             self.sync_block(v4, aud, v4cat)
             v4in = v4cat
         else:
@@ -733,7 +765,8 @@ class ForwardPlan:
         s1 = self.lateral(1, v2)
         s2 = self.lateral(2, v3)
         assert s0.t == s1.t == s2.t == s3.t == masks.t, "laterals must land on the adapter's 4 frames (model_utils.py:169)"
-        m96 = self.sa_masks(masks)
+        self.on_branch(0)
+        self.edge(1, 0)
         # top-down fusion, model_utils.py:566-568 (fp32)
         g2 = self.sa_gate(2, s2, m96, 1, sources=[(s3, 2)])
         g1 = self.sa_gate(1, s1, m96, 2, sources=[(g2, 2), (s3, 4)])
@@ -755,6 +788,41 @@ class ForwardPlan:
         for _name, fn in self.steps:
             fn()
 
+    def run_branched(self):
+        """Enqueue the steps on one stream per branch (branch 0 = the current stream) with event edges between them.
+        Under stream capture this records the fork / join structure of _build into the graph."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side_streams", None) is None:
+            self._side_streams = {}
+        streams = {0: main}
+
+        def stream_of(b):
+            if b not in streams:
+                if b not in self._side_streams:
+                    self._side_streams[b] = torch.cuda.Stream(device=self.device)
+                streams[b] = self._side_streams[b]
+            return streams[b]
+
+        used = set()
+        for ent in self.sched:
+            if ent[0] == "edge":
+                _, src, dst = ent
+                ev = torch.cuda.Event()
+                ev.record(stream_of(src))
+                stream_of(dst).wait_event(ev)
+                used.add(dst)
+            else:
+                b = self.step_branch[ent[1]]
+                fn = self.steps[ent[1]][1]
+                if b == 0:
+                    fn()
+                else:
+                    with torch.cuda.stream(stream_of(b)):
+                        fn()
+        for b in used:   # every side branch must have been joined back (a capture cannot end with unjoined streams)
+            if b != 0:
+                main.wait_stream(streams[b])
+
     def capture(self):
         """Capture the step list into a CUDA graph bound to static input buffers."""
         dev = self.device
@@ -769,7 +837,10 @@ class ForwardPlan:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run_eager()
+            if self.branches and any(e[0] == "edge" for e in self.sched):
+                self.run_branched()
+            else:
+                self.run_eager()
         self.graph = g
 
     def run(self, clips: torch.Tensor, audio: Optional[torch.Tensor]):
