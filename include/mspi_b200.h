@@ -158,6 +158,21 @@ int mspi_clip_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, 
 int mspi_clip_frames_to_padded_nhwc4(const float* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
                                      int hp, int wp, const int32_t* frame_map, int t_out, int dst_frames_per_clip,
                                      int dst_frame0, void* stream);
+
+/* uint8 frames [N][T][H][W][3] (decoder output; the reference converts them on the host: inference.py:154-165 Resize ->
+ * ToTensor (/255) -> Normalize(mean, std)) -> the same bf16 zero-padded 4-channel frames as mspi_clip_to_padded_nhwc4, the
+ * normalisation done in fp32 with IEEE division, so the result is bit-identical to converting the reference's normalised
+ * fp32 clip.  frame_map == NULL: all t frames in order; otherwise as mspi_clip_frames_to_padded_nhwc4.  mean3 / std3 are
+ * HOST pointers to three floats. */
+int mspi_clip_u8_to_padded_nhwc4(const void* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l, int hp,
+                                 int wp, const int32_t* frame_map, int t_out, int dst_frames_per_clip, int dst_frame0,
+                                 const float* mean3, const float* std3, void* stream);
+
+/* dst row i = src row idx[i], rows of row_bytes (multiple of 16) bytes; idx is a DEVICE array of n_rows indices, clamped to
+ * [0, src_rows).  Builds the per-window [B][T] views of the per-frame image-encoder feature cache: consecutive sliding
+ * windows of inference.py:120-150 share 15 of their 16 frames, and the image encoder (model_utils.py:357-385) is per frame. */
+int mspi_gather_rows(const void* src, const int32_t* idx, void* dst, int64_t n_rows, int64_t row_bytes, int64_t src_rows,
+                     void* stream);
 /* bf16/fp32 NDHWC (channel slice) -> fp32 NCDHW, used to hand taps back to PyTorch callers */
 int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n,
                         int c, int thw, void* stream);

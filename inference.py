@@ -10,6 +10,9 @@ What is kept (reference inference.py line numbers):
     per input frame named like the frame (:91).
 What is done differently (same results, fewer passes):
   * windows are batched (`--batch`, default 8) instead of one forward per frame;
+  * the image saliency encoder (ConvNeXt-T + smooth convs: 61 % of the forward's FLOPs) runs ONCE PER FRAME, not once per
+    window: consecutive windows share 15 of their 16 frames (:125-150), so its per-frame feature maps are cached on the
+    device and every window (time-flipped ones included) indexes the cache (`--no_feature_cache` restores the plain forward);
   * the wav is decoded and resampled once per video, not once per frame (:28-30 re-reads the whole file every step);
     the spectrogram of each window is computed on the GPU (mspi_logspec);
   * blur / exp / resize / min-max / uint8 run on the GPU (mspi_postprocess_maps); only uint8 images cross PCIe.
@@ -92,10 +95,12 @@ def audio_features(audio, windows, fps, device):
 
 
 @torch.no_grad()
-def process_batch(model, clips, feats, names, vname, img_size, args):
+def process_batch(model, clips, feats, names, vname, img_size, args, cache=None, frame_index=None):
     """Forward + GPU post-processing of a batch of windows; writes one image per window (inference.py:72-91)."""
     import cv2
-    if args.use_sound:
+    if cache is not None:
+        pred = model.forward_cached(clips, feats if args.use_sound else None, cache, frame_index)[0]
+    elif args.use_sound:
         pred = model(clips, feats)[0]
     else:
         pred = model(clips)[0]
@@ -135,6 +140,9 @@ def inference_dataset(model, args, device):
         fps = videos_fps[vname]
         img_size = (640, 480)  # inference.py:127
         frames = torch.stack([torch_transform(p, cfg.DATA.RESOLUTION)[0] for p in list_frames])  # [N,3,H,W], host
+        cache = None
+        if not args.no_feature_cache:   # image-encoder features of every frame, computed once (device resident, 118 KB / frame)
+            cache = model.encode_frames(frames.to(device, non_blocking=True), chunk=max(16, 16 * args.batch))
         # every window as (first frame, flipped?, output frame name) in the reference's order (:125-150)
         jobs = []
         for i in range(len_temporal - 1, len(list_frames)):
@@ -150,7 +158,11 @@ def inference_dataset(model, args, device):
                 clips.append(torch.flip(c, [1]) if flip else c)
             clips = torch.stack(clips).contiguous().to(device, non_blocking=True)
             feats = audio_features(audio, [(s, flip) for s, flip, _ in chunk], fps, device) if args.use_sound else None
-            process_batch(model, clips, feats, [n for _, _, n in chunk], vname, img_size, args)
+            index = None
+            if cache is not None:   # cache row of frame t of every window; a flipped window lists its frames backwards
+                index = torch.tensor([[s + (len_temporal - 1 - t if flip else t) for t in range(len_temporal)]
+                                      for s, flip, _ in chunk], dtype=torch.int32)
+            process_batch(model, clips, feats, [n for _, _, n in chunk], vname, img_size, args, cache, index)
 
 
 def main(argv=None):
@@ -164,6 +176,8 @@ def main(argv=None):
     parser.add_argument('--use_sound', default=True, type=bool)
     parser.add_argument('--batch', default=8, type=int, help="sliding windows per forward (the reference uses 1)")
     parser.add_argument('--random_init', action='store_true', help="skip checkpoint loading (smoke tests)")
+    parser.add_argument('--no_feature_cache', action='store_true',
+                        help="re-run the image encoder on all 16 frames of every window, as the reference does")
     args = parser.parse_args(argv)
     print(args)
     os.makedirs(args.save_path, exist_ok=True)

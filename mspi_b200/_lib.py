@@ -137,6 +137,9 @@ _SIGNATURES = {
     "mspi_clip_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_clip_frames_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                    _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mspi_clip_u8_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "mspi_gather_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "mspi_ndhwc_to_ncdhw": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_maxpool3d": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P]),
     "mspi_upsample_bilinear": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P]),

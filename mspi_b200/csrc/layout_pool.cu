@@ -158,6 +158,60 @@ __global__ void clip_to_padded_nhwc4_kernel(const float* __restrict__ src, __nv_
   }
 }
 
+// uint8 frames [N][T][H][W][3] (what a decoder hands over; inference.py:154-165 turns them into fp32 on the host) -> the
+// same bf16 zero-padded frames, with ToTensor's /255 and Normalize's (x - mean) / std done here in fp32 with IEEE division,
+// i.e. bit for bit what converting the reference's normalised fp32 clip gives.  A thread converts 4 pixels: 12 bytes in.
+struct NormParams { float mean[3], std[3]; };
+__global__ void clip_u8_to_padded_nhwc4_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int t,
+                                               int h, int w, int pad_t, int pad_l, int hp, int wp, ClipMap m, NormParams np) {
+  const int w4 = w >> 2;
+  const long long total = static_cast<long long>(n) * m.t_out * h * w4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xq = static_cast<int>(i % w4);
+    long long r = i / w4;
+    const int yy = static_cast<int>(r % h); r /= h;
+    const int j = static_cast<int>(r % m.t_out);
+    const long long b = r / m.t_out;
+    const int tt = m.map[j];
+    const uint8_t* sp = src + (((b * t + tt) * static_cast<long long>(h) + yy) * w + 4 * xq) * 3;   // 12 bytes, 4-byte aligned
+    const uint32_t u0 = __ldg(reinterpret_cast<const uint32_t*>(sp));
+    const uint32_t u1 = __ldg(reinterpret_cast<const uint32_t*>(sp) + 1);
+    const uint32_t u2 = __ldg(reinterpret_cast<const uint32_t*>(sp) + 2);
+    const uint32_t by[12] = {u0 & 255u, (u0 >> 8) & 255u, (u0 >> 16) & 255u, u0 >> 24, u1 & 255u, (u1 >> 8) & 255u,
+                             (u1 >> 16) & 255u, u1 >> 24, u2 & 255u, (u2 >> 8) & 255u, (u2 >> 16) & 255u, u2 >> 24};
+    float f[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = k % 3;
+      f[k] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(by[k]), 255.f), np.mean[c]), np.std[c]);
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], 0.f);
+    o0.z = pack_bf16x2(f[3], f[4]); o0.w = pack_bf16x2(f[5], 0.f);
+    o1.x = pack_bf16x2(f[6], f[7]); o1.y = pack_bf16x2(f[8], 0.f);
+    o1.z = pack_bf16x2(f[9], f[10]); o1.w = pack_bf16x2(f[11], 0.f);
+    const long long fr = b * m.dst_fpc + m.dst_f0 + j;
+    __nv_bfloat16* dp = dst + ((fr * hp + (yy + pad_t)) * static_cast<long long>(wp) + pad_l + 4 * xq) * 4;
+    reinterpret_cast<uint4*>(dp)[0] = o0;
+    reinterpret_cast<uint4*>(dp)[1] = o1;
+  }
+}
+
+// dst row i = src row idx[i] (rows of row_vecs 16-byte vectors): per-window views of per-frame feature maps.
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx, uint4* __restrict__ dst,
+                                   long long n_rows, int row_vecs, int src_rows) {
+  const long long total = n_rows * row_vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row_vecs;
+    const int v = static_cast<int>(i - r * row_vecs);
+    int s = __ldg(idx + r);
+    s = s < 0 ? 0 : (s >= src_rows ? src_rows - 1 : s);   // clamped: an index outside the cache must not fault
+    dst[i] = __ldg(src + static_cast<long long>(s) * row_vecs + v);
+  }
+}
+
 // [N][THW][C] -> [N][C][THW] through a 32x33 shared tile.
 template <typename T>
 __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, long long cstride, float* __restrict__ dst, int c,
@@ -551,6 +605,53 @@ extern "C" int mspi_clip_frames_to_padded_nhwc4(const float* src, void* dst, int
     MSPI_CHECK_ARG(m.map[j] >= 0 && m.map[j] < t, "frame_map[%d] = %d outside the clip", j, m.map[j]);
   }
   return clip_to_padded(src, dst, n, t, h, w, pad_t, pad_l, hp, wp, m, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mspi_clip_u8_to_padded_nhwc4(const void* src, void* dst, int n, int t, int h, int w, int pad_t, int pad_l,
+                                            int hp, int wp, const int32_t* frame_map, int t_out, int dst_frames_per_clip,
+                                            int dst_frame0, const float* mean3, const float* std3, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(src && dst && mean3 && std3 && n > 0 && t > 0 && t <= 32 && h > 0 && w > 0, "mspi_clip_u8_to_padded_nhwc4: bad argument");
+  MSPI_CHECK_ARG(w % 4 == 0 && pad_l % 2 == 0 && wp % 2 == 0 && hp >= h + pad_t && wp >= w + pad_l,
+                 "mspi_clip_u8_to_padded_nhwc4: w %% 4, even pad_l / wp and hp >= h+pad_t, wp >= w+pad_l required");
+  MSPI_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  ClipMap m;
+  if (frame_map == nullptr) {
+    m.t_out = t; m.dst_fpc = t; m.dst_f0 = 0;
+    for (int j = 0; j < 32; ++j) m.map[j] = j < t ? j : 0;
+  } else {
+    MSPI_CHECK_ARG(t_out >= 1 && t_out <= 32 && dst_frame0 >= 0 && dst_frame0 + t_out <= dst_frames_per_clip, "bad frame map");
+    m.t_out = t_out; m.dst_fpc = dst_frames_per_clip; m.dst_f0 = dst_frame0;
+    for (int j = 0; j < 32; ++j) {
+      m.map[j] = j < t_out ? frame_map[j] : 0;
+      MSPI_CHECK_ARG(m.map[j] >= 0 && m.map[j] < t, "frame_map[%d] = %d outside the clip", j, m.map[j]);
+    }
+  }
+  NormParams np;
+  for (int c = 0; c < 3; ++c) { np.mean[c] = mean3[c]; np.std[c] = std3[c]; }
+  const long long total = static_cast<long long>(n) * m.t_out * h * (w / 4);
+  clip_u8_to_padded_nhwc4_kernel<<<grid_for(total), kBlock, 0, stream>>>(static_cast<const uint8_t*>(src),
+                                                                         static_cast<__nv_bfloat16*>(dst), n, t, h, w, pad_t,
+                                                                         pad_l, hp, wp, m, np);
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
+}
+
+extern "C" int mspi_gather_rows(const void* src, const int32_t* idx, void* dst, int64_t n_rows, int64_t row_bytes,
+                                int64_t src_rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(src && idx && dst && n_rows > 0 && row_bytes > 0 && src_rows > 0, "mspi_gather_rows: bad argument");
+  MSPI_CHECK_ARG(row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+                 "mspi_gather_rows: rows must be multiples of 16 bytes, 16-byte aligned");
+  MSPI_CHECK_ARG(row_bytes / 16 < (1ll << 31) && src_rows < (1ll << 31), "mspi_gather_rows: row too long");
+  if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
+  const int row_vecs = static_cast<int>(row_bytes / 16);
+  gather_rows_kernel<<<grid_for(n_rows * row_vecs), kBlock, 0, stream>>>(static_cast<const uint4*>(src), idx,
+                                                                          static_cast<uint4*>(dst), n_rows, row_vecs,
+                                                                          static_cast<int>(src_rows));
+  MSPI_LAUNCH_CHECK();
+  return MSPI_OK;
 }
 
 extern "C" int mspi_ndhwc_to_ncdhw(const void* src, int src_dtype, int64_t src_cstride, float* dst, int n, int c,

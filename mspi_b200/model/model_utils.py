@@ -223,24 +223,70 @@ class _SaliencyBase(nn.Module):
         self._plans.clear()
         self._wcache.clear()
 
-    def plan_for(self, clips: torch.Tensor) -> ForwardPlan:
-        b, c, t, h, w = clips.shape
+    def plan_for(self, clips: torch.Tensor, mode: str = "full") -> ForwardPlan:
+        """The plan for this input: fp32 clips [B,3,T,H,W] (the reference's contract) or uint8 frames [B,T,H,W,3]."""
+        u8 = clips.dtype == torch.uint8
+        if u8:
+            b, t, h, w, c = clips.shape
+        else:
+            b, c, t, h, w = clips.shape
         if c != 3:
-            raise RuntimeError(f"expected clips [B,3,T,H,W], got {tuple(clips.shape)}")
-        if t != self.cfg.DATA.NUM_FRAMES:
+            raise RuntimeError(f"expected clips [B,3,T,H,W] (fp32) or [B,T,H,W,3] (uint8), got {tuple(clips.shape)}")
+        if mode != "image_encoder" and t != self.cfg.DATA.NUM_FRAMES:
             raise RuntimeError(f"clip has {t} frames, cfg.DATA.NUM_FRAMES is {self.cfg.DATA.NUM_FRAMES}")
-        key = (b, t, h, w, clips.device.index, self.use_cuda_graph, self.keep_taps)
+        graph = self.use_cuda_graph and mode == "full"
+        key = (mode, u8, b, t, h, w, clips.device.index, graph, self.keep_taps)
         plan = self._plans.get(key)
         if plan is None:
             m = self.cfg.MODEL
             plan = ForwardPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL),
                                lateral_stride=tuple(m.LATERAL_STRIDE), pool_stride=m.S3D.POOL_STRIDE,
                                device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER,
-                               weight_cache=self._wcache.setdefault(clips.device.index, {}))
-            if self.use_cuda_graph:
+                               weight_cache=self._wcache.setdefault(clips.device.index, {}), mode=mode, input_u8=u8)
+            if graph:
                 plan.capture()
             self._plans[key] = plan
         return plan
+
+    # -- per-frame image-encoder cache (sliding-window inference, inference.py:120-150) ---------------------------
+    @torch.no_grad()
+    def encode_frames(self, frames: torch.Tensor, chunk: int = 128):
+        """The image saliency encoder (model_utils.py:357-385: ConvNeXt-T + smooth convs) on N frames, once per frame:
+        frames fp32 [N,3,H,W] (normalised) or uint8 [N,H,W,3].  Returns the bf16 channels-last maps
+        (o1 [N,H/16,W/16,96], o0 [N,H/32,W/32,320]) that forward_cached() indexes."""
+        if not frames.is_cuda:
+            raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        n = frames.shape[0]
+        u8 = frames.dtype == torch.uint8
+        h, w = (frames.shape[1], frames.shape[2]) if u8 else (frames.shape[2], frames.shape[3])
+        o1 = torch.empty((n, h // 16, w // 16, 96), dtype=torch.bfloat16, device=frames.device)
+        o0 = torch.empty((n, h // 32, w // 32, 320), dtype=torch.bfloat16, device=frames.device)
+        with torch.cuda.device(frames.device):
+            for i in range(0, n, chunk):
+                part = frames[i:i + chunk].contiguous()
+                k = part.shape[0]
+                x = part.view(k, 1, h, w, 3) if u8 else part.float().view(k, 3, 1, h, w)
+                plan = self.plan_for(x, mode="image_encoder")
+                f1, f0 = plan.run(x, None)
+                o1[i:i + k].copy_(f1.buf.view(k, h // 16, w // 16, 96))
+                o0[i:i + k].copy_(f0.buf.view(k, h // 32, w // 32, 320))
+        return o1, o0
+
+    @torch.no_grad()
+    def forward_cached(self, clips, audios, feats, frame_index):
+        """forward() with the image-encoder features of every frame taken from `feats` = encode_frames(...) instead of being
+        recomputed: frame_index [B,T] (int) names, for window b and position t, the row of the cache holding that frame
+        (a time-flipped window simply lists its frames backwards).  Bit-identical to forward() on the same clips."""
+        if not clips.is_cuda:
+            raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("forward_cached() is an inference path: call model.eval()")
+        clips = clips.contiguous() if clips.dtype == torch.uint8 else clips.contiguous().float()
+        audios = audios.contiguous().float() if (self.has_audio and audios is not None) else None
+        with torch.cuda.device(clips.device):
+            plan = self.plan_for(clips, mode="cached")
+            out, loss = plan.run(clips, audios, feats, frame_index.to(clips.device))
+            return out.clone(), (loss[0].clone() if self.has_audio else 0)
 
     # -- training step (engine_train.py:27-76) ------------------------------------------------------
     def training_plan(self, clips: torch.Tensor, lr: float = 1e-4, gamma: float = 1.0, world_size: int = 1):
@@ -294,7 +340,8 @@ class _SaliencyBase(nn.Module):
         if self.training:
             raise RuntimeError("forward() is the inference path (eval-mode BatchNorm): call model.eval(); a training step "
                                "(train-mode forward + loss + backward + AdamW) is model.train_step(clips, audios, labels)")
-        clips = clips.contiguous().float()
+        # fp32 [B,3,T,H,W] normalised clips (the reference's contract) or uint8 [B,T,H,W,3] frames (normalised on the device)
+        clips = clips.contiguous() if clips.dtype == torch.uint8 else clips.contiguous().float()
         if audios is not None:
             audios = audios.contiguous().float()
         with torch.cuda.device(clips.device):

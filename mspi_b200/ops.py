@@ -477,6 +477,51 @@ def clip_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int,
     return run
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # timm.data.constants (inference.py:8,161)
+
+
+def clip_u8_to_padded(holder: dict, key: str, frames: torch.Tensor, n: int, t: int, h: int, w: int,
+                      mean=IMAGENET_MEAN, std=IMAGENET_STD, frame_map: Optional[Sequence[int]] = None,
+                      t_pad: int = 0) -> Callable[[], None]:
+    """uint8 frames [N,T,H,W,3] (holder[key] at run time) -> the same padded bf16 frames as clip_to_padded, with
+    ToTensor + Normalize (inference.py:154-165) folded in (fp32, IEEE division: bit-identical to converting the normalised
+    fp32 clip)."""
+    lib = _lib.load()
+    hp, wp = h + PAD_EXTRA, w + PAD_EXTRA
+    fm = list(range(t)) if frame_map is None else [f % t for f in frame_map]
+    t_out = len(fm)
+    fpc = t_out + 2 * t_pad
+    assert tuple(frames.shape) == (n * fpc, hp, wp, 4) and frames.dtype == torch.bfloat16
+    fp = _ptr(frames)
+    arr = (C.c_int32 * t_out)(*fm)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+
+    def run(_keep=(frames, arr, m3, s3)):
+        src = holder[key]
+        _lib.check(lib.mspi_clip_u8_to_padded_nhwc4(_ptr(src), fp, n, t, h, w, PAD_T, PAD_L, hp, wp, C.cast(arr, C.c_void_p), t_out,
+                                                    fpc, t_pad, C.cast(m3, C.c_void_p), C.cast(s3, C.c_void_p), _stream()),
+                   "clip_u8_to_padded_nhwc4")
+
+    return run
+
+
+def gather_rows(holder: dict, key: str, index: torch.Tensor, dst: torch.Tensor, row_elems: int) -> Callable[[], None]:
+    """dst[i] = holder[key][index[i]] over rows of `row_elems` elements (per-window views of the per-frame feature cache)."""
+    lib = _lib.load()
+    assert index.dtype == torch.int32 and index.is_cuda and dst.is_contiguous()
+    n_rows = index.numel()
+    row_bytes = row_elems * dst.element_size()
+    assert dst.numel() == n_rows * row_elems
+
+    def run(_keep=(index, dst)):
+        src = holder[key]
+        assert src.dtype == dst.dtype and src.is_contiguous() and src.numel() % row_elems == 0
+        _lib.check(lib.mspi_gather_rows(_ptr(src), _ptr(index), _ptr(dst), n_rows, row_bytes, src.numel() // row_elems, _stream()),
+                   "gather_rows")
+
+    return run
+
+
 def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale, shift, k: int, stride: int, pad: int,
               act: int, y: "Act", name: str = "stem", clips: int = 0, allow_wide: bool = True) -> Callable[[], None]:
     """(1,k,k)/stride conv with Cin=3 straight off the padded 4-channel frames (no im2col buffer).

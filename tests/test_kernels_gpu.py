@@ -231,6 +231,32 @@ def test_clip_frame_map_and_time_padding():
     assert torch.equal(v[:, 2:-2, ops.PAD_T:ops.PAD_T + h, ops.PAD_L:ops.PAD_L + w, :3], _bf(clip).permute(0, 2, 3, 4, 1))
 
 
+def test_clip_u8_conversion_is_bit_exact_and_gather_rows():
+    """mspi_clip_u8_to_padded_nhwc4 == mspi_clip_to_padded_nhwc4 of the host-normalised fp32 clip (bit for bit), with and
+    without a frame map; mspi_gather_rows copies / clamps rows."""
+    from mspi_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    n, t, h, w = 2, 8, 20, 24
+    u8 = torch.randint(0, 256, (n, t, h, w, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(ops.IMAGENET_MEAN).view(1, 1, 1, 1, 3), torch.tensor(ops.IMAGENET_STD).view(1, 1, 1, 1, 3)
+    clip = ((u8.float() / 255.0 - mean) / std).permute(0, 4, 1, 2, 3).contiguous().cuda()
+    for fmap, tpad in ((None, 0), ([0, 3, 6, 7], 0), (None, 2)):
+        t_out = t if fmap is None else len(fmap)
+        shape = (n * (t_out + 2 * tpad), h + ops.PAD_EXTRA, w + ops.PAD_EXTRA, 4)
+        a = torch.zeros(shape, dtype=torch.bfloat16, device="cuda")
+        b = torch.zeros(shape, dtype=torch.bfloat16, device="cuda")
+        ops.clip_to_padded({"c": clip}, "c", a, n, t, h, w, fmap, tpad)()
+        ops.clip_u8_to_padded({"c": u8.cuda()}, "c", b, n, t, h, w, frame_map=fmap, t_pad=tpad)()
+        torch.cuda.synchronize()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    src = torch.randn(11, 40, generator=g).to(torch.bfloat16).cuda()
+    idx = torch.tensor([3, 3, 0, 10, 7, -2, 99], dtype=torch.int32, device="cuda")
+    dst = torch.empty(7, 40, dtype=torch.bfloat16, device="cuda")
+    ops.gather_rows({"s": src}, "s", idx, dst, 40)()
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src[idx.clamp(0, 10).long()])
+
+
 def test_stem_conv_temporal_taps_per_clip():
     """SlowFast fast stem (5,7,7)/s(1,2,2) p(2,3,3), 3->8 (stem_helper.py:128-204): 35 taps, one launch per clip."""
     from mspi_b200 import ops

@@ -127,6 +127,51 @@ def test_forward_parity_at_the_benchmarked_configuration():
     assert (out2[perm] - out).abs().max() < 1e-4
 
 
+def _small_model(encoder="s3d", seed=7):
+    from oracle import mspi_oracle as orc
+    from tests.parity import build_product_model
+    sd = orc.make_state_dict(seed, "calibrated", encoder=encoder)
+    return build_product_model(sd, True, encoder=encoder)
+
+
+def test_feature_cache_matches_plain_forward_bit_for_bit():
+    """Row f1: sliding windows over a 40-frame synthetic video.  The image encoder runs once per frame
+    (model.encode_frames), every window — plain and time-flipped — indexes the cache (model.forward_cached); the maps must
+    equal the plain forward's, which re-encodes all 16 frames of every window (inference.py:120-150), bit for bit."""
+    model = _small_model()
+    g = torch.Generator().manual_seed(3)
+    n, T, H, W = 40, 16, 64, 96
+    frames = torch.randn(n, 3, H, W, generator=g)
+    cache = model.encode_frames(frames.cuda(), chunk=16)      # 3 chunks, the last one ragged
+    assert cache[0].shape == (n, H // 16, W // 16, 96) and cache[1].shape == (n, H // 32, W // 32, 320)
+    jobs = [(s, False) for s in range(0, n - T + 1, 3)] + [(0, True), (5, True), (24, True)]
+    for j0 in range(0, len(jobs), 4):
+        chunk = jobs[j0:j0 + 4]
+        clips = torch.stack([torch.flip(frames[s:s + T].permute(1, 0, 2, 3), [1]) if f else frames[s:s + T].permute(1, 0, 2, 3)
+                             for s, f in chunk]).contiguous().cuda()
+        aud = torch.randn(len(chunk), 1, 257, 111, generator=g).cuda()
+        index = torch.tensor([[s + (T - 1 - t if f else t) for t in range(T)] for s, f in chunk], dtype=torch.int32)
+        ref, ref_loss = model(clips, aud)
+        got, loss = model.forward_cached(clips, aud, cache, index)
+        assert torch.equal(got, ref), (got - ref).abs().max()
+        assert abs(float(loss) - float(ref_loss)) < 1e-6   # SimSiam loss: an atomic sum over (sample, pair) blocks
+
+
+def test_forward_accepts_uint8_frames():
+    """uint8 [B,T,H,W,3] frames, normalised on the device (ToTensor + Normalize of inference.py:154-165 folded into the clip
+    conversion kernel), give exactly the forward of the host-normalised fp32 clip."""
+    from mspi_b200 import ops
+    model = _small_model(seed=8)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (2, 16, 64, 96, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(ops.IMAGENET_MEAN).view(1, 1, 1, 1, 3), torch.tensor(ops.IMAGENET_STD).view(1, 1, 1, 1, 3)
+    clips = ((u8.float() / 255.0 - mean) / std).permute(0, 4, 1, 2, 3).contiguous()
+    aud = torch.randn(2, 1, 257, 111, generator=g)
+    ref, _ = model(clips.cuda(), aud.cuda())
+    got, _ = model(u8.cuda(), aud.cuda())
+    assert torch.equal(got, ref), (got - ref).abs().max()
+
+
 def test_inference_entry_point_on_synthetic_dataset(tmp_path):
     """inference.py (the reference's entry point, same CLI / dataset layout / output naming) end to end on a tiny
     synthetic AVAD-style dataset: 33 frames -> 18 forward windows + 15 time-flipped ones = one image per frame."""
