@@ -16,15 +16,15 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-int num_sms() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    sms = n;
-  }
-  return sms;
+int num_sms() {   // of the CURRENT device (cached per device: one process may drive several GPUs)
+  static int sms[64];
+  static bool known[64];
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64 && known[dev]) return sms[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64) { sms[dev] = n; known[dev] = true; }
+  return n;
 }
 
 }  // namespace mspi

@@ -8,7 +8,7 @@
 namespace mspi {
 namespace {
 
-__constant__ float kGauss11[11];
+struct Gauss11 { float w[11]; };   // passed as a kernel argument: valid on whichever device the launch goes to
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
@@ -17,7 +17,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 // Separable 11-tap blur through a shared tile, then exp.  Block = 32x8 outputs.
-__global__ void blur_exp_kernel(const float* __restrict__ x, float* __restrict__ y, int h, int w) {
+__global__ void blur_exp_kernel(const float* __restrict__ x, float* __restrict__ y, int h, int w, const Gauss11 kG) {
+  const float* kGauss11 = kG.w;
   constexpr int TW = 32, TH = 8, R = 5;
   __shared__ float tile[TH + 2 * R][TW + 2 * R];
   __shared__ float rows[TH + 2 * R][TW];
@@ -96,15 +97,12 @@ extern "C" int mspi_postprocess_maps(const float* log_maps, uint8_t* out, float*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(log_maps && out && work && b > 0 && h > 5 && w > 5 && oh > 0 && ow > 0, "mspi_postprocess_maps: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  static bool init = false;
-  if (!init) {
-    // cv2.getGaussianKernel(11, sigma=2.0): exp(-(i-5)^2 / (2 sigma^2)), normalised to sum 1
+  // cv2.getGaussianKernel(11, sigma=2.0): exp(-(i-5)^2 / (2 sigma^2)), normalised to sum 1
+  Gauss11 kG;
+  {
     double g[11], s = 0.0;
     for (int i = 0; i < 11; ++i) { g[i] = exp(-(i - 5) * (i - 5) / 8.0); s += g[i]; }
-    float gf[11];
-    for (int i = 0; i < 11; ++i) gf[i] = static_cast<float>(g[i] / s);
-    MSPI_CUDA(cudaMemcpyToSymbol(kGauss11, gf, sizeof(gf)));
-    init = true;
+    for (int i = 0; i < 11; ++i) kG.w[i] = static_cast<float>(g[i] / s);
   }
   // work: [b*h*w] blurred+exp | [b*oh*ow] resized | [2*b] min/max bit patterns
   float* blurred = work;
@@ -112,7 +110,7 @@ extern "C" int mspi_postprocess_maps(const float* log_maps, uint8_t* out, float*
   unsigned int* mm = reinterpret_cast<unsigned int*>(resized + static_cast<long long>(b) * oh * ow);
   {
     dim3 grid((w + 31) / 32, (h + 7) / 8, b), block(32, 8);
-    blur_exp_kernel<<<grid, block, 0, stream>>>(log_maps, blurred, h, w);
+    blur_exp_kernel<<<grid, block, 0, stream>>>(log_maps, blurred, h, w, kG);
     MSPI_LAUNCH_CHECK();
   }
   MSPI_CUDA(cudaMemsetAsync(mm, 0xFF, sizeof(unsigned int) * 2 * b, stream));  // min <- 0xFFFFFFFF; max fixed below

@@ -89,12 +89,12 @@ def forward_sharded(forward: Callable, clips: torch.Tensor, audios: Optional[tor
         loss = torch.zeros(1, dtype=torch.float32, device=clips.device)
     full = gather_maps(maps, n, group)
     dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-    return full, loss[0] / n
+    return full, loss[0] / max(n, 1)
 
 
 # ------------------------------------------------------------------------------------------ training (BASELINE config 5)
 def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> float:
-    """The training step's only collective: SUM all-reduce of the flat fp32 gradient buffer (411 tensors, 184 MB for
+    """The training step's only per-step collective: SUM all-reduce of the flat fp32 gradient buffer (411 tensors, 184 MB for
     MSPI-S3D) in one call — NCCL on GPUs, gloo in the CPU tests.  Returns the scale (1 / world_size) the optimiser kernel
     applies (`mspi_adamw_step(..., grad_scale)`), which together reproduce DistributedDataParallel's gradient averaging
     of per-rank batch-mean losses.  BatchNorm statistics stay per rank (the reference has no SyncBN)."""
@@ -102,6 +102,38 @@ def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> float:
     if world > 1:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world
+
+
+def broadcast_training_state(state, src: int = 0, group=None):
+    """What DistributedDataParallel does when it wraps a module: every rank takes rank `src`'s parameters and buffers.  The
+    decoder, SyncBlock and heads start from a random init (only the encoders are pretrained), so ranks that were not seeded
+    identically would otherwise train different replicas on averaged gradients.  One broadcast for the flat fp32 parameter
+    buffer, one per frozen tensor / BatchNorm buffer; the AdamW moments and the step count follow."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.broadcast(state.flat_p, src=src, group=group)
+    dist.broadcast(state.flat_m, src=src, group=group)
+    dist.broadcast(state.flat_v, src=src, group=group)
+    for k in sorted(state.live):
+        if k in state.offs:
+            continue            # a view into flat_p
+        t = state.live[k]
+        if t.is_floating_point() or t.dtype in (torch.int64, torch.int32):
+            dist.broadcast(t, src=src, group=group)
+    step = torch.tensor([state.step_count], dtype=torch.int64, device=state.flat_p.device)
+    dist.broadcast(step, src=src, group=group)
+    state.step_count = int(step.item())
+
+
+def parameters_checksum(state, group=None) -> bool:
+    """True when every rank holds the same parameters (sum and sum of squares of the flat buffer agree bit for bit)."""
+    s = torch.stack([state.flat_p.double().sum(), (state.flat_p.double() ** 2).sum()])
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return True
+    lo, hi = s.clone(), s.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool(torch.equal(lo, hi))
 
 
 def flat_layout(shapes, align: int = 4):

@@ -216,12 +216,14 @@ class _SaliencyBase(nn.Module):
     def load_state_dict(self, *a, **k):
         self._plans.clear()  # packed weights are derived from the parameters
         self._wcache.clear()
+        self._train_state = None   # the fp32 master copy / AdamW moments belong to the old parameters (see training_state)
         return super().load_state_dict(*a, **k)
 
     def invalidate_plans(self):
         """Call after mutating parameters in place (the packed bf16 weights are cached per input shape)."""
         self._plans.clear()
         self._wcache.clear()
+        self._train_state = None
 
     def plan_for(self, clips: torch.Tensor, mode: str = "full") -> ForwardPlan:
         """The plan for this input: fp32 clips [B,3,T,H,W] (the reference's contract) or uint8 frames [B,T,H,W,3]."""
@@ -289,9 +291,23 @@ class _SaliencyBase(nn.Module):
             return out.clone(), (loss[0].clone() if self.has_audio else 0)
 
     # -- training step (engine_train.py:27-76) ------------------------------------------------------
-    def training_plan(self, clips: torch.Tensor, lr: float = 1e-4, gamma: float = 1.0, world_size: int = 1):
-        """The TrainPlan (mspi_b200/train_engine.py) for this batch shape; it owns the fp32 master copy of the trainable
-        parameters (flat buffer, AdamW moments) from the moment it is created — `sync_from_training()` copies them back."""
+    def training_state(self, device):
+        """The TrainState (fp32 master parameters, AdamW moments, step count, live BatchNorm buffers) every training plan of
+        this model shares.  Created from the module's parameters at the first training call; load_state_dict() and
+        invalidate_plans() drop it (the next call starts again from the module's parameters with zero moments — restore
+        moments with load_optimizer_state_dict())."""
+        from ..train_engine import TrainState
+        st = getattr(self, "_train_state", None)
+        if st is None or st.device != device:
+            with torch.cuda.device(device):
+                st = TrainState(self.state_dict(), device)
+            self._train_state = st
+        return st
+
+    def training_plan(self, clips: torch.Tensor, lr: float = 1e-4, gamma: float = 1.0, world_size: int = 1,
+                      betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        """The TrainPlan (mspi_b200/train_engine.py) for this batch shape.  Plans of different shapes share one TrainState, so
+        a tail batch or a second resolution continues from the current weights, moments and step count."""
         from ..train_engine import TrainPlan
         if self.cfg.MODEL.MOTION_ENCODER != "s3d":
             raise NotImplementedError("the training step is implemented for the S3D motion encoder (BASELINE config 5)")
@@ -301,45 +317,72 @@ class _SaliencyBase(nn.Module):
         if plan is None:
             m = self.cfg.MODEL
             with torch.cuda.device(clips.device):
-                plan = TrainPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lr=lr, gamma=gamma, device=clips.device,
-                                 lateral_bool=tuple(m.LATERAL_BOOL), lateral_stride=tuple(m.LATERAL_STRIDE),
-                                 world_size=world_size)
+                plan = TrainPlan(self.training_state(clips.device), b, t, h, w, audio=self.has_audio, lr=lr, gamma=gamma,
+                                 device=clips.device, lateral_bool=tuple(m.LATERAL_BOOL), lateral_stride=tuple(m.LATERAL_STRIDE),
+                                 world_size=world_size, pool_stride=m.S3D.POOL_STRIDE, betas=betas, eps=eps,
+                                 weight_decay=weight_decay)
             self._plans[key] = plan
-        plan.lr, plan.gamma = lr, gamma
+        plan.lr, plan.betas, plan.adam_eps, plan.weight_decay, plan.world_size = lr, betas, eps, weight_decay, world_size
+        plan.set_gamma(gamma)
+        self._last_train_plan = plan
         return plan
 
-    def train_step(self, clips, audios, labels, lr: float = 1e-4, gamma: float = 1.0, allreduce=None, world_size: int = 1):
+    def train_step(self, clips, audios, labels, lr: float = 1e-4, gamma: float = 1.0, allreduce=None, world_size: int = 1,
+                   betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
         """One optimisation step of engine_train.py:27-76 — `model.train(); model.frozen_encoder()` forward,
-        `SalLoss()(output, label) + gamma*loss_va`, backward, (gradient all-reduce,) AdamW(lr, weight_decay=0).
+        `SalLoss()(output, label) + gamma*loss_va`, backward, (gradient all-reduce,) AdamW(lr, betas, eps, weight_decay).
         Returns a device tensor [loss, kld, cc, loss_va]."""
         if not clips.is_cuda:
             raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         with torch.cuda.device(clips.device):
-            plan = self.training_plan(clips, lr, gamma, world_size)
+            plan = self.training_plan(clips, lr, gamma, world_size, betas, eps, weight_decay)
             audios = audios.contiguous().float() if (self.has_audio and audios is not None) else None
             return plan.train_step(clips.contiguous().float(), audios, labels.contiguous().float(), allreduce).clone()
 
     def sync_from_training(self):
-        """Copy the trained parameters and BatchNorm buffers of the training plan back into this module."""
-        plans = [p for k, p in self._plans.items() if k[0] == "train"]
-        if not plans:
+        """Copy the trained parameters and BatchNorm buffers of the shared training state back into this module."""
+        st = getattr(self, "_train_state", None)
+        if st is None:
             return
-        sd = plans[-1].state_dict()
         with torch.no_grad():
             own = super().state_dict()
-            for k, v in sd.items():
+            for k, v in st.live.items():
                 if k in own:
                     own[k].copy_(v)
         for k in [k for k in self._plans if k[0] != "train"]:
             del self._plans[k]
+        self._wcache.clear()
+
+    def optimizer_state_dict(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> dict:
+        """AdamW state of the training step in torch.optim.AdamW.state_dict() form (per-parameter `step` / `exp_avg` /
+        `exp_avg_sq` in named_parameters() order of the trainable tensors): what the reference's checkpoints store under
+        'optimizer' (utils/optim.py:40-50) and `torch.optim.AdamW.load_state_dict` accepts."""
+        st = getattr(self, "_train_state", None)
+        if st is None:
+            return {"state": {}, "param_groups": []}
+        return st.optimizer_state_dict(lr, betas, eps, weight_decay)
+
+    def load_optimizer_state_dict(self, osd: dict, device=None):
+        """Restore AdamW moments and the step count (a torch.optim.AdamW.state_dict()) into the shared training state."""
+        dev = device if device is not None else next(self.parameters()).device
+        self.training_state(dev).load_optimizer_state_dict(osd)
 
     def _forward(self, clips, audios):
         if not clips.is_cuda:
             raise RuntimeError("mspi_b200 runs on CUDA (sm_100a) only: move the model inputs to the GPU; "
                                "there is no CPU fallback")
         if self.training:
-            raise RuntimeError("forward() is the inference path (eval-mode BatchNorm): call model.eval(); a training step "
-                               "(train-mode forward + loss + backward + AdamW) is model.train_step(clips, audios, labels)")
+            # engine_train.py:37 `output, loss_va = model(imgs, audio)` under model.train(); model.frozen_encoder(): the
+            # train-mode forward (batch-statistics BatchNorm outside the frozen encoders, running buffers updated).  The
+            # tensors carry no autograd graph — loss.backward() has no counterpart here; model.train_step() does forward,
+            # loss, backward and AdamW in one call.
+            if clips.dtype == torch.uint8:
+                raise RuntimeError("the training plan takes normalised fp32 clips")
+            with torch.cuda.device(clips.device):
+                plan = self.training_plan(clips.float())
+                aud = audios.contiguous().float() if (self.has_audio and audios is not None) else None
+                out, loss = plan.forward_train(clips.contiguous().float(), aud)
+                return out.clone(), loss[0].clone()
         # fp32 [B,3,T,H,W] normalised clips (the reference's contract) or uint8 [B,T,H,W,3] frames (normalised on the device)
         clips = clips.contiguous() if clips.dtype == torch.uint8 else clips.contiguous().float()
         if audios is not None:

@@ -98,3 +98,120 @@ def test_train_step_visual_only_model():
     assert abs(r["loss"] - r["ref_loss"]) <= 1e-2 * max(1.0, abs(r["ref_loss"])), (r["loss"], r["ref_loss"])
     assert r["loss_va"] == 0.0 and math.isfinite(r["grad_norm"]) and r["adamw_err"] < 1e-6
     assert abs(r["grad_norm"] - r["ref_grad_norm"]) <= 0.2 * r["ref_grad_norm"]
+
+
+def _train_fixture(seed=5, h=64, w=64, b=2):
+    import torch
+    from oracle import mspi_oracle as orc
+    from tests.parity import build_product_model
+    sd = orc.make_state_dict(seed, "calibrated")
+    model = build_product_model(sd)
+    clips, aud = orc.make_inputs(b, h, w, 2023)
+    gt, _ = orc.make_gt(orc.forward(sd, clips, aud)[0])
+    return sd, model, clips.cuda(), aud.cuda(), gt.cuda()
+
+
+def test_training_state_is_shared_across_batch_shapes():
+    """a second input shape must continue from the current weights / moments / step count, not from a stale copy
+    of the module with zero moments; sync_from_training() returns the state every plan trained."""
+    import torch
+    from oracle import mspi_oracle as orc
+    sd, model, clips, aud, gt = _train_fixture()
+    model.train()
+    model.train_step(clips, aud, gt)
+    model.train_step(clips, aud, gt)
+    c2, a2 = orc.make_inputs(1, 64, 96, 7)
+    g2, _ = orc.make_gt(orc.forward(sd, c2, a2)[0])
+    p_before = model._train_state.flat_p.clone()
+    model.train_step(c2.cuda(), a2.cuda(), g2.cuda())
+    plans = [p for k, p in model._plans.items() if k[0] == "train"]
+    assert len(plans) == 2 and plans[0].flat_p.data_ptr() == plans[1].flat_p.data_ptr()
+    assert plans[0].flat_m.data_ptr() == plans[1].flat_m.data_ptr()
+    assert model._train_state.step_count == 3 and plans[1].step_count == 3
+    moved = (model._train_state.flat_p - p_before).abs().max().item()
+    assert 0 < moved <= 1.1e-4          # one more AdamW step on top of the first two, not a restart from step 1
+    model.sync_from_training()
+    k = "readout.1.weight"
+    assert torch.equal(model.state_dict()[k], model._train_state.live[k])
+
+
+def test_optimizer_state_round_trips_through_torch_adamw():
+    """the AdamW state is exported in torch.optim.AdamW.state_dict() form (what the reference checkpoints under
+    'optimizer'), loads into a real torch AdamW over the trainable parameters, and restores moments + step count so that a
+    resumed run takes the same next step instead of restarting the bias correction."""
+    import torch
+    from tests.parity import build_product_model
+    sd, model, clips, aud, gt = _train_fixture(seed=6)
+    model.train()
+    for _ in range(2):
+        model.train_step(clips, aud, gt)
+    osd = model.optimizer_state_dict()
+    model.sync_from_training()
+    weights2 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    trainable = [p for n, p in model.named_parameters() if not n.startswith(("audnet.", "image_encoder."))]
+    assert len(osd["state"]) == len(trainable) == 411
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0)
+    opt.load_state_dict(osd)                                   # torch accepts it
+    st0 = opt.state[trainable[0]]
+    assert float(st0["step"]) == 2.0 and st0["exp_avg"].shape == trainable[0].shape
+    # resume: a fresh model from (weights after step 2, optimizer.state_dict()) vs the original run's third step
+    model2 = build_product_model(weights2)
+    model2.train()
+    model2.load_optimizer_state_dict(opt.state_dict())
+    assert model2._train_state.step_count == 2
+    r3b = model2.train_step(clips, aud, gt)
+    r3a = model.train_step(clips, aud, gt)
+    assert torch.allclose(r3a, r3b, rtol=1e-4, atol=1e-5), (r3a, r3b)
+    # (Adam turns the run-to-run noise of near-zero gradients — atomics in the BatchNorm statistics — into O(lr) differences
+    #  for a few parameters, so the comparison is on the mean step, against a restart without the state)
+    d_resumed = (model._train_state.flat_p - model2._train_state.flat_p).abs().mean().item()
+    model3 = build_product_model(weights2)
+    model3.train()
+    model3.train_step(clips, aud, gt)        # no optimizer state: bias correction restarts at step 1, |update| = lr
+    d_restart = (model._train_state.flat_p - model3._train_state.flat_p).abs().mean().item()
+    assert d_resumed < 0.1 * d_restart, (d_resumed, d_restart)
+
+
+def test_train_mode_forward_returns_map_and_loss_va():
+    """engine_train.py:37: `output, loss_va = model(imgs, audio)` under model.train(); model.frozen_encoder() — the train-mode
+    forward (batch-statistics BatchNorm): equals the map the training step's own forward produces, sums to one, moves the
+    BatchNorm running buffers, and differs from the eval-mode map."""
+    import torch
+    sd, model, clips, aud, gt = _train_fixture(seed=9)
+    model.eval()
+    out_eval, _ = model(clips, aud)
+    model.train()
+    model.frozen_encoder()
+    out, loss_va = model(clips, aud)
+    assert out.shape == (2, 64, 64) and loss_va.dim() == 0 and torch.isfinite(out).all()
+    assert (out.exp().sum((1, 2)) - 1).abs().max() < 1e-3
+    assert (out - out_eval).abs().max() > 1e-4                  # batch statistics, not the running ones
+    plan = model._last_train_plan
+    plan.forward_backward(clips, aud, gt)
+    assert (plan.out - out).abs().max() < 1e-5                  # same kernels (BatchNorm batch statistics via atomics)
+    model.sync_from_training()
+    key = "visnet.base1.0.bn_s.running_mean"
+    assert (model.state_dict()[key].cpu() - sd[key]).abs().max() > 0
+
+
+def test_train_one_epoch_with_a_real_torch_optimizer():
+    """train_one_epoch reads AdamW's hyper-parameters from the optimizer, returns the reference's meter names and leaves the
+    optimizer holding the real moments (so `optimizer.state_dict()` checkpoints them, utils/optim.py:40-50)."""
+    import copy
+    import torch
+    from mspi_b200.engine_train import train_one_epoch, validation_one_epoch
+    from mspi_b200.utils.loss import SalLoss
+    sd, model, clips, aud, gt = _train_fixture(seed=10)
+    cfg = copy.deepcopy(model.cfg)
+    cfg.DATA.USE_SOUND = True
+    trainable = [p for n, p in model.named_parameters() if not n.startswith(("audnet.", "image_encoder."))]
+    opt = torch.optim.AdamW(trainable, lr=2e-4, weight_decay=0)
+    crit = SalLoss()
+    batch = (clips.cpu(), aud.cpu(), gt.cpu())
+    stats = train_one_epoch(model, crit, [batch] * 2, opt, torch.device("cuda"), 0, cfg, start_steps=0, gamma=1.0)
+    assert set(stats) >= {"loss", "kld", "cc", "sim", "nss", "lr", "min_lr", "weight_decay", "grad_norm"}
+    assert stats["lr"] == 2e-4 and stats["grad_norm"] > 0 and 0 < stats["sim"] < 1
+    assert len(opt.state) == 411 and float(opt.state[trainable[0]]["step"]) == 2.0
+    assert crit.log["sim"].count == 2
+    val = validation_one_epoch(model, [batch], torch.device("cuda"), cfg)
+    assert set(val) == {"loss", "kld", "cc", "sim"} and all(v == v for v in val.values())
