@@ -464,6 +464,21 @@ def run_train(args, rank, world, local):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (t2.item() / 1e3)
+    # ---- the step's only collective, timed alone: NCCL SUM all-reduce of the flat fp32 gradient buffer
+    allreduce_ms = None
+    if world > 1:
+        for _ in range(2):
+            allreduce(plan.flat_g)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            allreduce(plan.flat_g)
+        a1.record()
+        barrier()
+        ta = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_ms = ta.item()
     # ---- per-kernel breakdown of one step (CUDA events, eager replay), rank 0
     roofline, kinds = None, None
     if rank == 0:
@@ -537,6 +552,8 @@ def run_train(args, rank, world, local):
                         "d2h_bytes_per_step": 16},
                 "gpu_launches": launches * K, "launches_per_step": launches, "loss_last_step": loss_last,
                 "trainable_parameters": plan.n_params, "grad_allreduce_bytes": plan.n_flat * 4 if world > 1 else 0,
+                "grad_allreduce_ms": allreduce_ms,
+                "grad_allreduce_busbw_gbs": (plan.n_flat * 4 * 2 * (world - 1) / world / allreduce_ms / 1e6) if allreduce_ms else None,
                 "clocks": clocks.summary(), "roofline": roofline, "kernel_kinds": kinds,
                 "activation_bytes_allocated": plan.bytes_alloc}
         line["cpu_baseline"] = train_cpu_baseline(B) if (world == 1 and not args.no_cpu_baseline) else None

@@ -125,3 +125,34 @@ def test_host_tiling_and_packing_logic():
     sc, sh = ops.fold_bn(g, b, m, v, 1e-3, conv_bias=torch.ones(7))
     x = torch.randn(7)
     assert torch.allclose((x + 1 - m) / torch.sqrt(v + 1e-3) * g + b, x * sc + sh, atol=1e-5)
+
+
+def test_image_encoder_checkpoint_load_is_loud():
+    """model_utils.py:514 loads the image-encoder checkpoint with strict=False: a checkpoint whose keys do not match would
+    silently leave the encoder at random init.  The product reports matched / missing / unexpected counts, maps the plain
+    timm ConvNeXt key layout (stem.0 / stages.k.) onto the FeatureListNet names, and raises when nothing matches."""
+    import pytest
+    import torch
+    from mspi_b200.model.model_utils import StaticSaliencyModelConvNext, load_image_encoder_checkpoint
+    m = StaticSaliencyModelConvNext()
+    own = {k: v.clone() + 1 for k, v in m.state_dict().items()}
+    rep = load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), own, verbose=False)
+    assert rep["matched"] == rep["of"] == len(own) and not rep["missing"] and not rep["unexpected"]
+    plain = {}
+    for k, v in own.items():
+        k2 = k.replace("encoder.stem_0", "stem.0").replace("encoder.stem_1", "stem.1")
+        for i in range(4):
+            k2 = k2.replace(f"encoder.stages_{i}.", f"stages.{i}.")
+        plain[k2] = v
+    plain["head.fc.weight"] = torch.zeros(3)
+    tgt = StaticSaliencyModelConvNext()
+    rep = load_image_encoder_checkpoint(tgt, plain, verbose=False)
+    assert rep["matched"] == len(own) and rep["unexpected"] == ["head.fc.weight"]
+    assert torch.equal(tgt.state_dict()["encoder.stages_2.blocks.4.mlp.fc1.weight"], own["encoder.stages_2.blocks.4.mlp.fc1.weight"])
+    bad = dict(own)
+    bad["smooth_0.0.weight"] = torch.zeros(1, 2, 3, 3)
+    rep = load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), bad, verbose=False)
+    assert rep["shape_mismatch"] == ["smooth_0.0.weight"] and "smooth_0.0.weight" in rep["missing"]
+    with pytest.raises(RuntimeError):
+        load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), {"backbone.conv1.weight": torch.zeros(1)}, verbose=False)
+    assert load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), {}, verbose=False)["matched"] == 0   # the tests' empty file

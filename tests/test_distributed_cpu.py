@@ -127,3 +127,79 @@ def test_gradient_allreduce_matches_ddp_averaging_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert all(ok and scale == 0.5 for _, ok, scale in res), res
+
+
+# ------------------------------------------------------------------------------------------ DDP-style parameter broadcast
+def _small_sd(seed):
+    g = torch.Generator().manual_seed(seed)
+    return {"visnet.a.weight": torch.randn(6, 5, generator=g), "visnet.a.bn.weight": torch.randn(6, generator=g),
+            "visnet.a.bn.running_mean": torch.randn(6, generator=g), "visnet.a.bn.running_var": torch.rand(6, generator=g),
+            "visnet.a.bn.num_batches_tracked": torch.tensor(seed), "audnet.c.weight": torch.randn(3, 3, generator=g),
+            "readout.0.bias": torch.randn(7, generator=g)}
+
+
+def _bcast_worker(rank, world, port, q):
+    """Ranks seeded differently (the decoder / heads are random-init): after broadcast_training_state every rank holds rank
+    0's parameters, buffers, moments and step count, and parameters_checksum() agrees."""
+    from mspi_b200.distributed import broadcast_training_state, parameters_checksum
+    from mspi_b200.train_engine import TrainState
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st = TrainState(_small_sd(10 + rank), "cpu")
+        st.flat_m.fill_(float(rank + 1))
+        st.step_count = 3 + rank
+        before = parameters_checksum(st)
+        broadcast_training_state(st)
+        ref = TrainState(_small_sd(10), "cpu")
+        ok = (not before) and parameters_checksum(st) and torch.equal(st.flat_p, ref.flat_p) and st.step_count == 3
+        ok = ok and torch.equal(st.live["visnet.a.bn.running_mean"], ref.live["visnet.a.bn.running_mean"])
+        ok = ok and torch.equal(st.live["audnet.c.weight"], ref.live["audnet.c.weight"]) and float(st.flat_m.max()) == 1.0
+        ok = ok and int(st.live["visnet.a.bn.num_batches_tracked"]) == 10
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_training_state_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
+
+def test_train_state_optimizer_state_dict_is_torch_adamw_compatible():
+    """TrainState <-> torch.optim.AdamW.state_dict(): export after some steps loads into torch's AdamW, and torch's own state
+    (after real torch steps) loads back with moments and step count intact (CPU; the kernels are not involved)."""
+    from mspi_b200.train_engine import TrainState, trainable_keys
+    sd = _small_sd(1)
+    st = TrainState(sd, "cpu")
+    keys = trainable_keys(sd)
+    assert keys == ["visnet.a.weight", "visnet.a.bn.weight", "readout.0.bias"] and st.n_params == 30 + 6 + 7
+    assert all(o % 4 == 0 for o in st.offs.values())
+    params = [torch.nn.Parameter(sd[k].clone()) for k in keys]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0)
+    for _ in range(3):
+        opt.zero_grad()
+        sum((p ** 2).sum() for p in params).backward()
+        opt.step()
+    st.load_optimizer_state_dict(opt.state_dict())
+    assert st.step_count == 3
+    assert torch.allclose(st.view(st.flat_m, keys[0]), opt.state[params[0]]["exp_avg"])
+    assert torch.allclose(st.view(st.flat_v, keys[2]), opt.state[params[2]]["exp_avg_sq"])
+    osd = st.optimizer_state_dict(1e-3, (0.9, 0.999), 1e-8, 0.0)
+    opt2 = torch.optim.AdamW([torch.nn.Parameter(sd[k].clone()) for k in keys], lr=1e-3, weight_decay=0)
+    opt2.load_state_dict(osd)
+    assert float(opt2.state[opt2.param_groups[0]["params"][1]]["step"]) == 3.0
+    fresh = TrainState(sd, "cpu")
+    assert fresh.optimizer_state_dict(1e-3, (0.9, 0.999), 1e-8, 0.0)["state"] == {}
+    with pytest.raises(ValueError):
+        fresh.load_optimizer_state_dict({"state": {0: opt.state_dict()["state"][0]}})
