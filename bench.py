@@ -577,6 +577,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN/cuBLAS) run on the same GPU")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-input end-to-end arms (multi-GPU sweeps of the other encoders)")
     ap.add_argument("--sliding", action="store_true", help="sliding-window workload with / without the per-frame feature cache")
     ap.add_argument("--frames", type=int, default=272, help="--sliding: frames of the synthetic video")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this file")
@@ -741,19 +742,21 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         return world * B * K / (t2.item() / 1e3)
 
-    pin_u8 = [torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    d_u8 = [torch.empty(B, T, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_value = e2e_measure(pin_u8, d_u8)
     h2d = B * (3 * T * H * W + 257 * 111 * 4)
-    d2h = B * H * W * 4
-    del pin_u8, d_u8
-    model._plans = {k: v for k, v in model._plans.items() if not (k[0] == "full" and k[1] is True)}   # drop the uint8 plan's 30 GB of buffers
-    torch.cuda.empty_cache()
-    pin = [torch.randn(B, 3, T, H, W).pin_memory() for _ in range(2)]
-    dclips = [torch.empty(B, 3, T, H, W, device=dev) for _ in range(2)]
-    e2e_fp32 = e2e_measure(pin, dclips)
     h2d_fp32 = B * (3 * T * H * W + 257 * 111) * 4
-    del pin, dclips
+    d2h = B * H * W * 4
+    e2e_value = e2e_fp32 = None
+    if not args.no_e2e:
+        pin_u8 = [torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        d_u8 = [torch.empty(B, T, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+        e2e_value = e2e_measure(pin_u8, d_u8)
+        del pin_u8, d_u8
+        model._plans = {k: v for k, v in model._plans.items() if not (k[0] == "full" and k[1] is True)}   # drop the uint8 plan's 30 GB of buffers
+        torch.cuda.empty_cache()
+        pin = [torch.randn(B, 3, T, H, W).pin_memory() for _ in range(2)]
+        dclips = [torch.empty(B, 3, T, H, W, device=dev) for _ in range(2)]
+        e2e_fp32 = e2e_measure(pin, dclips)
+        del pin, dclips
 
     # ------------------------------------------------------------------ per-kernel breakdown (CUDA events, eager replay)
     roofline, tf32_info, breakdown = None, None, None

@@ -731,7 +731,14 @@ class ForwardPlan:
         # x += up2(part1) + up4(part2) + up8(part3) in ONE pass over x (in place; the gate kernel without a mask)
         self.add(f"{p}.0+=up2,4,8", ops.sa_gate_fused(x, None, x, parts))
         sc, sh = self.bn(p + ".2", 1e-5, self.P(p + ".1.bias"))
-        x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
+        if os.environ.get("MSPI_READOUT1_BF16", "0") != "0":
+            # study switch: readout.1 (K = 5184, the largest tf32 layer) on bf16 operands
+            xb = self.new(x.n, x.t, x.h, x.w, x.c, torch.bfloat16)
+            self.add(p + ".0.cast", ops.cast_rows(x.buf, xb.buf, 1, x.pixels, x.c, x.cs, 0, xb.cs, 0))
+            x = self.conv(p + ".1", xb, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU, out_dtype=f32,
+                          dtype=torch.bfloat16, split_weights=os.environ.get("MSPI_READOUT1_BF16") == "2")
+        else:
+            x = self.conv(p + ".1", x, self.P(p + ".1.weight"), sc, sh, pad=(1, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
         sc, sh = self.bn(p + ".5", 1e-5, self.P(p + ".4.bias"))
         x = self.conv(p + ".4", x, self.P(p + ".4.weight"), sc, sh, pad=(0, 1, 1), act=ACT_RELU, out_dtype=f32, dtype=f32)
         # readout.7-9: Upsample(1,4,4) -> Conv(4,1,1)/s4 -> ReLU.  The conv mixes T and C only, the upsample H and
