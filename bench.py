@@ -702,6 +702,8 @@ def main():
     host_out = [torch.empty(B, H, W).pin_memory() for _ in range(2)]
     daud = [torch.empty(B, 1, 257, 111, device=dev) for _ in range(2)]
 
+    e2e_pending = [None]
+
     def e2e_measure(pin, dclips):
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
@@ -725,9 +727,15 @@ def main():
                 main_stream.wait_event(ready[s])
                 out, loss = model(dclips[s], daud[s])
                 freed[s].record(main_stream)
-                if world > 1:
-                    gather_maps(out, world * B)
+                if world > 1:   # NCCL all-gather of the maps on the communicator's stream, as in the device-resident loop
+                    h = gather_maps(out, world * B, async_op=True)
+                    if e2e_pending[0] is not None:
+                        e2e_pending[0].wait()
+                    e2e_pending[0] = h
                 host_out[s].copy_(out, non_blocking=True)  # D2H of this step's maps
+            if e2e_pending[0] is not None:
+                e2e_pending[0].wait()
+                e2e_pending[0] = None
             torch.cuda.synchronize()
 
         e2e_run(2)

@@ -36,6 +36,14 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kChunkBytes = 128 * 128;         // one K chunk of a 128-row operand tile: 16 KB
 constexpr int kMaxRing = 8;
 constexpr int kMaxHBuf = 3;
+// MSPI_MLP_DEBUG (study bits: skip GELU / TMEM loads / A2 stores / residual I/O) only exists in builds made with
+// -DMSPI_MLP_STUDY: as a run-time flag its dead branches still cost the epilogue 32 integer instructions per hidden chunk
+// (ptxas hoists the fake accumulator values above the branch; ncu source page, profiles/r02_fused_mlp.md).
+#ifdef MSPI_MLP_STUDY
+#define MLP_DBG(p, bit) ((p).debug & (bit))
+#else
+#define MLP_DBG(p, bit) 0
+#endif
 
 struct MlpParams {
   int m_rows, c, kc1, nh, m_tiles, x_bufs;
@@ -311,6 +319,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       int xs = 0;
       uint32_t xph = 0;
       uint32_t g = 0, ytile = 0;
+      uint32_t mb = 0, mph = 0;   // hidden buffer of chunk g and its phase
       int prev_j = -1;
       uint32_t prev_g = 0;
       // pair mode: the leader issues for both CTAs and every commit is multicast to both; the peer's MMA warp idles
@@ -356,8 +365,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         mbar_wait(x_full + 8 * xs, xph);
         tc_fence_after();
         for (int j = 0; j < p.nh; ++j) {
-          const uint32_t b = g % static_cast<uint32_t>(p.hbufs);
-          mbar_wait(h_empty + 8 * b, ((g / p.hbufs) & 1u) ^ 1u);  // the epilogue has read H[b] of chunk g - hbufs
+          const uint32_t b = mb;
+          mbar_wait(h_empty + 8 * b, mph ^ 1u);  // the epilogue has read H[b] of chunk g - hbufs
           tc_fence_after();
           for (int kc = 0; kc < p.kc1; ++kc) {
             mbar_wait(ring_full + 8 * stage, phase);
@@ -382,6 +391,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           prev_j = j;
           prev_g = g;
           ++g;
+          if (++mb == static_cast<uint32_t>(p.hbufs)) { mb = 0; mph ^= 1u; }
         }
         if (++xs == p.x_bufs) { xs = 0; xph ^= 1u; }
       }
@@ -399,6 +409,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t lane_y = tmem_y + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t g = 0, ytile = 0;
+    uint32_t hb = 0, hph = 0;   // TMEM hidden buffer of chunk g and its barrier phase (counters: no division in the loop)
     // The Y tile of a finished M tile is written one hidden chunk LATE (after the next tile's first GELU chunk): MMA2 of the
     // last chunk then has time to finish, and the residual rows requested right after the last GELU chunk have arrived.
     bool pend = false;
@@ -463,7 +474,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         tmem_ld16(lane_y + c0, acc);
         tmem_ld_wait();
-        if (pvalid && !(p.debug & 8)) {
+        if (pvalid && !MLP_DBG(p, 8)) {
           uint4 o2[2];
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
@@ -499,7 +510,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const long long grow = (static_cast<long long>(grp) * p.cl + rank) * 128 + row;
       const bool valid = grow < p.m_rows;
       for (int j = 0; j < p.nh; ++j) {
-        const uint32_t hb = g % static_cast<uint32_t>(p.hbufs), hph = (g / p.hbufs) & 1u;
         const uint32_t ab = g & 1u, aph = (g >> 1) & 1u;
         mbar_wait(h_full + 8 * hb, hph);
         mbar_wait(a2_empty + 8 * ab, aph ^ 1u);  // MMA2 of chunk g-2 has finished reading this staging buffer
@@ -509,14 +519,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         {
           uint32_t acc[32];
           __syncwarp();
-          if (!(p.debug & 2)) {
+          if (!MLP_DBG(p, 2)) {
             tmem_ld32(lane_addr + hb * kHC + colgrp * 32, acc);
             tmem_ld_wait();
           } else {
 #pragma unroll
             for (int q = 0; q < 32; ++q) acc[q] = 0x3f800000u + q + lane;
           }
-          if (p.debug & 1) {
+          if (MLP_DBG(p, 1)) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) packed[q] = pack_bf16x2(__uint_as_float(acc[2 * q]), __uint_as_float(acc[2 * q + 1]));
           } else if (p.packed_gelu) {
@@ -552,7 +562,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const uint32_t dst_row = a2_base + (ab * 2 + (colgrp >> 1)) * kChunkBytes + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (p.debug & 4) break;
+          if (MLP_DBG(p, 4)) break;
           const int piece = 4 * (colgrp & 1) + i;
           const uint32_t dst = dst_row + (static_cast<uint32_t>(piece ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * i]), "r"(packed[4 * i + 1]),
@@ -563,6 +573,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         if (lane == 0) arrive(a2_full + 8 * ab);
         ++g;
+        if (++hb == static_cast<uint32_t>(p.hbufs)) { hb = 0; hph ^= 1u; }
         if (j == 0 && pend) {
           y_epilogue();
           pend = false;
@@ -580,7 +591,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int b = 0; b < p.c / 32; ++b)
             tma_load_2d(ystage_base + static_cast<uint32_t>(b) * (128u * 64u), &map_r, res_full, b * 32, prow0);
         }
-      } else if (valid && !(p.debug & 8)) {
+      } else if (valid && !MLP_DBG(p, 8)) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int c0 = 16 * colgrp + 64 * u;
