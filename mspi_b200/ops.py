@@ -548,7 +548,9 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
         nf = fpc - (kt - 1)  # frames produced per launch
     oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     # outputs per GEMM row: the S3D stem computes 4 neighbouring output pixels from one 16-pixel (128-byte) window, see below
-    wide_ok = allow_wide and kt == 1 and y.c0 == 0 and y.cs == cout and os.environ.get("MSPI_STEM_WIDE", "1") != "0"
+    # (the temporal taps of the SlowFast fast stem are offsets along the clip's own frame axis: orthogonal to the wide rows)
+    wide_ok = allow_wide and (kt == 1 or os.environ.get("MSPI_STEM_WIDE_KT", "1") != "0") and y.c0 == 0 and y.cs == cout \
+        and os.environ.get("MSPI_STEM_WIDE", "1") != "0"
     wide = 1
     if wide_ok and (k, stride, pad) == (7, 2, 3) and ow % 4 == 0 and cout * 4 <= 256:
         wide = 4      # S3D conv_s: 16-pixel window (128 B), 4 outputs, N = 256

@@ -275,6 +275,29 @@ def test_stem_conv_temporal_taps_per_clip():
     assert _rel(y.to_ncdhw().cpu(), ref.relu()) < BF16_TOL
 
 
+@pytest.mark.parametrize("c,act,n,t,h,w", [(56, 4, 2, 4, 20, 32), (112, 0, 1, 3, 9, 48), (216, 4, 2, 2, 14, 24), (432, 1, 1, 4, 7, 12),
+                                           (56, 0, 1, 1, 5, 7), (80, 4, 1, 5, 11, 40)])
+def test_x3d_depthwise_3x3x3_tiled(c, act, n, t, h, w):
+    """The shared-memory tiled 3x3x3 depthwise kernel (stride 1; x3d.cu dw3d_tile_kernel): channel groups (C = 112 / 216 / 432),
+    1-3 strips per tile row, ragged tiles, single-frame clips (both temporal neighbours are padding), every activation."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(31)
+    creal = c - 2 if c in (56, 112, 216, 432) else c
+    x = torch.zeros(n, c, t, h, w)
+    x[:, :creal] = torch.randn(n, creal, t, h, w, generator=g)
+    wgt = torch.randn(creal, 1, 3, 3, 3, generator=g) * 0.3
+    scale, shift = torch.rand(creal, generator=g) + 0.5, torch.randn(creal, generator=g) * 0.1
+    xa = _act_from_ncdhw(x)
+    ya = Act.empty(n, t, h, w, c)
+    ops.dwconv3d_bn(xa, ya, wgt, scale, shift, 1, act)()
+    torch.cuda.synchronize()
+    ref = F.conv3d(_bf(x[:, :creal]), wgt, None, 1, 1, 1, creal) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    ref = ref * torch.sigmoid(ref) if act == 4 else (ref.relu() if act == 1 else ref)
+    got = ya.to_ncdhw().cpu()
+    assert _rel(got[:, :creal], ref) < BF16_TOL and (got[:, creal:] == 0).all()
+
+
 @pytest.mark.parametrize("c,stride,act", [(56, 2, 4), (112, 1, 0), (24, 1, 1)])
 def test_x3d_depthwise_and_se(c, stride, act):
     """X3DTransform.b + b_bn (+Swish) and the SE path (resnet_helper.py:47-73,213-351) against PyTorch."""
