@@ -120,8 +120,8 @@ class ClockSampler:
 
 
 def read_traffic():
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu pass (profiles/r01_roofline_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu pass (profiles/r02_roofline_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -807,7 +807,7 @@ def main():
                             "achieved": info["tflops"], "peak": peak, "unit": "TFLOP/s",
                             "frac": (info["tflops"] / peak) if info["tflops"] else None, "traffic": traffic,
                             "traffic_note": f"dram read+write bytes per launch, mean over the {tr['conv_gemm_bf16']['launches_per_step']} "
-                                            "bf16 launches of one step (ncu, profiles/r01_launches.csv)" if tr else None,
+                                            "bf16 launches of one step (ncu, profiles/r02_launches.csv)" if tr else None,
                             "hbm_gbs_from_traffic": (tr["conv_gemm_bf16"]["dram_bytes_per_step"] / ms_k / 1e6) if tr else None,
                             "hbm_peak_gbs": peaks["hbm"],
                             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
