@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmspi_b200.so")
+if os.environ.get("MSPI_LIB"):   # tuning aid: a library variant built with other compile-time switches (same ABI)
+    LIB_PATH = os.path.abspath(os.environ["MSPI_LIB"])
 
 MSPI_BF16, MSPI_F32 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID, ACT_SWISH = 0, 1, 2, 3, 4

@@ -31,7 +31,16 @@ namespace {
 #ifndef MSPI_EPI_SETS
 #define MSPI_EPI_SETS 2
 #endif
+#ifndef MSPI_EPI_STAGE_BUFS
+#define MSPI_EPI_STAGE_BUFS 1
+#endif
 constexpr int kEpiSets = MSPI_EPI_SETS;       // independent groups of 8 epilogue warps working on alternate column chunks
+// Output staging buffers per epilogue set: with one, a set's next chunk cannot be written to shared memory before the bulk
+// store of its previous chunk has finished READING the buffer (cp.async.bulk.wait_group.read 0 on the chunk's critical path);
+// with two, that store drains while the next chunk is computed and staged (wait_group.read 1).  Measured (round 2, same
+// box): two buffers are SLOWER — stage-2 fc1+GELU 0.232 -> 0.240 ms, stage-0 fc1 0.833 -> 0.882 ms — because the 32 KB come
+// out of the operand ring (one pipeline stage less); the store's read-back is not what bounds the chunk chain.  Default 1.
+constexpr int kStageBufs = kEpiSets > 1 ? MSPI_EPI_STAGE_BUFS : 2;
 constexpr int kEpiWarps = 8 * kEpiSets;       // per set: two warps per TMEM lane quarter, they split the chunk's columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // producer warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
@@ -156,7 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kBarrierBytes);
   float* s_shift = s_scale + p.ss_floats;
   const uint32_t stage_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
-  const uint32_t tiles_base = stage_base + (p.tma_store ? 2u * kABytes : 0u);
+  const uint32_t tiles_base = stage_base + (p.tma_store ? static_cast<uint32_t>(kEpiSets > 1 ? kEpiSets * kStageBufs : 2) * kABytes : 0u);
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -361,7 +370,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // staging buffers: kEpiSets == 1 alternates two buffers (store_seq & 1); with two sets each owns one buffer — the other
     // set's chunk lies between two uses, so the previous bulk store has long finished reading it
     uint32_t store_seq = 0;
-    const uint32_t my_stage = kEpiSets > 1 ? static_cast<uint32_t>(set) * kABytes : 0u;
+    const uint32_t my_stage = kEpiSets > 1 ? static_cast<uint32_t>(set) * kStageBufs * kABytes : 0u;
     const int bar_id = 1 + set;
     uint32_t chunk_seq = 0;  // column chunks processed by this CTA so far: chunk g of the kernel belongs to set g % kEpiSets
     for (int item = cid; item < total_items; item += ncl, chunk_seq += nchunks) {
@@ -531,10 +540,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         if (p.tma_store) {
           // staging buffer (store_seq & 1) is free once the bulk store issued two chunks ago has finished READING it
-          const uint32_t stage_buf = stage_base + (kEpiSets > 1 ? my_stage : (store_seq & 1u) * kABytes);
+          const uint32_t stage_buf = stage_base + (kEpiSets > 1 ? my_stage + (kStageBufs > 1 ? (store_seq & 1u) * kABytes : 0u)
+                                                                : (store_seq & 1u) * kABytes);
           const uint32_t stage_row = stage_buf + row * kRowBytes;
           if (leader) {
-            if (kEpiSets > 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (kEpiSets > 1 && kStageBufs == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
           asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
@@ -755,7 +765,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
                        (int)r, d->cout, d->o_dims[0], d->o_dims[1], d->o_dims[2], d->o_dims[3], (long long)d->o_strides[0],
                        (long long)d->o_strides[1], (long long)d->o_strides[2], (long long)d->o_strides[3]);
   }
-  const int out_stage_bytes = p.tma_store ? 2 * kABytes : 0;
+  const int out_stage_bytes = p.tma_store ? (kEpiSets > 1 ? kEpiSets * kStageBufs : 2) * kABytes : 0;
   p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes - out_stage_bytes) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   int cols = 32;
