@@ -49,6 +49,11 @@ int64_t mspi_launch_count(void);
  * [4] in the barrier after the stencil, [5] storing the result tile, summed since the last reset.  out8 has 8 entries.
  * Synchronises the device.  No counterpart in the reference. */
 int mspi_debug_dw_phase_cycles(uint64_t* out8, int reset);
+/* Same for the epilogue warps of mspi_conv_gemm, filled only by a study build of the library (-DMSPI_GEMM_STUDY, selected at
+ * run time through the MSPI_LIB environment variable): cycles [0] waiting for the accumulator, [1] in tcgen05.ld, [2] in the
+ * scale/shift/activation math, [3] waiting for the staging buffer, [4] staging + bulk-store issue, [5] chunks, [6] tiles,
+ * [7] the whole epilogue loop, summed over warps.  The release build returns zeros. */
+int mspi_debug_gemm_epilogue_cycles(uint64_t* out8, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

@@ -50,6 +50,17 @@ constexpr int kBarrierBytes = 1024;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 220 * 1024;
 
+// Study build (-DMSPI_GEMM_STUDY, loaded through MSPI_LIB): cycles the epilogue warps spend per phase, summed over warps.
+//   [0] waiting for the accumulator (tmem_full)   [1] tcgen05.ld + wait::ld   [2] scale/shift/activation/pack
+//   [3] staging buffer free (bulk wait_group.read + barrier)   [4] st.shared + proxy fence + barrier + bulk store issue
+//   [5] chunks   [6] tiles   [7] whole epilogue loop
+__device__ unsigned long long g_gemm_epi_cycles[8];
+#ifdef MSPI_GEMM_STUDY
+#define GEMM_CLK() clock64()
+#else
+#define GEMM_CLK() 0ll
+#endif
+
 struct GemmParams {
   int box[4];
   int tiles_d[4];
@@ -373,6 +384,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const uint32_t my_stage = kEpiSets > 1 ? static_cast<uint32_t>(set) * kStageBufs * kABytes : 0u;
     const int bar_id = 1 + set;
     uint32_t chunk_seq = 0;  // column chunks processed by this CTA so far: chunk g of the kernel belongs to set g % kEpiSets
+    long long cy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_loop0 = GEMM_CLK();
     for (int item = cid; item < total_items; item += ncl, chunk_seq += nchunks) {
       const int nt = item % p.n_tiles;
       int mt = (item / p.n_tiles) * p.cl + rank;
@@ -394,14 +407,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       valid = valid && (r == 0);
       if (dummy) org[3] = kFar;
 
+      // residual rows of this thread for one chunk (4 x 16 bytes), fetched early: issued just before use, every one of these
+      // loads (32 different lines per warp instruction) exposes a full L2 / DRAM round trip to the chunk's critical path
+      // (measured: 6500 cycles of "math" per chunk for ConvNeXt stage-2 fc2 + residual against 840 without the residual)
+      const int n_base = nt * p.bn;
+      const int first = kEpiSets > 1 ? static_cast<int>((static_cast<uint32_t>(set) + kEpiSets - chunk_seq % kEpiSets) % kEpiSets) : 0;
+      uint4 rq[4];
+#ifndef MSPI_EPI_RES_PREFETCH
+#define MSPI_EPI_RES_PREFETCH 0   // measured (same box): stage-2 fc2 + residual 0.193 -> 0.206 ms WITH the register prefetch (16 more live
+#endif                            // registers at the 96-register cap); the loads need a whole tile of lead, i.e. a TMA-staged tile
+      const bool pre_ok = MSPI_EPI_RES_PREFETCH && has_res && (p.r_dtype == MSPI_BF16 || !out_bf16);
+      auto fetch_res = [&](int ch_) {
+        const int c0_ = ch_ * CH + group * HC;
+        const int w_ = min(HC, p.bn - c0_);
+#pragma unroll
+        for (int g = 0; g < HC / 8; ++g) {
+          const int ng = n_base + c0_ + 8 * g;
+          if (valid && 8 * g < w_ && ng + 8 <= p.cout) {
+            if (p.r_dtype == MSPI_BF16) {
+              rq[g & 3] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + ng));
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const float*>(p.residual) + roff + ng);
+              rq[(2 * g) & 3] = __ldg(rp);
+              rq[(2 * g + 1) & 3] = __ldg(rp + 1);
+            }
+          }
+        }
+      };
+      if (pre_ok && first < nchunks) fetch_res(first);
+      const long long t_w0 = GEMM_CLK();
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
+      cy[0] += GEMM_CLK() - t_w0;
+      cy[6] += 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * p.bn);
-      const int n_base = nt * p.bn;
       // the sets alternate over the GLOBAL chunk sequence, so tiles with a single chunk (N <= 64 bf16 / 32 fp32: the stems,
-      // most Inception branches) alternate between the sets as well and two tiles' chains overlap
-      const int first = kEpiSets > 1 ? static_cast<int>((static_cast<uint32_t>(set) + kEpiSets - chunk_seq % kEpiSets) % kEpiSets) : 0;
+      // most Inception branches) alternate between the sets as well and two tiles' chains overlap (`first`, above)
       if (first >= nchunks) {  // this set has no chunk in the tile: release the accumulator buffer (after the tfull wait above,
                                // so a set can never get ahead of the MMA warp and arrive twice in one phase)
         tc_fence_before();
@@ -416,6 +458,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int width = min(HC, p.bn - c0);  // HC, 16 (bf16, odd multiple of 16), or <= 0 past the tile
         const int n0 = n_base + c0;
         uint32_t acc[HC];
+        const long long t_c0 = GEMM_CLK();
         __syncwarp();  // tcgen05.ld is warp-collective
         if constexpr (out_bf16) {
           if (width >= 32) {
@@ -430,6 +473,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (width > 0) tmem_ld16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(acc));
         }
         tmem_ld_wait();
+        const long long t_c1 = GEMM_CLK();
         if (width <= 0) {
 #pragma unroll
           for (int j = 0; j < HC; ++j) acc[j] = 0u;
@@ -441,58 +485,81 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int g = 0; g < HC / 8; ++g) {  // groups of 8 columns
           const int ng = n0 + 8 * g;
           const bool live = (8 * g < width) && (ng < p.cout);
-          float v[8];
+          const bool full8 = (ng + 8 <= p.cout);
+          // Packed fp32 pairs end to end (fma.rn.f32x2 / add / mul: one issue slot per two elements; the epilogue warps are
+          // bound by instruction issue — tools/prof_gemm_phases.py: 838 cycles of math per 32-element chunk without an
+          // activation, 1680 with GELU, against 3072 cycles of MMA for a 128x256x384 tile).  TMEM registers are consecutive,
+          // so (acc[2k], acc[2k+1]) already is a register pair.
+          F2 v2[4];
           {
             const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
-            v[0] = fmaf(__uint_as_float(acc[8 * g + 0]), s0.x, h0.x);
-            v[1] = fmaf(__uint_as_float(acc[8 * g + 1]), s0.y, h0.y);
-            v[2] = fmaf(__uint_as_float(acc[8 * g + 2]), s0.z, h0.z);
-            v[3] = fmaf(__uint_as_float(acc[8 * g + 3]), s0.w, h0.w);
-            v[4] = fmaf(__uint_as_float(acc[8 * g + 4]), s1.x, h1.x);
-            v[5] = fmaf(__uint_as_float(acc[8 * g + 5]), s1.y, h1.y);
-            v[6] = fmaf(__uint_as_float(acc[8 * g + 6]), s1.z, h1.z);
-            v[7] = fmaf(__uint_as_float(acc[8 * g + 7]), s1.w, h1.w);
+            v2[0] = fma2(pack2(__uint_as_float(acc[8 * g + 0]), __uint_as_float(acc[8 * g + 1])), pack2(s0.x, s0.y), pack2(h0.x, h0.y));
+            v2[1] = fma2(pack2(__uint_as_float(acc[8 * g + 2]), __uint_as_float(acc[8 * g + 3])), pack2(s0.z, s0.w), pack2(h0.z, h0.w));
+            v2[2] = fma2(pack2(__uint_as_float(acc[8 * g + 4]), __uint_as_float(acc[8 * g + 5])), pack2(s1.x, s1.y), pack2(h1.x, h1.y));
+            v2[3] = fma2(pack2(__uint_as_float(acc[8 * g + 6]), __uint_as_float(acc[8 * g + 7])), pack2(s1.z, s1.w), pack2(h1.z, h1.w));
           }
-          const bool full8 = (ng + 8 <= p.cout);
-          float res[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[j] = 0.f;
-          if (has_res && valid && live) {
-            if (full8 && p.r_dtype == MSPI_BF16) {
-              const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + ng));
-              unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
-              unpack_bf16x2(a.z, res[4], res[5]); unpack_bf16x2(a.w, res[6], res[7]);
-            } else if (full8) {
-              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + roff + ng);
-              const float4 a = __ldg(rp), b = __ldg(rp + 1);
-              res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
-              res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int n = min(ng + j, p.cout - 1);
-                res[j] = p.r_dtype == MSPI_BF16 ? bf2f(static_cast<const __nv_bfloat16*>(p.residual)[roff + n])
-                                                : static_cast<const float*>(p.residual)[roff + n];
+          const bool have_res = has_res && valid && live;
+          F2 r2[4];
+          if (have_res) {
+            if (pre_ok && full8) {   // prefetched before the accumulator wait / during the previous chunk's staging
+              if (p.r_dtype == MSPI_BF16) {
+                const uint4 a = rq[g];
+                r2[0] = pack2(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u));
+                r2[1] = pack2(__uint_as_float(a.y << 16), __uint_as_float(a.y & 0xffff0000u));
+                r2[2] = pack2(__uint_as_float(a.z << 16), __uint_as_float(a.z & 0xffff0000u));
+                r2[3] = pack2(__uint_as_float(a.w << 16), __uint_as_float(a.w & 0xffff0000u));
+              } else {
+                const uint4 a = rq[(2 * g) & 3], b = rq[(2 * g + 1) & 3];
+                r2[0] = pack2(__uint_as_float(a.x), __uint_as_float(a.y));
+                r2[1] = pack2(__uint_as_float(a.z), __uint_as_float(a.w));
+                r2[2] = pack2(__uint_as_float(b.x), __uint_as_float(b.y));
+                r2[3] = pack2(__uint_as_float(b.z), __uint_as_float(b.w));
               }
+            } else {
+              float res[8];
+              if (full8 && p.r_dtype == MSPI_BF16) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + roff + ng));
+                unpack_bf16x2(a.x, res[0], res[1]); unpack_bf16x2(a.y, res[2], res[3]);
+                unpack_bf16x2(a.z, res[4], res[5]); unpack_bf16x2(a.w, res[6], res[7]);
+              } else if (full8) {
+                const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + roff + ng);
+                const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w;
+                res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int n = min(ng + j, p.cout - 1);
+                  res[j] = p.r_dtype == MSPI_BF16 ? bf2f(static_cast<const __nv_bfloat16*>(p.residual)[roff + n])
+                                                  : static_cast<const float*>(p.residual)[roff + n];
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) r2[k] = pack2(res[2 * k], res[2 * k + 1]);
+            }
+            if (!res_after) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v2[k] = add2(v2[k], r2[k]);
             }
           }
-          if (out_bf16 && act == MSPI_ACT_GELU) {  // two elements per MUFU op (tc_ptx.cuh: gelu_pair)
+          float v[8];
+          if (out_bf16 && act == MSPI_ACT_GELU) {   // tanh form, one fp32 MUFU per element, everything else packed
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              if (has_res && !res_after) { v[j] += res[j]; v[j + 1] += res[j + 1]; }
-              gelu_pair(v[j], v[j + 1]);
-              if (has_res && res_after) { v[j] += res[j]; v[j + 1] += res[j + 1]; }
-            }
-          } else {
+            for (int k = 0; k < 4; ++k) v2[k] = gelu_pair_f32(v2[k]);
+          } else if (act != MSPI_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = v[j];
-              if (has_res && !res_after) x += res[j];
-              x = epi_act<out_bf16>(x, act);
-              if (has_res && res_after) x += res[j];
-              v[j] = x;
+            for (int k = 0; k < 4; ++k) {
+              float x0, x1;
+              unpack2(v2[k], x0, x1);
+              v2[k] = pack2(epi_act<out_bf16>(x0, act), epi_act<out_bf16>(x1, act));
             }
           }
+          if (have_res && res_after) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v2[k] = add2(v2[k], r2[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) unpack2(v2[k], v[2 * k], v[2 * k + 1]);
           if (p.tma_store) {
             if (out_bf16) {
               packed[4 * g + 0] = pack_bf16x2(v[0], v[1]);
@@ -529,6 +596,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
+        if (pre_ok && ch + kEpiSets < nchunks) fetch_res(ch + kEpiSets);   // lands while this chunk is staged and stored
         if (ch + kEpiSets >= nchunks) {
           // every TMEM read of this warp for this tile is done: hand the accumulator buffer back to the MMA warp now,
           // before the last chunk is staged and stored
@@ -538,6 +606,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if constexpr (pair) mbar_arrive_cluster(leader_smem(bar_tempty + 8 * as)); else mbar_arrive(bar_tempty + 8 * as);
           }
         }
+        const long long t_c2 = GEMM_CLK();
+        long long t_c3 = t_c2;
         if (p.tma_store) {
           // staging buffer (store_seq & 1) is free once the bulk store issued two chunks ago has finished READING it
           const uint32_t stage_buf = stage_base + (kEpiSets > 1 ? my_stage + (kStageBufs > 1 ? (store_seq & 1u) * kABytes : 0u)
@@ -548,6 +618,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
           asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          t_c3 = GEMM_CLK();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {  // this thread's four 16-byte pieces, 128B-swizzled like the tensor map expects
             const uint32_t dst = stage_row + (static_cast<uint32_t>((4 * group + j) ^ (row & 7)) << 4);
@@ -567,9 +638,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           ++store_seq;
         }
+        const long long t_c4 = GEMM_CLK();
+        cy[1] += t_c1 - t_c0; cy[2] += t_c2 - t_c1; cy[3] += t_c3 - t_c2; cy[4] += t_c4 - t_c3; cy[5] += 1;
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+#ifdef MSPI_GEMM_STUDY
+    cy[7] = GEMM_CLK() - t_loop0;
+    if (lane == 0)
+      for (int j = 0; j < 8; ++j) atomicAdd(&g_gemm_epi_cycles[j], static_cast<unsigned long long>(cy[j]));
+#endif
     if (p.tma_store && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
@@ -594,6 +672,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }  // namespace mspi
 
 using namespace mspi;
+
+extern "C" int mspi_debug_gemm_epilogue_cycles(uint64_t* out8, int reset) {
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  MSPI_CUDA(cudaDeviceSynchronize());
+  if (out8 != nullptr) {
+    MSPI_CUDA(cudaMemcpyFromSymbol(h, g_gemm_epi_cycles, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  }
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MSPI_CUDA(cudaMemcpyToSymbol(g_gemm_epi_cycles, z, sizeof(z)));
+  }
+  return MSPI_OK;
+}
 
 extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
                               const float* shift, const void* residual, void* y, void* stream_) {
