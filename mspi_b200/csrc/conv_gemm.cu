@@ -85,6 +85,9 @@ struct GemmParams {
   int tma_store;  // 1: epilogue stages 128-byte output rows in shared memory and TMA-stores them
   int pair;       // 1: CTA pair (cl == 2, tcgen05 cta_group::2): b_bytes is this CTA's HALF of the B tile
   uint32_t idesc2;
+  int res_tma;    // 1: the residual chunk arrives by TMA in the output staging buffer and is updated in place (fused_mlp.cu does
+                  // the same): lane-per-row global loads of it cost 6500 cycles per chunk on the epilogue's critical path
+  int y_box_bytes;  // bytes of one staged output / residual chunk: rows of the M box x 128
 };
 
 using namespace tc;
@@ -161,7 +164,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <int KIND, int OUT, int ACT, int RES, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ GemmParams p) {
+                 const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_r,
+                 const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool pair = PAIR;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -171,6 +175,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t bar_tfull = smem_base + 16 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_res = tmem_slot + 16;   // one per epilogue set: residual chunk landed in the staging buffer
   // staged epilogue vectors: scale[ss_floats], shift[ss_floats] (fp32); then, 1024 B aligned, the two output
   // staging buffers (TMA-store path) and the operand ring
   float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kBarrierBytes);
@@ -195,6 +200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, pair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues release the leader
     }
+    for (int s = 0; s < kEpiSets; ++s) mbar_init(bar_res + 8 * s, 1);
+    if (p.res_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -385,6 +392,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int bar_id = 1 + set;
     uint32_t chunk_seq = 0;  // column chunks processed by this CTA so far: chunk g of the kernel belongs to set g % kEpiSets
     long long cy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool res_tma = RES != 0 && p.res_tma != 0;   // residual through TMA + shared memory (needs the staged store path)
+    uint32_t res_phase = 0;
+    const uint32_t my_bar_res = bar_res + 8u * static_cast<uint32_t>(set);
     const long long t_loop0 = GEMM_CLK();
     for (int item = cid; item < total_items; item += ncl, chunk_seq += nchunks) {
       const int nt = item % p.n_tiles;
@@ -457,6 +467,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int c0 = ch * CH + group * HC;
         const int width = min(HC, p.bn - c0);  // HC, 16 (bf16, odd multiple of 16), or <= 0 past the tile
         const int n0 = n_base + c0;
+        if (res_tma && leader) {
+          // the staging buffer is free once the bulk store of this set's previous chunk has finished READING it; the residual
+          // chunk (same box, same swizzle as the store) then lands in it while the accumulator is read and scaled
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          const uint32_t sbuf = stage_base + (kEpiSets > 1 ? my_stage + (kStageBufs > 1 ? (store_seq & 1u) * kABytes : 0u)
+                                                           : (store_seq & 1u) * kABytes);
+          mbar_expect_tx(my_bar_res, static_cast<uint32_t>(p.y_box_bytes));
+          tma_load_5d(sbuf, &tma_r, my_bar_res, n_base + ch * CH, org[0], org[1], org[2], org[3]);
+        }
         uint32_t acc[HC];
         const long long t_c0 = GEMM_CLK();
         __syncwarp();  // tcgen05.ld is warp-collective
@@ -497,6 +516,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             v2[1] = fma2(pack2(__uint_as_float(acc[8 * g + 2]), __uint_as_float(acc[8 * g + 3])), pack2(s0.z, s0.w), pack2(h0.z, h0.w));
             v2[2] = fma2(pack2(__uint_as_float(acc[8 * g + 4]), __uint_as_float(acc[8 * g + 5])), pack2(s1.x, s1.y), pack2(h1.x, h1.y));
             v2[3] = fma2(pack2(__uint_as_float(acc[8 * g + 6]), __uint_as_float(acc[8 * g + 7])), pack2(s1.z, s1.w), pack2(h1.z, h1.w));
+          }
+          if (res_tma) {   // residual, activation and packing happen on the staged tile below
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float x0, x1;
+              unpack2(v2[k], x0, x1);
+              acc[8 * g + 2 * k] = __float_as_uint(x0);
+              acc[8 * g + 2 * k + 1] = __float_as_uint(x1);
+            }
+            continue;
           }
           const bool have_res = has_res && valid && live;
           F2 r2[4];
@@ -613,6 +642,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t stage_buf = stage_base + (kEpiSets > 1 ? my_stage + (kStageBufs > 1 ? (store_seq & 1u) * kABytes : 0u)
                                                                 : (store_seq & 1u) * kABytes);
           const uint32_t stage_row = stage_buf + row * kRowBytes;
+          if (res_tma) {
+            mbar_wait(my_bar_res, res_phase);   // the residual chunk has landed (the leader waited for the buffer before asking)
+            res_phase ^= 1u;
+            t_c3 = GEMM_CLK();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // this thread's four 16-byte pieces: read the residual, combine, write back in place
+              const uint32_t dst = stage_row + (static_cast<uint32_t>((4 * group + j) ^ (row & 7)) << 4);
+              uint4 rr;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(dst) : "memory");
+              uint4 o;
+              if constexpr (out_bf16) {
+                float rs[8], x[8];
+                unpack_bf16x2(rr.x, rs[0], rs[1]); unpack_bf16x2(rr.y, rs[2], rs[3]);
+                unpack_bf16x2(rr.z, rs[4], rs[5]); unpack_bf16x2(rr.w, rs[6], rs[7]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float t = __uint_as_float(acc[8 * j + e]);
+                  if (!res_after) t += rs[e];
+                  t = epi_act<out_bf16>(t, act);
+                  if (res_after) t += rs[e];
+                  x[e] = t;
+                }
+                o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+                o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+              } else {
+                const float rs[4] = {__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w)};
+                float x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float t = __uint_as_float(acc[4 * j + e]);
+                  if (!res_after) t += rs[e];
+                  t = epi_act<out_bf16>(t, act);
+                  if (res_after) t += rs[e];
+                  x[e] = t;
+                }
+                o = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
+          } else {
           if (leader) {
             if (kEpiSets > 1 && kStageBufs == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -625,6 +694,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]), "r"(packed[4 * j + 1]),
                          "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
                          : "memory");
+          }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
@@ -857,6 +927,37 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
                        (int)r, d->cout, d->o_dims[0], d->o_dims[1], d->o_dims[2], d->o_dims[3], (long long)d->o_strides[0],
                        (long long)d->o_strides[1], (long long)d->o_strides[2], (long long)d->o_strides[3]);
   }
+  // Residual through TMA: same box / swizzle as the staged store, so the chunk lands exactly where the epilogue writes its
+  // result.  Needs the staged store path, a residual of the output's dtype and 16-byte aligned residual row strides.
+  CUtensorMap map_r = map_y;
+  p.y_box_bytes = static_cast<int>(rows) * kRowBytes;
+  {
+    static const bool res_tma_on = [] { const char* e = getenv("MSPI_GEMM_RES_TMA"); return !e || atoi(e) != 0; }();
+    bool ok = res_tma_on && p.tma_store && d->has_residual && residual != nullptr && d->r_dtype == d->o_dtype &&
+              (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
+    for (int j = 0; j < 4 && ok; ++j)
+      if (p.o_dims[j] > 1 && (p.r_strides[j] * o_es) % 16 != 0) ok = false;
+    if (ok) {
+      cuuint64_t gdim[5], gstr[4];
+      cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
+      gdim[0] = static_cast<cuuint64_t>(d->cout);
+      bdim[0] = static_cast<cuuint32_t>(chunk_cols);
+      cuuint64_t span = static_cast<cuuint64_t>((d->cout * o_es + 15) / 16 * 16);
+      for (int j = 0; j < 4; ++j) {
+        gdim[j + 1] = static_cast<cuuint64_t>(p.o_dims[j]);
+        bdim[j + 1] = static_cast<cuuint32_t>(p.box[j]);
+        cuuint64_t st = static_cast<cuuint64_t>(p.r_strides[j]) * o_es;
+        if (p.o_dims[j] == 1 && (st == 0 || st % 16 != 0)) st = span;  // never dereferenced: any legal stride
+        gstr[j] = st;
+        if (st * gdim[j + 1] > span) span = st * gdim[j + 1];
+      }
+      CUresult r = encode(&map_r, d->o_dtype == MSPI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                          5, const_cast<void*>(residual), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { ok = false; map_r = map_y; }
+    }
+    p.res_tma = ok ? 1 : 0;
+  }
   const int out_stage_bytes = p.tma_store ? (kEpiSets > 1 ? kEpiSets * kStageBufs : 2) * kABytes : 0;
   p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes - out_stage_bytes) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
@@ -868,7 +969,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
 
   // Specialised instances for the (operand kind, output dtype, activation, residual) combinations the model
   // uses; anything else runs the generic instance that reads activation / residual mode at run time.
-  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
   const int res_mode = d->has_residual ? (d->res_after_act ? 2 : 1) : 0;
   Kern kern = nullptr;
 #define MSPI_PICK(K, O, A, R)                                                      \
@@ -907,7 +1008,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   if (grid <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   if (cl == 1) {
     if (total < grid) grid = static_cast<int>(total);
-    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, p);
+    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, map_r, p);
   } else {
     const long long items = static_cast<long long>((p.m_tiles + cl - 1) / cl) * p.n_tiles;
     long long nclusters = grid / cl;
@@ -925,7 +1026,7 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, p));
+    MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, map_r, p));
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
