@@ -57,6 +57,7 @@ class ForwardPlan:
         # entries meaning "branch dst waits for everything branch src has enqueued so far".  The list order of `steps` stays a
         # valid serial order, which is what run_eager(), the per-kernel breakdown and the training plan use.
         self.sched: List[Tuple] = []
+        self.input_steps = set()
         self.step_branch: List[int] = []
         self._branch = 0
         self.branches = os.environ.get("MSPI_GRAPH_BRANCHES", "1") != "0"
@@ -78,7 +79,11 @@ class ForwardPlan:
         self.bytes_alloc += a.buf.numel() * a.buf.element_size()
         return a
 
-    def add(self, name: str, fn: Callable[[], None]):
+    def add(self, name: str, fn: Callable[[], None], reads_input: bool = False):
+        """reads_input: the step reads the caller's clips / spectrograms.  Those steps stay OUTSIDE the captured graph and run
+        eagerly on the caller's tensors before every replay, so a replay needs no copy of the inputs into static buffers."""
+        if reads_input:
+            self.input_steps.add(len(self.steps))
         self.sched.append(("step", len(self.steps)))
         self.step_branch.append(self._branch)
         self.steps.append((name, fn))
@@ -160,7 +165,7 @@ class ForwardPlan:
                                        device=self.device)
             self.bytes_alloc += self._frames.numel() * 2
             conv = ops.clip_u8_to_padded if self.input_u8 else ops.clip_to_padded
-            self.add("clips.to_padded_nhwc4", conv(self._inputs, "clips", self._frames, B, T, H, W))
+            self.add("clips.to_padded_nhwc4", conv(self._inputs, "clips", self._frames, B, T, H, W), reads_input=True)
         return self._frames
 
     def padded_frames_variant(self, tag: str, frame_map, t_pad: int) -> torch.Tensor:
@@ -172,9 +177,10 @@ class ForwardPlan:
         self.bytes_alloc += fr.numel() * 2
         if self.input_u8:
             self.add(f"clips.to_padded_nhwc4[{tag}]", ops.clip_u8_to_padded(self._inputs, "clips", fr, B, T, H, W,
-                                                                           frame_map=frame_map, t_pad=t_pad))
+                                                                           frame_map=frame_map, t_pad=t_pad), reads_input=True)
         else:
-            self.add(f"clips.to_padded_nhwc4[{tag}]", ops.clip_to_padded(self._inputs, "clips", fr, B, T, H, W, frame_map, t_pad))
+            self.add(f"clips.to_padded_nhwc4[{tag}]", ops.clip_to_padded(self._inputs, "clips", fr, B, T, H, W, frame_map, t_pad),
+                     reads_input=True)
         return fr
 
     def stem_direct(self, name: str, w: torch.Tensor, scale, shift, k: int, stride: int, pad: int, act,
@@ -215,7 +221,7 @@ class ForwardPlan:
             ops._lib.check(lib.mspi_patch_gather(C.byref(pd), ops._ptr(src), ops._ptr(patches), ops._stream()),
                            f"patch_gather[{name}]")
 
-        self.add(name + ".gather", gather)
+        self.add(name + ".gather", gather, reads_input=True)
         w2 = torch.zeros((cout, k_pad), dtype=torch.float32, device=w.device)
         w5 = w if w.dim() == 5 else w[:, :, None]
         w2[:, :k] = w5.permute(0, 2, 3, 4, 1).reshape(cout, k)
@@ -836,7 +842,12 @@ class ForwardPlan:
         for _name, fn in self.steps:
             fn()
 
-    def run_branched(self):
+    def run_inputs(self):
+        """The steps that read the caller's tensors (clip conversion, spectrogram patch gather), on the current stream."""
+        for i in sorted(self.input_steps):
+            self.steps[i][1]()
+
+    def run_branched(self, skip_inputs: bool = False):
         """Enqueue the steps on one stream per branch (branch 0 = the current stream) with event edges between them.
         Under stream capture this records the fork / join structure of _build into the graph."""
         main = torch.cuda.current_stream()
@@ -860,6 +871,8 @@ class ForwardPlan:
                 stream_of(dst).wait_event(ev)
                 used.add(dst)
             else:
+                if skip_inputs and ent[1] in self.input_steps:
+                    continue
                 b = self.step_branch[ent[1]]
                 fn = self.steps[ent[1]][1]
                 if b == 0:
@@ -887,21 +900,23 @@ class ForwardPlan:
             self.run_eager()  # warm-up (module loading, attribute setting) outside capture
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # The graph holds everything EXCEPT the steps that read the caller's tensors: those run eagerly in front of every
+        # replay (run()), straight from the caller's buffers — a replay copies no inputs.
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if self.branches and any(e[0] == "edge" for e in self.sched):
-                self.run_branched()
+                self.run_branched(skip_inputs=True)
             else:
-                self.run_eager()
+                for i, (_name, fn) in enumerate(self.steps):
+                    if i not in self.input_steps:
+                        fn()
         self.graph = g
+        self.static_clips = self.static_audio = None   # only needed for the warm-up above
 
     def run(self, clips: torch.Tensor, audio: Optional[torch.Tensor], feats=None, frame_index=None):
         if self.graph is not None:
-            # callers that fill plan.static_clips / static_audio themselves (bench.py's upload path) skip the copies
-            if clips.data_ptr() != self.static_clips.data_ptr():
-                self.static_clips.copy_(clips, non_blocking=True)
-            if self.audio and audio.data_ptr() != self.static_audio.data_ptr():
-                self.static_audio.copy_(audio, non_blocking=True)
+            self.bind(clips, audio)
+            self.run_inputs()          # clip conversion / patch gather from the caller's tensors (not in the graph)
             self.graph.replay()
         else:
             self.bind(clips, audio, feats, frame_index)
