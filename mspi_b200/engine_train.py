@@ -109,6 +109,10 @@ def train_one_epoch(model, criterion, data_loader: Iterable, optimizer, device, 
             cur = optimizer.state_dict()
             osd["param_groups"] = cur["param_groups"]        # keep the caller's groups (schedulers edit them), replace the state
             optimizer.load_state_dict(osd)
+        elif osd["param_groups"]:
+            print("mspi_b200.train_one_epoch: the optimizer does not hold exactly the model's trainable tensors "
+                  f"({sum(len(g['params']) for g in optimizer.param_groups)} vs {len(osd['param_groups'][0]['params'])}); its state was "
+                  "not updated — checkpoint model.optimizer_state_dict() instead")
     sums, n = _sync_meters(sums, n, device)
     out = {k: v / max(n, 1) for k, v in sums.items()}
     out.update({"lr": lr, "min_lr": min_lr, "weight_decay": wd if wd > 0 else None})

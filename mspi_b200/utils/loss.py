@@ -1,7 +1,11 @@
 """SalLoss — same interface as utils/loss.py:6-49 of the reference: `SalLoss()(log_map, gt, fixations=None)`
 returns the scalar loss (KLD - CC, minus 0.1*NSS when fixations are given) and updates `.log[...]` meters.
 All reductions run in one CUDA kernel on the log map (exp fused); the meters read the five results with a
-single device->host copy instead of the reference's 4-5 `.item()` syncs."""
+single device->host copy instead of the reference's 4-5 `.item()` syncs.
+
+SalLoss here is a METRICS object: its forward runs under `torch.no_grad()` and the returned scalar carries no autograd graph,
+so the reference's `criterion(output, label).backward()` has no counterpart — the loss and its gradient are computed inside
+the training plan (`model.train_step`, mspi_salloss_bwd), which feeds this object's `.log` meters (engine_train.py)."""
 import torch
 import torch.nn as nn
 
