@@ -28,7 +28,8 @@ class ForwardPlan:
     def __init__(self, sd: Dict[str, torch.Tensor], batch: int, frames: int, height: int, width: int,
                  audio: bool = True, lateral_bool=(True, True, False, False), lateral_stride=(2, 2, 2, 2),
                  pool_stride: int = 1, device="cuda", keep_taps: bool = False, encoder: str = "s3d",
-                 pack_on_host: bool = True, weight_cache: Optional[dict] = None, mode: str = "full", input_u8: bool = False):
+                 pack_on_host: bool = True, weight_cache: Optional[dict] = None, mode: str = "full", input_u8: bool = False,
+                 liveness: Optional[dict] = None):
         assert (frames % 4 == 0 or mode == "image_encoder") and height % 32 == 0 and width % 32 == 0, \
             "T must be a multiple of 4 and H, W multiples of 32 (model_utils.py:506,566-570)"
         # Inference plans fold BatchNorm and pack the weights on the HOST (plain fp32 tensor arithmetic) and upload the packed
@@ -57,6 +58,11 @@ class ForwardPlan:
         # entries meaning "branch dst waits for everything branch src has enqueued so far".  The list order of `steps` stays a
         # valid serial order, which is what run_eager(), the per-kernel breakdown and the training plan use.
         self.sched: List[Tuple] = []
+        # activation memory: every self.new() is recorded; with `liveness` (from compute_liveness() of a probe build of the
+        # same plan) the memory of dead buffers is handed to later allocations of the same graph branch (arena.py)
+        from .arena import Arena
+        self._allocs: List[Tuple] = []
+        self._arena = Arena(liveness, device) if liveness is not None else None
         self.input_steps = set()
         self.step_branch: List[int] = []
         self._branch = 0
@@ -75,9 +81,28 @@ class ForwardPlan:
         return self.sd[name]
 
     def new(self, n, t, h, w, c, dtype=torch.bfloat16) -> Act:
-        a = Act.empty(n, t, h, w, c, dtype=dtype, device=self.device)
-        self.bytes_alloc += a.buf.numel() * a.buf.element_size()
+        k, step_now = len(self._allocs), len(self.steps)
+        if self._arena is not None:
+            before = self._arena.fresh_bytes
+            a = Act(self._arena.alloc(k, (n, t, h, w, c), dtype, step_now, self._branch))
+            self.bytes_alloc += self._arena.fresh_bytes - before
+        else:
+            a = Act.empty(n, t, h, w, c, dtype=dtype, device=self.device)
+            self.bytes_alloc += a.buf.numel() * a.buf.element_size()
+        self._allocs.append((k, a.buf, step_now, self._branch))
         return a
+
+    def compute_liveness(self) -> dict:
+        """{allocation index: (branch, last step touching it)} for the buffers whose memory may be re-used (arena.py)."""
+        from .arena import compute_liveness
+        pinned = [getattr(self, "logits", None), getattr(self, "out", None)]
+        pinned += [a.buf for a in self.taps.values()]
+        for nm in ("feat_o1", "feat_o0"):
+            if getattr(self, nm, None) is not None:
+                pinned.append(getattr(self, nm).buf)
+        live = compute_liveness(self._allocs, self.steps, self.step_branch, [t for t in pinned if t is not None])
+        live["__count__"] = len(self._allocs)
+        return live
 
     def add(self, name: str, fn: Callable[[], None], reads_input: bool = False):
         """reads_input: the step reads the caller's clips / spectrograms.  Those steps stay OUTSIDE the captured graph and run

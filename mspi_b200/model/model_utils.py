@@ -197,6 +197,7 @@ class _SaliencyBase(nn.Module):
         self.sa_2 = _sa(512)
         self._plans: Dict[Tuple, ForwardPlan] = {}
         self._wcache: Dict = {}      # packed, uploaded weights per device: shared by the plans of every batch shape
+        self._liveness: Dict = {}    # buffer life times per plan kind (activation arena, mspi_b200/arena.py)
         self.use_cuda_graph = False
         self.keep_taps = False
         if load_pretrained:
@@ -241,10 +242,24 @@ class _SaliencyBase(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             m = self.cfg.MODEL
-            plan = ForwardPlan(self.state_dict(), b, t, h, w, audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL),
-                               lateral_stride=tuple(m.LATERAL_STRIDE), pool_stride=m.S3D.POOL_STRIDE,
-                               device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER,
-                               weight_cache=self._wcache.setdefault(clips.device.index, {}), mode=mode, input_u8=u8)
+            sd = self.state_dict()
+            kw = dict(audio=self.has_audio, lateral_bool=tuple(m.LATERAL_BOOL), lateral_stride=tuple(m.LATERAL_STRIDE),
+                      pool_stride=m.S3D.POOL_STRIDE, device=clips.device, keep_taps=self.keep_taps, encoder=m.MOTION_ENCODER,
+                      weight_cache=self._wcache.setdefault(clips.device.index, {}), mode=mode, input_u8=u8)
+            liveness = None
+            if os.environ.get("MSPI_ARENA", "1") != "0":
+                # activation memory re-use: the life time of every buffer is read off a probe build of the same plan at batch 1
+                # (the sequence of allocations and launches does not depend on the batch size; checked below)
+                lkey = (mode, u8, t, h, w, clips.device.index, self.keep_taps)
+                liveness = self._liveness.get(lkey)
+                if liveness is None:
+                    probe = ForwardPlan(sd, 1, t, h, w, **kw)
+                    liveness = self._liveness[lkey] = probe.compute_liveness()
+                    del probe
+            plan = ForwardPlan(sd, b, t, h, w, liveness=liveness, **kw)
+            if liveness is not None and len(plan._allocs) != liveness["__count__"]:
+                raise RuntimeError("activation arena: the plan's allocation sequence differs from its probe build "
+                                   f"({len(plan._allocs)} vs {liveness['__count__']}); set MSPI_ARENA=0")
             if graph:
                 plan.capture()
             self._plans[key] = plan
