@@ -51,7 +51,7 @@ def compute_liveness(allocs, steps, step_branch, pinned: Iterable[torch.Tensor])
     import bisect
 
     def owner(t: torch.Tensor) -> Optional[int]:
-        if not t.is_cuda or t.numel() == 0:
+        if t.numel() == 0:
             return None
         p = t.data_ptr()
         j = bisect.bisect_right(starts, p) - 1

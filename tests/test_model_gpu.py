@@ -157,6 +157,32 @@ def test_feature_cache_matches_plain_forward_bit_for_bit():
         assert abs(float(loss) - float(ref_loss)) < 1e-6   # SimSiam loss: an atomic sum over (sample, pair) blocks
 
 
+def test_activation_arena_reuses_memory_without_changing_results(monkeypatch):
+    """mspi_b200/arena.py: the memory of dead activation buffers is handed to later allocations of the same graph branch.
+    Same maps bit for bit with and without it (eager and captured graph with its three branches), several times less memory."""
+    model = _small_model(seed=11)
+    g = torch.Generator().manual_seed(6)
+    clips = torch.randn(3, 3, 16, 96, 128, generator=g).cuda()
+    aud = torch.randn(3, 1, 257, 111, generator=g).cuda()
+    outs, mem = {}, {}
+    for arena in ("0", "1"):
+        for graph in (False, True):
+            monkeypatch.setenv("MSPI_ARENA", arena)
+            model.invalidate_plans()
+            model._liveness.clear()
+            model.use_cuda_graph = graph
+            model(clips, aud)
+            out, _ = model(clips, aud)
+            torch.cuda.synchronize()
+            outs[(arena, graph)] = out.clone()
+            mem[(arena, graph)] = next(iter(model._plans.values())).bytes_alloc
+    ref = outs[("0", False)]
+    for k, o in outs.items():
+        assert torch.equal(o, ref), (k, (o - ref).abs().max())
+    assert mem[("1", True)] < 0.45 * mem[("0", True)], mem
+    model.use_cuda_graph = False
+
+
 def test_forward_accepts_uint8_frames():
     """uint8 [B,T,H,W,3] frames, normalised on the device (ToTensor + Normalize of inference.py:154-165 folded into the clip
     conversion kernel), give exactly the forward of the host-normalised fp32 clip."""
