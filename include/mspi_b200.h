@@ -44,6 +44,11 @@ int mspi_version(void);
 const char* mspi_arch(void);
 /* Number of kernels launched by this library since load (process-wide counter). */
 int64_t mspi_launch_count(void);
+/* Programmatic dependent launch for the encoder kernels (conv_gemm, fused MLP, depthwise 7x7): the next kernel's prologue
+ * overlaps the previous kernel's drain; every such kernel executes griddepcontrol.wait before its first global access.
+ * Default on (environment MSPI_PDL=0 turns it off); returns the previous setting.  Set it BEFORE a plan is captured into a
+ * CUDA graph: the captured edges keep the kind they were captured with. */
+int mspi_set_pdl(int on);
 /* Profiling aid for the depthwise 7x7 + LayerNorm kernel (MSPI_DW_DEBUG=1 selects its instrumented instance): cycles the
  * warps spent [0] waiting for their tile, [1] in the stencil, [2] in the LayerNorm phase, [3] the number of warp samples,
  * [4] in the barrier after the stencil, [5] storing the result tile, summed since the last reset.  out8 has 8 entries.
@@ -103,6 +108,13 @@ typedef struct {
 
 int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
                    const float* shift, const void* residual, void* y, void* stream);
+/* Same convolution with a LayerNorm over channels as its epilogue (ConvNeXt stem: Conv2d 4x4/s4 + LayerNorm2d,
+ * timm convnext_tiny stem, model_utils.py:361):  y = LN(acc * scale + shift) * ln_weight + ln_bias, bf16.
+ * One N tile (cout == bn, 64 / 128 / 192 columns); a GEMM row holds ln_groups (1, 2, 4) groups of cout / ln_groups
+ * channels, each normalised on its own (the stem computes two output pixels per row).  Statistics in fp32, two passes
+ * over the accumulators; the fp32 conv output is never written. */
+int mspi_conv_gemm_ln(const MspiConvDesc* d, const void* x, const void* w, const float* scale, const float* shift,
+                      const float* ln_weight, const float* ln_bias, float ln_eps, int ln_groups, void* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Weight gradient of mspi_conv_gemm's convolution on tcgen05 tensor cores (training step, engine_train.py:74:
@@ -125,6 +137,14 @@ int mspi_conv_wgrad(const MspiConvDesc* d, const void* x, const void* dy, float*
 int mspi_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
                    const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
                    int64_t res_stride, int64_t y_stride, void* stream);
+/* Same block with the NEXT layer's LayerNorm fused into the store: y = LN_c(r + gamma * mlp(x)) * ln_weight + ln_bias, the
+ * statistics taken over the c channels of the bf16-rounded block output.  Serves the last block of ConvNeXt stages 0 and 1,
+ * whose output is read only by the following stage's downsample.0 LayerNorm2d (timm ConvNeXtStage.downsample,
+ * model_utils.py:361): the un-normalised block output is never written. */
+int mspi_mlp_fused_ln(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                      const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                      int64_t res_stride, int64_t y_stride, const float* ln_weight, const float* ln_bias, float ln_eps,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch gather (explicit im2col) for the layers whose input has too few channels for a TMA

@@ -130,11 +130,15 @@ _SIGNATURES = {
     "mspi_version": (C.c_int, []),
     "mspi_arch": (C.c_char_p, []),
     "mspi_launch_count": (C.c_int64, []),
+    "mspi_set_pdl": (C.c_int, [C.c_int]),
     "mspi_debug_dw_phase_cycles": (C.c_int, [C.c_void_p, C.c_int]),
     "mspi_debug_gemm_epilogue_cycles": (C.c_int, [C.c_void_p, C.c_int]),
     "mspi_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "mspi_conv_gemm_ln": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P]),
     "mspi_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "mspi_mlp_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _P]),
+    "mspi_mlp_fused_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P,
+                                    C.c_float, _P]),
     "mspi_patch_gather": (C.c_int, [C.POINTER(PatchDesc), _P, _P, _P]),
     "mspi_ncdhw_to_ndhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "mspi_clip_to_padded_nhwc4": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -1,4 +1,5 @@
 // Error reporting, version and launch accounting for the mspi_b200 C ABI.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -27,8 +28,24 @@ int num_sms() {   // of the CURRENT device (cached per device: one process may d
   return n;
 }
 
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("MSPI_PDL");
+    v = (!e || atoi(e) != 0) ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
 }  // namespace mspi
 
+extern "C" int mspi_set_pdl(int on) {
+  const int prev = mspi::pdl_enabled() ? 1 : 0;
+  mspi::g_pdl.store(on ? 1 : 0);
+  return prev;
+}
 extern "C" const char* mspi_last_error(void) { return mspi::g_err; }
 extern "C" int mspi_version(void) { return 1; }
 extern "C" const char* mspi_arch(void) { return "sm_100a"; }

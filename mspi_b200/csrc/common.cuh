@@ -38,8 +38,23 @@ inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed);
 
 int num_sms();
 
+// Programmatic dependent launch (MSPI_PDL, default on): a kernel launched with this attribute may become resident while the
+// previous kernel of its stream is still draining — every CTA of that kernel has passed pdl_launch_dependents() or exited —
+// and runs its prologue (barrier init, TMEM allocation, tensor-map prefetch) there; pdl_wait() then blocks until the
+// previous kernel has COMPLETED and its writes are visible.  Only kernels that execute pdl_wait() before their first global
+// access are launched this way.  Inside a captured graph the edge becomes a programmatic dependency.
+bool pdl_enabled();
+inline int pdl_attr(cudaLaunchAttribute* a) {   // fills *a and returns 1 when PDL is on, else 0
+  if (!pdl_enabled()) return 0;
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+
 // ---- device side ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -88,6 +88,14 @@ struct GemmParams {
   int res_tma;    // 1: the residual chunk arrives by TMA in the output staging buffer and is updated in place (fused_mlp.cu does
                   // the same): lane-per-row global loads of it cost 6500 cycles per chunk on the epilogue's critical path
   int y_box_bytes;  // bytes of one staged output / residual chunk: rows of the M box x 128
+  int n_stage_bufs; // 16 KB output staging buffers behind the epilogue vectors
+  // LayerNorm epilogue (LN instance): every GEMM row holds ln_groups groups of bn / ln_groups channels (the ConvNeXt stem
+  // computes two output pixels per row); each group is normalised over its channels in fp32 and stored as bf16
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int ln_groups;
+  int ln_extra;     // bytes behind the staged scale / shift vectors: weight and bias per column, partial sums
 };
 
 using namespace tc;
@@ -161,7 +169,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // the activation, 2 added after it); -1 selects the run-time value from the parameters (generic instance).
 // PAIR: the CTA-pair (cta_group::2) variant.  It is a separate instantiation because a kernel that contains cta_group::2
 // instructions can only be launched with an even cluster width (a plain launch fails with "cluster misconfiguration").
-template <int KIND, int OUT, int ACT, int RES, bool PAIR = false>
+template <int KIND, int OUT, int ACT, int RES, bool PAIR = false, bool LN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_r,
@@ -180,12 +188,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   // staging buffers (TMA-store path) and the operand ring
   float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kBarrierBytes);
   float* s_shift = s_scale + p.ss_floats;
-  const uint32_t stage_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + 1023u) & ~1023u;
-  const uint32_t tiles_base = stage_base + (p.tma_store ? static_cast<uint32_t>(kEpiSets > 1 ? kEpiSets * kStageBufs : 2) * kABytes : 0u);
+  const uint32_t stage_base = (smem_base + kBarrierBytes + 8u * p.ss_floats + static_cast<uint32_t>(p.ln_extra) + 1023u) & ~1023u;
+  const uint32_t tiles_base = stage_base + (p.tma_store ? static_cast<uint32_t>(p.n_stage_bufs) * kABytes : 0u);
+  float* s_lnw = s_shift + p.ss_floats;     // LN instance: [bn] weight, [bn] bias (per GEMM column), then the partial sums
+  float* s_lnb = s_lnw + p.bn;
+  float* s_part = s_lnb + p.bn;             // [2][4 column parts][128 rows]
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel of the stream may take this CTA's SM as soon as the CTA exits
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -217,9 +229,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  // Everything above ran while the previous kernel of the stream was still finishing; from here on this kernel reads what
+  // that kernel wrote (activations; in a training plan also the scale / shift vectors of the batch statistics).
+  pdl_wait();
   for (int i = threadIdx.x; i < p.ss_floats; i += kThreads) {
     s_scale[i] = (p.scale != nullptr && i < p.cout) ? __ldg(p.scale + i) : 1.f;
     s_shift[i] = (p.shift != nullptr && i < p.cout) ? __ldg(p.shift + i) : 0.f;
+  }
+  if constexpr (LN) {
+    const int gw = p.bn / p.ln_groups;
+    for (int i = threadIdx.x; i < p.bn; i += kThreads) {
+      s_lnw[i] = __ldg(p.ln_w + i % gw);
+      s_lnb[i] = __ldg(p.ln_b + i % gw);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -416,6 +438,99 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       valid = valid && (r == 0);
       if (dummy) org[3] = kFar;
+
+      if constexpr (LN) {
+        // ---- LayerNorm epilogue: the whole tile row (bn <= 192 columns) is in TMEM.  The 16 epilogue warps split it four
+        // ways per TMEM lane quarter: thread (row, part) owns bn / 4 consecutive columns, adds the conv bias, and the
+        // 4 / ln_groups threads that share a channel group exchange partial sums through shared memory — first the sums (mean),
+        // then the squared deviations (two passes over registers: the stem's channels have |mean| >> sigma, so E[x^2] - mean^2
+        // would cancel).  The normalised bf16 rows leave through the staging buffers and bulk tensor stores.
+        mbar_wait(bar_tfull + 8 * as, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+        const int part = (warp - 2) >> 2;
+        const int cw = p.bn >> 2;                    // 16, 32 or 48 columns per thread
+        const int c0 = part * cw;
+        uint32_t acc[3][16];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (16 * u < cw) tmem_ld16(taddr + c0 + 16 * u, acc[u]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (pair) mbar_arrive_cluster(leader_smem(bar_tempty + 8 * as)); else mbar_arrive(bar_tempty + 8 * as);
+        }
+        float s1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (16 * u < cw) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int c = c0 + 16 * u + e;
+              const float v = fmaf(__uint_as_float(acc[u][e]), s_scale[c], s_shift[c]);
+              acc[u][e] = __float_as_uint(v);
+              s1 += v;
+            }
+          }
+        const int ppg = 4 / p.ln_groups, g0 = (part / ppg) * ppg;
+        const float inv_gw = static_cast<float>(p.ln_groups) / static_cast<float>(p.bn);
+        s_part[part * 128 + row] = s1;
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        float mean = 0.f;
+        for (int q = 0; q < ppg; ++q) mean += s_part[(g0 + q) * 128 + row];
+        mean *= inv_gw;
+        float s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (16 * u < cw) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float dv = __uint_as_float(acc[u][e]) - mean;
+              s2 = fmaf(dv, dv, s2);
+            }
+          }
+        s_part[512 + part * 128 + row] = s2;
+        // the bulk stores of the previous tile have finished reading the staging buffers before anyone writes them again
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        float var = 0.f;
+        for (int q = 0; q < ppg; ++q) var += s_part[512 + (g0 + q) * 128 + row];
+        const float rstd = rsqrtf(var * inv_gw + p.ln_eps);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (16 * u < cw) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int c = c0 + 16 * u + 8 * h8;
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = fmaf((__uint_as_float(acc[u][8 * h8 + 2 * e]) - mean) * rstd, s_lnw[c + 2 * e], s_lnb[c + 2 * e]);
+                const float b = fmaf((__uint_as_float(acc[u][8 * h8 + 2 * e + 1]) - mean) * rstd, s_lnw[c + 2 * e + 1], s_lnb[c + 2 * e + 1]);
+                o[e] = pack_bf16x2(a, b);
+              }
+              const uint32_t piece = static_cast<uint32_t>(c) >> 3;       // 16-byte piece of the 128-byte chunk piece >> 3
+              const uint32_t dst = stage_base + (piece >> 3) * kABytes + static_cast<uint32_t>(row) * kRowBytes +
+                                   (((piece & 7u) ^ (static_cast<uint32_t>(row) & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (warp == 2 && lane == 0) {
+          for (int cb = 0; cb * 64 < p.bn; ++cb)
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tma_y),
+                "r"(stage_base + static_cast<uint32_t>(cb) * kABytes), "r"(cb * 64), "r"(org[0]), "r"(org[1]), "r"(org[2]),
+                "r"(org[3])
+                : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        continue;
+      }
 
       // residual rows of this thread for one chunk (4 x 16 bytes), fetched early: issued just before use, every one of these
       // loads (32 different lines per warp instruction) exposes a full L2 / DRAM round trip to the chunk's critical path
@@ -757,10 +872,12 @@ extern "C" int mspi_debug_gemm_epilogue_cycles(uint64_t* out8, int reset) {
   return MSPI_OK;
 }
 
-extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
-                              const float* shift, const void* residual, void* y, void* stream_) {
+static int conv_gemm_impl(const MspiConvDesc* d, const void* x, const void* w, const float* scale, const float* shift,
+                          const void* residual, void* y, const float* ln_w, const float* ln_b, float ln_eps, int ln_groups,
+                          void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(d && x && w && y, "mspi_conv_gemm: null argument");
+  const bool ln = ln_w != nullptr;
   MSPI_CHECK_ARG(d->a_dtype == MSPI_BF16 || d->a_dtype == MSPI_F32, "a_dtype %d", d->a_dtype);
   const int elsize = d->a_dtype == MSPI_BF16 ? 2 : 4;
   const int row_bytes = d->k_row_bytes > 0 ? d->k_row_bytes : kRowBytes;
@@ -895,7 +1012,19 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   p.a_tx_bytes = static_cast<int>(rows) * row_bytes;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   p.ss_floats = p.n_tiles * d->bn + 64;  // padded: the last staged chunk may run past the tile
-  const int ss_bytes = (8 * p.ss_floats + 1023) & ~1023;
+  if (ln) {
+    MSPI_CHECK_ARG(ln_b && ln_eps > 0.f && (ln_groups == 1 || ln_groups == 2 || ln_groups == 4), "LayerNorm epilogue: bad argument");
+    MSPI_CHECK_ARG(d->a_dtype == MSPI_BF16 && d->o_dtype == MSPI_BF16 && d->act == MSPI_ACT_NONE && !d->has_residual && !w_batched,
+                   "LayerNorm epilogue: bf16 operands and output, no activation, no residual");
+    MSPI_CHECK_ARG(d->cout == d->bn && d->bn % 64 == 0 && d->bn <= 192 && kEpiWarps == 16,
+                   "LayerNorm epilogue: one N tile of 64, 128 or 192 columns (cout %d, bn %d)", d->cout, d->bn);
+    p.ln_w = ln_w;
+    p.ln_b = ln_b;
+    p.ln_eps = ln_eps;
+    p.ln_groups = ln_groups;
+    p.ln_extra = 8 * d->bn + 2 * 4 * 128 * 4;
+  }
+  const int ss_bytes = (8 * p.ss_floats + p.ln_extra + 1023) & ~1023;
   MSPI_CHECK_ARG(ss_bytes <= 64 * 1024, "cout %d too large for the staged epilogue vectors", d->cout);
 
   // Output path: bulk tensor stores need 16-byte aligned row strides and N tiles that end on a 128-byte chunk.
@@ -958,7 +1087,10 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     }
     p.res_tma = ok ? 1 : 0;
   }
-  const int out_stage_bytes = p.tma_store ? (kEpiSets > 1 ? kEpiSets * kStageBufs : 2) * kABytes : 0;
+  if (ln) MSPI_CHECK_ARG(p.tma_store, "LayerNorm epilogue: output rows must allow bulk tensor stores (16-byte aligned strides)");
+  p.n_stage_bufs = ln ? (d->bn + 63) / 64 : (kEpiSets > 1 ? kEpiSets * kStageBufs : 2);
+  if (ln && p.n_stage_bufs < 2) p.n_stage_bufs = 2;
+  const int out_stage_bytes = p.tma_store ? p.n_stage_bufs * kABytes : 0;
   p.num_stages = (kSmemBudget - kBarrierBytes - 1024 - ss_bytes - out_stage_bytes) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   int cols = 32;
@@ -1001,6 +1133,9 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     else kern = d->o_dtype == MSPI_BF16 ? conv_gemm_kernel<MSPI_F32, MSPI_BF16, -1, -1>
                                         : conv_gemm_kernel<MSPI_F32, MSPI_F32, -1, -1>;
   }
+  if (ln)
+    kern = pair ? conv_gemm_kernel<MSPI_BF16, MSPI_BF16, MSPI_ACT_NONE, 0, true, true>
+                : conv_gemm_kernel<MSPI_BF16, MSPI_BF16, MSPI_ACT_NONE, 0, false, true>;
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
   MSPI_CHECK_ARG(total < (1ll << 31), "too many tiles");
@@ -1008,7 +1143,16 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
   if (grid <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   if (cl == 1) {
     if (total < grid) grid = static_cast<int>(total);
-    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_y, map_r, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(&attr[0]);
+    MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, map_r, p));
   } else {
     const long long items = static_cast<long long>((p.m_tiles + cl - 1) / cl) * p.n_tiles;
     long long nclusters = grid / cl;
@@ -1019,15 +1163,27 @@ extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* 
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + pdl_attr(&attr[1]);
     MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, map_r, p));
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
+}
+
+extern "C" int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const float* scale,
+                              const float* shift, const void* residual, void* y, void* stream) {
+  return conv_gemm_impl(d, x, w, scale, shift, residual, y, nullptr, nullptr, 0.f, 1, stream);
+}
+
+extern "C" int mspi_conv_gemm_ln(const MspiConvDesc* d, const void* x, const void* w, const float* scale, const float* shift,
+                                 const float* ln_weight, const float* ln_bias, float ln_eps, int ln_groups, void* y,
+                                 void* stream) {
+  MSPI_CHECK_ARG(ln_weight && ln_bias, "mspi_conv_gemm_ln: null LayerNorm vector");
+  return conv_gemm_impl(d, x, w, scale, shift, nullptr, y, ln_weight, ln_bias, ln_eps, ln_groups, stream);
 }

@@ -641,6 +641,8 @@ dw7x7_ln_r2_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
   const int tx = blockIdx.x, ty = blockIdx.y, n = n0 + blockIdx.z;
   const int x0 = tx * P, y0 = ty * S;
   const uint32_t bar = tc::smem_u32(&tma_bar);
+  pdl_launch_dependents();
+  pdl_wait();   // programmatic dependent launch (common.cuh): the blocks of the first wave are resident before the previous kernel ends
   if (threadIdx.x == 0) {
     tc::mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -800,8 +802,17 @@ int launch_dw7x7_r2(const MspiDwDesc* d, const void* x, const float* wgt, const 
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   for (long long n0 = 0; n0 < frames; n0 += 65535) {
     const unsigned nz = static_cast<unsigned>(frames - n0 < 65535 ? frames - n0 : 65535);
-    kern<<<dim3(tiles_x, tiles_y, nz), CQ * SP, smem, stream>>>(map, wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h,
-                                                              d->w, static_cast<int>(n0), d->ln_eps);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles_x, tiles_y, nz);
+    cfg.blockDim = dim3(CQ * SP, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(&attr[0]);
+    MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map, wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w,
+                                 static_cast<int>(n0), d->ln_eps));
     MSPI_LAUNCH_CHECK();
   }
   return MSPI_OK;
@@ -815,9 +826,11 @@ __global__ void dwt_kernel(const TI* __restrict__ x, const float* __restrict__ w
   const int cq = C >> 2;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n_hw * cq) return;
-  const int q = static_cast<int>(idx % cq);
-  const long long pos = idx / cq;  // n*HW + hw
-  const long long n = pos / HW, hw = pos % HW;
+  // 32-bit divisions whenever the index fits (common.cuh divmod): four 64-bit divisions were half of this kernel's instructions
+  long long r = idx;
+  const int q = divmod(r, cq);
+  const long long hw = divmod(r, HW);   // r: n*HW + hw -> n
+  const long long n = r;
   const long long base = (n * T * HW + hw) * C + 4 * q;
   const long long tstride = static_cast<long long>(HW) * C;
   float4 v[MAXT];

@@ -36,6 +36,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kChunkBytes = 128 * 128;         // one K chunk of a 128-row operand tile: 16 KB
 constexpr int kMaxRing = 8;
 constexpr int kMaxHBuf = 3;
+constexpr int kVecBytes = 12288;               // staged per-channel vectors (8 KB) + LayerNorm partial sums (4 KB)
 // MSPI_MLP_DEBUG (study bits: skip GELU / TMEM loads / A2 stores / residual I/O) only exists in builds made with
 // -DMSPI_MLP_STUDY: as a run-time flag its dead branches still cost the epilogue 32 integer instructions per hidden chunk
 // (ptxas hoists the fake accumulator values above the branch; ncu source page, profiles/r02_fused_mlp.md).
@@ -63,6 +64,12 @@ struct MlpParams {
                         // TMA (a warp's direct row accesses cost 32 L1 tag cycles per instruction: 6144 per 128 x 96 tile)
   int ystage_bytes;
   int packed_gelu;      // GELU on packed fp32 pairs (fma.rn.f32x2 / mul / add) with one fp32 tanh per element
+  // LayerNorm over the C channels of every output row, applied to the bf16-rounded block output before it is stored (the
+  // next stage's downsample.0 LayerNorm2d, model_utils.py:361 / timm ConvNeXtStage): y = LN(r + gamma * mlp(x)) * w + b.
+  // The block output itself is then never written: the downsample conv is its only reader.
+  const float* ln_w;    // [C] or null
+  const float* ln_b;    // [C]
+  float ln_eps;
 };
 
 __device__ __forceinline__ void ldg256(const __nv_bfloat16* p, uint4& a, uint4& b) {
@@ -139,7 +146,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // PAIR: CTA-pair instance (cluster of 2 required); a kernel that contains cta_group::2 instructions cannot be launched plainly.
-template <bool PAIR>
+template <bool PAIR, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
@@ -158,12 +165,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   float* s_b1 = reinterpret_cast<float*>(base_ptr + 1024);       // [4C]
   float* s_scale = s_b1 + 4 * p.c;                               // [C]
   float* s_shift = s_scale + p.c;                                // [C]
-  const uint32_t x_base = base + 1024 + 8192;                    // 2 x kc1 chunks
+  float* s_lnw = s_shift + p.c;                                  // [C]   (8 C floats <= 6 KB so far)
+  float* s_lnb = s_lnw + p.c;                                    // [C]
+  float2* s_part = reinterpret_cast<float2*>(base_ptr + 1024 + 8192);   // [4 column groups][128 rows] (sum, sum of squares)
+  const uint32_t x_base = base + 1024 + kVecBytes;               // 2 x kc1 chunks
   const uint32_t a2_base = x_base + static_cast<uint32_t>(p.x_bufs) * p.kc1 * kChunkBytes;  // 2 buffers x 2 chunks
   const uint32_t ystage_base = a2_base + 4u * kChunkBytes;       // [c/32 boxes][128 rows][64 B], 64B-swizzled (y_staged)
   const uint32_t ring_base = ystage_base + static_cast<uint32_t>(p.ystage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
@@ -200,10 +211,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  pdl_wait();   // barrier init / TMEM allocation above overlap the previous kernel's drain (common.cuh)
   for (int i = threadIdx.x; i < 4 * p.c; i += kThreads) s_b1[i] = __ldg(p.b1 + i);
   for (int i = threadIdx.x; i < p.c; i += kThreads) {
     s_scale[i] = __ldg(p.scale + i);
     s_shift[i] = __ldg(p.shift + i);
+    if (LN) {
+      s_lnw[i] = __ldg(p.ln_w + i);
+      s_lnb[i] = __ldg(p.ln_b + i);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -418,9 +434,148 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint4 resq[3][2];
     int prow0 = 0;                       // first row of the pending tile
     const bool io_thread = warp == 2 && lane == 0;
+    // ---- fused LayerNorm of the output rows (p.ln_w): a row's C channels are spread over the four column groups (same lane
+    // of four warps), so each thread sums its bf16-rounded outputs, the partial sums meet in shared memory, and every thread
+    // normalises its own columns.  s_part is safe to re-use from tile to tile: a thread reaches the next tile's Y epilogue
+    // nh >= 3 hidden chunks later, and the A2 staging ring (two chunks deep, every epilogue warp arrives per chunk) keeps the
+    // epilogue warps within two chunks of each other.
+    constexpr bool ln = LN;   // compile time: the plain instance keeps its register allocation
+    const float ln_inv_c = 1.f / static_cast<float>(p.c);
+    auto ln_add = [&](uint32_t pk, float& s1, float& s2) {
+      float a, b;
+      unpack_bf16x2(pk, a, b);
+      s1 += a + b;
+      s2 = fmaf(a, a, fmaf(b, b, s2));
+    };
+    auto ln_exchange = [&](float s1, float s2, float& mean, float& rstd) {
+      s_part[colgrp * 128 + row] = make_float2(s1, s2);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 v = s_part[q * 128 + row];
+        t1 += v.x;
+        t2 += v.y;
+      }
+      mean = t1 * ln_inv_c;
+      rstd = rsqrtf(fmaxf(fmaf(-mean, mean, t2 * ln_inv_c), 0.f) + p.ln_eps);
+    };
+    auto ln_apply = [&](uint32_t pk, int col, float mean, float rstd) {
+      float a, b;
+      unpack_bf16x2(pk, a, b);
+      a = fmaf((a - mean) * rstd, s_lnw[col], s_lnb[col]);
+      b = fmaf((b - mean) * rstd, s_lnw[col + 1], s_lnb[col + 1]);
+      return pack_bf16x2(a, b);
+    };
     auto y_epilogue = [&]() {
       mbar_wait(y_full, ytile & 1u);
       tc_fence_after();
+      if (LN && p.y_staged) {
+        // staged path (C <= 128: at most two 16-column pieces per thread).  Two passes over the accumulator instead of a
+        // register stash (a stash of the packed outputs spilled 264 bytes per thread through an L1 that the 227 KB of
+        // shared memory leave no room in: +0.32 ms per launch): pass 1 sums the bf16-rounded outputs, pass 2 recomputes
+        // them — same arithmetic, same rounding — normalises and overwrites the residual in the staging tile.
+        mbar_wait(res_full, ytile & 1u);
+        float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c0 = 16 * colgrp + 64 * u;
+            if (c0 >= p.c) break;
+            uint32_t acc[16];
+            __syncwarp();
+            tmem_ld16(lane_y + c0, acc);
+            tmem_ld_wait();
+            const uint32_t rowb = ystage_base + static_cast<uint32_t>(c0 >> 5) * (128u * 64u) + static_cast<uint32_t>(row) * 64u;
+            const uint32_t k0 = static_cast<uint32_t>(c0 & 31) >> 3, swz = (static_cast<uint32_t>(row) >> 1) & 3u;
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int col = c0 + 8 * h8;
+              const uint32_t addr = rowb + (((k0 + h8) ^ swz) << 4);
+              uint4 rr;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(addr) : "memory");
+              float res[8];
+              unpack_bf16x2(rr.x, res[0], res[1]); unpack_bf16x2(rr.y, res[2], res[3]);
+              unpack_bf16x2(rr.z, res[4], res[5]); unpack_bf16x2(rr.w, res[6], res[7]);
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float v0 = fmaf(__uint_as_float(acc[8 * h8 + 2 * e]), s_scale[col + 2 * e], s_shift[col + 2 * e]) + res[2 * e];
+                const float v1 = fmaf(__uint_as_float(acc[8 * h8 + 2 * e + 1]), s_scale[col + 2 * e + 1], s_shift[col + 2 * e + 1]) + res[2 * e + 1];
+                o[e] = pack_bf16x2(v0, v1);
+                if (pass == 0) ln_add(o[e], s1, s2); else o[e] = ln_apply(o[e], col + 2 * e, mean, rstd);
+              }
+              if (pass == 1)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+          }
+          if (pass == 0) ln_exchange(s1, s2, mean, rstd);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(y_empty);     // TMEM has been read twice: MMA2 of the next tile may overwrite Y
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every epilogue thread has written its pieces
+        if (io_thread) {
+          for (int b = 0; b < p.c / 32; ++b)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_y),
+                         "r"(ystage_base + static_cast<uint32_t>(b) * (128u * 64u)), "r"(b * 32), "r"(prow0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++ytile;
+        return;
+      }
+      if constexpr (LN) {
+        // direct path (C = 192: three 16-column pieces per thread, residual rows prefetched into registers): same two passes
+        float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int c0 = 16 * colgrp + 64 * u;
+            if (c0 >= p.c) break;
+            uint32_t acc[16];
+            __syncwarp();
+            tmem_ld16(lane_y + c0, acc);
+            tmem_ld_wait();
+            uint4 o2[2];
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int col = c0 + 8 * h8;
+              const uint4 rr = resq[u][h8];
+              float res[8];
+              unpack_bf16x2(rr.x, res[0], res[1]); unpack_bf16x2(rr.y, res[2], res[3]);
+              unpack_bf16x2(rr.z, res[4], res[5]); unpack_bf16x2(rr.w, res[6], res[7]);
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float v0 = fmaf(__uint_as_float(acc[8 * h8 + 2 * e]), s_scale[col + 2 * e], s_shift[col + 2 * e]) + (pvalid ? res[2 * e] : 0.f);
+                const float v1 = fmaf(__uint_as_float(acc[8 * h8 + 2 * e + 1]), s_scale[col + 2 * e + 1], s_shift[col + 2 * e + 1]) + (pvalid ? res[2 * e + 1] : 0.f);
+                o[e] = pack_bf16x2(v0, v1);
+                if (pass == 0) ln_add(o[e], s1, s2); else o[e] = ln_apply(o[e], col + 2 * e, mean, rstd);
+              }
+              o2[h8] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if (pass == 1 && pvalid) {
+              __nv_bfloat16* yp = p.y + pgrow * p.y_stride + c0;
+              if (p.wide_io) {
+                stg256(yp, o2[0], o2[1]);
+              } else {
+                *reinterpret_cast<uint4*>(yp) = o2[0];
+                *reinterpret_cast<uint4*>(yp + 8) = o2[1];
+              }
+            }
+          }
+          if (pass == 0) ln_exchange(s1, s2, mean, rstd);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(y_empty);
+        ++ytile;
+        return;
+      }
       if (p.y_staged) {
         mbar_wait(res_full, ytile & 1u);   // the residual tile has landed in the staging buffer
 #pragma unroll
@@ -629,9 +784,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
 using namespace mspi;
 
-extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
-                              const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
-                              int64_t res_stride, int64_t y_stride, void* stream_) {
+static int mlp_fused_impl(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                          const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                          int64_t res_stride, int64_t y_stride, const float* ln_w, const float* ln_b, float ln_eps,
+                          void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(x && w1 && b1 && w2 && scale && shift && residual && y && m > 0, "mspi_mlp_fused: null argument");
   MSPI_CHECK_ARG((c == 96 || c == 192) && c_pad % 64 == 0 && c_pad >= c && c_pad < c + 64, "mspi_mlp_fused: C %d / pad %d unsupported", c, c_pad);
@@ -682,6 +838,9 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   p.y = static_cast<__nv_bfloat16*>(y);
   p.res_stride = res_stride;
   p.y_stride = y_stride;
+  p.ln_w = ln_w;
+  p.ln_b = ln_b;
+  p.ln_eps = ln_eps;
   static const bool wide_on = [] { const char* e = getenv("MSPI_MLP_WIDE_IO"); return !e || atoi(e) != 0; }();
   p.wide_io = wide_on && (reinterpret_cast<uintptr_t>(residual) & 31) == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 &&
               (res_stride * 2) % 32 == 0 && (y_stride * 2) % 32 == 0;
@@ -707,12 +866,14 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kHC >> 3) << 17) | ((mdim >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(c >> 3) << 17) | ((mdim >> 4) << 24);
   p.x_bufs = c <= 96 ? 2 : 1;  // C = 192: the weight ring needs the room (30 pieces per tile, each one L2 round trip)
-  const int fixed = 1024 + 1024 + 8192 + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes + p.ystage_bytes;
+  const int fixed = 1024 + 1024 + kVecBytes + p.x_bufs * p.kc1 * kChunkBytes + 4 * kChunkBytes + p.ystage_bytes;
   p.ring_stages = (225 * 1024 - fixed) / p.ring_stage_bytes;
   if (p.ring_stages > kMaxRing) p.ring_stages = kMaxRing;
   MSPI_CHECK_ARG(p.ring_stages >= 2, "mspi_mlp_fused: shared memory leaves %d ring stages", p.ring_stages);
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.ring_stages) * p.ring_stage_bytes;
-  auto kern = pair ? fused_mlp_kernel<true> : fused_mlp_kernel<false>;
+  const bool lnk = ln_w != nullptr;
+  auto kern = pair ? (lnk ? fused_mlp_kernel<true, true> : fused_mlp_kernel<true, false>)
+                   : (lnk ? fused_mlp_kernel<false, true> : fused_mlp_kernel<false, false>);
   MSPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   p.cl = cl;
   if (const char* e = getenv("MSPI_MLP_DEBUG")) p.debug = atoi(e);
@@ -725,7 +886,7 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
@@ -733,18 +894,36 @@ extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, co
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent grid: as many clusters as can be resident at once (1 CTA per SM), never more than there are tile groups
-  static int max_clusters[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
-  if (max_clusters[pair][cl] == 0) {
+  static int max_clusters[4][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  const int ki = (pair ? 1 : 0) + (lnk ? 2 : 0);
+  if (max_clusters[ki][cl] == 0) {
     cfg.gridDim = dim3(num_sms() / cl * cl, 1, 1);
     int n = 0;
     MSPI_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    max_clusters[pair][cl] = n > 0 ? n : 1;
+    max_clusters[ki][cl] = n > 0 ? n : 1;
   }
-  int nclusters = max_clusters[pair][cl];
+  int nclusters = max_clusters[ki][cl];
   if (nclusters > num_sms() / cl) nclusters = num_sms() / cl;
   if (nclusters > groups) nclusters = groups;
   cfg.gridDim = dim3(nclusters * cl, 1, 1);
+  cfg.numAttrs = 1 + pdl_attr(&attr[1]);   // (the occupancy query above ran without it)
   MSPI_CUDA(cudaLaunchKernelEx(&cfg, kern, map_x, map_w1, map_w2, map_r, map_y, p));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
+}
+
+extern "C" int mspi_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                              const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                              int64_t res_stride, int64_t y_stride, void* stream) {
+  return mlp_fused_impl(x, w1, b1, w2, scale, shift, residual, y, m, c, c_pad, res_stride, y_stride, nullptr, nullptr, 0.f,
+                        stream);
+}
+
+extern "C" int mspi_mlp_fused_ln(const void* x, const void* w1, const float* b1, const void* w2, const float* scale,
+                                 const float* shift, const void* residual, void* y, int64_t m, int c, int c_pad,
+                                 int64_t res_stride, int64_t y_stride, const float* ln_weight, const float* ln_bias,
+                                 float ln_eps, void* stream) {
+  MSPI_CHECK_ARG(ln_weight && ln_bias && ln_eps > 0.f, "mspi_mlp_fused_ln: null LayerNorm vector");
+  return mlp_fused_impl(x, w1, b1, w2, scale, shift, residual, y, m, c, c_pad, res_stride, y_stride, ln_weight, ln_bias, ln_eps,
+                        stream);
 }

@@ -6,6 +6,7 @@ namespace mspi {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kGateMaxW = 1024;   // widest row the scale-ladder gate kernel stages gates for
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
@@ -453,48 +454,165 @@ struct GateSrc {
   const float* p[3];
   long long cs[3];
   int k[3];
+  int sh[3], sw[3];   // source height / width = h / k, w / k (computed on the host: no division in the kernel)
+  float inv[3];       // 1 / k
   int n;
 };
+// One output ROW (plane, oy) per block iteration: the row decomposition and everything that depends on oy only (source rows,
+// vertical weights, row base pointers) is block-uniform and computed once per row; a thread only splits its element index
+// into (ox, channel group) with one multiply-high.  The first version decomposed a linear index per element (three
+// divisions, six more for the source sizes): ~700 instructions per 32 output bytes, issue bound at 2.5 TB/s.
 template <int NS>   // number of top-down sources (compile time: the loads of all sources are issued before the first blend)
-__global__ void sa_gate_fused_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs,
-                                     long long total, int c8, int h, int w, GateSrc s) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long pix = i;
-    const int cc = divmod(pix, c8) * 8;
-    long long r = pix;
-    const int ox = divmod(r, w);
-    const int oy = divmod(r, h);
-    const long long plane = r;
-    const float g = m != nullptr ? 1.f + 1.f / (1.f + expf(-__ldg(m + pix))) : 1.f;   // no mask: plain y = x + sum up(src)
-    float f[8];
-    {
-      const float4* xp = reinterpret_cast<const float4*>(x + pix * xcs + cc);   // x may alias y (in place): no __ldg
-      const float4 a0 = xp[0], a1 = xp[1];
-      f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] *= g;
+__global__ void __launch_bounds__(256)
+sa_gate_fused_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs, int rows, int c8,
+                     int h, int w, unsigned c8_magic, GateSrc s) {
+  const int per_row = w * c8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int plane = row / h, oy = row - plane * h;
+    const float* r0[NS > 0 ? NS : 1];
+    const float* r1[NS > 0 ? NS : 1];
+    float ly[NS > 0 ? NS : 1];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const int k = s.k[j], sh = h / k, sw = w / k;
-      const float inv = 1.f / static_cast<float>(k);
-      const float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
-      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-      const int y1 = min(y0 + 1, sh - 1), x1 = min(x0 + 1, sw - 1);
-      const float ly = sy - y0, lx = sx - x0;
-      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-      const long long base = plane * sh * sw;
-      const float* sp = s.p[j] + cc;
-      float a[8], b[8], c[8], e2[8];
-      load_vec<float, 8>(sp + (base + static_cast<long long>(y0) * sw + x0) * s.cs[j], a);
-      load_vec<float, 8>(sp + (base + static_cast<long long>(y0) * sw + x1) * s.cs[j], b);
-      load_vec<float, 8>(sp + (base + static_cast<long long>(y1) * sw + x0) * s.cs[j], c);
-      load_vec<float, 8>(sp + (base + static_cast<long long>(y1) * sw + x1) * s.cs[j], e2);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] += w00 * a[e] + w01 * b[e] + w10 * c[e] + w11 * e2[e];
+      const float sy = fmaxf((oy + 0.5f) * s.inv[j] - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy), y1 = min(y0 + 1, s.sh[j] - 1);
+      ly[j] = sy - y0;
+      const long long base = static_cast<long long>(plane) * s.sh[j];
+      r0[j] = s.p[j] + (base + y0) * s.sw[j] * s.cs[j];
+      r1[j] = s.p[j] + (base + y1) * s.sw[j] * s.cs[j];
     }
-    store_vec<float, 8>(y + pix * ycs + cc, f);
+    const long long pix0 = static_cast<long long>(row) * w;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int ox = static_cast<int>(__umulhi(static_cast<unsigned>(e), c8_magic));
+      const int cc = (e - ox * c8) * 8;
+      const long long pix = pix0 + ox;
+      const float g = m != nullptr ? 1.f + 1.f / (1.f + expf(-__ldg(m + pix))) : 1.f;   // no mask: plain y = x + sum up(src)
+      float f[8];
+      {
+        const float4* xp = reinterpret_cast<const float4*>(x + pix * xcs + cc);   // x may alias y (in place): no __ldg
+        const float4 a0 = xp[0], a1 = xp[1];
+        f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] *= g;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float sx = fmaxf((ox + 0.5f) * s.inv[j] - 0.5f, 0.f);
+        const int x0 = static_cast<int>(sx), x1 = min(x0 + 1, s.sw[j] - 1);
+        const float lx = sx - x0;
+        const float w00 = (1.f - ly[j]) * (1.f - lx), w01 = (1.f - ly[j]) * lx, w10 = ly[j] * (1.f - lx), w11 = ly[j] * lx;
+        const long long o0 = x0 * s.cs[j] + cc, o1 = x1 * s.cs[j] + cc;
+        float a[8], b[8], c[8], e2[8];
+        load_vec<float, 8>(r0[j] + o0, a);
+        load_vec<float, 8>(r0[j] + o1, b);
+        load_vec<float, 8>(r1[j] + o0, c);
+        load_vec<float, 8>(r1[j] + o1, e2);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] += w00 * a[q] + w01 * b[q] + w10 * c[q] + w11 * e2[q];
+      }
+      store_vec<float, 8>(y + pix * ycs + cc, f);
+    }
+  }
+}
+
+// Same operation for the decoder's scale ladder (sources at 1/2, 1/4, 1/8 of the output: model_utils.py:566-568 and the
+// commuted readout.0), four output pixels x four channels per thread.  The row kernel above is bound by L1 bandwidth (ncu:
+// l1tex 90 %, issue 29 %): 24 gathered float4 per 32 output bytes.  Adjacent output pixels blend the SAME source pixels, and
+// for a power-of-two scale the horizontal phase of a 4-aligned pixel group is fixed, so a thread loads each source column of
+// its group once (4 + 3 + 2 columns x 2 rows for the three levels: 18 float4 per 64 output bytes, 2.4x less L1 traffic),
+// blends the two rows, then blends columns with compile-time weights.  align_corners=False with its clamps is the same as
+// replicating the border column, which is what clamping the column INDEX does.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {   // (1 - t) a + t b
+  const float u = 1.f - t;
+  return make_float4(fmaf(t, b.x, u * a.x), fmaf(t, b.y, u * a.y), fmaf(t, b.z, u * a.z), fmaf(t, b.w, u * a.w));
+}
+__device__ __forceinline__ void acc_lerp4(float4& f, float4 a, float4 b, float t) {
+  const float4 v = lerp4(a, b, t);
+  f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
+}
+template <int K>
+__device__ __forceinline__ void topdown_add4(float4 (&f)[4], const float* r0, const float* r1, float ly, long long cs, int sw,
+                                             int q) {
+  auto col = [&](int c) { return static_cast<long long>(min(max(c, 0), sw - 1)) * cs; };
+  if constexpr (K == 2) {
+    float4 v[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const long long o = col(2 * q - 1 + d);
+      v[d] = lerp4(ld4(r0 + o), ld4(r1 + o), ly);
+    }
+    acc_lerp4(f[0], v[0], v[1], 0.75f);
+    acc_lerp4(f[1], v[1], v[2], 0.25f);
+    acc_lerp4(f[2], v[1], v[2], 0.75f);
+    acc_lerp4(f[3], v[2], v[3], 0.25f);
+  } else if constexpr (K == 4) {
+    float4 v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const long long o = col(q - 1 + d);
+      v[d] = lerp4(ld4(r0 + o), ld4(r1 + o), ly);
+    }
+    acc_lerp4(f[0], v[0], v[1], 0.625f);
+    acc_lerp4(f[1], v[0], v[1], 0.875f);
+    acc_lerp4(f[2], v[1], v[2], 0.125f);
+    acc_lerp4(f[3], v[1], v[2], 0.375f);
+  } else {
+    static_assert(K == 8, "scale ladder 2, 4, 8");
+    const int par = q & 1, r = q >> 1;
+    const long long o0 = col(r - 1 + par), o1 = col(r + par);
+    const float4 v0 = lerp4(ld4(r0 + o0), ld4(r1 + o0), ly), v1 = lerp4(ld4(r0 + o1), ld4(r1 + o1), ly);
+    const float l0 = par ? 0.0625f : 0.5625f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_lerp4(f[i], v0, v1, l0 + 0.125f * i);
+  }
+}
+template <int NS>
+__global__ void __launch_bounds__(256)
+sa_gate_ladder_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs, int rows, int c4,
+                      int h, int w, unsigned c4_magic, GateSrc s) {
+  const int per_row = (w >> 2) * c4;
+  __shared__ float s_gate[kGateMaxW];   // 1 + sigmoid(mask) of the row's pixels: once per pixel, not once per channel quad
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int plane = row / h, oy = row - plane * h;
+    if (m != nullptr) {
+      __syncthreads();   // the previous row's gates have been read
+      for (int i = threadIdx.x; i < w; i += blockDim.x)
+        s_gate[i] = 1.f + 1.f / (1.f + expf(-__ldg(m + static_cast<long long>(row) * w + i)));
+      __syncthreads();
+    }
+    const float* r0[NS > 0 ? NS : 1];
+    const float* r1[NS > 0 ? NS : 1];
+    float ly[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float sy = fmaxf((oy + 0.5f) * s.inv[j] - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy), y1 = min(y0 + 1, s.sh[j] - 1);
+      ly[j] = sy - y0;
+      const long long base = static_cast<long long>(plane) * s.sh[j];
+      r0[j] = s.p[j] + (base + y0) * s.sw[j] * s.cs[j];
+      r1[j] = s.p[j] + (base + y1) * s.sw[j] * s.cs[j];
+    }
+    const long long pix0 = static_cast<long long>(row) * w;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int q = static_cast<int>(__umulhi(static_cast<unsigned>(e), c4_magic));
+      const int cc = (e - q * c4) * 4;
+      const long long pix = pix0 + 4 * q;
+      float4 f[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[i] = *reinterpret_cast<const float4*>(x + (pix + i) * xcs + cc);   // x may alias y (in place): no __ldg
+        if (m != nullptr) {
+          const float g = s_gate[4 * q + i];
+          f[i].x *= g; f[i].y *= g; f[i].z *= g; f[i].w *= g;
+        }
+      }
+      if constexpr (NS > 0) topdown_add4<2>(f, r0[0] + cc, r1[0] + cc, ly[0], s.cs[0], s.sw[0], q);
+      if constexpr (NS > 1) topdown_add4<4>(f, r0[1] + cc, r1[1] + cc, ly[1], s.cs[1], s.sw[1], q);
+      if constexpr (NS > 2) topdown_add4<8>(f, r0[2] + cc, r1[2] + cc, ly[2], s.cs[2], s.sw[2], q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(y + (pix + i) * ycs + cc) = f[i];
+    }
   }
 }
 
@@ -761,15 +879,40 @@ extern "C" int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float
     s.p[j] = srcs[j];
     s.cs[j] = src_cstrides[j];
     s.k[j] = src_scales[j];
+    s.sh[j] = h / src_scales[j];
+    s.sw[j] = w / src_scales[j];
+    s.inv[j] = 1.f / static_cast<float>(src_scales[j]);
   }
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  const long long total = static_cast<long long>(nt) * h * w * (c / 8);
-  const int grid = grid_for(total);
+  const long long rows_ll = static_cast<long long>(nt) * h;
+  const int c8 = c / 8;
+  MSPI_CHECK_ARG(rows_ll < (1ll << 31) && static_cast<long long>(w) * c8 < (1ll << 31) / c8,
+                 "mspi_sa_gate_fused: %lld rows of %d x %d elements exceed the row kernel's index range", rows_ll, w, c8);
+  const int rows = static_cast<int>(rows_ll);
+  if (rows == 0) return MSPI_OK;
+  const unsigned magic = static_cast<unsigned>(((1ull << 32) + c8 - 1) / c8);   // e / c8 == umulhi(e, magic) for e * c8 < 2^32
+  const int grid = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  bool ladder = nsrc > 0 && w % 4 == 0 && w <= kGateMaxW && x_cstride % 4 == 0 && y_cstride % 4 == 0 &&
+                ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  for (int j = 0; j < nsrc; ++j)
+    ladder = ladder && src_scales[j] == (2 << j) && src_cstrides[j] % 4 == 0 && (reinterpret_cast<uintptr_t>(srcs[j]) & 15) == 0;
+  static const bool ladder_on = [] { const char* e = getenv("MSPI_GATE_LADDER"); return !e || atoi(e) != 0; }();
+  if (ladder && ladder_on) {
+    const int c4 = c / 4;
+    const unsigned magic4 = static_cast<unsigned>(((1ull << 32) + c4 - 1) / c4);
+    switch (nsrc) {
+      case 1: sa_gate_ladder_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
+      case 2: sa_gate_ladder_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
+      default: sa_gate_ladder_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
+    }
+    MSPI_LAUNCH_CHECK();
+    return MSPI_OK;
+  }
   switch (nsrc) {
-    case 0: sa_gate_fused_kernel<0><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
-    case 1: sa_gate_fused_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
-    case 2: sa_gate_fused_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
-    default: sa_gate_fused_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, total, c / 8, h, w, s); break;
+    case 0: sa_gate_fused_kernel<0><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
+    case 1: sa_gate_fused_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
+    case 2: sa_gate_fused_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
+    default: sa_gate_fused_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;

@@ -52,6 +52,11 @@ class ForwardPlan:
         assert mode in ("full", "image_encoder", "cached")
         self.mode, self.input_u8 = mode, input_u8
         self.fuse_mlp = os.environ.get("MSPI_FUSE_MLP", "1") != "0"
+        # downsample.0 LayerNorm inside the last fused MLP of stages 0 / 1 (mspi_mlp_fused_ln): measured SLOWER than the
+        # separate LayerNorm kernel (C = 96: +0.29 ms on the MLP launch against a 0.245 ms LayerNorm; C = 192: +0.14 against
+        # 0.13) — the fused kernel is bound by its epilogue warps' instruction stream, the LayerNorm kernel by HBM.  Off.
+        self.fuse_ds_norm = os.environ.get("MSPI_FUSE_DS_NORM", "0") != "0"
+        self.fuse_stem_norm = os.environ.get("MSPI_FUSE_STEM_NORM", "1") != "0"
         self.fuse_mixed = os.environ.get("MSPI_FUSE_MIXED", "1") != "0"
         self.steps: List[Tuple[str, Callable[[], None]]] = []
         # Branch schedule (see _build / run_branched): `sched` interleaves ("step", index) entries with ("edge", src, dst)
@@ -209,9 +214,9 @@ class ForwardPlan:
         return fr
 
     def stem_direct(self, name: str, w: torch.Tensor, scale, shift, k: int, stride: int, pad: int, act,
-                    out: Act, frames: Optional[torch.Tensor] = None, clips: int = 0) -> Act:
+                    out: Act, frames: Optional[torch.Tensor] = None, clips: int = 0, ln=None) -> Act:
         fr = self.padded_frames() if frames is None else frames
-        run = ops.stem_conv(fr, self.H, self.W, w, scale, shift, k, stride, pad, act, out, name, clips=clips)
+        run = ops.stem_conv(fr, self.H, self.W, w, scale, shift, k, stride, pad, act, out, name, clips=clips, ln=ln)
         self.add(name, run)
         self.flops += run.flops
         return out
@@ -505,20 +510,30 @@ class ForwardPlan:
         B, T, H, W = self.B, self.T, self.H, self.W
         nf = B * T
         h, w = H // 4, W // 4
-        x32 = self.stem_direct(p + "stem_0", self.P(p + "stem_0.weight"), None, self.P(p + "stem_0.bias"), 4, 4, 0,
-                               ACT_NONE, self.new(nf, 1, h, w, 96, torch.float32))
-        x = self.new(nf, 1, h, w, 96)
-        self.add(p + "stem_1", ops.layernorm(x32.buf, x.buf, nf * h * w, 96, self.P(p + "stem_1.weight"),
-                                             self.P(p + "stem_1.bias"), 1e-6))
+        if self.fuse_stem_norm and not self.keep_taps and ops.stem_conv_ln_ok(W, 96, 4, 4, 0):
+            # stem_1 (LayerNorm2d) as the epilogue of the stem GEMM: the fp32 conv output (1 GB at B = 32) is never written
+            x = self.stem_direct(p + "stem_0+1", self.P(p + "stem_0.weight"), None, self.P(p + "stem_0.bias"), 4, 4, 0,
+                                 ACT_NONE, self.new(nf, 1, h, w, 96),
+                                 ln=(self.P(p + "stem_1.weight"), self.P(p + "stem_1.bias"), 1e-6))
+        else:
+            x32 = self.stem_direct(p + "stem_0", self.P(p + "stem_0.weight"), None, self.P(p + "stem_0.bias"), 4, 4, 0,
+                                   ACT_NONE, self.new(nf, 1, h, w, 96, torch.float32))
+            x = self.new(nf, 1, h, w, 96)
+            self.add(p + "stem_1", ops.layernorm(x32.buf, x.buf, nf * h * w, 96, self.P(p + "stem_1.weight"),
+                                                 self.P(p + "stem_1.bias"), 1e-6))
         dims, depths = (96, 192, 384, 768), (3, 3, 9, 3)
         feats = []
+        normed = False
         for s, (d, depth) in enumerate(zip(dims, depths)):
             q = f"{p}stages_{s}."
             if s > 0:
-                xn = self.new(nf, 1, h, w, dims[s - 1])
-                self.add(q + "downsample.0", ops.layernorm(x.buf, xn.buf, nf * h * w, dims[s - 1],
-                                                           self.P(q + "downsample.0.weight"),
-                                                           self.P(q + "downsample.0.bias"), 1e-6))
+                if normed:      # the previous stage's last fused MLP already stored LayerNorm(x)
+                    xn, normed = x, False
+                else:
+                    xn = self.new(nf, 1, h, w, dims[s - 1])
+                    self.add(q + "downsample.0", ops.layernorm(x.buf, xn.buf, nf * h * w, dims[s - 1],
+                                                               self.P(q + "downsample.0.weight"),
+                                                               self.P(q + "downsample.0.bias"), 1e-6))
                 x = self.conv(q + "downsample.1", xn, self.P(q + "downsample.1.weight"), None,
                               self.P(q + "downsample.1.bias"), (1, 2, 2))
                 h, w = h // 2, w // 2
@@ -530,9 +545,16 @@ class ForwardPlan:
                 if d in (96, 192) and self.fuse_mlp:
                     # stages 0 and 1: fc1 + GELU + fc2 + layer scale + residual in one kernel, hidden tile on chip
                     out = self.new(nf, 1, h, w, d)
+                    # last block of the stage: its output feeds only the next stage's downsample.0 LayerNorm2d, which the
+                    # kernel applies before storing (a training plan keeps the un-normalised output for the backward pass)
+                    ln = None
+                    if j == depth - 1 and self.fuse_ds_norm and not self.keep_taps:
+                        nq = f"{p}stages_{s + 1}.downsample.0."
+                        ln = (self.P(nq + "weight"), self.P(nq + "bias"), 1e-6)
+                        normed = True
                     run = ops.mlp_fused(y, out, x, self.P(b + "mlp.fc1.weight"), self.P(b + "mlp.fc1.bias"),
-                                        self.P(b + "mlp.fc2.weight"), self.P(b + "mlp.fc2.bias"), self.P(b + "gamma"))
-                    self.add(b + "mlp(fused)", run)
+                                        self.P(b + "mlp.fc2.weight"), self.P(b + "mlp.fc2.bias"), self.P(b + "gamma"), ln=ln)
+                    self.add(b + ("mlp(fused)+norm" if ln else "mlp(fused)"), run)
                     self.flops += run.flops
                     x = out
                     continue

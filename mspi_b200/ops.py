@@ -522,9 +522,21 @@ def gather_rows(holder: dict, key: str, index: torch.Tensor, dst: torch.Tensor, 
     return run
 
 
+def stem_conv_ln_ok(w: int, cout: int, k: int, stride: int, pad: int) -> bool:
+    """Whether stem_conv's GEMM for this geometry is one N tile the LayerNorm epilogue takes (ConvNeXt stem: two output pixels
+    per row, N = 192)."""
+    if (k, stride, pad) != (4, 4, 0) or os.environ.get("MSPI_STEM_WIDE", "1") == "0":
+        return False
+    ow = (w + 2 * pad - k) // stride + 1
+    wide = 2 if ow % 2 == 0 and cout * 2 <= 256 else 1
+    return (cout * wide) % 64 == 0 and cout * wide <= 192
+
+
 def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale, shift, k: int, stride: int, pad: int,
-              act: int, y: "Act", name: str = "stem", clips: int = 0, allow_wide: bool = True) -> Callable[[], None]:
+              act: int, y: "Act", name: str = "stem", clips: int = 0, allow_wide: bool = True, ln=None) -> Callable[[], None]:
     """(1,k,k)/stride conv with Cin=3 straight off the padded 4-channel frames (no im2col buffer).
+    ln = (weight, bias, eps): LayerNorm over the output channels as the GEMM's epilogue (mspi_conv_gemm_ln; bf16 output);
+    stem_conv_ln_ok() says whether a geometry qualifies.
 
     One row of the filter (k taps x 4 channels, at most 8 pixels) is a contiguous 16-byte aligned run of the frame;
     the filter rows are the GEMM's taps and each is fetched by one TMA box whose inner extent is that run
@@ -611,6 +623,14 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     d.bn = choose_bn(gemm_n, 64 if y.dtype == torch.bfloat16 else 32)
     d.o_dtype = _DT[y.dtype]
     d.act = act
+    if ln is not None:
+        assert y.dtype == torch.bfloat16 and act == ACT_NONE and kt == 1 and gemm_n % 64 == 0 and gemm_n <= 192 \
+            and wide in (1, 2, 4), "stem_conv: geometry does not qualify for the LayerNorm epilogue"
+        d.bn = gemm_n
+        lw = ln[0].detach().float().contiguous().to(frames.device)
+        lb = ln[1].detach().float().contiguous().to(frames.device)
+        ln_eps = float(ln[2])
+        assert lw.numel() == cout and lb.numel() == cout
     sc = None if scale is None else scale.detach().float().repeat(wide).contiguous().to(frames.device)
     sh = None if shift is None else shift.detach().float().repeat(wide).contiguous().to(frames.device)
     launches = 1 if kt == 1 else clips
@@ -620,10 +640,16 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     w_ptr = _ptr(packed)
     assert y.pixels == launches * nf * oh * ow and y.c == cout
 
-    def run(_keep=(frames, packed, sc, sh, y.buf, d)):
-        for xp_, yp_ in zip(x_ptrs, y_ptrs):
-            _lib.check(lib.mspi_conv_gemm(C.byref(d), xp_, w_ptr, _ptr(sc), _ptr(sh), C.c_void_p(0), yp_, _stream()),
-                       f"conv_gemm[{name}]")
+    if ln is not None:
+        def run(_keep=(frames, packed, sc, sh, y.buf, d, lw, lb)):
+            for xp_, yp_ in zip(x_ptrs, y_ptrs):
+                _lib.check(lib.mspi_conv_gemm_ln(C.byref(d), xp_, w_ptr, _ptr(sc), _ptr(sh), _ptr(lw), _ptr(lb), ln_eps, wide,
+                                                 yp_, _stream()), f"conv_gemm_ln[{name}]")
+    else:
+        def run(_keep=(frames, packed, sc, sh, y.buf, d)):
+            for xp_, yp_ in zip(x_ptrs, y_ptrs):
+                _lib.check(lib.mspi_conv_gemm(C.byref(d), xp_, w_ptr, _ptr(sc), _ptr(sh), C.c_void_p(0), yp_, _stream()),
+                           f"conv_gemm[{name}]")
 
     run.mode = "stem"
     run.desc = d
@@ -633,8 +659,10 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
 
 
 # ------------------------------------------------------------------------------------------ fused ConvNeXt MLP
-def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma) -> Callable[[], None]:
-    """y = residual + gamma * (fc2(gelu(fc1(x)))) in one kernel (mspi_mlp_fused); C = 96 / 192, bf16."""
+def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma, ln=None) -> Callable[[], None]:
+    """y = residual + gamma * (fc2(gelu(fc1(x)))) in one kernel (mspi_mlp_fused); C = 96 / 192, bf16.
+    ln = (weight, bias, eps): y = LayerNorm_c(that) instead — the next stage's downsample.0 norm fused into the store
+    (mspi_mlp_fused_ln)."""
     lib = _lib.load()
     dev = x.buf.device
     c = x.c
@@ -652,9 +680,19 @@ def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma) 
     xp, yp, rp = x.ptr, y.ptr, residual.ptr
     rs, ys = residual.cs, y.cs
 
-    def run(_keep=(x.buf, y.buf, residual.buf, w1, w2, b1, g, sh)):
-        _lib.check(lib.mspi_mlp_fused(xp, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(sh), rp, yp, m, c, c_pad, rs, ys,
-                                      _stream()), "mlp_fused")
+    if ln is not None:
+        lw = ln[0].detach().float().contiguous().to(dev)
+        lb = ln[1].detach().float().contiguous().to(dev)
+        eps = float(ln[2])
+        assert lw.numel() == c and lb.numel() == c
+
+        def run(_keep=(x.buf, y.buf, residual.buf, w1, w2, b1, g, sh, lw, lb)):
+            _lib.check(lib.mspi_mlp_fused_ln(xp, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(sh), rp, yp, m, c, c_pad, rs, ys,
+                                             _ptr(lw), _ptr(lb), eps, _stream()), "mlp_fused_ln")
+    else:
+        def run(_keep=(x.buf, y.buf, residual.buf, w1, w2, b1, g, sh)):
+            _lib.check(lib.mspi_mlp_fused(xp, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(sh), rp, yp, m, c, c_pad, rs, ys,
+                                          _stream()), "mlp_fused")
 
     run.flops = 2.0 * m * c * 4 * c * 2
     return run

@@ -198,6 +198,34 @@ def test_stem_conv_on_padded_frames(k, stride, pad, cout, odt):
     assert _rel(got, ref) < (BF16_TOL if odt == torch.bfloat16 else 1e-4)
 
 
+@pytest.mark.parametrize("b,t,h,w", [(2, 3, 32, 64), (1, 5, 44, 72), (3, 2, 224, 384)])
+def test_stem_conv_with_layernorm_epilogue(b, t, h, w):
+    """ConvNeXt stem (Conv2d 4x4/s4 + LayerNorm2d, timm convnext_tiny) in one launch: mspi_conv_gemm_ln normalises each of
+    the two output pixels of a GEMM row over its 96 channels.  Inputs with a large common offset (|mean| >> sigma per pixel,
+    what the stem sees on bright frames) check the two-pass statistics; reference = F.conv2d + F.layer_norm in fp32."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(23)
+    cout = 96
+    clip = torch.randn(b, 3, t, h, w, generator=g) + 2.0
+    wgt = torch.randn(cout, 3, 4, 4, generator=g) / 48 ** 0.5 + 0.05
+    bias = torch.randn(cout, generator=g) * 0.1
+    lw, lb = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    assert ops.stem_conv_ln_ok(w, cout, 4, 4, 0)
+    frames = torch.zeros(b * t, h + ops.PAD_EXTRA, w + ops.PAD_EXTRA, 4, dtype=torch.bfloat16, device="cuda")
+    ops.clip_to_padded({"clips": clip.cuda()}, "clips", frames, b, t, h, w)()
+    oh, ow = h // 4, w // 4
+    y = Act(torch.full((b, t, oh, ow, cout), 7.0, dtype=torch.bfloat16, device="cuda"))
+    ops.stem_conv(frames, h, w, wgt, None, bias, 4, 4, 0, 0, y, ln=(lw, lb, 1e-6))()
+    torch.cuda.synchronize()
+    x2 = _bf(clip).permute(0, 2, 1, 3, 4).reshape(b * t, 3, h, w)
+    conv = F.conv2d(x2, _bf(wgt), bias, 4, 0).permute(0, 2, 3, 1)            # [bt, oh, ow, c]
+    ref = F.layer_norm(conv, (cout,), lw, lb, 1e-6).view(b, t, oh, ow, cout)
+    got = y.buf.float().cpu()
+    assert _rel(got, ref) < BF16_TOL
+    assert (got - ref).abs().max() < 0.04 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_1x1_spatial_stride_pick_mode():
     """ResBlock.branch1 (1x1x1 conv, stride (1,2,2), resnet_helper.py:556-566) as a strided TMA view, no gather."""
     got, ref, mode = _run_conv(24, 48, (1, 1, 1), (1, 2, 2), (0, 0, 0), (2, 3, 12, 20), seed=31)
@@ -524,6 +552,40 @@ def test_mlp_fused(c, m):
     assert torch.equal(ra.buf.view(m, c), ya.buf.view(m, c))
 
 
+@pytest.mark.parametrize("c,m", [(96, 128 * 5 + 37), (192, 128 * 3 + 5), (96, 128 * 300), (192, 128 * 299 + 1)])
+def test_mlp_fused_with_layernorm_store(c, m):
+    """Last block of ConvNeXt stages 0 / 1: the next stage's downsample.0 LayerNorm2d is applied to the bf16-rounded block
+    output before it is stored (mspi_mlp_fused_ln).  Reference: the plain fused kernel followed by the LayerNorm kernel the
+    plan used before (both already tested against PyTorch), and PyTorch's layer_norm on the same rounded rows."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(m, c, generator=g)
+    r = torch.randn(m, c, generator=g) * 3 + 0.7
+    w1 = torch.randn(4 * c, c, generator=g) / c ** 0.5
+    b1 = torch.randn(4 * c, generator=g) * 0.1
+    w2 = torch.randn(c, 4 * c, generator=g) / (4 * c) ** 0.5
+    b2 = torch.randn(c, generator=g) * 0.1
+    gamma = torch.rand(c, generator=g) + 0.5
+    lw, lb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.2
+    xa = Act(x.to(torch.bfloat16).cuda().view(1, 1, 1, m, c))
+    ra = Act(r.to(torch.bfloat16).cuda().view(1, 1, 1, m, c))
+    y0 = Act(torch.zeros((1, 1, 1, m, c), dtype=torch.bfloat16, device="cuda"))
+    y1 = Act(torch.full((1, 1, 1, m, c), 7.0, dtype=torch.bfloat16, device="cuda"))
+    y2 = Act(torch.full((1, 1, 1, m, c), 7.0, dtype=torch.bfloat16, device="cuda"))
+    ops.mlp_fused(xa, y0, ra, w1, b1, w2, b2, gamma)()
+    ops.layernorm(y0.buf, y1.buf, m, c, lw, lb, 1e-6)()
+    ops.mlp_fused(xa, y2, ra, w1, b1, w2, b2, gamma, ln=(lw, lb, 1e-6))()
+    torch.cuda.synchronize()
+    two_step = y1.buf.view(m, c).float().cpu()
+    got = y2.buf.view(m, c).float().cpu()
+    ref = F.layer_norm(y0.buf.view(m, c).float().cpu(), (c,), lw, lb, 1e-6)
+    assert _rel(got, ref) < BF16_TOL and _rel(two_step, ref) < BF16_TOL
+    # same statistics up to fp32 summation order: the two results differ by at most one bf16 step on a few elements
+    d = (got - two_step).abs()
+    assert d.max() <= 2 ** -6 * max(1.0, ref.abs().max().item()) and (d > 0).float().mean() < 0.02, (d.max(), (d > 0).float().mean())
+
+
 def test_sa_gate_token_mean_simsiam():
     from mspi_b200 import _lib, ops
     from mspi_b200.ops import Act
@@ -624,22 +686,28 @@ def test_postprocess_maps_against_cv2():
         assert got[i].max() == 255 and got[i].min() == 0
 
 
-def test_sa_gate_fused_with_topdown_sums():
-    """y = x*sigmoid(l) + x + up2(a) + up4(b) + up8(c) in one kernel (model_utils.py:167-170,566-568) vs PyTorch."""
+@pytest.mark.parametrize("scales,w,mask,inplace", [((2, 4, 8), 24, True, False), ((2, 4), 24, True, False),
+                                                   ((2,), 8, True, False), ((2, 4, 8), 40, False, True),
+                                                   ((4, 2), 24, True, False), ((2, 4, 8), 8, True, False),
+                                                   ((2,), 6, False, False), ((), 24, True, False)])
+def test_sa_gate_fused_with_topdown_sums(scales, w, mask, inplace):
+    """y = x*sigmoid(l) + x + up2(a) + up4(b) + up8(c) in one kernel (model_utils.py:167-170,566-568) vs PyTorch: the
+    scale-ladder kernel (2, 4, 8 in order, width a multiple of 4: four pixels per thread, border columns clamped), the row
+    kernel for everything else, the mask-free in-place form readout.0 uses."""
     from mspi_b200 import ops
     from mspi_b200.ops import Act
     g = torch.Generator().manual_seed(8)
-    n, t, h, w, c = 2, 2, 16, 24, 16
+    n, t, h, c = 2, 2, 16, 16
     x = torch.randn(n, c, t, h, w, generator=g)
     l = torch.randn(n, 1, t, h, w, generator=g)
-    srcs = [(torch.randn(n, c, t, h // k, w // k, generator=g), k) for k in (2, 4, 8)]
-    ref = x * torch.sigmoid(l) + x
+    srcs = [(torch.randn(n, c, t, h // k, w // k, generator=g), k) for k in scales]
+    ref = x * torch.sigmoid(l) + x if mask else x.clone()
     for a, k in srcs:
         ref = ref + F.interpolate(a, scale_factor=(1, k, k), mode="trilinear", align_corners=False)
     xa = _act_from_ncdhw(x, 24, 8, dtype=torch.float32)
-    ya = Act(torch.zeros(n, t, h, w, c, device="cuda"))
+    ya = xa if inplace else Act(torch.zeros(n, t, h, w, c, device="cuda"))
     sa = [(_act_from_ncdhw(a, dtype=torch.float32), k) for a, k in srcs]
-    lg = l.permute(0, 2, 3, 4, 1).contiguous().cuda().view(-1)
+    lg = l.permute(0, 2, 3, 4, 1).contiguous().cuda().view(-1) if mask else None
     ops.sa_gate_fused(xa, lg, ya, sa)()
     torch.cuda.synchronize()
     assert (ya.to_ncdhw().cpu() - ref).abs().max() < 1e-5
