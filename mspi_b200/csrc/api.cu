@@ -39,6 +39,11 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+bool pdl_small_enabled() {
+  static const bool on = [] { const char* e = getenv("MSPI_PDL_SMALL"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 }  // namespace mspi
 
 extern "C" int mspi_set_pdl(int on) {

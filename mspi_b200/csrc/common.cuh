@@ -44,11 +44,25 @@ int num_sms();
 // previous kernel has COMPLETED and its writes are visible.  Only kernels that execute pdl_wait() before their first global
 // access are launched this way.  Inside a captured graph the edge becomes a programmatic dependency.
 bool pdl_enabled();
+bool pdl_small_enabled();   // MSPI_PDL_SMALL: the same for the small elementwise / pooling / norm kernels (launch_pdl)
 inline int pdl_attr(cudaLaunchAttribute* a) {   // fills *a and returns 1 when PDL is on, else 0
   if (!pdl_enabled()) return 0;
   a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
   a->val.programmaticStreamSerializationAllowed = 1;
   return 1;
+}
+// kern<<<grid, block, smem, stream>>>(args...) with the attribute above; only for kernels that start with pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_small_enabled() ? pdl_attr(&attr[0]) : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---- device side ---------------------------------------------------------------------------

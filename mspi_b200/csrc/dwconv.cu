@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(CQ * S, (CQ * S <= 192 && P == 16) ? MSPI_DW_M
 dw7x7_ln_kernel(const __grid_constant__ CUtensorMap map_x, const TI* __restrict__ x, const float* __restrict__ wgt,
                 const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                 void* __restrict__ y, int out_bf16, int H, int W, int tiles_x, int n0, float eps, int cs_arg, int use_tma) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   // cs: channels of the tensor (pixel stride).  cs == C (GROUPED false, a compile-time stride: the weight and output addresses
   // become immediates): the block owns whole pixels and can normalise them.  cs > C (GROUPED): the blocks of grid.y each own a
   // group of C channels (the stencil is per channel) and LayerNorm runs as a second kernel.
@@ -823,6 +825,8 @@ int launch_dw7x7_r2(const MspiDwDesc* d, const void* x, const float* wgt, const 
 template <typename TI, int MAXT>
 __global__ void dwt_kernel(const TI* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                            void* __restrict__ y, int out_bf16, long long n_hw, int T, int HW, int C, int kt) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int cq = C >> 2;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n_hw * cq) return;
@@ -907,9 +911,9 @@ int launch_dw7x7(const MspiDwDesc* d, const void* x, const float* wgt, const flo
   }
   for (long long n0 = 0; n0 < frames; n0 += 65535) {   // grid.z limit
     const unsigned nz = static_cast<unsigned>(frames - n0 < 65535 ? frames - n0 : 65535);
-    kern<<<dim3(tiles_x * groups, tiles_y, nz), CQ * S, smem, stream>>>(
-        map, static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x,
-        static_cast<int>(n0), d->ln_eps, C * groups, use_tma);
+    MSPI_CUDA(launch_pdl(kern, dim3(tiles_x * groups, tiles_y, nz), CQ * S, smem, stream,
+                         map, static_cast<const TI*>(x), wgt, bias, ln_w, ln_b, y, d->out_dtype == MSPI_BF16 ? 1 : 0, d->h, d->w, tiles_x,
+                         static_cast<int>(n0), d->ln_eps, C * groups, use_tma));
     MSPI_LAUNCH_CHECK();
   }
   return MSPI_OK;
@@ -1000,11 +1004,11 @@ int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const
     MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv_t: grid out of range");
     const int ob = d->out_dtype == MSPI_BF16 ? 1 : 0;
     if (d->in_dtype == MSPI_BF16)
-      dwt_kernel<__nv_bfloat16, 8><<<static_cast<int>(blocks), threads, 0, stream>>>(
-          static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt);
+      MSPI_CUDA(launch_pdl(dwt_kernel<__nv_bfloat16, 8>, static_cast<int>(blocks), threads, 0, stream, 
+          static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
     else
-      dwt_kernel<float, 8><<<static_cast<int>(blocks), threads, 0, stream>>>(static_cast<const float*>(x), wgt, bias, y,
-                                                                            ob, n_hw, d->t, HW, d->c, d->kt);
+      MSPI_CUDA(launch_pdl(dwt_kernel<float, 8>, static_cast<int>(blocks), threads, 0, stream, static_cast<const float*>(x), wgt, bias, y,
+                                                                            ob, n_hw, d->t, HW, d->c, d->kt));
     MSPI_LAUNCH_CHECK();
     return MSPI_OK;
   }

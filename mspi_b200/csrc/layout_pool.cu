@@ -44,6 +44,8 @@ __device__ __forceinline__ void store_vec(T* p, const float (&v)[VEC]) {
 __global__ void patch_gather_nhwc_kernel(MspiPatchDesc d, const __nv_bfloat16* __restrict__ src,
                                          __nv_bfloat16* __restrict__ dst, long long total_chunks, int chunks_per_row,
                                          int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_chunks;
        i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / chunks_per_row;
@@ -71,6 +73,8 @@ __global__ void patch_gather_nhwc_kernel(MspiPatchDesc d, const __nv_bfloat16* _
 // produces 8 consecutive K elements of one row (one 16 B store).
 __global__ void patch_gather_generic_kernel(MspiPatchDesc d, const void* __restrict__ src,
                                             __nv_bfloat16* __restrict__ dst, long long total_chunks, int chunks_per_row) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int ktot = d.kt * d.kh * d.kw * d.c;
   const long long thw = static_cast<long long>(d.t) * d.h * d.w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_chunks;
@@ -202,6 +206,8 @@ __global__ void clip_u8_to_padded_nhwc4_kernel(const uint8_t* __restrict__ src, 
 // dst row i = src row idx[i] (rows of row_vecs 16-byte vectors): per-window views of per-frame feature maps.
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx, uint4* __restrict__ dst,
                                    long long n_rows, int row_vecs, int src_rows) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const long long total = n_rows * row_vecs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -239,6 +245,8 @@ __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, long long cstri
 // ------------------------------------------------------------------------- max pool
 __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                  long long total, int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -282,6 +290,8 @@ __global__ void maxpool3d_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict
 template <int KT, int KH, int KW>
 __global__ void maxpool3d_fixed_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                        long long total, int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -329,6 +339,8 @@ __global__ void maxpool3d_fixed_kernel(MspiPoolDesc d, const __nv_bfloat16* __re
 // instead of 27.
 __global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                   long long total, int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -391,6 +403,8 @@ __global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restric
 // area_pixel_compute_source_index), second index clamped at size-1.
 template <typename TI, typename TO, int VEC>
 __global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __restrict__ y, long long total, int cv) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int oh_ = d.h * d.k, ow_ = d.w * d.k;
   const float inv = 1.f / static_cast<float>(d.k);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -433,6 +447,8 @@ __global__ void upsample_kernel(MspiUpDesc d, const TI* __restrict__ x, TO* __re
 template <typename T>
 __global__ void sa_gate_kernel(const T* __restrict__ x, long long xcs, const float* __restrict__ m, T* __restrict__ y,
                                long long ycs, long long total, int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long pix = i;
@@ -466,6 +482,8 @@ template <int NS>   // number of top-down sources (compile time: the loads of al
 __global__ void __launch_bounds__(256)
 sa_gate_fused_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs, int rows, int c8,
                      int h, int w, unsigned c8_magic, GateSrc s) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int per_row = w * c8;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int plane = row / h, oy = row - plane * h;
@@ -571,6 +589,8 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 sa_gate_ladder_kernel(const float* x, long long xcs, const float* __restrict__ m, float* y, long long ycs, int rows, int c4,
                       int h, int w, unsigned c4_magic, GateSrc s) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int per_row = (w >> 2) * c4;
   __shared__ float s_gate[kGateMaxW];   // 1 + sigmoid(mask) of the row's pixels: once per pixel, not once per channel quad
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -618,6 +638,8 @@ sa_gate_ladder_kernel(const float* x, long long xcs, const float* __restrict__ m
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                 __nv_bfloat16* __restrict__ y, long long n8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = ldg16(a + i * 8), v = ldg16(b + i * 8);
@@ -636,6 +658,8 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 template <typename TI, typename TO>
 __global__ void cast_rows_kernel(const TI* __restrict__ src, long long srs, long long sgs, TO* __restrict__ dst,
                                  long long drs, long long dgs, int rows, int c, long long total) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ch = static_cast<int>(i % c);
@@ -667,11 +691,11 @@ extern "C" int mspi_patch_gather(const MspiPatchDesc* d, const void* src, void* 
   const int cpr = d->k_pad / 8;
   const long long total = m * cpr;
   if (d->src_layout == 1 && d->c % 8 == 0 && d->src_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    patch_gather_nhwc_kernel<<<grid_for(total), kBlock, 0, stream>>>(
-        *d, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), total, cpr, d->c / 8);
+    MSPI_CUDA(launch_pdl(patch_gather_nhwc_kernel, grid_for(total), kBlock, 0, stream, 
+        *d, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), total, cpr, d->c / 8));
   } else {
-    patch_gather_generic_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, src, static_cast<__nv_bfloat16*>(dst),
-                                                                        total, cpr);
+    MSPI_CUDA(launch_pdl(patch_gather_generic_kernel, grid_for(total), kBlock, 0, stream, *d, src, static_cast<__nv_bfloat16*>(dst),
+                                                                        total, cpr));
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
@@ -765,9 +789,9 @@ extern "C" int mspi_gather_rows(const void* src, const int32_t* idx, void* dst, 
   MSPI_CHECK_ARG(row_bytes / 16 < (1ll << 31) && src_rows < (1ll << 31), "mspi_gather_rows: row too long");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const int row_vecs = static_cast<int>(row_bytes / 16);
-  gather_rows_kernel<<<grid_for(n_rows * row_vecs), kBlock, 0, stream>>>(static_cast<const uint4*>(src), idx,
+  MSPI_CUDA(launch_pdl(gather_rows_kernel, grid_for(n_rows * row_vecs), kBlock, 0, stream, static_cast<const uint4*>(src), idx,
                                                                           static_cast<uint4*>(dst), n_rows, row_vecs,
-                                                                          static_cast<int>(src_rows));
+                                                                          static_cast<int>(src_rows)));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -798,8 +822,8 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
   if (d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 1 && d->ph == 1 &&
       d->pw == 1 && d->ot == d->t && d->oh == d->h && d->ow == d->w) {
     const long long rows = static_cast<long long>(d->n) * d->t * d->h * c8;
-    maxpool333_kernel<<<grid_for(rows), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
-                                                             static_cast<__nv_bfloat16*>(y), rows, c8);
+    MSPI_CUDA(launch_pdl(maxpool333_kernel, grid_for(rows), kBlock, 0, stream, *d, static_cast<const __nv_bfloat16*>(x),
+                                                             static_cast<__nv_bfloat16*>(y), rows, c8));
     MSPI_LAUNCH_CHECK();
     return MSPI_OK;
   }
@@ -808,8 +832,8 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
                          d->pt < d->kt && d->ph < d->kh && d->pw < d->kw;
 #define MSPI_POOL_FIXED(KT, KH, KW)                                                                                       \
   if (starts_in && d->kt == KT && d->kh == KH && d->kw == KW) {                                                             \
-    maxpool3d_fixed_kernel<KT, KH, KW><<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),   \
-                                                                                static_cast<__nv_bfloat16*>(y), total, c8); \
+    MSPI_CUDA(launch_pdl(maxpool3d_fixed_kernel<KT, KH, KW>, grid_for(total), kBlock, 0, stream, *d, static_cast<const __nv_bfloat16*>(x),   \
+                                                                                static_cast<__nv_bfloat16*>(y), total, c8)); \
     MSPI_LAUNCH_CHECK();                                                                                                  \
     return MSPI_OK;                                                                                                       \
   }
@@ -818,8 +842,8 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
   MSPI_POOL_FIXED(2, 2, 2)
   MSPI_POOL_FIXED(1, 2, 2)
 #undef MSPI_POOL_FIXED
-  maxpool3d_kernel<<<grid_for(total), kBlock, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x),
-                                                           static_cast<__nv_bfloat16*>(y), total, c8);
+  MSPI_CUDA(launch_pdl(maxpool3d_kernel, grid_for(total), kBlock, 0, stream, *d, static_cast<const __nv_bfloat16*>(x),
+                                                           static_cast<__nv_bfloat16*>(y), total, c8));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -837,13 +861,13 @@ extern "C" int mspi_upsample_bilinear(const MspiUpDesc* d, const void* x, void* 
   const int g = grid_for(total);
   using bf = __nv_bfloat16;
   if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16)
-    upsample_kernel<bf, bf, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const bf*>(x), static_cast<bf*>(y), total, cv);
+    MSPI_CUDA(launch_pdl(upsample_kernel<bf, bf, VEC>, g, kBlock, 0, stream, *d, static_cast<const bf*>(x), static_cast<bf*>(y), total, cv));
   else if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_F32)
-    upsample_kernel<bf, float, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const bf*>(x), static_cast<float*>(y), total, cv);
+    MSPI_CUDA(launch_pdl(upsample_kernel<bf, float, VEC>, g, kBlock, 0, stream, *d, static_cast<const bf*>(x), static_cast<float*>(y), total, cv));
   else if (d->in_dtype == MSPI_F32 && d->out_dtype == MSPI_F32)
-    upsample_kernel<float, float, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const float*>(x), static_cast<float*>(y), total, cv);
+    MSPI_CUDA(launch_pdl(upsample_kernel<float, float, VEC>, g, kBlock, 0, stream, *d, static_cast<const float*>(x), static_cast<float*>(y), total, cv));
   else
-    upsample_kernel<float, bf, VEC><<<g, kBlock, 0, stream>>>(*d, static_cast<const float*>(x), static_cast<bf*>(y), total, cv);
+    MSPI_CUDA(launch_pdl(upsample_kernel<float, bf, VEC>, g, kBlock, 0, stream, *d, static_cast<const float*>(x), static_cast<bf*>(y), total, cv));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -856,11 +880,11 @@ extern "C" int mspi_sa_gate(const void* x, int64_t x_cstride, const float* mask_
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const long long total = pixels * (c / 8);
   if (dtype == MSPI_BF16)
-    sa_gate_kernel<__nv_bfloat16><<<grid_for(total), kBlock, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cstride, mask_logits, static_cast<__nv_bfloat16*>(y), y_cstride, total, c / 8);
+    MSPI_CUDA(launch_pdl(sa_gate_kernel<__nv_bfloat16>, grid_for(total), kBlock, 0, stream, 
+        static_cast<const __nv_bfloat16*>(x), x_cstride, mask_logits, static_cast<__nv_bfloat16*>(y), y_cstride, total, c / 8));
   else
-    sa_gate_kernel<float><<<grid_for(total), kBlock, 0, stream>>>(static_cast<const float*>(x), x_cstride, mask_logits,
-                                                                  static_cast<float*>(y), y_cstride, total, c / 8);
+    MSPI_CUDA(launch_pdl(sa_gate_kernel<float>, grid_for(total), kBlock, 0, stream, static_cast<const float*>(x), x_cstride, mask_logits,
+                                                                  static_cast<float*>(y), y_cstride, total, c / 8));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -901,18 +925,18 @@ extern "C" int mspi_sa_gate_fused(const float* x, int64_t x_cstride, const float
     const int c4 = c / 4;
     const unsigned magic4 = static_cast<unsigned>(((1ull << 32) + c4 - 1) / c4);
     switch (nsrc) {
-      case 1: sa_gate_ladder_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
-      case 2: sa_gate_ladder_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
-      default: sa_gate_ladder_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s); break;
+      case 1: MSPI_CUDA(launch_pdl(sa_gate_ladder_kernel<1>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s)); break;
+      case 2: MSPI_CUDA(launch_pdl(sa_gate_ladder_kernel<2>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s)); break;
+      default: MSPI_CUDA(launch_pdl(sa_gate_ladder_kernel<3>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c4, h, w, magic4, s)); break;
     }
     MSPI_LAUNCH_CHECK();
     return MSPI_OK;
   }
   switch (nsrc) {
-    case 0: sa_gate_fused_kernel<0><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
-    case 1: sa_gate_fused_kernel<1><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
-    case 2: sa_gate_fused_kernel<2><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
-    default: sa_gate_fused_kernel<3><<<grid, kBlock, 0, stream>>>(x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s); break;
+    case 0: MSPI_CUDA(launch_pdl(sa_gate_fused_kernel<0>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s)); break;
+    case 1: MSPI_CUDA(launch_pdl(sa_gate_fused_kernel<1>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s)); break;
+    case 2: MSPI_CUDA(launch_pdl(sa_gate_fused_kernel<2>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s)); break;
+    default: MSPI_CUDA(launch_pdl(sa_gate_fused_kernel<3>, grid, kBlock, 0, stream, x, x_cstride, mask_logits, y, y_cstride, rows, c8, h, w, magic, s)); break;
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
@@ -922,9 +946,9 @@ extern "C" int mspi_add_bf16(const void* a, const void* b, void* y, int64_t n, v
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(a && b && y && n % 8 == 0, "mspi_add_bf16: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  add_bf16_kernel<<<grid_for(n / 8), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
+  MSPI_CUDA(launch_pdl(add_bf16_kernel, grid_for(n / 8), kBlock, 0, stream, static_cast<const __nv_bfloat16*>(a),
                                                           static_cast<const __nv_bfloat16*>(b),
-                                                          static_cast<__nv_bfloat16*>(y), n / 8);
+                                                          static_cast<__nv_bfloat16*>(y), n / 8));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -939,17 +963,17 @@ extern "C" int mspi_cast_rows(const void* src, int src_dtype, int64_t src_rstrid
   const int g = grid_for(total);
   using bf = __nv_bfloat16;
   if (src_dtype == MSPI_F32 && dst_dtype == MSPI_BF16)
-    cast_rows_kernel<float, bf><<<g, kBlock, 0, stream>>>(static_cast<const float*>(src), src_rstride, src_gstride,
-                                                          static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total);
+    MSPI_CUDA(launch_pdl(cast_rows_kernel<float, bf>, g, kBlock, 0, stream, static_cast<const float*>(src), src_rstride, src_gstride,
+                                                          static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total));
   else if (src_dtype == MSPI_BF16 && dst_dtype == MSPI_F32)
-    cast_rows_kernel<bf, float><<<g, kBlock, 0, stream>>>(static_cast<const bf*>(src), src_rstride, src_gstride,
-                                                          static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total);
+    MSPI_CUDA(launch_pdl(cast_rows_kernel<bf, float>, g, kBlock, 0, stream, static_cast<const bf*>(src), src_rstride, src_gstride,
+                                                          static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total));
   else if (src_dtype == MSPI_BF16)
-    cast_rows_kernel<bf, bf><<<g, kBlock, 0, stream>>>(static_cast<const bf*>(src), src_rstride, src_gstride,
-                                                       static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total);
+    MSPI_CUDA(launch_pdl(cast_rows_kernel<bf, bf>, g, kBlock, 0, stream, static_cast<const bf*>(src), src_rstride, src_gstride,
+                                                       static_cast<bf*>(dst), dst_rstride, dst_gstride, rows, c, total));
   else
-    cast_rows_kernel<float, float><<<g, kBlock, 0, stream>>>(static_cast<const float*>(src), src_rstride, src_gstride,
-                                                             static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total);
+    MSPI_CUDA(launch_pdl(cast_rows_kernel<float, float>, g, kBlock, 0, stream, static_cast<const float*>(src), src_rstride, src_gstride,
+                                                             static_cast<float*>(dst), dst_rstride, dst_gstride, rows, c, total));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -17,6 +17,8 @@ template <int MAXP, typename TI>
 __global__ void dwconv_ln_kernel(MspiDwDesc d, const TI* __restrict__ x, const float* __restrict__ wgt,
                                  const float* __restrict__ bias, const float* __restrict__ ln_w,
                                  const float* __restrict__ ln_b, void* __restrict__ y, long long pixels) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const int c = d.c, pairs = c >> 1;
@@ -107,6 +109,8 @@ __device__ __forceinline__ float ld_elem(const TI* p, long long i) { return stat
 template <typename TI, typename TO>
 __global__ void layernorm_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ b, const float* __restrict__ pos, TO* __restrict__ y) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < d.rows;
@@ -160,6 +164,8 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
 template <typename TI, typename TO, int NI, int G>
 __global__ void layernorm_vec_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ b, const float* __restrict__ pos, TO* __restrict__ y) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const int c4 = d.c >> 2;
@@ -282,6 +288,8 @@ template <typename TI, typename TO, int LPR, int NV, int G>
 __global__ void __launch_bounds__(256)
 layernorm_rows8_kernel(MspiLnDesc d, const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                        const float* __restrict__ pos, TO* __restrict__ y) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   constexpr int RPW = 32 / LPR;   // rows side by side in a warp
   const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
   const int warps = blockDim.x >> 5;
@@ -490,6 +498,8 @@ attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int head
 //  kernels are the glue: the row softmax and the K-major copy of V the second GEMM needs.)
 // One warp per score row: max, exp / sum, normalise; fp32 in place.
 __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int n, long long stride) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < rows;
@@ -511,6 +521,8 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int n
 
 // qkv [B][N][3][H][HD] (v = index 2) -> vt [B][H][HD][n_pad] (keys contiguous), 32x32 tiles through shared memory.
 __global__ void transpose_v_kernel(const float* __restrict__ qkv, float* __restrict__ vt, int n, int heads, int hd, int n_pad) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float tile[32][33];
   const int bh = blockIdx.z, b = bh / heads, h = bh % heads;
   const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -531,6 +543,8 @@ __global__ void transpose_v_kernel(const float* __restrict__ qkv, float* __restr
 // ------------------------------------------------------------------------- token mean
 template <typename T>
 __global__ void token_mean_kernel(const T* __restrict__ x, float* __restrict__ y, int rows, int r0, int r1, int c) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int b = blockIdx.y;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
@@ -544,6 +558,8 @@ __global__ void token_mean_kernel(const T* __restrict__ x, float* __restrict__ y
 // grid (B, 2): one block per (sample, pair); out must be zero on entry (the host wrapper clears it)
 __global__ void simsiam_kernel(const float* __restrict__ pv, const float* __restrict__ za, const float* __restrict__ pa,
                                const float* __restrict__ zv, float* __restrict__ out, int bsz, int c) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[32];
   const int b = blockIdx.x, pair = blockIdx.y;
   const float* p = (pair == 0 ? pv : pa) + static_cast<long long>(b) * c;
@@ -593,11 +609,11 @@ extern "C" int mspi_dwconv_ln(const MspiDwDesc* d, const void* x, const float* w
 #define MSPI_DW_LAUNCH(MAXP)                                                                                         \
   do {                                                                                                                 \
     if (d->in_dtype == MSPI_BF16)                                                                                      \
-      dwconv_ln_kernel<MAXP, __nv_bfloat16><<<g, threads, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x), wgt,  \
-                                                                       bias, ln_w, ln_b, y, pixels);                   \
+      MSPI_CUDA(launch_pdl(dwconv_ln_kernel<MAXP, __nv_bfloat16>, g, threads, 0, stream, *d, static_cast<const __nv_bfloat16*>(x), wgt,  \
+                                                                       bias, ln_w, ln_b, y, pixels));                   \
     else                                                                                                               \
-      dwconv_ln_kernel<MAXP, float><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), wgt, bias, ln_w,      \
-                                                               ln_b, y, pixels);                                       \
+      MSPI_CUDA(launch_pdl(dwconv_ln_kernel<MAXP, float>, g, threads, 0, stream, *d, static_cast<const float*>(x), wgt, bias, ln_w,      \
+                                                               ln_b, y, pixels));                                       \
   } while (0)
   if (pairs <= 96) MSPI_DW_LAUNCH(3);
   else if (pairs <= 192) MSPI_DW_LAUNCH(6);
@@ -648,8 +664,8 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
     long long nb = (d->rows + per - 1) / per;                                                                            \
     if (nb > vcap) nb = vcap;                                                                                            \
     if (nb < 1) nb = 1;                                                                                                  \
-    layernorm_rows8_kernel<TI, TO, LPR, NV, G><<<static_cast<int>(nb), threads, 0, stream>>>(                            \
-        *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y));                                                  \
+    MSPI_CUDA(launch_pdl(layernorm_rows8_kernel<TI, TO, LPR, NV, G>, static_cast<int>(nb), threads, 0, stream,                             \
+        *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)));                                                  \
   } while (0)
 #define MSPI_LN_R8_C(TI, TO)                                                                                             \
   do {                                                                                                                   \
@@ -673,13 +689,13 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
 #define MSPI_LN_VEC(TI, TO)                                                                                              \
   do {                                                                                                                   \
     if (d->c <= 128)                                                                                                     \
-      layernorm_vec_kernel<TI, TO, 1, 8><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      MSPI_CUDA(launch_pdl(layernorm_vec_kernel<TI, TO, 1, 8>, gv, threads, 0, stream, *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y))); \
     else if (d->c <= 256)                                                                                                \
-      layernorm_vec_kernel<TI, TO, 2, 4><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      MSPI_CUDA(launch_pdl(layernorm_vec_kernel<TI, TO, 2, 4>, gv, threads, 0, stream, *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y))); \
     else if (d->c <= 512)                                                                                                \
-      layernorm_vec_kernel<TI, TO, 4, 2><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      MSPI_CUDA(launch_pdl(layernorm_vec_kernel<TI, TO, 4, 2>, gv, threads, 0, stream, *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y))); \
     else                                                                                                                 \
-      layernorm_vec_kernel<TI, TO, 8, 1><<<gv, threads, 0, stream>>>(*d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y)); \
+      MSPI_CUDA(launch_pdl(layernorm_vec_kernel<TI, TO, 8, 1>, gv, threads, 0, stream, *d, static_cast<const TI*>(x), w, b, pos, static_cast<TO*>(y))); \
   } while (0)
     if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16) MSPI_LN_VEC(bf, bf);
     else if (d->in_dtype == MSPI_BF16) MSPI_LN_VEC(bf, float);
@@ -690,13 +706,13 @@ extern "C" int mspi_layernorm(const MspiLnDesc* d, const void* x, const float* w
     return MSPI_OK;
   }
   if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_BF16)
-    layernorm_kernel<bf, bf><<<g, threads, 0, stream>>>(*d, static_cast<const bf*>(x), w, b, pos, static_cast<bf*>(y));
+    MSPI_CUDA(launch_pdl(layernorm_kernel<bf, bf>, g, threads, 0, stream, *d, static_cast<const bf*>(x), w, b, pos, static_cast<bf*>(y)));
   else if (d->in_dtype == MSPI_BF16 && d->out_dtype == MSPI_F32)
-    layernorm_kernel<bf, float><<<g, threads, 0, stream>>>(*d, static_cast<const bf*>(x), w, b, pos, static_cast<float*>(y));
+    MSPI_CUDA(launch_pdl(layernorm_kernel<bf, float>, g, threads, 0, stream, *d, static_cast<const bf*>(x), w, b, pos, static_cast<float*>(y)));
   else if (d->in_dtype == MSPI_F32 && d->out_dtype == MSPI_BF16)
-    layernorm_kernel<float, bf><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), w, b, pos, static_cast<bf*>(y));
+    MSPI_CUDA(launch_pdl(layernorm_kernel<float, bf>, g, threads, 0, stream, *d, static_cast<const float*>(x), w, b, pos, static_cast<bf*>(y)));
   else
-    layernorm_kernel<float, float><<<g, threads, 0, stream>>>(*d, static_cast<const float*>(x), w, b, pos, static_cast<float*>(y));
+    MSPI_CUDA(launch_pdl(layernorm_kernel<float, float>, g, threads, 0, stream, *d, static_cast<const float*>(x), w, b, pos, static_cast<float*>(y)));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -735,7 +751,7 @@ extern "C" int mspi_softmax_rows(float* s, int64_t rows, int n, int64_t stride, 
   long long blocks = (rows + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  softmax_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(s, rows, n, stride);
+  MSPI_CUDA(launch_pdl(softmax_rows_kernel, static_cast<int>(blocks), threads, 0, stream, s, rows, n, stride));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -745,7 +761,7 @@ extern "C" int mspi_transpose_v(const float* qkv, float* vt, int b, int n, int h
   MSPI_CHECK_ARG(qkv && vt && b > 0 && n > 0 && heads > 0 && hd > 0 && n_pad >= n, "mspi_transpose_v: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   dim3 grid((n_pad + 31) / 32, (hd + 31) / 32, b * heads), block(32, 8);
-  transpose_v_kernel<<<grid, block, 0, stream>>>(qkv, vt, n, heads, hd, n_pad);
+  MSPI_CUDA(launch_pdl(transpose_v_kernel, grid, block, 0, stream, qkv, vt, n, heads, hd, n_pad));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -757,9 +773,9 @@ extern "C" int mspi_token_mean(const void* x, int x_dtype, float* y, int b, int 
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   dim3 grid((c + 127) / 128, b);
   if (x_dtype == MSPI_BF16)
-    token_mean_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, rows, r0, r1, c);
+    MSPI_CUDA(launch_pdl(token_mean_kernel<__nv_bfloat16>, grid, 128, 0, stream, static_cast<const __nv_bfloat16*>(x), y, rows, r0, r1, c));
   else
-    token_mean_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), y, rows, r0, r1, c);
+    MSPI_CUDA(launch_pdl(token_mean_kernel<float>, grid, 128, 0, stream, static_cast<const float*>(x), y, rows, r0, r1, c));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -770,7 +786,7 @@ extern "C" int mspi_simsiam_loss(const float* p_v, const float* z_a, const float
   MSPI_CHECK_ARG(p_v && z_a && p_a && z_v && out && b > 0 && c > 0, "mspi_simsiam_loss: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   MSPI_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
-  simsiam_kernel<<<dim3(b, 2), 256, 0, stream>>>(p_v, z_a, p_a, z_v, out, b, c);
+  MSPI_CUDA(launch_pdl(simsiam_kernel, dim3(b, 2), 256, 0, stream, p_v, z_a, p_a, z_v, out, b, c));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

@@ -39,6 +39,8 @@ __device__ __forceinline__ float block_min_f(float v, float* red) {
 // ------------------------------------------------------------------------- log-softmax over pixels
 __global__ void __launch_bounds__(kRedThreads) logsoftmax2d_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                   long long pixels) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float redf[32];
   __shared__ double redd[32];
   const float* xb = x + blockIdx.x * pixels;
@@ -193,7 +195,7 @@ extern "C" int mspi_logsoftmax2d(const float* x, float* y, int b, int64_t pixels
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(x && y && b > 0 && pixels > 0, "mspi_logsoftmax2d: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  logsoftmax2d_kernel<<<b, kRedThreads, 0, stream>>>(x, y, pixels);
+  MSPI_CUDA(launch_pdl(logsoftmax2d_kernel, b, kRedThreads, 0, stream, x, y, pixels));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }

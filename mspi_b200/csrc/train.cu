@@ -592,6 +592,8 @@ template <typename TI>
 __global__ void conv_c1_fwd_kernel(const TI* __restrict__ x, long long xcs, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ y, long long planes, int h, int wd,
                                    int strip) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   // one warp = a 4-pixel wide, `strip`-row tall column of one plane, walked top to bottom with the three input rows under
   // the current output row in registers (lane = channel): every input pixel is loaded 1.5 times instead of 9
   const int lane = threadIdx.x & 31;
@@ -1151,11 +1153,11 @@ extern "C" int mspi_conv_c1_fwd(const void* x, int x_dtype, int64_t x_cstride, c
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   if (x_dtype == MSPI_BF16)
-    conv_c1_fwd_kernel<__nv_bfloat16><<<static_cast<int>(blocks), warps * 32, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cstride, w, bias, y, planes, h, wd, strip);
+    MSPI_CUDA(launch_pdl(conv_c1_fwd_kernel<__nv_bfloat16>, static_cast<int>(blocks), warps * 32, 0, stream, 
+        static_cast<const __nv_bfloat16*>(x), x_cstride, w, bias, y, planes, h, wd, strip));
   else
-    conv_c1_fwd_kernel<float><<<static_cast<int>(blocks), warps * 32, 0, stream>>>(static_cast<const float*>(x), x_cstride, w,
-                                                                                  bias, y, planes, h, wd, strip);
+    MSPI_CUDA(launch_pdl(conv_c1_fwd_kernel<float>, static_cast<int>(blocks), warps * 32, 0, stream, static_cast<const float*>(x), x_cstride, w,
+                                                                                  bias, y, planes, h, wd, strip));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
