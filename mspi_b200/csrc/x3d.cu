@@ -37,6 +37,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // thread = (output position, 8 channels).  wgt: fp32 [kt*kh*kw][C] with the BatchNorm scale folded in, shift fp32 [C].
 __global__ void dw3d_kernel(MspiDw3dDesc d, const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
                             const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long total, int c8) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -85,6 +87,8 @@ template <int P, int S, int ACT>
 __global__ void dw3d_strip_kernel(MspiDw3dDesc d, const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, long long total, int c8,
                                   int strips) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   constexpr int NIN = (P - 1) * S + 3;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -169,6 +173,8 @@ __global__ void __launch_bounds__(160)
 dw3d_tile_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ wgt, const float* __restrict__ shift,
                  __nv_bfloat16* __restrict__ y, int T, int H, int W, int C, long long out_cstride, int TR, int SC, int cg8_arg,
                  int tiles_x, int nthreads) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   constexpr int P = 8;
   const int CG8 = CG8T > 0 ? CG8T : cg8_arg;
   extern __shared__ __align__(128) uint8_t dw3_smem[];
@@ -293,8 +299,8 @@ static int launch_dw3d_tile(const MspiDw3dDesc* d, const void* x, const float* w
 #define MSPI_DW3T_(A, G)                                                                                                     \
   {                                                                                                                          \
     MSPI_CUDA(cudaFuncSetAttribute(dw3d_tile_kernel<A, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));        \
-    dw3d_tile_kernel<A, G><<<grid, block, smem, stream>>>(map, wgt, shift, yb, d->t, d->h, d->w, d->c, d->out_cstride, tr, sc,   \
-                                                          cg8, tiles_x, nthreads);                                          \
+    MSPI_CUDA(launch_pdl(dw3d_tile_kernel<A, G>, grid, block, smem, stream, map, wgt, shift, yb, d->t, d->h, d->w, d->c, d->out_cstride, tr, sc,   \
+                                                          cg8, tiles_x, nthreads));                                          \
   }
 #define MSPI_DW3T(A)                                                                                                         \
   {                                                                                                                          \
@@ -317,6 +323,8 @@ static int launch_dw3d_tile(const MspiDw3dDesc* d, const void* x, const float* w
 template <int MAXT>
 __global__ void dwt_bn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ shift,
                               __nv_bfloat16* __restrict__ y, long long n_hw, int T, int HW, int C, int kt, int act) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int c8 = C >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n_hw * c8) return;
@@ -365,6 +373,8 @@ __global__ void dwt_bn_kernel(const __nv_bfloat16* __restrict__ x, const float* 
 // pair x row lane) and adds its partial sums to out[n][c] (fp32 atomics; out is zeroed by the caller's memset node).
 __global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int c,
                                    long long cstride, long long rows_per_block, float scale) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   extern __shared__ float part[];  // [blockDim.y][c]
   const int n = blockIdx.y;
   const long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
@@ -391,6 +401,8 @@ __global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, float* _
 __global__ void se_gate_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate, int c,
                                int cfc) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   extern __shared__ float sm[];  // mean[c] + hidden[cfc]
   float* m_s = sm;
   float* h_s = sm + c;
@@ -415,6 +427,8 @@ __global__ void se_gate_kernel(const float* __restrict__ mean, const float* __re
 // y = act(x * gate[n][c]) over [N][rows][C] bf16 (in place allowed).
 __global__ void scale_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate, __nv_bfloat16* __restrict__ y,
                                  long long rows, int c8, long long total, int act) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cg = static_cast<int>(i % c8);
@@ -460,9 +474,9 @@ extern "C" int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const floa
     const long long n_hw = static_cast<long long>(d->n) * HW;
     const long long blocks = (n_hw * c8 + 127) / 128;
     MSPI_CHECK_ARG(blocks < (1ll << 31), "grid out of range");
-    dwt_bn_kernel<16><<<static_cast<int>(blocks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), wgt, shift,
+    MSPI_CUDA(launch_pdl(dwt_bn_kernel<16>, static_cast<int>(blocks), 128, 0, stream, static_cast<const __nv_bfloat16*>(x), wgt, shift,
                                                                     static_cast<__nv_bfloat16*>(y), n_hw, d->t, HW, d->c,
-                                                                    d->kt, d->act);
+                                                                    d->kt, d->act));
   } else if (d->kt == 3 && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) {
     if (d->sh == 1) {   // shared-memory tiled kernel; 1 = shape not covered
       const int rc = launch_dw3d_tile(d, x, wgt, shift, y, stream);
@@ -478,9 +492,9 @@ extern "C" int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const floa
     const int g = static_cast<int>(blocks);
 #define MSPI_DW3D(PP, SS)                                                                                                   \
     switch (d->act) {                                                                                                        \
-      case MSPI_ACT_NONE: dw3d_strip_kernel<PP, SS, MSPI_ACT_NONE><<<g, 128, 0, stream>>>(*d, xb, wgt, shift, yb, threads, c8, strips); break;   \
-      case MSPI_ACT_RELU: dw3d_strip_kernel<PP, SS, MSPI_ACT_RELU><<<g, 128, 0, stream>>>(*d, xb, wgt, shift, yb, threads, c8, strips); break;   \
-      case MSPI_ACT_SWISH: dw3d_strip_kernel<PP, SS, MSPI_ACT_SWISH><<<g, 128, 0, stream>>>(*d, xb, wgt, shift, yb, threads, c8, strips); break; \
+      case MSPI_ACT_NONE: MSPI_CUDA(launch_pdl(dw3d_strip_kernel<PP, SS, MSPI_ACT_NONE>, g, 128, 0, stream, *d, xb, wgt, shift, yb, threads, c8, strips)); break;   \
+      case MSPI_ACT_RELU: MSPI_CUDA(launch_pdl(dw3d_strip_kernel<PP, SS, MSPI_ACT_RELU>, g, 128, 0, stream, *d, xb, wgt, shift, yb, threads, c8, strips)); break;   \
+      case MSPI_ACT_SWISH: MSPI_CUDA(launch_pdl(dw3d_strip_kernel<PP, SS, MSPI_ACT_SWISH>, g, 128, 0, stream, *d, xb, wgt, shift, yb, threads, c8, strips)); break; \
       default: return set_error(MSPI_ERR_ARG, "mspi_dwconv3d_bn: activation %d", d->act);                                  \
     }
     if (P == 8) { MSPI_DW3D(8, 1) }
@@ -488,8 +502,8 @@ extern "C" int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const floa
     else { MSPI_DW3D(4, 2) }
 #undef MSPI_DW3D
   } else {
-    dw3d_kernel<<<grid_for(total), 256, 0, stream>>>(*d, static_cast<const __nv_bfloat16*>(x), wgt, shift,
-                                                     static_cast<__nv_bfloat16*>(y), total, c8);
+    MSPI_CUDA(launch_pdl(dw3d_kernel, grid_for(total), 256, 0, stream, *d, static_cast<const __nv_bfloat16*>(x), wgt, shift,
+                                                     static_cast<__nv_bfloat16*>(y), total, c8));
   }
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
@@ -508,8 +522,8 @@ extern "C" int mspi_channel_mean(const void* x, float* out, int n, int64_t rows,
   if (chunks < 1) chunks = 1;
   const long long rpb = (rows + chunks - 1) / chunks;
   dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), n), block(tx, ty);
-  channel_sum_kernel<<<grid, block, sizeof(float) * ty * c, stream>>>(static_cast<const __nv_bfloat16*>(x), out, rows, c,
-                                                                      cstride, rpb, 1.f / static_cast<float>(rows));
+  MSPI_CUDA(launch_pdl(channel_sum_kernel, grid, block, sizeof(float) * ty * c, stream, static_cast<const __nv_bfloat16*>(x), out, rows, c,
+                                                                      cstride, rpb, 1.f / static_cast<float>(rows)));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -519,7 +533,7 @@ extern "C" int mspi_se_gate(const float* mean, const float* w1, const float* b1,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MSPI_CHECK_ARG(mean && w1 && b1 && w2 && b2 && gate && n > 0 && c > 0 && cfc > 0 && c + cfc <= 8192, "mspi_se_gate: bad argument");
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
-  se_gate_kernel<<<n, 256, sizeof(float) * (c + cfc), stream>>>(mean, w1, b1, w2, b2, gate, c, cfc);
+  MSPI_CUDA(launch_pdl(se_gate_kernel, n, 256, sizeof(float) * (c + cfc), stream, mean, w1, b1, w2, b2, gate, c, cfc));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
@@ -532,8 +546,8 @@ extern "C" int mspi_scale_act(const void* x, const float* gate, void* y, int n, 
   if (num_sms() <= 0) return set_error(MSPI_ERR_CUDA, "no CUDA device");
   const int c8 = c / 8;
   const long long total = static_cast<long long>(n) * rows * c8;
-  scale_act_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), gate,
-                                                        static_cast<__nv_bfloat16*>(y), rows, c8, total, act);
+  MSPI_CUDA(launch_pdl(scale_act_kernel, grid_for(total), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), gate,
+                                                        static_cast<__nv_bfloat16*>(y), rows, c8, total, act));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
 }
