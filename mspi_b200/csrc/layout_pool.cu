@@ -398,6 +398,84 @@ __global__ void maxpool333_kernel(MspiPoolDesc d, const __nv_bfloat16* __restric
   }
 }
 
+// Same pooling from a shared-memory tile (the default): a block owns one sample, a strip of `hs` output rows, 16 channels
+// (one 32-byte sector per pixel) and ALL T <= 8 frames.  The (hs + 2) x W x T input tile is fetched once with cp.async — every
+// load of the block is in flight at the same time — and each thread then reduces 9 neighbours per frame from shared memory
+// and slides the 3-frame maximum over t in registers.  The sliding-window kernel above walks a row serially (9 loads, wait,
+// reduce, next column): ncu showed 14-18 long-scoreboard stalls per issue at 22 % occupancy, 1.1-2.1 TB/s, and its L2 -> L1
+// traffic is 9x the tensor (profiles/r02_small_kernels.md).  Here the tensor is read 1 + 2 / hs times.
+constexpr int kPoolTileMaxT = 8;
+constexpr int kPoolTileSmem = 74 * 1024;
+__global__ void __launch_bounds__(256) maxpool333_tile_kernel(MspiPoolDesc d, const __nv_bfloat16* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ y, int hs, int strips, int cgroups,
+                                                              int lanes) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  extern __shared__ uint4 pool_tile[];   // [T][hs + 2][W][2]
+  const int T = d.t, H = d.h, W = d.w, R = hs + 2;
+  int r = blockIdx.x;
+  const int cgp = r % cgroups;
+  r /= cgroups;
+  const int strip = r % strips, n = r / strips;
+  const int h0 = strip * hs, rows = min(hs, H - h0);
+  const int xw = threadIdx.x % (2 * W), ry = threadIdx.x / (2 * W);   // (column, 8-channel half) and row lane of this thread
+  const int w = xw >> 1, v = xw & 1;
+  const long long coff = static_cast<long long>(cgp * 2 + v) * 8;
+  if (ry < lanes) {
+    for (int q = ry; q < T * R; q += lanes) {
+      const int t = q / R, rr = q - t * R;
+      const int hsrc = min(max(h0 - 1 + rr, 0), H - 1);   // a duplicated row does not change a maximum
+      const __nv_bfloat16* src = x + ((static_cast<long long>(n * T + t) * H + hsrc) * W + w) * d.in_cstride + coff;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(&pool_tile[(q * W + w) * 2 + v]));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (ry >= lanes) return;
+  const int wl = max(w - 1, 0), wr = min(w + 1, W - 1);
+  for (int hl = ry; hl < rows; hl += lanes) {
+    __nv_bfloat162 m[kPoolTileMaxT][4];
+#pragma unroll
+    for (int t = 0; t < kPoolTileMaxT; ++t) {
+      if (t < T) {
+        const uint4* base = pool_tile + static_cast<size_t>(t * R + hl) * W * 2 + v;
+        uint4 a = base[wl * 2];
+        m[t][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x);
+        m[t][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+        m[t][2] = *reinterpret_cast<const __nv_bfloat162*>(&a.z);
+        m[t][3] = *reinterpret_cast<const __nv_bfloat162*>(&a.w);
+#pragma unroll
+        for (int k = 1; k < 9; ++k) {
+          const int kh = k / 3, kw = k - 3 * kh;
+          const uint4 b = base[(kh * W + (kw == 0 ? wl : (kw == 1 ? w : wr))) * 2];
+          m[t][0] = __hmax2(m[t][0], *reinterpret_cast<const __nv_bfloat162*>(&b.x));
+          m[t][1] = __hmax2(m[t][1], *reinterpret_cast<const __nv_bfloat162*>(&b.y));
+          m[t][2] = __hmax2(m[t][2], *reinterpret_cast<const __nv_bfloat162*>(&b.z));
+          m[t][3] = __hmax2(m[t][3], *reinterpret_cast<const __nv_bfloat162*>(&b.w));
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kPoolTileMaxT; ++t) {
+      if (t < T) {
+        constexpr int kNext = kPoolTileMaxT - 1;
+        const int ta = t > 0 ? t - 1 : 0, tn = t < kNext ? t + 1 : t;   // compile-time indices (t is unrolled)
+        const bool has_next = t + 1 < T;
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 nx = has_next ? m[tn][j] : m[t][j];
+          const __nv_bfloat162 q = __hmax2(__hmax2(m[ta][j], m[t][j]), nx);
+          ow[j] = *reinterpret_cast<const uint32_t*>(&q);
+        }
+        const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(y + ((static_cast<long long>(n * T + t) * H + h0 + hl) * W + w) * d.out_cstride + coff) = o;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- bilinear upsample
 // align_corners=False, integer scale k: src = (dst + 0.5)/k - 0.5 clamped at 0 (PyTorch's
 // area_pixel_compute_source_index), second index clamped at size-1.
@@ -821,6 +899,30 @@ extern "C" int mspi_maxpool3d(const MspiPoolDesc* d, const void* x, void* y, voi
   const long long total = static_cast<long long>(d->n) * d->ot * d->oh * d->ow * c8;
   if (d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 1 && d->ph == 1 &&
       d->pw == 1 && d->ot == d->t && d->oh == d->h && d->ow == d->w) {
+    // shared-memory tile kernel (MSPI_POOL_TILE, default on): T <= 8 frames, 16-channel groups, rows of up to 128 pixels
+    static const bool tile_on = [] { const char* e = getenv("MSPI_POOL_TILE"); return !e || atoi(e) != 0; }();
+    if (tile_on && d->t <= kPoolTileMaxT && c8 % 2 == 0 && 2 * d->w <= 256) {
+      const size_t row_bytes = static_cast<size_t>(d->t) * d->w * 32;     // one tile row: all frames, 16 channels
+      int hs = static_cast<int>(kPoolTileSmem / row_bytes) - 2;
+      if (hs > d->h) hs = d->h;
+      if (hs >= 2 || hs == d->h) {
+        const int lanes = (256 / (2 * d->w)) < 1 ? 1 : 256 / (2 * d->w);
+        const int threads = 2 * d->w * lanes;
+        const int strips = (d->h + hs - 1) / hs, cgroups = c8 / 2;
+        const size_t smem = row_bytes * (hs + 2);
+        const long long blocks = static_cast<long long>(d->n) * strips * cgroups;
+        MSPI_CHECK_ARG(blocks < (1ll << 31), "mspi_maxpool3d: too many tiles");
+        static bool attr_set = false;
+        if (!attr_set) {
+          MSPI_CUDA(cudaFuncSetAttribute(maxpool333_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolTileSmem));
+          attr_set = true;
+        }
+        MSPI_CUDA(launch_pdl(maxpool333_tile_kernel, static_cast<unsigned>(blocks), threads, smem, stream, *d,
+                             static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), hs, strips, cgroups, lanes));
+        MSPI_LAUNCH_CHECK();
+        return MSPI_OK;
+      }
+    }
     const long long rows = static_cast<long long>(d->n) * d->t * d->h * c8;
     MSPI_CUDA(launch_pdl(maxpool333_kernel, grid_for(rows), kBlock, 0, stream, *d, static_cast<const __nv_bfloat16*>(x),
                                                              static_cast<__nv_bfloat16*>(y), rows, c8));

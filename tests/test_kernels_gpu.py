@@ -380,6 +380,27 @@ def test_maxpool_variants():
         assert torch.equal(ya.to_ncdhw().cpu(), ref), f"maxpool {k} {s} {p}"  # selection only: bit-exact
 
 
+@pytest.mark.parametrize("n,c,t,h,w", [(2, 32, 8, 28, 48), (3, 48, 4, 14, 24), (2, 64, 2, 7, 12), (1, 16, 1, 5, 20),
+                                       (2, 32, 8, 9, 48), (1, 32, 3, 30, 128)])
+def test_maxpool333_tile_kernel(n, c, t, h, w):
+    """Inception pooling branch (3,3,3)/1 pad 1 (s3d.py:134) from a shared-memory tile: 16-channel groups, all frames of a row
+    strip per block, partial last strips, channel-slice strides on both sides; selection only, so bit-exact against
+    F.max_pool3d (the sliding-window kernel it replaces stays reachable with MSPI_POOL_TILE=0 and for odd channel-group
+    counts, test_maxpool_variants)."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, c, t, h, w, generator=g)
+    xa = _act_from_ncdhw(x, c + 16, 8)
+    ref = F.max_pool3d(_bf(x), (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    buf = torch.zeros(n, t, h, w, c + 24, dtype=torch.bfloat16, device="cuda")
+    ya = Act(buf, 16, c)
+    ops.maxpool3d(xa, ya, (3, 3, 3), (1, 1, 1), (1, 1, 1))()
+    torch.cuda.synchronize()
+    assert torch.equal(ya.to_ncdhw().cpu(), ref)
+    assert (buf[..., :16] == 0).all() and (buf[..., 16 + c:] == 0).all()     # neighbouring channels untouched
+
+
 @pytest.mark.parametrize("k", [2, 4, 8])
 def test_upsample_bilinear(k):
     from mspi_b200 import ops
