@@ -1003,12 +1003,23 @@ int dwconv_fast_path(const MspiDwDesc* d, const void* x, const float* wgt, const
     const long long blocks = (total + threads - 1) / threads;
     MSPI_CHECK_ARG(blocks < (1ll << 31), "dwconv_t: grid out of range");
     const int ob = d->out_dtype == MSPI_BF16 ? 1 : 0;
-    if (d->in_dtype == MSPI_BF16)
-      MSPI_CUDA(launch_pdl(dwt_kernel<__nv_bfloat16, 8>, static_cast<int>(blocks), threads, 0, stream, 
-          static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
-    else
-      MSPI_CUDA(launch_pdl(dwt_kernel<float, 8>, static_cast<int>(blocks), threads, 0, stream, static_cast<const float*>(x), wgt, bias, y,
-                                                                            ob, n_hw, d->t, HW, d->c, d->kt));
+    // T <= 4 (the decoder's laterals at the default clip length): the 4-frame instance keeps half the registers of the
+    // 8-frame one (82 registers left 22 % of the warp slots occupied on a kernel that only waits for HBM)
+    if (d->in_dtype == MSPI_BF16) {
+      if (d->t <= 4)
+        MSPI_CUDA(launch_pdl(dwt_kernel<__nv_bfloat16, 4>, static_cast<int>(blocks), threads, 0, stream,
+                             static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
+      else
+        MSPI_CUDA(launch_pdl(dwt_kernel<__nv_bfloat16, 8>, static_cast<int>(blocks), threads, 0, stream,
+                             static_cast<const __nv_bfloat16*>(x), wgt, bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
+    } else {
+      if (d->t <= 4)
+        MSPI_CUDA(launch_pdl(dwt_kernel<float, 4>, static_cast<int>(blocks), threads, 0, stream, static_cast<const float*>(x), wgt,
+                             bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
+      else
+        MSPI_CUDA(launch_pdl(dwt_kernel<float, 8>, static_cast<int>(blocks), threads, 0, stream, static_cast<const float*>(x), wgt,
+                             bias, y, ob, n_hw, d->t, HW, d->c, d->kt));
+    }
     MSPI_LAUNCH_CHECK();
     return MSPI_OK;
   }

@@ -183,6 +183,34 @@ def test_activation_arena_reuses_memory_without_changing_results(monkeypatch):
     model.use_cuda_graph = False
 
 
+@pytest.mark.parametrize("encoder", ["s3d", "x3dl"])
+def test_programmatic_dependent_launch_does_not_change_results(encoder):
+    """mspi_set_pdl: with programmatic dependent launch the next kernel's prologue overlaps the previous kernel's drain, and every
+    kernel waits (griddepcontrol.wait) before its first global access — so the maps of the captured three-branch graph must
+    be the same bits with and without it, replay after replay."""
+    from mspi_b200 import _lib
+    lib = _lib.load()
+    model = _small_model(encoder=encoder, seed=13)
+    g = torch.Generator().manual_seed(9)
+    clips = torch.randn(3, 3, 16, 64, 96, generator=g).cuda()
+    aud = torch.randn(3, 1, 257, 111, generator=g).cuda()
+    prev = lib.mspi_set_pdl(0)
+    try:
+        outs = {}
+        for on in (0, 1):
+            lib.mspi_set_pdl(on)
+            model.invalidate_plans()
+            model.use_cuda_graph = True
+            for _ in range(3):
+                out, _l = model(clips, aud)
+            torch.cuda.synchronize()
+            outs[on] = out.clone()
+        assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()
+    finally:
+        lib.mspi_set_pdl(prev)
+        model.use_cuda_graph = False
+
+
 def test_forward_accepts_uint8_frames():
     """uint8 [B,T,H,W,3] frames, normalised on the device (ToTensor + Normalize of inference.py:154-165 folded into the clip
     conversion kernel), give exactly the forward of the host-normalised fp32 clip."""
