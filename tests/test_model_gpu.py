@@ -205,7 +205,15 @@ def test_programmatic_dependent_launch_does_not_change_results(encoder):
                 out, _l = model(clips, aud)
             torch.cuda.synchronize()
             outs[on] = out.clone()
-        assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()
+            if on == 0:      # run-to-run spread without PDL: X3D's SE means are fp32 atomic sums, so its maps are not bit-stable
+                again, _l = model(clips, aud)
+                torch.cuda.synchronize()
+                spread = (again - outs[0]).abs().max().item()
+        diff = (outs[0] - outs[1]).abs().max().item()
+        if encoder == "s3d":
+            assert spread == 0.0 and diff == 0.0, (spread, diff)
+        else:
+            assert diff <= max(4 * spread, 1e-6 * outs[0].abs().max().item()), (spread, diff)
     finally:
         lib.mspi_set_pdl(prev)
         model.use_cuda_graph = False
