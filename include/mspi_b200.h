@@ -116,6 +116,13 @@ int mspi_conv_gemm(const MspiConvDesc* d, const void* x, const void* w, const fl
 int mspi_conv_gemm_ln(const MspiConvDesc* d, const void* x, const void* w, const float* scale, const float* shift,
                       const float* ln_weight, const float* ln_bias, float ln_eps, int ln_groups, void* y, void* stream);
 
+/* (1,3,3) convolution, stride 1, zero padding (0,1,1), Cin = Cout = c = 8 or 16, + per-channel shift (+ ReLU), bf16 NDHWC
+ * channel-slice views in and out: SlowFast fast-pathway BottleneckTransform.branch2.b with dim_inner 8 / 16
+ * (backbones/SlowFast/resnet_helper.py:323-341) on CUDA cores — nine K = 8 taps are no work for a tensor-core tile.
+ * w_packed: fp32 [9 taps (kh, kw)][ci][co] with the BatchNorm scale already multiplied in; shift: fp32 [c] or null. */
+int mspi_conv133_small(const void* x, int64_t x_cstride, const float* w_packed, const float* shift, void* y,
+                       int64_t y_cstride, int64_t planes, int h, int w, int c, int act, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Weight gradient of mspi_conv_gemm's convolution on tcgen05 tensor cores (training step, engine_train.py:74:
  * loss.backward() through nn.Conv3d / nn.Linear):

@@ -134,6 +134,7 @@ _SIGNATURES = {
     "mspi_debug_dw_phase_cycles": (C.c_int, [C.c_void_p, C.c_int]),
     "mspi_debug_gemm_epilogue_cycles": (C.c_int, [C.c_void_p, C.c_int]),
     "mspi_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "mspi_conv133_small": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_conv_gemm_ln": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P]),
     "mspi_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "mspi_mlp_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _P]),

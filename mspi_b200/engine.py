@@ -138,6 +138,15 @@ class ForwardPlan:
     def conv(self, name: str, x: Act, w: torch.Tensor, scale=None, shift=None, stride=(1, 1, 1), pad=(0, 0, 0),
              act=ACT_NONE, out: Optional[Act] = None, residual: Optional[Act] = None, res_after_act=False,
              out_dtype=torch.bfloat16, dtype=torch.bfloat16, split_weights=False) -> Act:
+        if act in (ACT_NONE, ACT_RELU) and not split_weights and not self.keep_taps and \
+                ops.conv133_small_ok(w, stride, pad, x, dtype, out_dtype, residual):
+            # SlowFast fast pathway, dim_inner 8 / 16: nine K = 8 taps are no work for a tensor-core tile (4 TFLOP/s)
+            if out is None:
+                out = self.new(x.n, x.t, x.h, x.w, w.shape[0], out_dtype)
+            run = ops.conv133_small(x, out, w, scale, shift, act)
+            self.add(name, run)
+            self.flops += run.flops
+            return out
         c = Conv(w, scale, shift, stride=stride, pad=pad, act=act, dtype=dtype, res_after_act=res_after_act,
                  device=self.device, name=name, split_weights=split_weights, cache=getattr(self, "wcache", None))
         if out is None:

@@ -658,6 +658,36 @@ def stem_conv(frames: torch.Tensor, h: int, w: int, weight: torch.Tensor, scale,
     return run
 
 
+# ------------------------------------------------------------------------------------------ few-channel (1,3,3) conv
+def conv133_small_ok(w: torch.Tensor, stride, pad, x: "Act", dtype, out_dtype, residual) -> bool:
+    """Whether a conv is the few-channel (1,3,3) layer mspi_conv133_small serves (SlowFast fast pathway, dim_inner 8 / 16)."""
+    return (w.dim() == 5 and tuple(w.shape[2:]) == (1, 3, 3) and w.shape[0] == w.shape[1] and w.shape[0] in (8, 16)
+            and tuple(stride) == (1, 1, 1) and tuple(pad) == (0, 1, 1) and residual is None and dtype == torch.bfloat16
+            and out_dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and x.c == w.shape[1] and x.c0 % 8 == 0
+            and x.cs % 8 == 0 and os.environ.get("MSPI_SMALLC_CONV", "1") != "0")
+
+
+def conv133_small(x: "Act", y: "Act", weight: torch.Tensor, scale, shift, act: int) -> Callable[[], None]:
+    """y = act(conv(1,3,3)(x) * scale + shift) for Cin = Cout = 8 / 16 on CUDA cores (mspi_conv133_small); the BatchNorm scale
+    is multiplied into the fp32 weights on the host."""
+    lib = _lib.load()
+    c = weight.shape[0]
+    assert (y.n, y.t, y.h, y.w, y.c) == (x.n, x.t, x.h, x.w, c) and y.dtype == torch.bfloat16 and y.c0 % 8 == 0 and y.cs % 8 == 0
+    w = weight.detach().float()[:, :, 0]                       # [co, ci, 3, 3]
+    if scale is not None:
+        w = w * scale.detach().float().view(-1, 1, 1, 1)
+    wp = w.permute(2, 3, 1, 0).contiguous().view(-1).to(x.buf.device)     # [kh][kw][ci][co]
+    sh = None if shift is None else shift.detach().float().contiguous().to(x.buf.device)
+    xp, yp, xcs, ycs = x.ptr, y.ptr, x.cs, y.cs
+    planes, h, wd = x.n * x.t, x.h, x.w
+
+    def run(_keep=(x.buf, y.buf, wp, sh)):
+        _lib.check(lib.mspi_conv133_small(xp, xcs, _ptr(wp), _ptr(sh), yp, ycs, planes, h, wd, c, act, _stream()), "conv133_small")
+
+    run.flops = 2.0 * x.pixels * c * c * 9
+    return run
+
+
 # ------------------------------------------------------------------------------------------ fused ConvNeXt MLP
 def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma, ln=None) -> Callable[[], None]:
     """y = residual + gamma * (fc2(gelu(fc1(x)))) in one kernel (mspi_mlp_fused); C = 96 / 192, bf16.

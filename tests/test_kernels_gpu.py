@@ -226,6 +226,29 @@ def test_stem_conv_with_layernorm_epilogue(b, t, h, w):
     assert (got - ref).abs().max() < 0.04 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("c,n,t,h,w", [(8, 2, 5, 14, 24), (16, 2, 3, 9, 13), (8, 1, 2, 56, 96), (16, 1, 2, 28, 48)])
+def test_conv133_small_channels(c, n, t, h, w):
+    """SlowFast fast-pathway branch2.b (resnet_helper.py:323-341, dim_inner 8 / 16): (1,3,3) conv + BN + ReLU on CUDA cores
+    (mspi_conv133_small) against F.conv3d on the bf16-rounded input; ragged widths, channel-slice views on both sides, and the
+    plan's dispatch (ForwardPlan.conv sends exactly these layers here)."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(n, c, t, h, w, generator=g)
+    wgt = torch.randn(c, c, 1, 3, 3, generator=g) / (9 * c) ** 0.5
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    xa = _act_from_ncdhw(x, c + 8, 8)
+    buf = torch.zeros(n, t, h, w, c + 16, dtype=torch.bfloat16, device="cuda")
+    ya = Act(buf, 8, c)
+    assert ops.conv133_small_ok(wgt, (1, 1, 1), (0, 1, 1), xa, torch.bfloat16, torch.bfloat16, None)
+    ops.conv133_small(xa, ya, wgt, scale, shift, 1)()
+    torch.cuda.synchronize()
+    ref = (F.conv3d(_bf(x), wgt, None, 1, (0, 1, 1)) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)).relu()
+    assert _rel(ya.to_ncdhw().cpu(), ref) < BF16_TOL
+    assert (buf[..., :8] == 0).all() and (buf[..., 8 + c:] == 0).all()
+    assert not ops.conv133_small_ok(wgt, (1, 2, 2), (0, 1, 1), xa, torch.bfloat16, torch.bfloat16, None)
+
+
 def test_conv_1x1_spatial_stride_pick_mode():
     """ResBlock.branch1 (1x1x1 conv, stride (1,2,2), resnet_helper.py:556-566) as a strided TMA view, no gather."""
     got, ref, mode = _run_conv(24, 48, (1, 1, 1), (1, 2, 2), (0, 0, 0), (2, 3, 12, 20), seed=31)
