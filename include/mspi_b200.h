@@ -269,6 +269,12 @@ typedef struct {
   int32_t act;
 } MspiDw3dDesc;
 int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y, void* stream);
+/* The same layer AND the per-(sample, channel) mean of its output, fp32 [n][c] — the squeeze of the SE block that follows
+ * X3DTransform.b (resnet_helper.py:47-73, 327-333) — accumulated by the depthwise kernel itself where its shared-memory tile
+ * form applies (16 partial means per (sample, channel) in `work`, then summed: the blocks of one sample would otherwise queue
+ * on one atomic unit per channel), else by mspi_channel_mean. */
+int mspi_dwconv3d_bn_mean(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y,
+                          float* mean_out, float* work /* scratch, fp32 [n][16][c] */, void* stream);
 /* Squeeze-Excitation (resnet_helper.py:47-73): out[n][c] = mean over rows of x[n][rows][c] (bf16, pixel stride cstride); */
 int mspi_channel_mean(const void* x, float* out, int n, int64_t rows, int c, int64_t cstride, void* stream);
 /* gate[n][c] = sigmoid(w2 relu(w1 mean[n] + b1) + b2), w1 fp32 [cfc][c], w2 fp32 [c][cfc]; */

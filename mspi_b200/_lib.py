@@ -153,6 +153,7 @@ _SIGNATURES = {
     "mspi_upsample_bilinear": (C.c_int, [C.POINTER(UpDesc), _P, _P, _P]),
     "mspi_dwconv_ln": (C.c_int, [C.POINTER(DwDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_dwconv3d_bn": (C.c_int, [C.POINTER(Dw3dDesc), _P, _P, _P, _P, _P]),
+    "mspi_dwconv3d_bn_mean": (C.c_int, [C.POINTER(Dw3dDesc), _P, _P, _P, _P, _P, _P, _P]),
     "mspi_channel_mean": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int64, _P]),
     "mspi_se_gate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mspi_scale_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),

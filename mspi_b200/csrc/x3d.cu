@@ -168,14 +168,31 @@ __global__ void dw3d_strip_kernel(MspiDw3dDesc d, const __nv_bfloat16* __restric
 // box of the 5-D view (c, w, h, t, n): coordinates outside the tensor — spatial borders and the frames before / after the
 // clip — are zero-filled by the copy engine, which is exactly the convolution's padding.  A thread owns 8 channels of a strip
 // of 8 output pixels (64 accumulators as fp32 pairs); per (kt, kh) it reads 10 vectors from shared memory for 96 packed FMAs.
+constexpr int kSeSlots = 16;
+// mean[n][c] = sum over the kSeSlots partial means work[n][slot][c] the tiled depthwise kernel accumulated
+__global__ void slot_sum_kernel(const float* __restrict__ work, float* __restrict__ mean, int n, int c) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i - s * c;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSeSlots; ++k) t += work[(static_cast<long long>(s) * kSeSlots + k) * c + ch];
+  mean[i] = t;
+}
+
 template <int ACT, int CG8T>   // CG8T: channel octets per group at compile time (shared-memory offsets become immediates), 0 = run time
 __global__ void __launch_bounds__(160)
 dw3d_tile_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ wgt, const float* __restrict__ shift,
                  __nv_bfloat16* __restrict__ y, int T, int H, int W, int C, long long out_cstride, int TR, int SC, int cg8_arg,
-                 int tiles_x, int nthreads) {
+                 int tiles_x, int nthreads, float* __restrict__ mean_out, float mean_scale) {
   pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
   pdl_wait();
   constexpr int P = 8;
+  // mean_out: the SE block's per-(sample, channel) mean of this layer's output (resnet_helper.py:47-73), accumulated here —
+  // block-wide partial sums in shared memory, one atomic per channel and block — instead of by a separate pass over y
+  __shared__ __align__(16) float s_part[160 * 8];   // per-thread partial sums (shared atomics: 16-way contention, +30 % kernel time)
   const int CG8 = CG8T > 0 ? CG8T : cg8_arg;
   extern __shared__ __align__(128) uint8_t dw3_smem[];
   __shared__ __align__(8) unsigned long long bar_mem;
@@ -203,7 +220,8 @@ dw3d_tile_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restr
   }
   __syncthreads();
   tc::mbar_wait(bar, 0);
-  if (!active) return;
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
   const __nv_bfloat16* tile = reinterpret_cast<const __nv_bfloat16*>(dw3_smem);
   const float4* wq = reinterpret_cast<const float4*>(wgt + c0) + 2 * cg;
   const int wstride = C / 4;   // float4 per tap row
@@ -238,7 +256,7 @@ dw3d_tile_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restr
     }
   }
   const int oy = y0 + r;
-  if (oy >= H) return;
+  if (oy < H) {
   __nv_bfloat16* yrow = y + ((static_cast<long long>(n) * T + ot) * H + oy) * static_cast<long long>(W) * out_cstride + c0 + 8 * cg;
 #pragma unroll
   for (int p = 0; p < P; ++p) {
@@ -250,13 +268,34 @@ dw3d_tile_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restr
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = act_f(f[e], ACT);
       *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ox) * out_cstride) = pack8(f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) csum[e] += f[e];
+    }
+  }
+  }
+  }   // active
+  if (mean_out != nullptr) {   // block-uniform
+    if (active) {
+      float4* q = reinterpret_cast<float4*>(s_part + tid * 8);
+      q[0] = make_float4(csum[0], csum[1], csum[2], csum[3]);
+      q[1] = make_float4(csum[4], csum[5], csum[6], csum[7]);
+    }
+    __syncthreads();
+    if (tid < CG) {            // thread = channel: add up the strips' partial sums (thread st * CG8 + cg holds channels 8 cg ..)
+      const int cgi = tid >> 3, e = tid & 7;
+      float t = 0.f;
+      for (int st2 = cgi; st2 < nthreads; st2 += CG8) t += s_part[st2 * 8 + e];
+      // kSeSlots partial means per (sample, channel): the 672 blocks of a sample would otherwise queue on one L2 atomic unit
+      // per channel (measured: +35 us per launch); slot_sum_kernel adds the slots up
+      const int slot = (blockIdx.x + blockIdx.y * 3 + blockIdx.z * 5) % kSeSlots;
+      atomicAdd(mean_out + (static_cast<long long>(n) * kSeSlots + slot) * C + c0 + tid, t * mean_scale);
     }
   }
 }
 
 // Returns 1 when the shape is not covered (the caller falls back to the strip kernel).
 static int launch_dw3d_tile(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, float* mean_out = nullptr) {
   static const bool on = [] { const char* e = getenv("MSPI_DW3D_TILE"); return !e || atoi(e) != 0; }();
   if (!on || d->sh != 1 || d->sw != 1 || d->in_cstride != d->c) return 1;
   const int c8 = d->c / 8;
@@ -294,13 +333,15 @@ static int launch_dw3d_tile(const MspiDw3dDesc* d, const void* x, const float* w
   const long long frames = static_cast<long long>(d->n) * d->t;
   if (frames > 65535 || tiles_y > 65535) return 1;
   const int block = (nthreads + 31) / 32 * 32;
+  const float mean_scale = 1.f / (static_cast<float>(d->t) * d->h * d->w);
+  if (mean_out != nullptr && (nthreads > 160 || block < cg8 * 8)) return 1;   // the block reduces its channels through s_part[160][8]
   dim3 grid(tiles_x * groups, tiles_y, static_cast<unsigned>(frames));
   auto yb = static_cast<__nv_bfloat16*>(y);
 #define MSPI_DW3T_(A, G)                                                                                                     \
   {                                                                                                                          \
     MSPI_CUDA(cudaFuncSetAttribute(dw3d_tile_kernel<A, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));        \
     MSPI_CUDA(launch_pdl(dw3d_tile_kernel<A, G>, grid, block, smem, stream, map, wgt, shift, yb, d->t, d->h, d->w, d->c, d->out_cstride, tr, sc,   \
-                                                          cg8, tiles_x, nthreads));                                          \
+                                                          cg8, tiles_x, nthreads, mean_out, mean_scale));                    \
   }
 #define MSPI_DW3T(A)                                                                                                         \
   {                                                                                                                          \
@@ -550,4 +591,31 @@ extern "C" int mspi_scale_act(const void* x, const float* gate, void* y, int n, 
                                                         static_cast<__nv_bfloat16*>(y), rows, c8, total, act));
   MSPI_LAUNCH_CHECK();
   return MSPI_OK;
+}
+
+// Depthwise conv + shift + activation AND the per-(sample, channel) mean of its output (the SE block's squeeze,
+// resnet_helper.py:47-73): the shared-memory tile kernel accumulates the mean while it stores y; layers it does not cover
+// (stride 2, odd shapes) run the plain kernel and the separate reduction.  mean_out: fp32 [n][c]; work: fp32 [n][16][c] scratch.
+extern "C" int mspi_dwconv3d_bn_mean(const MspiDw3dDesc* d, const void* x, const float* wgt, const float* shift, void* y,
+                                     float* mean_out, float* work, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MSPI_CHECK_ARG(d && x && wgt && shift && y && mean_out && work, "mspi_dwconv3d_bn_mean: null argument");
+  static const bool fuse = [] { const char* e = getenv("MSPI_SE_MEAN_FUSED"); return !e || atoi(e) != 0; }();
+  if (fuse && d->kt == 3 && d->kh == 3 && d->kw == 3 && d->sh == 1 && d->sw == 1 && d->c % 8 == 0 && d->in_cstride % 8 == 0 &&
+      d->out_cstride % 8 == 0 && d->oh == d->h && d->ow == d->w &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(wgt) |
+        reinterpret_cast<uintptr_t>(shift)) & 15) == 0 && num_sms() > 0) {
+    MSPI_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * d->n * kSeSlots * d->c, stream));
+    const int rc = launch_dw3d_tile(d, x, wgt, shift, y, stream, work);
+    if (rc == MSPI_OK) {
+      const int total = d->n * d->c;
+      MSPI_CUDA(launch_pdl(slot_sum_kernel, (total + 255) / 256, 256, 0, stream, static_cast<const float*>(work), mean_out, d->n, d->c));
+      MSPI_LAUNCH_CHECK();
+      return MSPI_OK;
+    }
+    if (rc != 1) return rc;
+  }
+  const int rc = mspi_dwconv3d_bn(d, x, wgt, shift, y, stream_);
+  if (rc != MSPI_OK) return rc;
+  return mspi_channel_mean(y, mean_out, d->n, static_cast<int64_t>(d->t) * d->oh * d->ow, d->c, d->out_cstride, stream_);
 }

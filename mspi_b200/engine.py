@@ -386,14 +386,19 @@ class ForwardPlan:
         has_se = (q + ".branch2.se.fc1.weight") in self.sd
         sc, sh = self.bn(q + ".branch2.b_bn", 1e-5)
         b = self.new(x.n, x.t, x.h // stride, x.w // stride, ip)
-        self.add(q + ".branch2.b", ops.dwconv3d_bn(a, b, self.P(q + ".branch2.b.weight"), sc, sh, stride,
-                                                   ops.ACT_NONE if has_se else ops.ACT_SWISH))
+        # SE squeeze (mean over t, h, w of b) accumulated by the depthwise kernel itself: one pass over b less per SE block
+        mean = None
+        if has_se and os.environ.get("MSPI_SE_MEAN_FUSED", "1") != "0":
+            mean = torch.empty((x.n, ip), dtype=torch.float32, device=self.device)
+        self.add(q + (".branch2.b+mean" if mean is not None else ".branch2.b"),
+                 ops.dwconv3d_bn(a, b, self.P(q + ".branch2.b.weight"), sc, sh, stride,
+                                 ops.ACT_NONE if has_se else ops.ACT_SWISH, mean=mean))
         self.flops += 2.0 * b.pixels * inner * 27
         if has_se:
             se = q + ".branch2.se."
-            for nm, fn in zip(("mean", "fc", "scale+swish"),
-                              ops.se_block(b, self.P(se + "fc1.weight"), self.P(se + "fc1.bias"), self.P(se + "fc2.weight"),
-                                           self.P(se + "fc2.bias"))):
+            fns = ops.se_block(b, self.P(se + "fc1.weight"), self.P(se + "fc1.bias"), self.P(se + "fc2.weight"),
+                               self.P(se + "fc2.bias"), mean=mean)
+            for nm, fn in zip(("mean", "fc", "scale+swish")[3 - len(fns):], fns):
                 self.add(se + nm, fn)
         short = self.res_shortcut(q, x, stride)
         sc, sh = self.bn(q + ".branch2.c_bn", 1e-5)

@@ -730,7 +730,7 @@ def mlp_fused(x: Act, y: Act, residual: Act, fc1_w, fc1_b, fc2_w, fc2_b, gamma, 
 
 # ------------------------------------------------------------------------------------------ X3D pieces
 def dwconv3d_bn(x: Act, y: Act, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
-                stride_hw: int = 1, act: int = ACT_NONE) -> Callable[[], None]:
+                stride_hw: int = 1, act: int = ACT_NONE, mean: Optional[torch.Tensor] = None) -> Callable[[], None]:
     """Depthwise Conv3d [C,1,kt,kh,kw] ("same" padding, stride (1,s,s)) + per-channel scale/shift + activation.
     The channel count of x / y may exceed the weight's (buffers padded to a multiple of 8): extra channels get zero
     weights and zero shift, so they stay zero."""
@@ -757,15 +757,24 @@ def dwconv3d_bn(x: Act, y: Act, weight: torch.Tensor, scale: Optional[torch.Tens
     assert (y.n, y.t) == (x.n, x.t) and x.c0 % 8 == 0 and y.c0 % 8 == 0
     xp, yp = x.ptr, y.ptr
 
-    def run(_keep=(x.buf, y.buf, wt, sh, d)):
-        _lib.check(lib.mspi_dwconv3d_bn(C.byref(d), xp, _ptr(wt), _ptr(sh), yp, _stream()), "dwconv3d_bn")
+    if mean is not None:      # SE squeeze accumulated by the depthwise kernel (mspi_dwconv3d_bn_mean): fp32 [n][cp]
+        assert mean.dtype == torch.float32 and tuple(mean.shape) == (x.n, cp) and y.c0 == 0 and y.cs == cp
+        work = torch.empty((x.n, 16, cp), dtype=torch.float32, device=dev)     # partial means (kSeSlots = 16)
+
+        def run(_keep=(x.buf, y.buf, wt, sh, d, mean, work)):
+            _lib.check(lib.mspi_dwconv3d_bn_mean(C.byref(d), xp, _ptr(wt), _ptr(sh), yp, _ptr(mean), _ptr(work), _stream()),
+                       "dwconv3d_bn_mean")
+    else:
+        def run(_keep=(x.buf, y.buf, wt, sh, d)):
+            _lib.check(lib.mspi_dwconv3d_bn(C.byref(d), xp, _ptr(wt), _ptr(sh), yp, _stream()), "dwconv3d_bn")
 
     return run
 
 
-def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH) -> List[Callable[[], None]]:
+def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH, mean: Optional[torch.Tensor] = None) -> List[Callable[[], None]]:
     """SE (+ the Swish that follows it in X3DTransform): x <- act(x * sigmoid(fc2(relu(fc1(mean_thw(x)))))), in place.
-    resnet_helper.py:47-73,327-333.  Three launches: channel mean, the two FCs, scale+act."""
+    resnet_helper.py:47-73,327-333.  Three launches: channel mean, the two FCs, scale+act; with `mean` (fp32 [n][c], already
+    filled by the layer that produced x: dwconv3d_bn(..., mean=)) the first one is dropped."""
     lib = _lib.load()
     dev = x.buf.device
     cp, n = x.c, x.n
@@ -782,7 +791,10 @@ def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH) -> List[C
     b2 = torch.zeros(cp, dtype=torch.float32, device=w1.device)
     b2[:c] = fc2_b.detach().float()
     b2 = b2.to(dev)
-    mean = torch.empty((n, cp), dtype=torch.float32, device=dev)
+    have_mean = mean is not None
+    if not have_mean:
+        mean = torch.empty((n, cp), dtype=torch.float32, device=dev)
+    assert mean.dtype == torch.float32 and tuple(mean.shape) == (n, cp)
     gate = torch.empty((n, cp), dtype=torch.float32, device=dev)
     rows = x.t * x.h * x.w
     xp = x.ptr
@@ -798,7 +810,7 @@ def se_block(x: Act, fc1_w, fc1_b, fc2_w, fc2_b, act: int = ACT_SWISH) -> List[C
     def k_scale(_keep=keep):
         _lib.check(lib.mspi_scale_act(xp, _ptr(gate), xp, n, rows, cp, act, _stream()), "scale_act")
 
-    return [k_mean, k_gate, k_scale]
+    return [k_gate, k_scale] if have_mean else [k_mean, k_gate, k_scale]
 
 
 # ------------------------------------------------------------------------------------------ other ops

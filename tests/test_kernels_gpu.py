@@ -388,6 +388,45 @@ def test_x3d_depthwise_and_se(c, stride, act):
     assert _rel(got2[:, :creal], z) < BF16_TOL and (got2[:, creal:] == 0).all()
 
 
+@pytest.mark.parametrize("c,stride,n,t,h,w", [(56, 1, 2, 4, 20, 32), (112, 1, 2, 3, 9, 48), (216, 1, 3, 2, 14, 24),
+                                              (432, 1, 2, 4, 7, 12), (56, 2, 2, 4, 20, 32), (56, 1, 1, 1, 5, 7)])
+def test_x3d_depthwise_with_fused_se_mean(c, stride, n, t, h, w):
+    """mspi_dwconv3d_bn_mean: the SE squeeze (mean over t, h, w per sample and channel, resnet_helper.py:47-73) accumulated by
+    the tiled depthwise kernel while it stores its output; stride-2 and tiny shapes fall back to the separate reduction.
+    The conv output must be the plain call's bits, the mean PyTorch's mean of it, and se_block(mean=) the plain SE result."""
+    from mspi_b200 import ops
+    from mspi_b200.ops import Act
+    g = torch.Generator().manual_seed(33)
+    creal = c - 2
+    x = torch.zeros(n, c, t, h, w)
+    x[:, :creal] = torch.randn(n, creal, t, h, w, generator=g)
+    wgt = torch.randn(creal, 1, 3, 3, 3, generator=g) * 0.3
+    scale, shift = torch.rand(creal, generator=g) + 0.5, torch.randn(creal, generator=g) * 0.1 + 0.3
+    xa = _act_from_ncdhw(x)
+    oh, ow = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y0, y1 = Act.empty(n, t, oh, ow, c), Act.empty(n, t, oh, ow, c)
+    mean = torch.full((n, c), 7.0, dtype=torch.float32, device="cuda")
+    ops.dwconv3d_bn(xa, y0, wgt, scale, shift, stride, 0)()
+    ops.dwconv3d_bn(xa, y1, wgt, scale, shift, stride, 0, mean=mean)()
+    torch.cuda.synchronize()
+    assert torch.equal(y0.buf, y1.buf)
+    ref = F.conv3d(_bf(x[:, :creal]), wgt, None, (1, stride, stride), 1, 1, creal) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    m = mean.cpu()
+    assert (m[:, :creal] - ref.mean((2, 3, 4))).abs().max() < 2e-3 * max(1.0, ref.mean((2, 3, 4)).abs().max().item())
+    assert (m[:, creal:] == 0).all()
+    cfc = 8
+    w1, b1 = torch.randn(cfc, creal, 1, 1, 1, generator=g) * 0.3, torch.randn(cfc, generator=g) * 0.1
+    w2, b2 = torch.randn(creal, cfc, 1, 1, 1, generator=g) * 0.3, torch.randn(creal, generator=g) * 0.1
+    fns = ops.se_block(y1, w1, b1, w2, b2, mean=mean)
+    assert len(fns) == 2
+    for fn in fns:
+        fn()
+    for fn in ops.se_block(y0, w1, b1, w2, b2):
+        fn()
+    torch.cuda.synchronize()
+    assert _rel(y1.buf.float().cpu(), y0.buf.float().cpu()) < BF16_TOL
+
+
 def test_maxpool_variants():
     from mspi_b200 import ops
     from mspi_b200.ops import Act
