@@ -410,6 +410,60 @@ __global__ void dwt_bn_kernel(const __nv_bfloat16* __restrict__ x, const float* 
   }
 }
 
+// The same layer as a sliding window over t: a thread keeps the KT frames under the current output frame (KT x 4 registers)
+// and the two frames it will need next, instead of all T frames of its position.  dwt_bn_kernel<16> holds 16 frames x 8
+// channels plus the unrolled tap weights in 231 registers: two 128-thread blocks per SM, 12 % of the warp slots, 1.15 ms for
+// the 1.06 GB of the X3D stem's temporal conv (ncu, profiles/r02_small_kernels.md §5).  Weights come from L1 per use.
+template <int KT>
+__global__ void __launch_bounds__(128)
+dwt_bn_slide_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ shift,
+                    __nv_bfloat16* __restrict__ y, long long n_hw, int T, int HW, int C, int act) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  constexpr int PT = KT / 2, AHEAD = 2;
+  const int c8 = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_hw * c8) return;
+  long long r = idx;
+  const int cg = divmod(r, c8);
+  const long long hw = divmod(r, HW), n = r;
+  const long long base = (n * T * HW + hw) * C + 8 * cg;
+  const long long tstride = static_cast<long long>(HW) * C;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto frame = [&](int f) { return (f >= 0 && f < T) ? __ldg(reinterpret_cast<const uint4*>(x + base + f * tstride)) : zero; };
+  uint4 ring[KT + AHEAD];   // ring[j] = input frame t - PT + j
+#pragma unroll
+  for (int j = 0; j < KT + AHEAD; ++j) ring[j] = frame(j - PT);
+  float sh[8];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg), b = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cg + 1);
+    sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = b.x; sh[5] = b.y; sh[6] = b.z; sh[7] = b.w;
+  }
+  for (int t = 0; t < T; ++t) {
+    const uint4 nxt = frame(t + 1 - PT + KT + AHEAD - 1);   // the frame that enters the ring after this step
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sh[j];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      float f[8];
+      unpack8(ring[k], f);
+      const float4* wp = reinterpret_cast<const float4*>(wgt + static_cast<long long>(k) * C) + 2 * cg;
+      const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j], act);
+    *reinterpret_cast<uint4*>(y + base + t * tstride) = pack8(acc);
+#pragma unroll
+    for (int j = 0; j + 1 < KT + AHEAD; ++j) ring[j] = ring[j + 1];
+    ring[KT + AHEAD - 1] = nxt;
+  }
+}
+
 // Per-(sample, channel) sum over `rows` positions: grid (chunks, N); a block reduces its chunk of rows (threads: channel
 // pair x row lane) and adds its partial sums to out[n][c] (fp32 atomics; out is zeroed by the caller's memset node).
 __global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int c,
@@ -515,6 +569,14 @@ extern "C" int mspi_dwconv3d_bn(const MspiDw3dDesc* d, const void* x, const floa
     const long long n_hw = static_cast<long long>(d->n) * HW;
     const long long blocks = (n_hw * c8 + 127) / 128;
     MSPI_CHECK_ARG(blocks < (1ll << 31), "grid out of range");
+    static const bool slide = [] { const char* e = getenv("MSPI_DWT_SLIDE"); return !e || atoi(e) != 0; }();
+    if (slide && d->kt == 5)
+      MSPI_CUDA(launch_pdl(dwt_bn_slide_kernel<5>, static_cast<int>(blocks), 128, 0, stream, static_cast<const __nv_bfloat16*>(x), wgt,
+                           shift, static_cast<__nv_bfloat16*>(y), n_hw, d->t, HW, d->c, d->act));
+    else if (slide && d->kt == 3)
+      MSPI_CUDA(launch_pdl(dwt_bn_slide_kernel<3>, static_cast<int>(blocks), 128, 0, stream, static_cast<const __nv_bfloat16*>(x), wgt,
+                           shift, static_cast<__nv_bfloat16*>(y), n_hw, d->t, HW, d->c, d->act));
+    else
     MSPI_CUDA(launch_pdl(dwt_bn_kernel<16>, static_cast<int>(blocks), 128, 0, stream, static_cast<const __nv_bfloat16*>(x), wgt, shift,
                                                                     static_cast<__nv_bfloat16*>(y), n_hw, d->t, HW, d->c,
                                                                     d->kt, d->act));
