@@ -156,3 +156,42 @@ def test_image_encoder_checkpoint_load_is_loud():
     with pytest.raises(RuntimeError):
         load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), {"backbone.conv1.weight": torch.zeros(1)}, verbose=False)
     assert load_image_encoder_checkpoint(StaticSaliencyModelConvNext(), {}, verbose=False)["matched"] == 0   # the tests' empty file
+
+
+def test_dispatch_predicates_of_the_specialised_kernels(monkeypatch):
+    """Host logic that routes a layer to a specialised kernel: the few-channel (1,3,3) conv of the SlowFast fast pathway
+    (ops.conv133_small_ok), the ConvNeXt stem with its LayerNorm epilogue (ops.stem_conv_ln_ok), the launch-protocol switch
+    (mspi_set_pdl returns the previous setting)."""
+    from mspi_b200 import _lib, ops
+
+    class FakeAct:           # the predicate only reads these attributes
+        def __init__(self, c, c0=0, cs=None, dtype=torch.bfloat16):
+            self.c, self.c0, self.cs, self.dtype = c, c0, cs or c, dtype
+
+    bf, f32 = torch.bfloat16, torch.float32
+    w8 = torch.zeros(8, 8, 1, 3, 3)
+    ok = lambda *a, **k: ops.conv133_small_ok(*a, **k)
+    assert ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8), bf, bf, None)
+    assert ok(torch.zeros(16, 16, 1, 3, 3), (1, 1, 1), (0, 1, 1), FakeAct(16, 8, 32), bf, bf, None)
+    assert not ok(w8, (1, 2, 2), (0, 1, 1), FakeAct(8), bf, bf, None)                # strided: implicit GEMM
+    assert not ok(w8, (1, 1, 1), (1, 1, 1), FakeAct(8), bf, bf, None)                # temporal padding: not this layer
+    assert not ok(torch.zeros(8, 8, 3, 3, 3), (1, 1, 1), (0, 1, 1), FakeAct(8), bf, bf, None)
+    assert not ok(torch.zeros(32, 32, 1, 3, 3), (1, 1, 1), (0, 1, 1), FakeAct(32), bf, bf, None)
+    assert not ok(torch.zeros(16, 8, 1, 3, 3), (1, 1, 1), (0, 1, 1), FakeAct(8), bf, bf, None)
+    assert not ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8), f32, bf, None) and not ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8), bf, f32, None)
+    assert not ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8), bf, bf, object())            # residual: implicit GEMM epilogue
+    assert not ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8, 4, 16), bf, bf, None)         # pixel vectors must stay 16-byte aligned
+    monkeypatch.setenv("MSPI_SMALLC_CONV", "0")
+    assert not ok(w8, (1, 1, 1), (0, 1, 1), FakeAct(8), bf, bf, None)
+    monkeypatch.delenv("MSPI_SMALLC_CONV")
+
+    assert ops.stem_conv_ln_ok(384, 96, 4, 4, 0) and ops.stem_conv_ln_ok(96, 96, 4, 4, 0)
+    assert not ops.stem_conv_ln_ok(388, 96, 4, 4, 0)          # odd output width: one pixel per row, N = 96 is not a 64-multiple
+    assert not ops.stem_conv_ln_ok(384, 96, 7, 2, 3) and not ops.stem_conv_ln_ok(384, 160, 4, 4, 0)
+    monkeypatch.setenv("MSPI_STEM_WIDE", "0")
+    assert not ops.stem_conv_ln_ok(384, 96, 4, 4, 0)
+    monkeypatch.delenv("MSPI_STEM_WIDE")
+
+    lib = _lib.load()
+    prev = lib.mspi_set_pdl(0)
+    assert lib.mspi_set_pdl(1) == 0 and lib.mspi_set_pdl(prev) == 1
